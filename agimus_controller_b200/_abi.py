@@ -1,0 +1,96 @@
+"""ctypes mirror of ``include/agx.h`` (structs and constants only — no library is loaded here).
+
+Shared by the product loader (``_lib.py``) and, in tests, by the oracle loader (``oracle/orc.py``).
+"""
+import ctypes as C
+
+import numpy as np
+
+AGX_MAX_NV = 16
+AGX_JOINT_REVOLUTE = 0
+AGX_JOINT_PRISMATIC = 1
+
+AGX_OK = 0
+AGX_EINVAL = -1
+AGX_EUNSUPPORTED = -2
+AGX_ECUDA = -3
+AGX_ENOMEM = -4
+
+AGX_STATUS_CONVERGED = 0
+AGX_STATUS_MAXITER = 1
+AGX_STATUS_REGMAX = 2
+AGX_STATUS_NAN = 3
+
+_D = C.c_double
+_I = C.c_int32
+
+
+class AgxModel(C.Structure):
+    """``struct agx_model`` — kinematic-tree table."""
+
+    _fields_ = [
+        ("nv", _I),
+        ("frame_parent", _I),
+        ("parent", _I * AGX_MAX_NV),
+        ("jtype", _I * AGX_MAX_NV),
+        ("axis", (_D * 3) * AGX_MAX_NV),
+        ("placement_R", (_D * 9) * AGX_MAX_NV),
+        ("placement_p", (_D * 3) * AGX_MAX_NV),
+        ("mass", _D * AGX_MAX_NV),
+        ("com", (_D * 3) * AGX_MAX_NV),
+        ("inertia", (_D * 6) * AGX_MAX_NV),
+        ("armature", _D * AGX_MAX_NV),
+        ("gravity", _D * 3),
+        ("frame_R", _D * 9),
+        ("frame_p", _D * 3),
+    ]
+
+
+class AgxFddpOpts(C.Structure):
+    """``struct agx_fddp_opts``."""
+
+    _fields_ = [
+        ("reg_min", _D),
+        ("reg_max", _D),
+        ("reg_incfactor", _D),
+        ("reg_decfactor", _D),
+        ("th_grad", _D),
+        ("th_stepdec", _D),
+        ("th_stepinc", _D),
+        ("th_acceptstep", _D),
+        ("th_acceptnegstep", _D),
+        ("th_stop", _D),
+        ("reg_init", _D),
+        ("fixed_iters", _I),
+        ("n_alphas", _I),
+    ]
+
+
+def ref_size(nv: int) -> int:
+    """Doubles per node reference record: [xref nx][wx nx][uref nu][wu nu][Rref 9][pref 3][wpose 6]."""
+    return 6 * nv + 18
+
+
+def default_fddp_opts(fixed_iters: bool = False) -> AgxFddpOpts:
+    """Crocoddyl ``SolverFDDP`` defaults."""
+    return AgxFddpOpts(
+        reg_min=1e-9,
+        reg_max=1e9,
+        reg_incfactor=10.0,
+        reg_decfactor=10.0,
+        th_grad=1e-12,
+        th_stepdec=0.5,
+        th_stepinc=0.01,
+        th_acceptstep=0.1,
+        th_acceptnegstep=2.0,
+        th_stop=1e-9,
+        reg_init=float("nan"),
+        fixed_iters=1 if fixed_iters else 0,
+        n_alphas=10,
+    )
+
+
+def fill_array(dst, src) -> None:
+    """Copy a (nested) numpy array into a (nested) ctypes array."""
+    a = np.ascontiguousarray(src)
+    C.memmove(dst, a.ctypes.data, min(C.sizeof(dst), a.nbytes))

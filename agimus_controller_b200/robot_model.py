@@ -1,0 +1,290 @@
+"""Kinematic-tree tables — the flattened counterpart of ``RobotModels.robot_model``.
+
+Reference: ``agimus_controller/agimus_controller/factory/robot_model.py:88-351`` builds a Pinocchio
+model from a URDF, locks joints with ``buildReducedModel`` (``:231-259``) and exposes ``robot_model``
+and ``armature``.  Neither Pinocchio nor a URDF parser dependency is needed on the solve path: the
+kernels only consume the numeric table built here (``agx_model`` in ``include/agx.h``).
+
+``RobotTable.from_links`` does the work of ``buildReducedModel`` for fixed / locked joints: bodies
+behind a locked joint are merged into their moving ancestor (mass, centre of mass, inertia with the
+parallel-axis term).  ``panda_table`` instantiates it with the Franka Panda description used by every
+reference test (``agimus_controller/tests/test_ocp_croco_base.py:109-135``; numbers in SURVEY.md
+Appendix A, validated against the reference's golden file by ``tests/test_oracle_golden.py``).
+"""
+from __future__ import annotations
+
+import dataclasses
+import typing as T
+
+import numpy as np
+
+from . import _abi
+
+# Angles exactly as written in the public URDF (truncated pi/2, pi/4).
+_HALF_PI = 1.57079632679
+_QUARTER_PI = 0.785398163397
+
+
+def rpy_to_matrix(r: float, p: float, y: float) -> np.ndarray:
+    """URDF fixed-axis roll/pitch/yaw -> rotation matrix ``Rz(y) Ry(p) Rx(r)``."""
+    cr, sr, cp, sp, cy, sy = np.cos(r), np.sin(r), np.cos(p), np.sin(p), np.cos(y), np.sin(y)
+    rx = np.array([[1, 0, 0], [0, cr, -sr], [0, sr, cr]])
+    ry = np.array([[cp, 0, sp], [0, 1, 0], [-sp, 0, cp]])
+    rz = np.array([[cy, -sy, 0], [sy, cy, 0], [0, 0, 1]])
+    return rz @ ry @ rx
+
+
+def _sym(i6: T.Sequence[float]) -> np.ndarray:
+    xx, xy, xz, yy, yz, zz = i6
+    return np.array([[xx, xy, xz], [xy, yy, yz], [xz, yz, zz]], dtype=np.float64)
+
+
+@dataclasses.dataclass
+class Link:
+    """One URDF link + the joint that attaches it to ``parent`` (``None`` = world)."""
+
+    name: str
+    parent: T.Optional[str]
+    joint_name: str
+    joint_type: str  # "revolute" | "prismatic" | "fixed"
+    xyz: T.Sequence[float]
+    rpy: T.Sequence[float]
+    axis: T.Sequence[float] = (0.0, 0.0, 1.0)
+    mass: float = 0.0
+    com: T.Sequence[float] = (0.0, 0.0, 0.0)
+    inertia: T.Sequence[float] = (0.0, 0.0, 0.0, 0.0, 0.0, 0.0)  # xx xy xz yy yz zz about the COM
+
+
+@dataclasses.dataclass
+class RobotTable:
+    """Numeric kinematic tree (what the device kernels consume)."""
+
+    joint_names: list[str]
+    parent: np.ndarray  # [nv] int, -1 = world
+    jtype: np.ndarray  # [nv] int
+    axis: np.ndarray  # [nv,3]
+    placement_R: np.ndarray  # [nv,3,3]
+    placement_p: np.ndarray  # [nv,3]
+    mass: np.ndarray  # [nv]
+    com: np.ndarray  # [nv,3]
+    inertia: np.ndarray  # [nv,3,3] about the COM
+    armature: np.ndarray  # [nv]
+    gravity: np.ndarray  # [3]
+    frames: dict[str, tuple[int, np.ndarray, np.ndarray]]  # name -> (parent joint, R, p)
+    frame_name: str = ""
+
+    @property
+    def nv(self) -> int:
+        return len(self.joint_names)
+
+    @property
+    def nq(self) -> int:
+        return self.nv
+
+    @property
+    def nx(self) -> int:
+        return 2 * self.nv
+
+    def with_frame(self, frame_name: str) -> "RobotTable":
+        assert frame_name in self.frames, f"Frame '{frame_name}' does not exist!"
+        return dataclasses.replace(self, frame_name=frame_name)
+
+    def with_armature(self, armature) -> "RobotTable":
+        a = np.broadcast_to(np.asarray(armature, dtype=np.float64), (self.nv,)).copy()
+        return dataclasses.replace(self, armature=a)
+
+    def perturbed(self, link: int, param: int, delta: float) -> "RobotTable":
+        """One inertial parameter of body ``link`` shifted by ``delta``: ``param`` 0-5 = inertia
+        xx xy xz yy yz zz, 6-8 = COM x y z, 9 = mass
+        (agimus_controller_examples/.../model_sensibility/evaluate_model_sensibility.py:9-49)."""
+        t = dataclasses.replace(
+            self, mass=self.mass.copy(), com=self.com.copy(), inertia=self.inertia.copy()
+        )
+        if param < 6:
+            r, c = [(0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2)][param]
+            t.inertia[link, r, c] += delta
+            if r != c:
+                t.inertia[link, c, r] += delta
+        elif param < 9:
+            t.com[link, param - 6] += delta
+        else:
+            t.mass[link] += delta
+        return t
+
+    def to_struct(self) -> _abi.AgxModel:
+        assert self.nv <= _abi.AGX_MAX_NV
+        assert self.frame_name, "select the task frame with with_frame() first"
+        m = _abi.AgxModel()
+        m.nv = self.nv
+        fpar, fR, fp = self.frames[self.frame_name]
+        m.frame_parent = int(fpar)
+        for i in range(self.nv):
+            m.parent[i] = int(self.parent[i])
+            m.jtype[i] = int(self.jtype[i])
+            I = self.inertia[i]
+            i6 = [I[0, 0], I[0, 1], I[0, 2], I[1, 1], I[1, 2], I[2, 2]]
+            for k in range(3):
+                m.axis[i][k] = float(self.axis[i, k])
+                m.placement_p[i][k] = float(self.placement_p[i, k])
+                m.com[i][k] = float(self.com[i, k])
+            for k in range(9):
+                m.placement_R[i][k] = float(self.placement_R[i].reshape(9)[k])
+            for k in range(6):
+                m.inertia[i][k] = float(i6[k])
+            m.mass[i] = float(self.mass[i])
+            m.armature[i] = float(self.armature[i])
+        for k in range(3):
+            m.gravity[k] = float(self.gravity[k])
+            m.frame_p[k] = float(fp[k])
+        for k in range(9):
+            m.frame_R[k] = float(np.asarray(fR).reshape(9)[k])
+        return m
+
+    @staticmethod
+    def from_links(
+        links: list[Link],
+        locked_joints: T.Iterable[str] = (),
+        frames: T.Optional[dict[str, tuple[str, T.Sequence[float], T.Sequence[float]]]] = None,
+        armature: T.Union[float, T.Sequence[float]] = 0.0,
+        gravity: T.Sequence[float] = (0.0, 0.0, -9.81),
+    ) -> "RobotTable":
+        """Reduce a link list: fixed and locked joints (at q = 0) are folded into the moving ancestor."""
+        locked = set(locked_joints)
+        by_name = {l.name: l for l in links}
+        moving: list[Link] = [
+            l for l in links if l.joint_type != "fixed" and l.joint_name not in locked
+        ]
+        index = {l.name: i for i, l in enumerate(moving)}
+        nv = len(moving)
+        # placement of every link frame in its moving ancestor's body frame
+        anchor: dict[str, tuple[int, np.ndarray, np.ndarray]] = {}
+
+        def resolve(name: str) -> tuple[int, np.ndarray, np.ndarray]:
+            if name in anchor:
+                return anchor[name]
+            l = by_name[name]
+            if name in index:
+                res = (index[name], np.eye(3), np.zeros(3))
+            else:
+                R = rpy_to_matrix(*l.rpy)
+                p = np.asarray(l.xyz, dtype=np.float64)
+                if l.parent is None:
+                    res = (-1, R, p)
+                else:
+                    pi, Rp, pp = resolve(l.parent)
+                    res = (pi, Rp @ R, pp + Rp @ p)
+            anchor[name] = res
+            return res
+
+        parent = np.full(nv, -1, dtype=np.int32)
+        jtype = np.zeros(nv, dtype=np.int32)
+        axis = np.zeros((nv, 3))
+        pl_R = np.zeros((nv, 3, 3))
+        pl_p = np.zeros((nv, 3))
+        for i, l in enumerate(moving):
+            R = rpy_to_matrix(*l.rpy)
+            p = np.asarray(l.xyz, dtype=np.float64)
+            if l.parent is None:
+                parent[i], pl_R[i], pl_p[i] = -1, R, p
+            else:
+                pi, Rp, pp = resolve(l.parent)
+                parent[i], pl_R[i], pl_p[i] = pi, Rp @ R, pp + Rp @ p
+            jtype[i] = (
+                _abi.AGX_JOINT_REVOLUTE if l.joint_type == "revolute" else _abi.AGX_JOINT_PRISMATIC
+            )
+            axis[i] = np.asarray(l.axis, dtype=np.float64)
+        # merge inertias
+        parts: list[list[tuple[float, np.ndarray, np.ndarray]]] = [[] for _ in range(nv)]
+        for l in links:
+            if l.mass <= 0.0:
+                continue
+            bi, R, p = resolve(l.name)
+            if bi < 0:
+                continue  # welded to the world: no dynamics
+            parts[bi].append((l.mass, p + R @ np.asarray(l.com), R @ _sym(l.inertia) @ R.T))
+        mass = np.zeros(nv)
+        com = np.zeros((nv, 3))
+        inertia = np.zeros((nv, 3, 3))
+        for i in range(nv):
+            m = sum(pt[0] for pt in parts[i])
+            mass[i] = m
+            if m > 0:
+                com[i] = sum(pt[0] * pt[1] for pt in parts[i]) / m
+            for mk, ck, Ik in parts[i]:
+                d = ck - com[i]
+                inertia[i] += Ik + mk * (np.dot(d, d) * np.eye(3) - np.outer(d, d))
+        fr: dict[str, tuple[int, np.ndarray, np.ndarray]] = {}
+        for l in links:
+            bi, R, p = resolve(l.name)
+            if bi >= 0:
+                fr[l.name] = (bi, R, p)
+        for name, (plink, xyz, rpy) in (frames or {}).items():
+            bi, R, p = resolve(plink)
+            Rf = rpy_to_matrix(*rpy)
+            fr[name] = (bi, R @ Rf, p + R @ np.asarray(xyz, dtype=np.float64))
+        arm = np.broadcast_to(np.asarray(armature, dtype=np.float64), (nv,)).copy()
+        return RobotTable(
+            joint_names=[l.joint_name for l in moving],
+            parent=parent,
+            jtype=jtype,
+            axis=axis,
+            placement_R=pl_R,
+            placement_p=pl_p,
+            mass=mass,
+            com=com,
+            inertia=inertia,
+            armature=arm,
+            gravity=np.asarray(gravity, dtype=np.float64),
+            frames=fr,
+        )
+
+
+def panda_links() -> list[Link]:
+    """Franka Panda (example-robot-data description)."""
+    h = _HALF_PI
+    L = Link
+    return [
+        L("panda_link1", None, "panda_joint1", "revolute", (0, 0, 0.333), (0, 0, 0), (0, 0, 1),
+          4.970684, (0.003875, 0.002081, -0.04762),
+          (0.70337, -0.000139, 0.006772, 0.70661, 0.019169, 0.009117)),
+        L("panda_link2", "panda_link1", "panda_joint2", "revolute", (0, 0, 0), (-h, 0, 0), (0, 0, 1),
+          0.646926, (-0.003141, -0.02872, 0.003495),
+          (0.007962, -0.003925, 0.010254, 0.02811, 0.000704, 0.025995)),
+        L("panda_link3", "panda_link2", "panda_joint3", "revolute", (0, -0.316, 0), (h, 0, 0), (0, 0, 1),
+          3.228604, (0.027518, 0.039252, -0.066502),
+          (0.037242, -0.004761, -0.011396, 0.036155, -0.012805, 0.01083)),
+        L("panda_link4", "panda_link3", "panda_joint4", "revolute", (0.0825, 0, 0), (h, 0, 0), (0, 0, 1),
+          3.587895, (-0.05317, 0.104419, 0.027454),
+          (0.025853, 0.007796, -0.001332, 0.019552, 0.008641, 0.028323)),
+        L("panda_link5", "panda_link4", "panda_joint5", "revolute", (-0.0825, 0.384, 0), (-h, 0, 0), (0, 0, 1),
+          1.225946, (-0.011953, 0.041065, -0.038437),
+          (0.035549, -0.002117, -0.004037, 0.029474, 0.000229, 0.008627)),
+        L("panda_link6", "panda_link5", "panda_joint6", "revolute", (0, 0, 0), (h, 0, 0), (0, 0, 1),
+          1.666555, (0.060149, -0.014117, -0.010517),
+          (0.001964, 0.000109, -0.001158, 0.004354, 0.000341, 0.005433)),
+        L("panda_link7", "panda_link6", "panda_joint7", "revolute", (0.088, 0, 0), (h, 0, 0), (0, 0, 1),
+          0.735522, (0.010517, -0.004252, 0.061597),
+          (0.012516, -0.000428, -0.001196, 0.010027, -0.000741, 0.004815)),
+        L("panda_link8", "panda_link7", "panda_joint8", "fixed", (0, 0, 0.107), (0, 0, 0)),
+        L("panda_hand", "panda_link8", "panda_hand_joint", "fixed", (0, 0, 0), (0, 0, -_QUARTER_PI), (0, 0, 1),
+          0.73, (-0.01, 0, 0.03), (0.001, 0, 0, 0.0025, 0, 0.0017)),
+        L("panda_leftfinger", "panda_hand", "panda_finger_joint1", "prismatic", (0, 0, 0.0584), (0, 0, 0),
+          (0, 1, 0), 0.015, (0, 0, 0), (2.375e-6, 0, 0, 2.375e-6, 0, 7.5e-7)),
+        L("panda_rightfinger", "panda_hand", "panda_finger_joint2", "prismatic", (0, 0, 0.0584), (0, 0, 0),
+          (0, -1, 0), 0.015, (0, 0, 0), (2.375e-6, 0, 0, 2.375e-6, 0, 7.5e-7)),
+    ]
+
+
+PANDA_FRAMES = {"panda_hand_tcp": ("panda_hand", (0, 0, 0.1034), (0, 0, 0))}
+PANDA_Q_NOMINAL = np.array([0.0, -0.78, 0.0, -2.35, 0.0, 1.57, 0.78])  # dummy_mpc_test.py:89
+
+
+def panda_table(
+    lock_fingers: bool = True,
+    armature: T.Union[float, T.Sequence[float]] = 0.1,
+    frame: str = "panda_hand_tcp",
+) -> RobotTable:
+    """7-DoF (fingers locked at 0, as every reference test does) or 9-DoF Panda table."""
+    locked = ("panda_finger_joint1", "panda_finger_joint2") if lock_fingers else ()
+    t = RobotTable.from_links(panda_links(), locked, PANDA_FRAMES, armature=armature)
+    return t.with_frame(frame)

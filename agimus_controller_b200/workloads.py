@@ -1,0 +1,49 @@
+"""Synthetic workloads of BASELINE.json / SURVEY.md §8(d), as host-side tables.
+
+Each builder returns a dict with ``table`` (RobotTable), ``refs`` [B,T+1,rs], ``dts`` [T], ``x0`` [B,nx],
+``xs_ws`` [B,T+1,nx], ``us_ws`` [B,T,nu].  ``rnea`` is the inverse-dynamics callable used for the
+gravity-compensation warm start (``warm_start_reference.py:77-87``): the device one in the product
+path, the oracle's in CPU tests.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .problem import pack_refs
+from .robot_model import PANDA_Q_NOMINAL, panda_table
+
+TOOL_DOWN = np.diag([1.0, -1.0, -1.0])  # quaternion x = 1 (dummy_mpc_test.py:104-107)
+
+
+def goal_reaching_batch(B, T=50, dt=0.01, seed=0, rnea=None, target_R=TOOL_DOWN, target_p=(0.5, 0.2, 0.5),
+                        w_q=0.01, w_v=0.01, w_u=1e-4, w_pose=1e3, armature=0.1, q_spread=0.3, v_spread=0.1):
+    """Config 2: B Panda goal-reaching OCPs (``ocp_goal_reaching.yaml`` cost stack, weights of
+    ``tests/test_ocp_croco_generic.py:182-188``), randomised initial states."""
+    table = panda_table(lock_fingers=True, armature=armature)
+    nv = table.nv
+    rng = np.random.default_rng(seed)
+    q0 = PANDA_Q_NOMINAL + rng.uniform(-q_spread, q_spread, size=(B, nv))
+    v0 = rng.uniform(-v_spread, v_spread, size=(B, nv))
+    x0 = np.concatenate([q0, v0], axis=1)
+    xref = np.concatenate([PANDA_Q_NOMINAL, np.zeros(nv)])
+    wx = np.concatenate([np.full(nv, w_q), np.full(nv, w_v)])
+    refs = pack_refs(nv, T, B, xref, wx, np.zeros(nv), np.full(nv, w_u), np.asarray(target_R), np.asarray(target_p),
+                     np.full(6, w_pose))
+    dts = np.full(T, dt)
+    xs_ws = np.repeat(x0[:, None, :], T + 1, axis=1)
+    z = np.zeros_like(q0)
+    u0 = rnea(q0, z, z) if rnea is not None else np.zeros_like(q0)
+    us_ws = np.repeat(np.asarray(u0).reshape(B, 1, nv), T, axis=1)
+    return dict(table=table, refs=refs, dts=dts, x0=x0, xs_ws=np.ascontiguousarray(xs_ws),
+                us_ws=np.ascontiguousarray(us_ws))
+
+
+def golden_problem():
+    """The reference's own golden OCP (``tests/test_ocp_croco_base.py:21-98, :140-158``): Panda, T = 9,
+    IAM-Euler default step 1e-3, x0 = 0, zero warm start, target SE3(I, [1,1,1])."""
+    table = panda_table(lock_fingers=True, armature=0.1)
+    nv, T = table.nv, 9
+    refs = pack_refs(nv, T, 1, np.zeros(2 * nv), np.full(2 * nv, 0.1), np.zeros(nv), np.full(nv, 1e-4), np.eye(3),
+                     np.ones(3), np.ones(6), wpose_terminal=np.full(6, 50.0))
+    return dict(table=table, refs=refs, dts=np.full(T, 1e-3), x0=np.zeros((1, 2 * nv)),
+                xs_ws=np.zeros((1, T + 1, 2 * nv)), us_ws=np.zeros((1, T, nv)))

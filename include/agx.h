@@ -1,0 +1,152 @@
+/*
+ * agx.h — C ABI of the B200-native batched OCP solve path.
+ *
+ * This is the drop-in boundary for the arithmetic that agimus_controller reaches
+ * through Boost.Python today (reference paths relative to /root/reference):
+ *
+ *   crocoddyl.ShootingProblem(x0, running, terminal)   agimus_controller/agimus_controller/ocp_base_croco.py:55-62
+ *   solver.solve(xs, us, max_iters)                    agimus_controller/agimus_controller/ocp_base_croco.py:172
+ *   problem.calc / problem.calcDiff                    agimus_controller_ros/agimus_controller_ros/mpc_debugger_node.py:300-301
+ *   problem.rollout(us)                                agimus_controller/tests/test_warm_start_shift_previous_reference.py:76
+ *   runningModels[0].calc(data, x, u) -> xnext         agimus_controller/agimus_controller/ocp_base_croco.py:184-189
+ *   per-tick reference / weight setters                agimus_controller/agimus_controller/ocp/ocp_croco_generic.py:855-892
+ *   pin.rnea warm start                                agimus_controller/agimus_controller/warm_start_reference.py:77-87
+ *
+ * Conventions
+ *  - every array is fp64, C order, and lives in DEVICE memory unless the name ends in _host;
+ *  - the caller owns every buffer; the library borrows pointers for the duration of the
+ *    stream-ordered call and never allocates inside agx_solve;
+ *  - every entry point returns 0 on success, a negative AGX_E* code otherwise; no C++
+ *    exception crosses the boundary; agx_last_error() gives a message;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *  - state x = [q (nv); v (nv)], nx = ndx = 2 nv, nu = nv (full actuation, vector-space state);
+ *  - policy convention (Crocoddyl): u = us - k - K (x - xs), K is [nu, nx] row-major.
+ */
+#ifndef AGX_H_
+#define AGX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AGX_MAX_NV 16
+
+/* joint types */
+#define AGX_JOINT_REVOLUTE 0
+#define AGX_JOINT_PRISMATIC 1
+
+/* error codes */
+#define AGX_OK 0
+#define AGX_EINVAL -1       /* bad argument */
+#define AGX_EUNSUPPORTED -2 /* model / problem shape the kernels do not cover */
+#define AGX_ECUDA -3        /* CUDA runtime error */
+#define AGX_ENOMEM -4
+
+/* per-problem solver status (out_status) */
+#define AGX_STATUS_CONVERGED 0 /* stop criterion met with a feasible trajectory */
+#define AGX_STATUS_MAXITER 1   /* iteration budget used */
+#define AGX_STATUS_REGMAX 2    /* regularisation hit reg_max */
+#define AGX_STATUS_NAN 3       /* non-finite value met */
+
+/*
+ * Kinematic-tree table: what factory/robot_model.py:88-351 (RobotModels.robot_model, .armature)
+ * flattens to.  Joint i moves body i; parent[i] < i, -1 = world.  placement = joint frame in the
+ * parent body frame; inertia about the COM in body axes, order xx xy xz yy yz zz.
+ * The task frame (ResidualModelFramePlacement id, ocp_croco_generic.py:197-219) is attached to
+ * body frame_parent with placement (frame_R, frame_p).
+ */
+typedef struct agx_model {
+  int32_t nv;
+  int32_t frame_parent;
+  int32_t parent[AGX_MAX_NV];
+  int32_t jtype[AGX_MAX_NV];
+  double axis[AGX_MAX_NV][3];
+  double placement_R[AGX_MAX_NV][9];
+  double placement_p[AGX_MAX_NV][3];
+  double mass[AGX_MAX_NV];
+  double com[AGX_MAX_NV][3];
+  double inertia[AGX_MAX_NV][6];
+  double armature[AGX_MAX_NV];
+  double gravity[3];
+  double frame_R[9];
+  double frame_p[3];
+} agx_model;
+
+/*
+ * FDDP parameters (Crocoddyl SolverFDDP defaults are what agx_fddp_opts_default fills).
+ * fixed_iters != 0: run exactly max_iter iterations, no early exit (benchmark mode).
+ */
+typedef struct agx_fddp_opts {
+  double reg_min, reg_max, reg_incfactor, reg_decfactor;
+  double th_grad, th_stepdec, th_stepinc, th_acceptstep, th_acceptnegstep, th_stop;
+  double reg_init; /* NaN -> reg_min */
+  int32_t fixed_iters;
+  int32_t n_alphas; /* step lengths 2^-n, n = 0..n_alphas-1 (<= 10) */
+} agx_fddp_opts;
+
+typedef struct agx_handle agx_handle;
+
+/* Size in doubles of one node's reference record:
+ *   [xref nx][wx nx][uref nu][wu nu][Rref 9][pref 3][wpose 6]
+ * wx/wu/wpose are the activation weights already multiplied by the CostModelSum weight
+ * (ocp_croco_generic.py:577-585, :688-691); an inactive cost has zero weights.  The terminal
+ * node (t = T) ignores uref/wu.  Layout of `refs`: [B][T+1][agx_ref_size(nv)]. */
+int agx_ref_size(int nv);
+
+void agx_fddp_opts_default(agx_fddp_opts* opts);
+
+/* Build a handle for B problems with T running nodes on CUDA device `device`.
+ * dts_host: T step sizes (host memory; ocp_param_base.py:67-78 timesteps).
+ * models_host: 1 model shared by the batch (n_models = 1) or one per problem (n_models = B). */
+int agx_create(const agx_model* models_host, int n_models, const double* dts_host, int B, int T,
+               int device, agx_handle** out);
+int agx_destroy(agx_handle* h);
+const char* agx_last_error(const agx_handle* h);
+
+/* Replaces the per-tick reference/weight setter loop (ocp_croco_generic.py:855-892).
+ * refs: device [B][T+1][ref_size]; copied into the handle (stream ordered). */
+int agx_set_refs(agx_handle* h, const double* refs, void* stream);
+
+/* problem.calc: xs [B][T+1][nx], us [B][T][nu] -> out_cost [B][T+1] (node costs),
+ * out_xnext [B][T+1][nx] (terminal row = xs_T). Either output may be NULL. */
+int agx_calc(agx_handle* h, const double* xs, const double* us, double* out_cost,
+             double* out_xnext, void* stream);
+
+/* problem.calc + problem.calcDiff, dense per-node outputs (row-major):
+ *  Fx [B][T+1][nx][nx], Fu [B][T+1][nx][nu], Lx [B][T+1][nx], Lu [B][T+1][nu],
+ *  Lxx [B][T+1][nx][nx], Lxu [B][T+1][nx][nu], Luu [B][T+1][nu][nu].
+ * Terminal rows hold Fx = I, Fu = 0, Lu = Lxu = Luu = 0.  Any output may be NULL. */
+int agx_calc_diff(agx_handle* h, const double* xs, const double* us, double* out_cost,
+                  double* out_xnext, double* Fx, double* Fu, double* Lx, double* Lu, double* Lxx,
+                  double* Lxu, double* Luu, void* stream);
+
+/* problem.rollout(us): x0 [B][nx], us [B][T][nu] -> out_xs [B][T+1][nx]. */
+int agx_rollout(agx_handle* h, const double* x0, const double* us, double* out_xs, void* stream);
+
+/* IntegratedActionModelEuler.calc for n independent (x, u) pairs with step dt
+ * (ocp_base_croco.py:184-189; model 0 of the handle). x [n][nx], u [n][nu] -> out_xnext [n][nx]. */
+int agx_integrate(agx_handle* h, const double* x, const double* u, double dt, int n,
+                  double* out_xnext, void* stream);
+
+/* pin.rnea(model, data, q, v, a) for n independent triples (warm_start_reference.py:77-87). */
+int agx_rnea(agx_handle* h, const double* q, const double* v, const double* a, int n,
+             double* out_tau, void* stream);
+
+/* solver.solve(xs, us, max_iter) with problem.x0 = x0 (ocp_base_croco.py:158, :172).
+ * In:  x0 [B][nx], xs_ws [B][T+1][nx], us_ws [B][T][nu].
+ * Out: out_xs [B][T+1][nx], out_us [B][T][nu], out_K [B][T][nu][nx], out_k [B][T][nu] (may be NULL),
+ *      out_cost [B], out_iters [B] (int32), out_status [B] (int32), out_stop [B] (may be NULL). */
+int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double* us_ws,
+              int max_iter, const agx_fddp_opts* opts, double* out_xs, double* out_us,
+              double* out_K, double* out_k, double* out_cost, int32_t* out_iters,
+              int32_t* out_status, double* out_stop, void* stream);
+
+/* Number of kernel launches the library issued on this handle since creation (bench evidence). */
+long long agx_launch_count(const agx_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGX_H_ */
