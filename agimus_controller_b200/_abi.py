@@ -94,3 +94,44 @@ def fill_array(dst, src) -> None:
     """Copy a (nested) numpy array into a (nested) ctypes array."""
     a = np.ascontiguousarray(src)
     C.memmove(dst, a.ctypes.data, min(C.sizeof(dst), a.nbytes))
+
+
+_P = C.c_void_p
+
+
+def bind(lib: C.CDLL) -> C.CDLL:
+    """Declare the prototypes of every entry point of ``include/agx.h`` on a loaded library."""
+    H = C.c_void_p
+    lib.agx_ref_size.argtypes = [C.c_int]
+    lib.agx_ref_size.restype = C.c_int
+    lib.agx_fddp_opts_default.argtypes = [C.POINTER(AgxFddpOpts)]
+    lib.agx_fddp_opts_default.restype = None
+    lib.agx_create.argtypes = [C.POINTER(AgxModel), C.c_int, _P, C.c_int, C.c_int, C.c_int, C.POINTER(H)]
+    lib.agx_create.restype = C.c_int
+    lib.agx_destroy.argtypes = [H]
+    lib.agx_destroy.restype = C.c_int
+    lib.agx_last_error.argtypes = [H]
+    lib.agx_last_error.restype = C.c_char_p
+    lib.agx_set_refs.argtypes = [H, _P, _P]
+    lib.agx_set_refs.restype = C.c_int
+    lib.agx_calc.argtypes = [H, _P, _P, _P, _P, _P]
+    lib.agx_calc.restype = C.c_int
+    lib.agx_calc_diff.argtypes = [H] + [_P] * 12
+    lib.agx_calc_diff.restype = C.c_int
+    lib.agx_rollout.argtypes = [H, _P, _P, _P, _P]
+    lib.agx_rollout.restype = C.c_int
+    lib.agx_integrate.argtypes = [H, _P, _P, C.c_double, C.c_int, _P, _P]
+    lib.agx_integrate.restype = C.c_int
+    lib.agx_rnea.argtypes = [H, _P, _P, _P, C.c_int, _P, _P]
+    lib.agx_rnea.restype = C.c_int
+    lib.agx_solve.argtypes = [H, _P, _P, _P, C.c_int, C.POINTER(AgxFddpOpts)] + [_P] * 9
+    lib.agx_solve.restype = C.c_int
+    lib.agx_launch_count.argtypes = [H]
+    lib.agx_launch_count.restype = C.c_longlong
+    return lib
+
+
+EXPORTED_SYMBOLS = (
+    "agx_ref_size", "agx_fddp_opts_default", "agx_create", "agx_destroy", "agx_last_error", "agx_set_refs",
+    "agx_calc", "agx_calc_diff", "agx_rollout", "agx_integrate", "agx_rnea", "agx_solve", "agx_launch_count",
+)

@@ -1,0 +1,324 @@
+// agx_api.cu — C ABI of the batched OCP solve path (include/agx.h) over the kernels in agx_kernels.cuh.
+//
+// The boundary this file implements is the one agimus_controller crosses at
+// agimus_controller/agimus_controller/ocp_base_croco.py:55-64 (ShootingProblem + solver
+// construction), :158/:172 (x0 + solver.solve) and :184-189 (integrate); see include/agx.h for the
+// full list.  Everything is stream-ordered on the caller's stream; nothing is allocated inside
+// agx_solve (the optional internal K buffer is allocated on first use only when out_K is NULL).
+//
+// The same translation unit also compiles with g++ against tests/emul/cpu_simt.h (-DAGX_EMULATE),
+// where "device" memory is host memory and a launch runs the kernel's threads as fibers.  That
+// build is test infrastructure; the product library is the nvcc build and has no CPU fallback.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/agx.h"
+#include "agx_kernels.cuh"
+
+#if AGX_GPU
+#include <cuda_runtime.h>
+#endif
+
+namespace {
+
+using namespace agx;
+
+#if AGX_GPU
+typedef cudaStream_t stream_t;
+#define AGX_LAUNCH(h, kernel, grid, block, smem, stream, ...)                                \
+  do {                                                                                        \
+    kernel<<<dim3((unsigned)(grid)), dim3((unsigned)(block)), (smem), (stream)>>>(__VA_ARGS__); \
+    ++(h)->launches;                                                                          \
+  } while (0)
+inline bool dev_alloc(void** p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 8) == cudaSuccess; }
+inline void dev_free(void* p) { if (p) cudaFree(p); }
+inline bool copy_h2d(void* d, const void* s, size_t n, stream_t st) {
+  return cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, st) == cudaSuccess;
+}
+inline bool copy_d2d(void* d, const void* s, size_t n, stream_t st) {
+  return cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st) == cudaSuccess;
+}
+inline const char* dev_check() {
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+#else
+typedef void* stream_t;
+#define AGX_LAUNCH(h, kernel, grid, block, smem, stream, ...)                                       \
+  do {                                                                                               \
+    simt::launch(dim3((unsigned)(grid)), dim3((unsigned)(block)), [&]() { kernel(__VA_ARGS__); }); \
+    ++(h)->launches;                                                                                 \
+  } while (0)
+inline bool dev_alloc(void** p, size_t bytes) { *p = std::calloc(bytes ? bytes : 8, 1); return *p != nullptr; }
+inline void dev_free(void* p) { std::free(p); }
+inline bool copy_h2d(void* d, const void* s, size_t n, stream_t) { std::memcpy(d, s, n); return true; }
+inline bool copy_d2d(void* d, const void* s, size_t n, stream_t) { std::memmove(d, s, n); return true; }
+inline const char* dev_check() { return nullptr; }
+#endif
+
+constexpr int NODE_CTA = 64;   // threads per CTA of the (problem, node) kernels: 8 octets
+constexpr int SEQ_CTA = 32;    // threads per CTA of the per-problem kernels: 4 octets
+
+// agx_model -> device table (agx_octet_base.h layout).  Returns false for shapes the kernels do not
+// cover yet: anything but a 7-joint serial chain of revolute-z joints.
+bool flatten_model(const agx_model& m, double* out, std::string& why) {
+  if (m.nv != NJ) { why = "only nv = 7 is supported by the sm_100a kernels"; return false; }
+  for (int i = 0; i < NJ; ++i) {
+    if (m.parent[i] != i - 1) { why = "only serial chains are supported"; return false; }
+    if (m.jtype[i] != AGX_JOINT_REVOLUTE || m.axis[i][0] != 0.0 || m.axis[i][1] != 0.0 || m.axis[i][2] != 1.0) {
+      why = "only revolute joints about local z are supported";
+      return false;
+    }
+  }
+  if (m.frame_parent < 0 || m.frame_parent >= NJ) { why = "frame_parent out of range"; return false; }
+  for (int k = 0; k < MODEL_SIZE; ++k) out[k] = 0.0;
+  for (int j = 0; j < NJ; ++j) {
+    for (int k = 0; k < 9; ++k) out[(MF_RP + k) * 8 + j] = m.placement_R[j][k];
+    for (int k = 0; k < 3; ++k) out[(MF_PP + k) * 8 + j] = m.placement_p[j][k];
+    out[MF_MASS * 8 + j] = m.mass[j];
+    for (int k = 0; k < 3; ++k) out[(MF_COM + k) * 8 + j] = m.com[j][k];
+    for (int k = 0; k < 6; ++k) out[(MF_INERTIA + k) * 8 + j] = m.inertia[j][k];
+    out[MF_ARM * 8 + j] = m.armature[j];
+  }
+  // lane 7 (idle): identity placement, no inertia
+  out[(MF_RP + 0) * 8 + 7] = out[(MF_RP + 4) * 8 + 7] = out[(MF_RP + 8) * 8 + 7] = 1.0;
+  for (int k = 0; k < 3; ++k) out[MT_GRAV + k] = m.gravity[k];
+  for (int k = 0; k < 9; ++k) out[MT_FR + k] = m.frame_R[k];
+  for (int k = 0; k < 3; ++k) out[MT_FP + k] = m.frame_p[k];
+  out[MT_FP + 3] = (double)m.frame_parent;
+  return true;
+}
+
+}  // namespace
+
+struct agx_handle {
+  int B = 0, T = 0, device = 0, n_models = 0;
+  double* d_model = nullptr;
+  double* d_refs = nullptr;
+  double* d_dts = nullptr;
+  double* d_x0 = nullptr;
+  double* d_K_internal = nullptr;
+  agx::Work W{};
+  agx::SolverState S{};
+  void* state_block = nullptr;
+  long long launches = 0;
+  std::string err;
+};
+
+namespace {
+
+int fail(agx_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+int check_launch(agx_handle* h, const char* what) {
+  if (const char* e = dev_check()) return fail(h, AGX_ECUDA, std::string(what) + ": " + e);
+  return AGX_OK;
+}
+agx::Problem problem_of(const agx_handle* h) {
+  agx::Problem P;
+  P.model = h->d_model; P.refs = h->d_refs; P.dts = h->d_dts;
+  P.n_models = h->n_models; P.B = h->B; P.T = h->T;
+  return P;
+}
+#if AGX_GPU
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#else
+struct DeviceGuard { explicit DeviceGuard(int) {} };
+#endif
+
+}  // namespace
+
+extern "C" {
+
+int agx_ref_size(int nv) { return 6 * nv + 18; }
+
+void agx_fddp_opts_default(agx_fddp_opts* o) {
+  o->reg_min = 1e-9; o->reg_max = 1e9; o->reg_incfactor = 10.0; o->reg_decfactor = 10.0;
+  o->th_grad = 1e-12; o->th_stepdec = 0.5; o->th_stepinc = 0.01; o->th_acceptstep = 0.1;
+  o->th_acceptnegstep = 2.0; o->th_stop = 1e-9;
+  o->reg_init = nan("");
+  o->fixed_iters = 0; o->n_alphas = 10;
+}
+
+const char* agx_last_error(const agx_handle* h) { return h ? h->err.c_str() : "null handle"; }
+long long agx_launch_count(const agx_handle* h) { return h ? h->launches : 0; }
+
+int agx_destroy(agx_handle* h) {
+  if (!h) return AGX_OK;
+  {
+    DeviceGuard g(h->device);
+    dev_free(h->d_model); dev_free(h->d_refs); dev_free(h->d_dts); dev_free(h->d_x0); dev_free(h->d_K_internal);
+    dev_free(h->W.xs); dev_free(h->W.us); dev_free(h->W.rec); dev_free(h->W.fs); dev_free(h->W.gv); dev_free(h->W.k);
+    dev_free(h->state_block);
+  }
+  delete h;
+  return AGX_OK;
+}
+
+int agx_create(const agx_model* models_host, int n_models, const double* dts_host, int B, int T, int device,
+               agx_handle** out) {
+  if (!out) return AGX_EINVAL;
+  *out = nullptr;
+  if (!models_host || !dts_host || B <= 0 || T <= 0 || (n_models != 1 && n_models != B)) return AGX_EINVAL;
+  agx_handle* h = new (std::nothrow) agx_handle;
+  if (!h) return AGX_ENOMEM;
+  *out = h;  // returned even on failure so the caller can read agx_last_error, then agx_destroy
+  h->B = B; h->T = T; h->device = device; h->n_models = n_models;
+  double* tab = (double*)std::malloc(sizeof(double) * MODEL_SIZE * (size_t)n_models);
+  if (!tab) return fail(h, AGX_ENOMEM, "host allocation failed");
+  for (int i = 0; i < n_models; ++i) {
+    std::string why;
+    if (!flatten_model(models_host[i], tab + (size_t)i * MODEL_SIZE, why)) {
+      std::free(tab);
+      return fail(h, AGX_EUNSUPPORTED, why);
+    }
+  }
+#if AGX_GPU
+  if (cudaSetDevice(device) != cudaSuccess) {
+    std::free(tab);
+    return fail(h, AGX_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(cudaGetLastError()));
+  }
+#endif
+  const size_t T1 = (size_t)T + 1, nB = (size_t)B;
+  bool ok = true;
+  ok = ok && dev_alloc((void**)&h->d_model, sizeof(double) * MODEL_SIZE * n_models);
+  ok = ok && dev_alloc((void**)&h->d_refs, sizeof(double) * nB * T1 * REF_SIZE);
+  ok = ok && dev_alloc((void**)&h->d_dts, sizeof(double) * T);
+  ok = ok && dev_alloc((void**)&h->d_x0, sizeof(double) * nB * NX);
+  ok = ok && dev_alloc((void**)&h->W.xs, sizeof(double) * 2 * nB * T1 * NX);
+  ok = ok && dev_alloc((void**)&h->W.us, sizeof(double) * 2 * nB * T * NJ);
+  ok = ok && dev_alloc((void**)&h->W.rec, sizeof(double) * nB * T1 * REC_SIZE);
+  ok = ok && dev_alloc((void**)&h->W.fs, sizeof(double) * nB * T1 * NX);
+  ok = ok && dev_alloc((void**)&h->W.gv, sizeof(double) * nB * T1 * NX);
+  ok = ok && dev_alloc((void**)&h->W.k, sizeof(double) * nB * T * NJ);
+  // solver state: 5 double arrays + 7 int arrays in one block
+  const size_t state_bytes = nB * (5 * sizeof(double) + 7 * sizeof(int32_t)) + 64;
+  ok = ok && dev_alloc(&h->state_block, state_bytes);
+  if (!ok) { std::free(tab); return fail(h, AGX_ENOMEM, "device allocation failed"); }
+  double* dp = (double*)h->state_block;
+  h->S.xreg = dp; h->S.cost = dp + nB; h->S.dg = dp + 2 * nB; h->S.dq = dp + 3 * nB; h->S.stop = dp + 4 * nB;
+  int32_t* ip = (int32_t*)(dp + 5 * nB);
+  h->S.is_feasible = ip; h->S.was_feasible = ip + nB; h->S.recalc = ip + 2 * nB; h->S.done = ip + 3 * nB;
+  h->S.status = ip + 4 * nB; h->S.iters = ip + 5 * nB; h->S.cur = ip + 6 * nB;
+  ok = copy_h2d(h->d_model, tab, sizeof(double) * MODEL_SIZE * n_models, 0) && copy_h2d(h->d_dts, dts_host, sizeof(double) * T, 0);
+#if AGX_GPU
+  ok = ok && cudaStreamSynchronize(0) == cudaSuccess;
+#endif
+  std::free(tab);
+  if (!ok) return fail(h, AGX_ECUDA, "upload of the model tables failed");
+  return AGX_OK;
+}
+
+int agx_set_refs(agx_handle* h, const double* refs, void* stream) {
+  if (!h || !refs) return AGX_EINVAL;
+  DeviceGuard g(h->device);
+  if (!copy_d2d(h->d_refs, refs, sizeof(double) * (size_t)h->B * (h->T + 1) * REF_SIZE, (stream_t)stream))
+    return fail(h, AGX_ECUDA, "agx_set_refs: copy failed");
+  return AGX_OK;
+}
+
+int agx_calc(agx_handle* h, const double* xs, const double* us, double* out_cost, double* out_xnext, void* stream) {
+  if (!h || !xs || !us) return AGX_EINVAL;
+  DeviceGuard g(h->device);
+  const long long ents = (long long)h->B * (h->T + 1);
+  const int opc = NODE_CTA / 8;
+  AGX_LAUNCH(h, calc_kernel, (ents + opc - 1) / opc, NODE_CTA, sizeof(double) * OCT_BOARD * opc, (stream_t)stream,
+             problem_of(h), xs, us, out_cost, out_xnext);
+  return check_launch(h, "agx_calc");
+}
+
+int agx_calc_diff(agx_handle* h, const double* xs, const double* us, double* out_cost, double* out_xnext, double* Fx,
+                  double* Fu, double* Lx, double* Lu, double* Lxx, double* Lxu, double* Luu, void* stream) {
+  if (!h || !xs || !us) return AGX_EINVAL;
+  DeviceGuard g(h->device);
+  const long long ents = (long long)h->B * (h->T + 1);
+  const int opc = NODE_CTA / 8;
+  AGX_LAUNCH(h, calc_diff_kernel, (ents + opc - 1) / opc, NODE_CTA, sizeof(double) * OCT_BOARD * opc, (stream_t)stream,
+             problem_of(h), xs, us, (const int32_t*)nullptr, (const int32_t*)nullptr, (const int32_t*)nullptr, h->W.rec);
+  const long long rows = ents * NX;
+  AGX_LAUNCH(h, expand_kernel, (rows + 127) / 128, 128, 0, (stream_t)stream, problem_of(h), (const double*)h->W.rec,
+             out_cost, out_xnext, Fx, Fu, Lx, Lu, Lxx, Lxu, Luu);
+  return check_launch(h, "agx_calc_diff");
+}
+
+int agx_rollout(agx_handle* h, const double* x0, const double* us, double* out_xs, void* stream) {
+  if (!h || !x0 || !us || !out_xs) return AGX_EINVAL;
+  DeviceGuard g(h->device);
+  const int opc = SEQ_CTA / 8;
+  AGX_LAUNCH(h, rollout_kernel, (h->B + opc - 1) / opc, SEQ_CTA, sizeof(double) * OCT_BOARD * opc, (stream_t)stream,
+             problem_of(h), x0, us, out_xs);
+  return check_launch(h, "agx_rollout");
+}
+
+int agx_integrate(agx_handle* h, const double* x, const double* u, double dt, int n, double* out_xnext, void* stream) {
+  if (!h || !x || !u || !out_xnext || n < 0) return AGX_EINVAL;
+  if (n == 0) return AGX_OK;
+  DeviceGuard g(h->device);
+  const int opc = NODE_CTA / 8;
+  AGX_LAUNCH(h, integrate_kernel, (n + opc - 1) / opc, NODE_CTA, sizeof(double) * OCT_BOARD * opc, (stream_t)stream,
+             (const double*)h->d_model, x, u, dt, n, out_xnext);
+  return check_launch(h, "agx_integrate");
+}
+
+int agx_rnea(agx_handle* h, const double* q, const double* v, const double* a, int n, double* out_tau, void* stream) {
+  if (!h || !q || !v || !a || !out_tau || n < 0) return AGX_EINVAL;
+  if (n == 0) return AGX_OK;
+  DeviceGuard g(h->device);
+  const int opc = NODE_CTA / 8;
+  AGX_LAUNCH(h, rnea_kernel, (n + opc - 1) / opc, NODE_CTA, sizeof(double) * OCT_BOARD * opc, (stream_t)stream,
+             (const double*)h->d_model, q, v, a, n, out_tau);
+  return check_launch(h, "agx_rnea");
+}
+
+int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double* us_ws, int max_iter,
+              const agx_fddp_opts* opts, double* out_xs, double* out_us, double* out_K, double* out_k,
+              double* out_cost, int32_t* out_iters, int32_t* out_status, double* out_stop, void* stream) {
+  if (!h || !x0 || !xs_ws || !us_ws || !out_xs || !out_us || !out_cost || !out_iters || !out_status || max_iter < 0)
+    return AGX_EINVAL;
+  DeviceGuard g(h->device);
+  stream_t st = (stream_t)stream;
+  agx_fddp_opts od;
+  if (!opts) { agx_fddp_opts_default(&od); opts = &od; }
+  if (opts->n_alphas < 1 || opts->n_alphas > 10) return fail(h, AGX_EINVAL, "n_alphas must be in 1..10");
+  FddpOpts O;
+  O.reg_min = opts->reg_min; O.reg_max = opts->reg_max; O.reg_incfactor = opts->reg_incfactor;
+  O.reg_decfactor = opts->reg_decfactor; O.th_grad = opts->th_grad; O.th_stepdec = opts->th_stepdec;
+  O.th_stepinc = opts->th_stepinc; O.th_acceptstep = opts->th_acceptstep; O.th_acceptnegstep = opts->th_acceptnegstep;
+  O.th_stop = opts->th_stop; O.reg_init = opts->reg_init; O.fixed_iters = opts->fixed_iters; O.n_alphas = opts->n_alphas;
+  const size_t nB = (size_t)h->B, T = (size_t)h->T, T1 = T + 1;
+  if (!out_K && !h->d_K_internal) {
+    if (!dev_alloc((void**)&h->d_K_internal, sizeof(double) * nB * T * NJ * NX))
+      return fail(h, AGX_ENOMEM, "allocation of the internal gain buffer failed");
+  }
+  Work W = h->W;
+  W.K = out_K ? out_K : h->d_K_internal;
+  W.x0 = h->d_x0;
+  if (!copy_d2d(h->d_x0, x0, sizeof(double) * nB * NX, st)) return fail(h, AGX_ECUDA, "agx_solve: x0 copy failed");
+  const Problem P = problem_of(h);
+  const long long n_init = (long long)(nB * T1 * NX);
+  AGX_LAUNCH(h, init_kernel, (n_init + 255) / 256, 256, 0, st, P, W, h->S, O, xs_ws, us_ws);
+  const long long ents = (long long)(nB * T1);
+  const int opc_n = NODE_CTA / 8, opc_s = SEQ_CTA / 8;
+  for (int it = 0; it < max_iter; ++it) {
+    AGX_LAUNCH(h, calc_diff_kernel, (ents + opc_n - 1) / opc_n, NODE_CTA, sizeof(double) * OCT_BOARD * opc_n, st, P,
+               (const double*)W.xs, (const double*)W.us, (const int32_t*)h->S.cur, (const int32_t*)h->S.recalc,
+               (const int32_t*)h->S.done, W.rec);
+    AGX_LAUNCH(h, backward_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * BW_SIZE * opc_s, st, P, W, h->S, O);
+    AGX_LAUNCH(h, forward_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * (OCT_BOARD + 16) * opc_s, st, P, W,
+               h->S, O);
+  }
+  const long long n_fin = (long long)(nB * T * NJ * NX);
+  AGX_LAUNCH(h, finalize_kernel, (n_fin + 255) / 256, 256, 0, st, P, W, h->S, out_xs, out_us, out_K, out_k, out_cost,
+             out_iters, out_status, out_stop);
+  return check_launch(h, "agx_solve");
+}
+
+}  // extern "C"

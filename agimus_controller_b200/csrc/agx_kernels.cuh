@@ -1,0 +1,799 @@
+// agx_kernels.cuh — the CUDA kernels of the batched FDDP solve path (fp64, sm_100a, no tensor cores).
+//
+//   calc_diff_kernel   one octet per (problem, node): problem.calc + calcDiff  -> compact node record
+//   calc_kernel        one octet per (problem, node): problem.calc             -> cost, xnext
+//   backward_kernel    one octet per problem: gaps, Riccati sweep t = T-1..0 with regularisation
+//                      retries, gains K/k, expected-improvement terms  (SolverFDDP::backwardPass,
+//                      computeGains, updateExpectedImprovement)
+//   forward_kernel     one octet per problem: line search over alpha = 2^-n, nonlinear rollout with
+//                      gap contraction, acceptance test, regularisation update, stop criterion
+//                      (SolverFDDP::forwardPass, tryStep, expectedImprovement, solve loop body)
+//   rollout_kernel / integrate_kernel / rnea_kernel / expand_kernel / init_kernel / finalize_kernel
+//
+// Reference entry points replaced: solver.solve at
+// agimus_controller/agimus_controller/ocp_base_croco.py:172 and the Crocoddyl objects built at
+// :36-64; algorithm statements in SURVEY.md Appendix B.4/B.5.
+//
+// No host synchronisation happens inside a solve: all per-problem decisions (step acceptance,
+// regularisation, termination) are taken on the device and kept in SolverState.
+#ifndef AGX_KERNELS_CUH_
+#define AGX_KERNELS_CUH_
+
+#include "agx_octet_base.h"
+#include "agx_dynamics.inl"
+#include "agx_node.inl"
+
+namespace agx {
+
+struct Problem {
+  const double* model;  // [n_models][MODEL_SIZE]
+  const double* refs;   // [B][T+1][REF_SIZE]
+  const double* dts;    // [T]
+  int n_models;         // 1 (shared) or B (one table per problem)
+  int B, T;
+};
+
+struct FddpOpts {
+  double reg_min, reg_max, reg_incfactor, reg_decfactor;
+  double th_grad, th_stepdec, th_stepinc, th_acceptstep, th_acceptnegstep, th_stop;
+  double reg_init;
+  int fixed_iters, n_alphas;
+};
+
+// workspace of a solve (device pointers owned by the handle)
+struct Work {
+  double* xs;    // [2][B][T+1][NX]   candidate / trial, selected per problem by SolverState::cur
+  double* us;    // [2][B][T][NJ]
+  double* rec;   // [B][T+1][REC_SIZE]
+  double* fs;    // [B][T+1][NX]      gaps
+  double* gv;    // [B][T+1][NX]      Vxx_t fs_t
+  double* K;     // [B][T][NJ][NX]
+  double* k;     // [B][T][NJ]
+  const double* x0;  // [B][NX]
+};
+
+constexpr int OCT_BOARD = BRD_A + BRD_B;  // doubles of shared memory per octet in the node kernels
+
+#define AGX_OCTET_SETUP()                                   \
+  const int j = (int)(threadIdx.x & 7u);                    \
+  const unsigned omask = 0xFFu << (threadIdx.x & 24u);      \
+  const int oct_in_cta = (int)(threadIdx.x >> 3);           \
+  const int octs_per_cta = (int)(blockDim.x >> 3);          \
+  const long long ent = (long long)blockIdx.x * octs_per_cta + oct_in_cta;
+
+AGX_DEV const double* model_of(const Problem& P, int b) {
+  return P.model + (P.n_models > 1 ? (size_t)b * MODEL_SIZE : 0);
+}
+
+AGX_DEV void lane_load_state(LaneDyn& d, int j, const double* x, const double* u) {
+  const bool live = j < NJ;
+  d.q = live ? x[j] : 0.0;
+  d.qd = live ? x[NJ + j] : 0.0;
+  d.u = (live && u) ? u[j] : 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// calc + calcDiff of one node; writes the compact record.  Returns the node cost (scaled).
+AGX_DEV double node_calc_diff(LaneDyn& d, int j, unsigned omask, const double* __restrict__ model,
+                              const double* __restrict__ ref, double dt, bool terminal, double* sa, double* sb,
+                              double* __restrict__ rec) {
+  node_kinematics(d, j, omask, model, sa);
+  double lq, lv, lu, Lqq[NJ];
+  const double l = node_costs<true>(d, j, omask, model, ref, terminal, sa, &lq, &lv, &lu, Lqq);
+  const bool live = j < NJ;
+  const int jj = live ? j : 0;
+  const double wv = live ? ref[NX + NJ + jj] : 0.0;
+  const double wu = (live && !terminal) ? ref[2 * NX + NJ + jj] : 0.0;
+  if (terminal) {
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) {
+      rec[(RK_AQ + i) * 8 + j] = 0.0;
+      rec[(RK_AV + i) * 8 + j] = 0.0;
+      rec[(RK_MI + i) * 8 + j] = 0.0;
+      rec[(RK_LQQ + i) * 8 + j] = Lqq[i];
+    }
+    rec[RK_LVV * 8 + j] = wv;
+    rec[RK_LUU * 8 + j] = 0.0;
+    rec[RK_LQ * 8 + j] = lq;
+    rec[RK_LV * 8 + j] = lv;
+    rec[RK_LU * 8 + j] = 0.0;
+    rec[RK_QN * 8 + j] = d.q;
+    rec[RK_VN * 8 + j] = d.qd;
+    rec[RK_COST * 8 + j] = l;
+    return l;
+  }
+  double L[28], rinv[NJ], qdd[NJ];
+  const bool ok = node_forward_dynamics<true>(d, j, omask, model, sa, sb, L, rinv, qdd);
+  node_rnea_derivatives(d, j, omask, sa, sb);
+  double aq[NJ], av[NJ], mi[NJ], ej[NJ];
+  solve_column(L, rinv, d.tq, -dt, aq);
+  solve_column(L, rinv, d.tv, -dt, av);
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) ej[i] = (i == j) ? 1.0 : 0.0;
+  solve_column(L, rinv, ej, dt, mi);
+  const double cost = ok ? dt * l : nan("");
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) {
+    rec[(RK_AQ + i) * 8 + j] = aq[i];
+    rec[(RK_AV + i) * 8 + j] = av[i];
+    rec[(RK_MI + i) * 8 + j] = mi[i];
+    rec[(RK_LQQ + i) * 8 + j] = dt * Lqq[i];
+  }
+  rec[RK_LVV * 8 + j] = dt * wv;
+  rec[RK_LUU * 8 + j] = dt * wu;
+  rec[RK_LQ * 8 + j] = dt * lq;
+  rec[RK_LV * 8 + j] = dt * lv;
+  rec[RK_LU * 8 + j] = dt * lu;
+  rec[RK_QN * 8 + j] = d.q + (d.qd * dt + d.qdd * (dt * dt));
+  rec[RK_VN * 8 + j] = d.qd + d.qdd * dt;
+  rec[RK_COST * 8 + j] = cost;
+  return cost;
+}
+
+// calc of one node: cost (scaled) and this lane's entries of xnext.  Returns false on failure.
+AGX_DEV bool node_calc(LaneDyn& d, int j, unsigned omask, const double* __restrict__ model,
+                       const double* __restrict__ ref, double dt, bool terminal, double* sa, double* sb, double* cost,
+                       double* qn, double* vn) {
+  node_kinematics(d, j, omask, model, sa);
+  const double l = node_costs<false>(d, j, omask, model, ref, terminal, sa, nullptr, nullptr, nullptr, nullptr);
+  if (terminal) {
+    *cost = l;
+    *qn = d.q;
+    *vn = d.qd;
+    return true;
+  }
+  double L[28], rinv[NJ], qdd[NJ];
+  const bool ok = node_forward_dynamics<false>(d, j, omask, model, sa, sb, L, rinv, qdd);
+  *cost = dt * l;
+  *qn = d.q + (d.qd * dt + d.qdd * (dt * dt));
+  *vn = d.qd + d.qdd * dt;
+  return ok;
+}
+
+// ---------------------------------------------------------------------------------------------
+// xs/us addressing: `cur` (may be null) selects one of two stacked buffers per problem
+AGX_DEV size_t buf_of(const int32_t* cur, int b, bool other) {
+  if (!cur) return 0;
+  const int c = cur[b] & 1;
+  return (size_t)(other ? (c ^ 1) : c);
+}
+
+__global__ void calc_diff_kernel(Problem P, const double* __restrict__ xs, const double* __restrict__ us,
+                                 const int32_t* __restrict__ cur, const int32_t* __restrict__ recalc,
+                                 const int32_t* __restrict__ done, double* __restrict__ rec) {
+  AGX_SMEM(smem);
+  AGX_OCTET_SETUP();
+  const int T1 = P.T + 1;
+  if (ent >= (long long)P.B * T1) return;
+  const int b = (int)(ent / T1), t = (int)(ent % T1);
+  if (done && done[b]) return;
+  if (recalc && !recalc[b]) return;
+  double* sa = smem + oct_in_cta * OCT_BOARD;
+  double* sb = sa + BRD_A;
+  const size_t buf = buf_of(cur, b, false);
+  const double* x = xs + ((buf * P.B + b) * T1 + t) * NX;
+  const bool terminal = t == P.T;
+  const double* u = terminal ? nullptr : us + ((buf * P.B + b) * P.T + t) * NJ;
+  LaneDyn d;
+  lane_load_state(d, j, x, u);
+  node_calc_diff(d, j, omask, model_of(P, b), P.refs + (size_t)ent * REF_SIZE, terminal ? 0.0 : P.dts[t], terminal, sa,
+                 sb, rec + (size_t)ent * REC_SIZE);
+}
+
+__global__ void calc_kernel(Problem P, const double* __restrict__ xs, const double* __restrict__ us,
+                            double* __restrict__ out_cost, double* __restrict__ out_xnext) {
+  AGX_SMEM(smem);
+  AGX_OCTET_SETUP();
+  const int T1 = P.T + 1;
+  if (ent >= (long long)P.B * T1) return;
+  const int b = (int)(ent / T1), t = (int)(ent % T1);
+  double* sa = smem + oct_in_cta * OCT_BOARD;
+  double* sb = sa + BRD_A;
+  const bool terminal = t == P.T;
+  LaneDyn d;
+  lane_load_state(d, j, xs + (size_t)ent * NX, terminal ? nullptr : us + ((size_t)b * P.T + t) * NJ);
+  double c, qn, vn;
+  const bool ok = node_calc(d, j, omask, model_of(P, b), P.refs + (size_t)ent * REF_SIZE, terminal ? 0.0 : P.dts[t],
+                            terminal, sa, sb, &c, &qn, &vn);
+  if (!ok) c = nan("");
+  if (out_cost && j == 0) out_cost[ent] = c;
+  if (out_xnext && j < NJ) {
+    out_xnext[(size_t)ent * NX + j] = qn;
+    out_xnext[(size_t)ent * NX + NJ + j] = vn;
+  }
+}
+
+// dense view of the records (problem.calcDiff data: Fx Fu Lx Lu Lxx Lxu Luu); one thread per (node, row)
+__global__ void expand_kernel(Problem P, const double* __restrict__ rec, double* out_cost, double* out_xnext,
+                              double* Fx, double* Fu, double* Lx, double* Lu, double* Lxx, double* Lxu, double* Luu) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int T1 = P.T + 1;
+  const long long n = gid / NX;
+  const int r = (int)(gid % NX);
+  if (n >= (long long)P.B * T1) return;
+  const int t = (int)(n % T1);
+  const bool terminal = t == P.T;
+  const double h = terminal ? 0.0 : P.dts[t];
+  const double* R = rec + (size_t)n * REC_SIZE;
+  const int i = r % NJ;        // joint row inside the q / v block
+  const bool top = r < NJ;     // q rows
+  if (out_cost && r == 0) out_cost[n] = R[RK_COST * 8];
+  if (out_xnext) out_xnext[n * NX + r] = R[(top ? RK_QN : RK_VN) * 8 + i];
+  if (Lx) Lx[n * NX + r] = R[(top ? RK_LQ : RK_LV) * 8 + i];
+  if (Lu && top) Lu[n * NJ + i] = R[RK_LU * 8 + i];
+  for (int c = 0; c < NJ; ++c) {
+    const double aq = R[(RK_AQ + i) * 8 + c], av = R[(RK_AV + i) * 8 + c], mi = R[(RK_MI + i) * 8 + c];
+    const double s = top ? h : 1.0;
+    if (Fx) {
+      Fx[(n * NX + r) * NX + c] = s * aq + ((top && c == i) ? 1.0 : 0.0);
+      Fx[(n * NX + r) * NX + NJ + c] =
+          terminal ? ((!top && c == i) ? 1.0 : 0.0) : s * (av + ((c == i) ? 1.0 : 0.0));
+    }
+    if (Fu) Fu[(n * NX + r) * NJ + c] = s * mi;
+    if (Lxx) {
+      Lxx[(n * NX + r) * NX + c] = top ? R[(RK_LQQ + i) * 8 + c] : 0.0;
+      Lxx[(n * NX + r) * NX + NJ + c] = (!top && c == i) ? R[RK_LVV * 8 + i] : 0.0;
+    }
+    if (Lxu) Lxu[(n * NX + r) * NJ + c] = 0.0;
+    if (Luu && top) Luu[(n * NJ + i) * NJ + c] = (c == i) ? R[RK_LUU * 8 + i] : 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Riccati sweep.  Lane j owns columns j and j+7 of every 14-wide matrix.  With
+//   G = [dt aq, I + dt av] (7x14), S = [dt I; I] (14x7), N = dt Minv:  Fx = [I 0; 0 0] + S G, Fu = S N
+// the products collapse to 7-deep ones:  Z = S^T V', Vs = Z S, W = Vs G + [Z_q 0],
+//   Qxx = Lxx + [V'_qq 0; 0 0] + G^T W + [Z_q^T G; 0],  Qux = N^T W,  Quu = Luu + N^T Vs N,
+//   Qx = Lx + [v'_q; 0] + G^T S^T v',  Qu = Lu + N^T S^T v'.
+constexpr int BW_VS = 0;      // [7][8]
+constexpr int BW_G = 56;      // [7][16]
+constexpr int BW_ZQ = 168;    // [7][8]
+constexpr int BW_N = 224;     // [7][8]
+constexpr int BW_QUX = 280;   // [7][16]
+constexpr int BW_L = 392;     // [7][8]
+constexpr int BW_SV = 448;    // [8]
+constexpr int BW_QU = 456;    // [8]
+constexpr int BW_FS = 464;    // [16]
+constexpr int BW_V = 480;     // [14][16]
+constexpr int BW_SIZE = 704;
+
+__global__ void backward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
+  AGX_SMEM(smem);
+  AGX_OCTET_SETUP();
+  const int b = (int)ent;
+  if (b >= P.B) return;
+  if (S.done[b]) return;
+  double* sm = smem + oct_in_cta * BW_SIZE;
+  const int T = P.T, T1 = T + 1;
+  const bool live = j < NJ;
+  const int jj = live ? j : 0;
+  const size_t buf = buf_of(S.cur, b, false);
+  const double* xs = W.xs + (buf * P.B + b) * (size_t)T1 * NX;
+  const double* rec0 = W.rec + (size_t)b * T1 * REC_SIZE;
+  double* fsb = W.fs + (size_t)b * T1 * NX;
+  double* gvb = W.gv + (size_t)b * T1 * NX;
+  double* Kb = W.K + (size_t)b * T * NJ * NX;
+  double* kb = W.k + (size_t)b * T * NJ;
+  const bool feasible = S.is_feasible[b] != 0;
+  double xreg = S.xreg[b];
+
+  // total cost of the candidate and the gaps (SolverAbstract::computeDynamicFeasibility)
+  double cost = 0.0;
+  for (int t = 0; t <= T; ++t) cost += rec0[(size_t)t * REC_SIZE + RK_COST * 8];
+  if (!feasible && live) {
+    fsb[j] = W.x0[(size_t)b * NX + j] - xs[j];
+    fsb[NJ + j] = W.x0[(size_t)b * NX + NJ + j] - xs[NJ + j];
+    for (int t = 0; t < T; ++t) {
+      const double* R = rec0 + (size_t)t * REC_SIZE;
+      fsb[(t + 1) * NX + j] = R[RK_QN * 8 + j] - xs[(t + 1) * NX + j];
+      fsb[(t + 1) * NX + NJ + j] = R[RK_VN * 8 + j] - xs[(t + 1) * NX + NJ + j];
+    }
+  }
+  AGX_OSYNC();
+
+  bool failed = !(cost == cost) ? true : false;  // a NaN node cost marks a failed calcDiff
+  double dg = 0.0, dq = 0.0;
+  for (;;) {
+    bool ok = !failed;
+    double V0[NX], V1[NX], vx0, vx1;
+    double dgp = 0.0, dqp = 0.0;  // per-lane partial sums
+    if (ok) {
+      // ---- terminal node
+      const double* R = rec0 + (size_t)T * REC_SIZE;
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) {
+        V0[i] = live ? R[(RK_LQQ + i) * 8 + jj] : 0.0;
+        V0[NJ + i] = 0.0;
+        V1[i] = 0.0;
+        V1[NJ + i] = 0.0;
+      }
+      const double lvv = live ? R[RK_LVV * 8 + jj] : 0.0;
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) {
+        if (i == j) { V0[i] += xreg; V1[NJ + i] = lvv + xreg; }
+      }
+      vx0 = live ? R[RK_LQ * 8 + jj] : 0.0;
+      vx1 = live ? R[RK_LV * 8 + jj] : 0.0;
+      if (!feasible) {
+        if (live) { sm[BW_FS + j] = fsb[T * NX + j]; sm[BW_FS + NJ + j] = fsb[T * NX + NJ + j]; }
+        AGX_OSYNC();
+        double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+        for (int r = 0; r < NX; ++r) { g0 += V0[r] * sm[BW_FS + r]; g1 += V1[r] * sm[BW_FS + r]; }
+        vx0 += g0; vx1 += g1;
+        if (live) {
+          gvb[T * NX + j] = g0; gvb[T * NX + NJ + j] = g1;
+          dgp -= vx0 * sm[BW_FS + j] + vx1 * sm[BW_FS + NJ + j];
+          dqp += g0 * sm[BW_FS + j] + g1 * sm[BW_FS + NJ + j];
+        }
+        AGX_OSYNC();
+      }
+    }
+    // ---- running nodes
+    for (int t = T - 1; ok && t >= 0; --t) {
+      const double* R = rec0 + (size_t)t * REC_SIZE;
+      const double h = P.dts[t];
+      double G0[NJ], G1[NJ], Nc[NJ], Lqq[NJ];
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) {
+        G0[i] = live ? R[(RK_AQ + i) * 8 + jj] : 0.0;
+        G1[i] = (live ? R[(RK_AV + i) * 8 + jj] : 0.0) + ((i == j) ? 1.0 : 0.0);
+        Nc[i] = live ? R[(RK_MI + i) * 8 + jj] : 0.0;
+        Lqq[i] = live ? R[(RK_LQQ + i) * 8 + jj] : 0.0;
+      }
+      const double lvv = live ? R[RK_LVV * 8 + jj] : 0.0, luu = live ? R[RK_LUU * 8 + jj] : 0.0;
+      const double lq = live ? R[RK_LQ * 8 + jj] : 0.0, lv = live ? R[RK_LV * 8 + jj] : 0.0;
+      const double lu = live ? R[RK_LU * 8 + jj] : 0.0;
+      double Z0[NJ], Z1[NJ];
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) {
+        Z0[i] = h * V0[i] + V0[NJ + i];
+        Z1[i] = h * V1[i] + V1[NJ + i];
+      }
+      const double sv = h * vx0 + vx1;
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) {
+        sm[BW_VS + i * 8 + j] = h * Z0[i] + Z1[i];
+        sm[BW_G + i * 16 + j] = G0[i];
+        sm[BW_G + i * 16 + 8 + j] = G1[i];
+        sm[BW_ZQ + i * 8 + j] = Z0[i];
+        sm[BW_N + i * 8 + j] = Nc[i];
+      }
+      sm[BW_SV + j] = sv;
+      if (!feasible && live) { sm[BW_FS + j] = fsb[t * NX + j]; sm[BW_FS + NJ + j] = fsb[t * NX + NJ + j]; }
+      AGX_OSYNC();
+      // W = Vs G + [Zq 0] ; VN = Vs N
+      double W0[NJ], W1[NJ], VN[NJ];
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) {
+        double a0 = Z0[i], a1 = 0.0, a2 = 0.0;
+#pragma unroll
+        for (int m = 0; m < NJ; ++m) {
+          const double vs = sm[BW_VS + i * 8 + m];
+          a0 += vs * G0[m];
+          a1 += vs * G1[m];
+          a2 += vs * Nc[m];
+        }
+        W0[i] = a0; W1[i] = a1; VN[i] = a2;
+      }
+      // Qxx columns
+      double Q0[NX], Q1[NX];
+#pragma unroll
+      for (int r = 0; r < NJ; ++r) {
+        double a0 = Lqq[r] + V0[r], a1 = V1[r];  // Lxx + [V'qq 0; 0 0]  (column j+7, q rows: V'[r][j+7]? no: zero)
+        a1 = 0.0;
+        double b0 = 0.0, b1 = (r == j) ? lvv : 0.0;
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) {
+          const double gq = sm[BW_G + i * 16 + r], gv = sm[BW_G + i * 16 + 8 + r], zq = sm[BW_ZQ + i * 8 + r];
+          a0 += gq * W0[i] + zq * G0[i];
+          a1 += gq * W1[i] + zq * G1[i];
+          b0 += gv * W0[i];
+          b1 += gv * W1[i];
+        }
+        Q0[r] = a0; Q1[r] = a1; Q0[NJ + r] = b0; Q1[NJ + r] = b1;
+      }
+      // Qux columns, Quu column, Qx, Qu
+      double U0[NJ], U1[NJ], Quu[NJ];
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+        for (int m = 0; m < NJ; ++m) {
+          const double n = sm[BW_N + m * 8 + i];
+          a0 += n * W0[m];
+          a1 += n * W1[m];
+          a2 += n * VN[m];
+        }
+        U0[i] = a0; U1[i] = a1;
+        Quu[i] = a2 + ((i == j) ? (luu + xreg) : 0.0);
+      }
+      double qx0 = lq + vx0, qx1 = lv, qu = lu;
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) {
+        const double s = sm[BW_SV + i];
+        qx0 += G0[i] * s;
+        qx1 += G1[i] * s;
+        qu += Nc[i] * s;
+      }
+      if (!live) {
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) Quu[i] = (i == 0) ? 1.0 : 0.0;
+      }
+      double QuuC[NJ];
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) QuuC[i] = Quu[i];
+      AGX_OSYNC();  // all reads of VS/G/ZQ/N done before QUX/L are (re)written
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) {
+        sm[BW_QUX + i * 16 + j] = U0[i];
+        sm[BW_QUX + i * 16 + 8 + j] = U1[i];
+      }
+      sm[BW_QU + j] = qu;
+#pragma unroll
+      for (int k = 0; k < NJ; ++k) {
+        chol_pivot(Quu, j, k, sm + BW_L);
+        AGX_OSYNC();
+        chol_update(Quu, j, k, sm + BW_L);
+      }
+      double L[28], rinv[NJ];
+      ok = chol_load(sm + BW_L, L, rinv);
+      if (!ok) break;
+      // gains
+      double K0[NJ], K1[NJ], kk[NJ];
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) { K0[i] = U0[i]; K1[i] = U1[i]; kk[i] = sm[BW_QU + i]; }
+      chol_solve7(L, rinv, K0);
+      chol_solve7(L, rinv, K1);
+      chol_solve7(L, rinv, kk);
+      // value function
+      double nvx0 = qx0, nvx1 = qx1;
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) {
+        const double qui = sm[BW_QU + i];
+        nvx0 -= K0[i] * qui;
+        nvx1 -= K1[i] * qui;
+      }
+#pragma unroll
+      for (int r = 0; r < NJ; ++r) {
+        double a0 = Q0[r], a1 = Q1[r], b0 = Q0[NJ + r], b1 = Q1[NJ + r];
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) {
+          const double xq = sm[BW_QUX + i * 16 + r], xv = sm[BW_QUX + i * 16 + 8 + r];
+          a0 -= xq * K0[i];
+          a1 -= xq * K1[i];
+          b0 -= xv * K0[i];
+          b1 -= xv * K1[i];
+        }
+        sm[BW_V + r * 16 + j] = a0;
+        sm[BW_V + r * 16 + 8 + j] = a1;
+        sm[BW_V + (NJ + r) * 16 + j] = b0;
+        sm[BW_V + (NJ + r) * 16 + 8 + j] = b1;
+        Q0[r] = a0; Q1[r] = a1; Q0[NJ + r] = b0; Q1[NJ + r] = b1;
+      }
+      AGX_OSYNC();
+      // symmetrise (row c of the unsymmetrised matrix is read back from the board)
+#pragma unroll
+      for (int r = 0; r < NJ; ++r) {
+        V0[r] = 0.5 * (Q0[r] + sm[BW_V + jj * 16 + r]);
+        V0[NJ + r] = 0.5 * (Q0[NJ + r] + sm[BW_V + jj * 16 + 8 + r]);
+        V1[r] = 0.5 * (Q1[r] + sm[BW_V + (NJ + jj) * 16 + r]);
+        V1[NJ + r] = 0.5 * (Q1[NJ + r] + sm[BW_V + (NJ + jj) * 16 + 8 + r]);
+      }
+#pragma unroll
+      for (int i = 0; i < NJ; ++i)
+        if (i == j) { V0[i] += xreg; V1[NJ + i] += xreg; }
+      if (!live) {
+#pragma unroll
+        for (int r = 0; r < NX; ++r) { V0[r] = 0.0; V1[r] = 0.0; }
+      }
+      vx0 = nvx0; vx1 = nvx1;
+      // expected improvement pieces and gap terms
+      if (live) {
+        double quuk = 0.0;
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) quuk += QuuC[i] * kk[i];
+        double kj = 0.0;
+#pragma unroll
+        for (int i = 0; i < NJ; ++i)
+          if (i == j) kj = kk[i];
+        dgp += qu * kj;
+        dqp -= kj * quuk;
+        kb[t * NJ + j] = kj;
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) {
+          Kb[(t * NJ + i) * NX + j] = K0[i];
+          Kb[(t * NJ + i) * NX + NJ + j] = K1[i];
+        }
+      }
+      if (!feasible) {
+        double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+        for (int r = 0; r < NX; ++r) { g0 += V0[r] * sm[BW_FS + r]; g1 += V1[r] * sm[BW_FS + r]; }
+        vx0 += g0; vx1 += g1;
+        if (live) {
+          gvb[t * NX + j] = g0; gvb[t * NX + NJ + j] = g1;
+          dgp -= vx0 * sm[BW_FS + j] + vx1 * sm[BW_FS + NJ + j];
+          dqp += g0 * sm[BW_FS + j] + g1 * sm[BW_FS + NJ + j];
+        }
+      }
+      AGX_OSYNC();
+    }
+    if (ok) {
+      // non-finite value function = failed sweep (SolverDDP::backwardPass raises on NaN)
+      double chk = vx0 + vx1;
+#pragma unroll
+      for (int r = 0; r < NX; ++r) chk += V0[r] + V1[r];
+      chk = octet_sum(live ? chk : 0.0, omask);
+      if (!(chk - chk == 0.0)) ok = false;
+    }
+    if (ok) {
+      dg = octet_sum(dgp, omask);
+      dq = octet_sum(dqp, omask);
+      break;
+    }
+    // increaseRegularization and retry without recalc
+    failed = false;
+    xreg *= O.reg_incfactor;
+    if (xreg > O.reg_max) xreg = O.reg_max;
+    if (xreg == O.reg_max) {
+      if (j == 0) { S.status[b] = 2; S.done[b] = 1; }
+      break;
+    }
+  }
+  if (j == 0) {
+    S.xreg[b] = xreg;
+    S.cost[b] = cost;
+    S.dg[b] = dg;
+    S.dq[b] = dq;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Line search + acceptance + regularisation / stop logic of one FDDP iteration.
+__global__ void forward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
+  AGX_SMEM(smem);
+  AGX_OCTET_SETUP();
+  const int b = (int)ent;
+  if (b >= P.B) return;
+  if (S.done[b]) return;
+  double* sa = smem + oct_in_cta * (OCT_BOARD + 16);
+  double* sb = sa + BRD_A;
+  double* sdx = sb + BRD_B;  // [14]
+  const int T = P.T, T1 = T + 1;
+  const bool live = j < NJ;
+  const int jj = live ? j : 0;
+  const double* model = model_of(P, b);
+  const size_t buf = buf_of(S.cur, b, false), obuf = buf ^ 1;
+  const double* xs = W.xs + (buf * P.B + b) * (size_t)T1 * NX;
+  const double* us = W.us + (buf * P.B + b) * (size_t)T * NJ;
+  double* xt = W.xs + (obuf * P.B + b) * (size_t)T1 * NX;
+  double* ut = W.us + (obuf * P.B + b) * (size_t)T * NJ;
+  const double* fsb = W.fs + (size_t)b * T1 * NX;
+  const double* gvb = W.gv + (size_t)b * T1 * NX;
+  const double* Kb = W.K + (size_t)b * T * NJ * NX;
+  const double* kb = W.k + (size_t)b * T * NJ;
+  const double* refs = P.refs + (size_t)b * T1 * REF_SIZE;
+  const bool feasible = S.is_feasible[b] != 0;
+  const double cost = S.cost[b], dg = S.dg[b], dq = S.dq[b];
+  const double x0q = live ? W.x0[(size_t)b * NX + jj] : 0.0, x0v = live ? W.x0[(size_t)b * NX + NJ + jj] : 0.0;
+
+  double steplength = 1.0, d1 = 0.0, d2 = 0.0, cost_try = 0.0;
+  bool accepted = false, have_d = false;
+  for (int ia = 0; ia < O.n_alphas; ++ia) {
+    steplength = ldexp(1.0, -ia);
+    const bool contract = !(feasible || ia == 0);
+    double xq = x0q, xv = x0v;
+    double ctry = 0.0, dvp = 0.0;
+    bool ok = true;
+    for (int t = 0; t <= T; ++t) {
+      double tq = xq, tv = xv;
+      if (contract && live) {
+        tq += fsb[t * NX + j] * (steplength - 1.0);
+        tv += fsb[t * NX + NJ + j] * (steplength - 1.0);
+      }
+      const double dxq = live ? tq - xs[t * NX + jj] : 0.0, dxv = live ? tv - xs[t * NX + NJ + jj] : 0.0;
+      if (live) {
+        xt[t * NX + j] = tq;
+        xt[t * NX + NJ + j] = tv;
+        if (!feasible) dvp += gvb[t * NX + j] * dxq + gvb[t * NX + NJ + j] * dxv;
+      }
+      LaneDyn d;
+      d.q = tq; d.qd = tv; d.u = 0.0;
+      const bool terminal = t == T;
+      if (!terminal) {
+        if (live) { sdx[j] = dxq; sdx[NJ + j] = dxv; }
+        AGX_OSYNC();
+        if (live) {
+          double s = 0.0;
+#pragma unroll
+          for (int m = 0; m < NX; ++m) s += Kb[(t * NJ + j) * NX + m] * sdx[m];
+          d.u = us[t * NJ + j] - kb[t * NJ + j] * steplength - s;
+          ut[t * NJ + j] = d.u;
+        }
+      }
+      double c, qn, vn;
+      const bool okn = node_calc(d, j, omask, model, refs + (size_t)t * REF_SIZE, terminal ? 0.0 : P.dts[t], terminal,
+                                 sa, sb, &c, &qn, &vn);
+      ok = ok && okn;
+      ctry += c;
+      xq = qn; xv = vn;
+      if (!(ctry - ctry == 0.0)) { ok = false; break; }  // NaN / inf: reject this step length
+    }
+    if (!ok) continue;
+    cost_try = ctry;
+    const double dv = feasible ? 0.0 : octet_sum(dvp, omask);
+    const double dV = cost - cost_try;
+    d1 = dg + dv;
+    d2 = dq - 2.0 * dv;
+    have_d = true;
+    const double dVexp = steplength * (d1 + 0.5 * steplength * d2);
+    if (dVexp >= 0.0) {
+      if (d1 < O.th_grad || dV > O.th_acceptstep * dVexp) accepted = true;
+    } else {
+      if (dV > O.th_acceptnegstep * dVexp) accepted = true;
+    }
+    if (accepted) break;
+  }
+  if (j == 0) {
+    bool was_feasible = S.was_feasible[b] != 0;
+    if (accepted) {
+      was_feasible = feasible;
+      S.was_feasible[b] = feasible ? 1 : 0;
+      S.is_feasible[b] = (feasible || steplength == 1.0) ? 1 : 0;
+      S.cost[b] = cost_try;
+      S.cur[b] = (int32_t)obuf;
+      S.recalc[b] = 1;
+    } else {
+      S.recalc[b] = 0;
+    }
+    double xreg = S.xreg[b];
+    int status = 1, done = 0;
+    if (steplength > O.th_stepdec) {
+      xreg /= O.reg_decfactor;
+      if (xreg < O.reg_min) xreg = O.reg_min;
+    }
+    if (steplength <= O.th_stepinc) {
+      xreg *= O.reg_incfactor;
+      if (xreg > O.reg_max) xreg = O.reg_max;
+      if (xreg == O.reg_max) { status = 2; done = 1; }
+    }
+    S.xreg[b] = xreg;
+    S.iters[b] += 1;
+    if (!done) {
+      const double stop = have_d ? fabs(d1 + 0.5 * d2) : S.stop[b];
+      S.stop[b] = stop;
+      if (!O.fixed_iters && was_feasible && stop < O.th_stop) { status = 0; done = 1; }
+    }
+    if (done) { S.status[b] = status; S.done[b] = 1; }
+  }
+}
+
+// problem.rollout(us): one octet per problem
+__global__ void rollout_kernel(Problem P, const double* __restrict__ x0, const double* __restrict__ us,
+                               double* __restrict__ out_xs) {
+  AGX_SMEM(smem);
+  AGX_OCTET_SETUP();
+  const int b = (int)ent;
+  if (b >= P.B) return;
+  double* sa = smem + oct_in_cta * OCT_BOARD;
+  double* sb = sa + BRD_A;
+  const int T = P.T, T1 = T + 1;
+  const bool live = j < NJ;
+  const int jj = live ? j : 0;
+  double xq = live ? x0[(size_t)b * NX + jj] : 0.0, xv = live ? x0[(size_t)b * NX + NJ + jj] : 0.0;
+  double* xo = out_xs + (size_t)b * T1 * NX;
+  if (live) { xo[j] = xq; xo[NJ + j] = xv; }
+  for (int t = 0; t < T; ++t) {
+    LaneDyn d;
+    d.q = xq; d.qd = xv; d.u = live ? us[((size_t)b * T + t) * NJ + jj] : 0.0;
+    double c, qn, vn;
+    const bool ok = node_calc(d, j, omask, model_of(P, b), P.refs + ((size_t)b * T1 + t) * REF_SIZE, P.dts[t], false,
+                              sa, sb, &c, &qn, &vn);
+    xq = ok ? qn : nan("");
+    xv = ok ? vn : nan("");
+    if (live) { xo[(t + 1) * NX + j] = xq; xo[(t + 1) * NX + NJ + j] = xv; }
+  }
+}
+
+// IntegratedActionModelEuler.calc -> xnext for n independent (x, u) pairs (costs skipped)
+__global__ void integrate_kernel(const double* __restrict__ model, const double* __restrict__ x,
+                                 const double* __restrict__ u, double dt, int n, double* __restrict__ out) {
+  AGX_SMEM(smem);
+  AGX_OCTET_SETUP();
+  if (ent >= n) return;
+  double* sa = smem + oct_in_cta * OCT_BOARD;
+  double* sb = sa + BRD_A;
+  LaneDyn d;
+  lane_load_state(d, j, x + (size_t)ent * NX, u + (size_t)ent * NJ);
+  node_kinematics(d, j, omask, model, sa);
+  double L[28], rinv[NJ], qdd[NJ];
+  const bool ok = node_forward_dynamics<false>(d, j, omask, model, sa, sb, L, rinv, qdd);
+  if (j < NJ) {
+    out[(size_t)ent * NX + j] = ok ? d.q + (d.qd * dt + d.qdd * (dt * dt)) : nan("");
+    out[(size_t)ent * NX + NJ + j] = ok ? d.qd + d.qdd * dt : nan("");
+  }
+}
+
+// pin.rnea(q, v, a) for n independent triples: tau = nle(q, v) + M(q) a (no armature)
+__global__ void rnea_kernel(const double* __restrict__ model, const double* __restrict__ q,
+                            const double* __restrict__ v, const double* __restrict__ a, int n,
+                            double* __restrict__ out_tau) {
+  AGX_SMEM(smem);
+  AGX_OCTET_SETUP();
+  if (ent >= n) return;
+  double* sa = smem + oct_in_cta * OCT_BOARD;
+  double* sb = sa + BRD_A;
+  const bool live = j < NJ;
+  const int jj = live ? j : 0;
+  LaneDyn d;
+  d.q = live ? q[(size_t)ent * NJ + jj] : 0.0;
+  d.qd = live ? v[(size_t)ent * NJ + jj] : 0.0;
+  d.u = 0.0;
+  d.qdd = live ? a[(size_t)ent * NJ + jj] : 0.0;
+  node_kinematics(d, j, omask, model, sa);
+  const double zero6[6] = {0, 0, 0, 0, 0, 0};
+  const double agrav[6] = {-model[MT_GRAV + 0], -model[MT_GRAV + 1], -model[MT_GRAV + 2], 0, 0, 0};
+  vec6_store(d.s, j, sa);
+  AGX_OSYNC();
+  vec6_prefix_excl(d.vp, j, zero6, sa);
+  AGX_OSYNC();
+  body_terms(d, j, model, nullptr, false);
+  // bias acceleration including the joint accelerations: g = c qd + J qdd
+#pragma unroll
+  for (int k = 0; k < 6; ++k) d.g[k] += d.J[k] * d.qdd;
+  vec6_store(d.g, j, sa);
+  AGX_OSYNC();
+  vec6_prefix_excl(d.a0p, j, agrav, sa);
+  AGX_OSYNC();
+  body_force(d);
+  vec6_store(d.Z + 22, j, sa);
+  AGX_OSYNC();
+  vec6_suffix_incl(d.Z + 22, j, sa);
+  (void)sb;
+  if (live) out_tau[(size_t)ent * NJ + j] = dot6(d.J, d.Z + 22);
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void init_kernel(Problem P, Work W, SolverState S, FddpOpts O, const double* __restrict__ xs_ws,
+                            const double* __restrict__ us_ws) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int T1 = P.T + 1;
+  const long long nxs = (long long)P.B * T1 * NX, nus = (long long)P.B * P.T * NJ;
+  if (gid < nxs) W.xs[gid] = xs_ws[gid];
+  if (gid < nus) W.us[gid] = us_ws[gid];
+  if (gid < P.B) {
+    const int b = (int)gid;
+    S.xreg[b] = (O.reg_init == O.reg_init) ? O.reg_init : O.reg_min;
+    S.cost[b] = 0.0; S.dg[b] = 0.0; S.dq[b] = 0.0; S.stop[b] = 0.0;
+    S.is_feasible[b] = 0; S.was_feasible[b] = 0; S.recalc[b] = 1; S.done[b] = 0;
+    S.status[b] = 1; S.iters[b] = 0; S.cur[b] = 0;
+  }
+}
+
+__global__ void finalize_kernel(Problem P, Work W, SolverState S, double* out_xs, double* out_us, double* out_K,
+                                double* out_k, double* out_cost, int32_t* out_iters, int32_t* out_status,
+                                double* out_stop) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int T1 = P.T + 1;
+  const long long per_xs = (long long)T1 * NX, per_us = (long long)P.T * NJ, per_K = (long long)P.T * NJ * NX;
+  if (gid < P.B * per_xs) {
+    const int b = (int)(gid / per_xs);
+    out_xs[gid] = W.xs[(size_t)(S.cur[b] & 1) * P.B * per_xs + gid];
+  }
+  if (gid < P.B * per_us) {
+    const int b = (int)(gid / per_us);
+    out_us[gid] = W.us[(size_t)(S.cur[b] & 1) * P.B * per_us + gid];
+    if (out_k) out_k[gid] = W.k[gid];
+  }
+  if (out_K && out_K != W.K && gid < P.B * per_K) out_K[gid] = W.K[gid];
+  if (gid < P.B) {
+    out_cost[gid] = S.cost[gid];
+    out_iters[gid] = S.iters[gid];
+    out_status[gid] = S.status[gid];
+    if (out_stop) out_stop[gid] = S.stop[gid];
+  }
+}
+
+}  // namespace agx
+#endif  // AGX_KERNELS_CUH_
