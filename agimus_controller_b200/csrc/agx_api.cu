@@ -106,6 +106,14 @@ struct agx_handle {
   void* state_block = nullptr;
   long long launches = 0;
   std::string err;
+  // optional per-phase device timing (bench evidence): event pairs around the solve's kernels
+  bool timing = false;
+  int n_pairs = 0;
+#if AGX_GPU
+  cudaEvent_t ev[2 * 2048];
+  int ev_made = 0;
+#endif
+  int pair_phase[2048];
 };
 
 namespace {
@@ -118,6 +126,22 @@ int check_launch(agx_handle* h, const char* what) {
   if (const char* e = dev_check()) return fail(h, AGX_ECUDA, std::string(what) + ": " + e);
   return AGX_OK;
 }
+#if AGX_GPU
+inline void phase_begin(agx_handle* h, int phase, cudaStream_t st) {
+  if (!h->timing || h->n_pairs >= 2048) return;
+  while (h->ev_made < 2 * (h->n_pairs + 1)) cudaEventCreate(&h->ev[h->ev_made++]);
+  h->pair_phase[h->n_pairs] = phase;
+  cudaEventRecord(h->ev[2 * h->n_pairs], st);
+}
+inline void phase_end(agx_handle* h, cudaStream_t st) {
+  if (!h->timing || h->n_pairs >= 2048) return;
+  cudaEventRecord(h->ev[2 * h->n_pairs + 1], st);
+  ++h->n_pairs;
+}
+#else
+inline void phase_begin(agx_handle*, int, void*) {}
+inline void phase_end(agx_handle*, void*) {}
+#endif
 agx::Problem problem_of(const agx_handle* h) {
   agx::Problem P;
   P.model = h->d_model; P.refs = h->d_refs; P.dts = h->d_dts;
@@ -158,6 +182,9 @@ int agx_destroy(agx_handle* h) {
     dev_free(h->d_model); dev_free(h->d_refs); dev_free(h->d_dts); dev_free(h->d_x0); dev_free(h->d_K_internal);
     dev_free(h->W.xs); dev_free(h->W.us); dev_free(h->W.rec); dev_free(h->W.fs); dev_free(h->W.gv); dev_free(h->W.k);
     dev_free(h->state_block);
+#if AGX_GPU
+    for (int i = 0; i < h->ev_made; ++i) cudaEventDestroy(h->ev[i]);
+#endif
   }
   delete h;
   return AGX_OK;
@@ -278,6 +305,88 @@ int agx_rnea(agx_handle* h, const double* q, const double* v, const double* a, i
   return check_launch(h, "agx_rnea");
 }
 
+#if AGX_GPU
+namespace {
+// FP64 FMA throughput probe: 8 independent dependent-chains per thread, 2 flops per DFMA
+__global__ void fp64_probe_kernel(double* out, int n) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-7;
+  for (int i = 0; i < n; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 12345.678) out[0] = s;  // never true: keeps the chains alive
+}
+}  // namespace
+#endif
+
+int agx_probe_fp64(int device, double seconds, double* out_tflops, double* out_ms) {
+  if (!out_tflops) return AGX_EINVAL;
+#if AGX_GPU
+  DeviceGuard g(device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return AGX_ECUDA;
+  double* d = nullptr;
+  if (cudaMalloc(&d, 64) != cudaSuccess) return AGX_ENOMEM;
+  const int ctas = prop.multiProcessorCount * 8, threads = 256, n = 1 << 14;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  fp64_probe_kernel<<<ctas, threads>>>(d, n);  // warm-up
+  cudaDeviceSynchronize();
+  float ms1 = 0.f;
+  cudaEventRecord(e0);
+  fp64_probe_kernel<<<ctas, threads>>>(d, n);
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  cudaEventElapsedTime(&ms1, e0, e1);
+  int reps = (int)(seconds * 1e3 / (ms1 > 1e-3f ? ms1 : 1e-3f));
+  if (reps < 1) reps = 1;
+  if (reps > 2000) reps = 2000;
+  float ms = 0.f;
+  cudaEventRecord(e0);
+  for (int r = 0; r < reps; ++r) fp64_probe_kernel<<<ctas, threads>>>(d, n);
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  cudaEventElapsedTime(&ms, e0, e1);
+  const double flops = 2.0 * 8.0 * (double)n * threads * (double)ctas * reps;
+  *out_tflops = flops / (ms * 1e-3) / 1e12;
+  if (out_ms) *out_ms = ms;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d);
+  return cudaGetLastError() == cudaSuccess ? AGX_OK : AGX_ECUDA;
+#else
+  (void)device; (void)seconds;
+  *out_tflops = 0.0;
+  if (out_ms) *out_ms = 0.0;
+  return AGX_EUNSUPPORTED;
+#endif
+}
+
+int agx_set_timing(agx_handle* h, int enable) {
+  if (!h) return AGX_EINVAL;
+  h->timing = enable != 0;
+  h->n_pairs = 0;
+  return AGX_OK;
+}
+
+int agx_get_timing(agx_handle* h, double* out_ms, long long* out_launches) {
+  if (!h || !out_ms || !out_launches) return AGX_EINVAL;
+  for (int p = 0; p < 3; ++p) { out_ms[p] = 0.0; out_launches[p] = 0; }
+#if AGX_GPU
+  DeviceGuard g(h->device);
+  for (int i = 0; i < h->n_pairs; ++i) {
+    if (cudaEventSynchronize(h->ev[2 * i + 1]) != cudaSuccess) return fail(h, AGX_ECUDA, "agx_get_timing: event sync failed");
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev[2 * i], h->ev[2 * i + 1]);
+    out_ms[h->pair_phase[i]] += ms;
+    out_launches[h->pair_phase[i]] += 1;
+  }
+#endif
+  h->n_pairs = 0;
+  return AGX_OK;
+}
+
 int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double* us_ws, int max_iter,
               const agx_fddp_opts* opts, double* out_xs, double* out_us, double* out_K, double* out_k,
               double* out_cost, int32_t* out_iters, int32_t* out_status, double* out_stop, void* stream) {
@@ -308,12 +417,18 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
   const long long ents = (long long)(nB * T1);
   const int opc_n = NODE_CTA / 8, opc_s = SEQ_CTA / 8;
   for (int it = 0; it < max_iter; ++it) {
+    phase_begin(h, 0, st);
     AGX_LAUNCH(h, calc_diff_kernel, (ents + opc_n - 1) / opc_n, NODE_CTA, sizeof(double) * OCT_BOARD * opc_n, st, P,
                (const double*)W.xs, (const double*)W.us, (const int32_t*)h->S.cur, (const int32_t*)h->S.recalc,
                (const int32_t*)h->S.done, W.rec);
+    phase_end(h, st);
+    phase_begin(h, 1, st);
     AGX_LAUNCH(h, backward_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * BW_SIZE * opc_s, st, P, W, h->S, O);
+    phase_end(h, st);
+    phase_begin(h, 2, st);
     AGX_LAUNCH(h, forward_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * (OCT_BOARD + 16) * opc_s, st, P, W,
                h->S, O);
+    phase_end(h, st);
   }
   const long long n_fin = (long long)(nB * T * NJ * NX);
   AGX_LAUNCH(h, finalize_kernel, (n_fin + 255) / 256, 256, 0, st, P, W, h->S, out_xs, out_us, out_K, out_k, out_cost,

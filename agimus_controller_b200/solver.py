@@ -1,0 +1,192 @@
+"""Batched shooting problem + FDDP solver on one B200: thin torch-tensor front end of the C ABI.
+
+Replaces, for a batch of ``B`` independent OCPs, the objects the reference builds at
+``agimus_controller/agimus_controller/ocp_base_croco.py:36-80`` (``crocoddyl.ShootingProblem`` and the
+solver) and the calls it makes on them: ``problem.calc/calcDiff`` (``mpc_debugger_node.py:300-301``),
+``problem.rollout`` (``tests/test_warm_start_shift_previous_reference.py:76``), ``solver.solve``
+(``ocp_base_croco.py:172``), ``runningModels[0].calc`` (``ocp_base_croco.py:184-189``) and ``pin.rnea``
+(``warm_start_reference.py:77-87``).  Every tensor is fp64, C-contiguous, on the handle's CUDA device;
+calls are enqueued on torch's current stream and never synchronise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import typing as T
+
+import numpy as np
+import torch
+
+from . import _abi
+from ._lib import lib
+from .robot_model import RobotTable
+
+
+def _ptr(t: T.Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def probe_fp64_tflops(device: int = 0, seconds: float = 0.5) -> float:
+    """Sustained FP64 FMA throughput of the device (roofline denominator of the fp64 kernels)."""
+    out = C.c_double()
+    rc = lib().agx_probe_fp64(int(device), float(seconds), C.byref(out), None)
+    if rc != 0:
+        raise RuntimeError(f"agx_probe_fp64 failed ({rc})")
+    return float(out.value)
+
+
+class BatchedShootingProblem:
+    """``B`` shooting problems with ``T`` running nodes sharing one horizon layout."""
+
+    def __init__(self, tables: T.Union[RobotTable, T.Sequence[RobotTable]], dts: T.Sequence[float], B: int,
+                 device: T.Union[int, torch.device, str, None] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("agimus_controller_b200 needs a CUDA device (no CPU fallback)")
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("agimus_controller_b200 needs a CUDA device (no CPU fallback)")
+        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        if isinstance(tables, RobotTable):
+            structs = [tables.to_struct()]
+            self.table = tables
+        else:
+            structs = [t.to_struct() for t in tables]
+            self.table = tables[0]
+        arr = (_abi.AgxModel * len(structs))(*structs)
+        self.dts = np.ascontiguousarray(dts, dtype=np.float64)
+        self.B, self.T = int(B), int(len(self.dts))
+        self.nv = self.table.nv
+        self.nx = 2 * self.nv
+        self.ref_size = _abi.ref_size(self.nv)
+        self._h = C.c_void_p()
+        rc = lib().agx_create(arr, len(structs), self.dts.ctypes.data, self.B, self.T, self.device.index,
+                              C.byref(self._h))
+        if rc != 0:
+            msg = lib().agx_last_error(self._h).decode() if self._h else ""
+            if self._h:
+                lib().agx_destroy(self._h)
+            self._h = None
+            raise RuntimeError(f"agx_create failed ({rc}): {msg}")
+        self._refs_set = False
+
+    # ------------------------------------------------------------------ helpers
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib().agx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise RuntimeError(f"agx error {rc}: {lib().agx_last_error(self._h).decode()}")
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _t(self, x, shape) -> torch.Tensor:
+        t = torch.as_tensor(x, dtype=torch.float64, device=self.device).contiguous()
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f"expected shape {tuple(shape)}, got {tuple(t.shape)}")
+        return t
+
+    def _empty(self, *shape, dtype=torch.float64) -> torch.Tensor:
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().agx_launch_count(self._h))
+
+    def set_timing(self, enable: bool) -> None:
+        self._check(lib().agx_set_timing(self._h, 1 if enable else 0))
+
+    def get_timing(self) -> dict:
+        """Per-phase device time (ms) and launch counts since the last read (synchronises)."""
+        ms = (C.c_double * 3)()
+        n = (C.c_longlong * 3)()
+        self._check(lib().agx_get_timing(self._h, ms, n))
+        names = ("calc_diff", "backward", "forward")
+        return {k: dict(ms=float(ms[i]), launches=int(n[i])) for i, k in enumerate(names)}
+
+    # ------------------------------------------------------------------ problem data
+    def set_refs(self, refs) -> None:
+        """Per-node references and weights, ``[B, T+1, ref_size]`` (``problem.pack_refs``)."""
+        r = self._t(refs, (self.B, self.T + 1, self.ref_size))
+        self._check(lib().agx_set_refs(self._h, _ptr(r), self._stream()))
+        self._refs_set = True
+
+    # ------------------------------------------------------------------ problem.calc / calcDiff / rollout
+    def calc(self, xs, us):
+        xs = self._t(xs, (self.B, self.T + 1, self.nx))
+        us = self._t(us, (self.B, self.T, self.nv))
+        cost, xnext = self._empty(self.B, self.T + 1), self._empty(self.B, self.T + 1, self.nx)
+        self._check(lib().agx_calc(self._h, _ptr(xs), _ptr(us), _ptr(cost), _ptr(xnext), self._stream()))
+        return cost, xnext
+
+    def calc_diff(self, xs, us) -> dict:
+        xs = self._t(xs, (self.B, self.T + 1, self.nx))
+        us = self._t(us, (self.B, self.T, self.nv))
+        B, T1, nx, nv = self.B, self.T + 1, self.nx, self.nv
+        out = dict(cost=self._empty(B, T1), xnext=self._empty(B, T1, nx), Fx=self._empty(B, T1, nx, nx),
+                   Fu=self._empty(B, T1, nx, nv), Lx=self._empty(B, T1, nx), Lu=self._empty(B, T1, nv),
+                   Lxx=self._empty(B, T1, nx, nx), Lxu=self._empty(B, T1, nx, nv), Luu=self._empty(B, T1, nv, nv))
+        out["Lu"].zero_()
+        out["Luu"].zero_()
+        self._check(lib().agx_calc_diff(
+            self._h, _ptr(xs), _ptr(us), *[_ptr(out[k]) for k in
+                                           ("cost", "xnext", "Fx", "Fu", "Lx", "Lu", "Lxx", "Lxu", "Luu")],
+            self._stream()))
+        return out
+
+    def rollout(self, x0, us):
+        x0 = self._t(x0, (self.B, self.nx))
+        us = self._t(us, (self.B, self.T, self.nv))
+        xs = self._empty(self.B, self.T + 1, self.nx)
+        self._check(lib().agx_rollout(self._h, _ptr(x0), _ptr(us), _ptr(xs), self._stream()))
+        return xs
+
+    def integrate(self, x, u, dt: float):
+        x = torch.as_tensor(x, dtype=torch.float64, device=self.device).contiguous().reshape(-1, self.nx)
+        u = torch.as_tensor(u, dtype=torch.float64, device=self.device).contiguous().reshape(-1, self.nv)
+        out = torch.empty_like(x)
+        self._check(lib().agx_integrate(self._h, _ptr(x), _ptr(u), float(dt), x.shape[0], _ptr(out), self._stream()))
+        return out
+
+    def rnea(self, q, v, a):
+        q = torch.as_tensor(q, dtype=torch.float64, device=self.device).contiguous().reshape(-1, self.nv)
+        v = torch.as_tensor(v, dtype=torch.float64, device=self.device).contiguous().reshape(-1, self.nv)
+        a = torch.as_tensor(a, dtype=torch.float64, device=self.device).contiguous().reshape(-1, self.nv)
+        tau = torch.empty_like(q)
+        self._check(lib().agx_rnea(self._h, _ptr(q), _ptr(v), _ptr(a), q.shape[0], _ptr(tau), self._stream()))
+        return tau
+
+    # ------------------------------------------------------------------ solver.solve
+    def alloc_outputs(self, with_k: bool = True) -> dict:
+        B, T, nx, nv = self.B, self.T, self.nx, self.nv
+        out = dict(xs=self._empty(B, T + 1, nx), us=self._empty(B, T, nv), K=self._empty(B, T, nv, nx),
+                   cost=self._empty(B), iters=self._empty(B, dtype=torch.int32),
+                   status=self._empty(B, dtype=torch.int32), stop=self._empty(B))
+        if with_k:
+            out["k"] = self._empty(B, T, nv)
+        return out
+
+    def solve(self, x0, xs_ws, us_ws, max_iter: int, opts: T.Optional[_abi.AgxFddpOpts] = None,
+              out: T.Optional[dict] = None) -> dict:
+        """FDDP from the warm start ``(xs_ws, us_ws)`` with ``problem.x0 = x0``; stream-ordered, no sync."""
+        if not self._refs_set:
+            raise RuntimeError("set_refs() must be called before solve()")
+        x0 = self._t(x0, (self.B, self.nx))
+        xs_ws = self._t(xs_ws, (self.B, self.T + 1, self.nx))
+        us_ws = self._t(us_ws, (self.B, self.T, self.nv))
+        if out is None:
+            out = self.alloc_outputs()
+        if opts is None:
+            opts = _abi.default_fddp_opts()
+        self._check(lib().agx_solve(
+            self._h, _ptr(x0), _ptr(xs_ws), _ptr(us_ws), int(max_iter), C.byref(opts), _ptr(out["xs"]),
+            _ptr(out["us"]), _ptr(out["K"]), _ptr(out.get("k")), _ptr(out["cost"]), _ptr(out["iters"]),
+            _ptr(out["status"]), _ptr(out.get("stop")), self._stream()))
+        return out

@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py — OCP solves/s of the batched FDDP solve path (BASELINE.json metric, config 2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch: B = 4096 Panda goal-reaching OCPs (T = 50,
+dt = 0.01, randomised initial states), exactly 10 FDDP iterations each (cfg 2).
+N > 1 (torchrun, one rank per GPU): every rank solves its own slab of 4096 problems (weak scaling, no
+data-path collective; one NCCL all_gather of cost/iters/status per step).
+
+Printed JSON (rank 0, one line):
+  value        solves/s with inputs resident in HBM (device-timed with CUDA events, max over ranks)
+  e2e          same metric through the public API with HOST buffers: pinned H2D of x0 / warm start /
+               references and D2H of xs, us, K[:, 0], cost, iters, status inside the timed region
+  roofline     the dominant kernel against the FP64 (non-tensor) peak measured in-run by a DFMA probe,
+               plus its HBM side; durations from CUDA-event pairs around every launch of the step
+  cpu_baseline the CPU restatement (oracle, OpenMP one problem per thread) on a bounded sample
+--impl reference times that CPU restatement as the reference arm (Crocoddyl itself cannot be installed:
+its sources are not in the reference tree and there is no network).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_PER_GPU = 4096
+T_NODES = 50
+DT = 0.01
+N_ITERS = 10
+METRIC = "OCP solves/sec, Panda T=50 batch 4096, fixed 10 FDDP iterations"
+WORKLOAD = "cfg2: 4096 Panda goal-reaching OCPs per GPU, T=50, dt=0.01, randomised x0, fixed 10 FDDP iterations"
+
+# agreed algorithmic work per node and iteration, FMA = 2 flops
+FLOP_CALC_DIFF = 16000.0
+FLOP_BACKWARD = 23500.0
+FLOP_FORWARD = 3500.0
+REC_BYTES = 288 * 8
+
+
+def build_workload(B, seed, rnea):
+    """cfg-2 tables; `rnea` supplies the gravity-compensation warm start (device kernel in our arm)."""
+    from agimus_controller_b200 import panda_table
+    from agimus_controller_b200.workloads import goal_reaching_batch
+
+    m = panda_table().to_struct()
+    w = goal_reaching_batch(B, T=T_NODES, dt=DT, seed=seed, rnea=rnea)
+    return w, m
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm, smax, reasons = [], None, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0]))
+                smax = float(r[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def time_cpu(orc, m, w, n, max_iter, threads=0):
+    from agimus_controller_b200 import _abi
+
+    opts = _abi.default_fddp_opts(fixed_iters=True)
+    sl = slice(0, n)
+    t0 = time.perf_counter()
+    orc.solve(m, w["refs"][sl], w["dts"], w["x0"][sl], w["xs_ws"][sl], w["us_ws"][sl], max_iter, opts, nthreads=threads)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    """Reference arm: the CPU restatement of the path on the host cores (rank 0 only)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    from oracle import orc
+
+    cores = len(os.sched_getaffinity(0))
+    n = 64 * cores if args.sample is None else args.sample
+    n = min(n, B_PER_GPU)
+    from agimus_controller_b200 import panda_table
+
+    m0 = panda_table().to_struct()
+    w, m = build_workload(B_PER_GPU, 0, lambda q, v, a: orc.rnea(m0, q, v, a))
+    for _ in range(args.warmup):
+        time_cpu(orc, m, w, n, N_ITERS)
+    t = [time_cpu(orc, m, w, n, N_ITERS) for _ in range(args.steps)]
+    total = sum(t)
+    value = n * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": f"first {n} of the 4096 problems per step"},
+        "cpu_baseline": {"value": value, "unit": "solves/s", "cores": orc.num_threads(), "kind": "port",
+                         "sample": f"{n} problems x {args.steps} steps, OpenMP one problem per thread, "
+                                   "CPU restatement of Crocoddyl FDDP (oracle/agx_oracle.cpp)"},
+        "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from agimus_controller_b200 import _abi
+    from agimus_controller_b200.solver import BatchedShootingProblem, probe_fp64_tflops
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the solve path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = B_PER_GPU
+    from agimus_controller_b200 import panda_table
+
+    opts = _abi.default_fddp_opts(fixed_iters=True)
+    prob = BatchedShootingProblem(panda_table(), np.full(T_NODES, DT), B, device=dev)
+    w, m = build_workload(B, rank, lambda q, v, a: prob.rnea(q, v, a).cpu().numpy())
+    # resident inputs
+    refs_d = torch.as_tensor(w["refs"], device=dev)
+    x0_d = torch.as_tensor(w["x0"], device=dev)
+    xs_d = torch.as_tensor(w["xs_ws"], device=dev)
+    us_d = torch.as_tensor(w["us_ws"], device=dev)
+    prob.set_refs(refs_d)
+    out = prob.alloc_outputs()
+    stats = torch.empty(B, 3, dtype=torch.float64, device=dev)
+    gathered = torch.empty(world * B, 3, dtype=torch.float64, device=dev) if world > 1 else None
+
+    def step_resident():
+        prob.solve(x0_d, xs_d, us_d, N_ITERS, opts, out=out)
+        if world > 1:
+            stats[:, 0] = out["cost"]
+            stats[:, 1] = out["iters"]
+            stats[:, 2] = out["status"]
+            dist.all_gather_into_tensor(gathered, stats)
+
+    # host-side buffers of the end-to-end arm (pinned)
+    pin = lambda a: torch.as_tensor(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
+    h_refs, h_x0, h_xs, h_us = pin(w["refs"]), pin(w["x0"]), pin(w["xs_ws"]), pin(w["us_ws"])
+    d_refs, d_x0, d_xs, d_us = (torch.empty_like(t, device=dev) for t in (h_refs, h_x0, h_xs, h_us))
+    r_xs = torch.empty(out["xs"].shape, dtype=torch.float64).pin_memory()
+    r_us = torch.empty(out["us"].shape, dtype=torch.float64).pin_memory()
+    r_K0 = torch.empty((B,) + tuple(out["K"].shape[2:]), dtype=torch.float64).pin_memory()
+    r_cost = torch.empty(B, dtype=torch.float64).pin_memory()
+    r_iters = torch.empty(B, dtype=torch.int32).pin_memory()
+    r_status = torch.empty(B, dtype=torch.int32).pin_memory()
+    h2d_bytes = sum(t.numel() * t.element_size() for t in (h_refs, h_x0, h_xs, h_us))
+    d2h_bytes = sum(t.numel() * t.element_size() for t in (r_xs, r_us, r_K0, r_cost, r_iters, r_status))
+
+    def step_e2e():
+        d_refs.copy_(h_refs, non_blocking=True)
+        d_x0.copy_(h_x0, non_blocking=True)
+        d_xs.copy_(h_xs, non_blocking=True)
+        d_us.copy_(h_us, non_blocking=True)
+        prob.set_refs(d_refs)
+        prob.solve(d_x0, d_xs, d_us, N_ITERS, opts, out=out)
+        r_xs.copy_(out["xs"], non_blocking=True)
+        r_us.copy_(out["us"], non_blocking=True)
+        r_K0.copy_(out["K"][:, 0], non_blocking=True)
+        r_cost.copy_(out["cost"], non_blocking=True)
+        r_iters.copy_(out["iters"], non_blocking=True)
+        r_status.copy_(out["status"], non_blocking=True)
+        if world > 1:
+            stats[:, 0] = out["cost"]
+            stats[:, 1] = out["iters"]
+            stats[:, 2] = out["status"]
+            dist.all_gather_into_tensor(gathered, stats)
+        torch.cuda.current_stream().synchronize()  # the caller reads the result on the host
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    fp64_peak = probe_fp64_tflops(local, 0.5) if (rank == 0 and not args.no_probe) else None
+
+    for _ in range(max(args.warmup, 1)):
+        step_resident()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    prob.set_timing(True)
+    l0 = prob.launch_count
+    ms_total = timed(step_resident, args.steps)
+    launches = prob.launch_count - l0
+    phases = prob.get_timing()
+    prob.set_timing(False)
+    clocks = sampler.stop() if sampler else None
+
+    for _ in range(max(min(args.warmup, 2), 1)):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # single-problem MPC latency (cfg 1 shape: B = 1, T = 20, <= 10 iterations), rank 0 only
+    lat = None
+    if rank == 0 and not args.no_latency:
+        from agimus_controller_b200.workloads import goal_reaching_batch
+
+        w1 = goal_reaching_batch(1, T=20, dt=DT, seed=0, rnea=lambda q, v, a: prob.rnea(q, v, a).cpu().numpy())
+        p1 = BatchedShootingProblem(w1["table"], w1["dts"], 1, device=dev)
+        p1.set_refs(w1["refs"])
+        o1 = p1.alloc_outputs()
+        a1 = [torch.as_tensor(w1[k], device=dev) for k in ("x0", "xs_ws", "us_ws")]
+        ts = []
+        for i in range(60):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            p1.solve(*a1, N_ITERS, opts, out=o1)
+            _ = o1["us"][0, 0].cpu()
+            ts.append(time.perf_counter() - t0)
+        ts = np.array(ts[10:]) * 1e3
+        lat = {"p50_ms": float(np.percentile(ts, 50)), "p99_ms": float(np.percentile(ts, 99)),
+               "workload": "cfg1 shape: B=1, T=20, 10 fixed FDDP iterations, host wall clock incl. launch + 1 D2H"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    solves = world * B * args.steps
+    value = solves / (ms_total * 1e-3)
+    e2e_value = solves / (ms_e2e * 1e-3)
+
+    # dominant kernel: algorithmic flops per launch / mean launch duration
+    T1 = T_NODES + 1
+    flops = {"calc_diff": FLOP_CALC_DIFF * B * T1, "backward": FLOP_BACKWARD * B * T_NODES,
+             "forward": FLOP_FORWARD * B * T1}
+    bytes_alg = {"calc_diff": B * T1 * (REC_BYTES + (14 + 7 + 60) * 8),
+                 "backward": B * (T1 * REC_BYTES + T_NODES * (98 + 7) * 8 + T1 * (14 * 3) * 8),
+                 "forward": B * T1 * ((14 * 4 + 7 * 3 + 98 + 60) * 8)}
+    per = {}
+    for k, v in phases.items():
+        if v["launches"]:
+            mean_ms = v["ms"] / v["launches"]
+            per[k] = {"ms_per_launch": mean_ms, "launches": v["launches"], "share_of_step": v["ms"] / ms_total,
+                      "tflops": flops[k] / (mean_ms * 1e-3) / 1e12, "gbs": bytes_alg[k] / (mean_ms * 1e-3) / 1e9}
+    top = max(per, key=lambda k: per[k]["ms_per_launch"] * per[k]["launches"]) if per else None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    roofline = None
+    if top:
+        roofline = {
+            "kernel": top + "_kernel", "bound": "fp64", "achieved": per[top]["tflops"], "peak": fp64_peak,
+            "unit": "TFLOP/s", "frac": per[top]["tflops"] / fp64_peak if fp64_peak else None, "traffic": None,
+            "peak_source": "in-run DFMA probe (agx_probe_fp64); MEASURED_PEAKS.json carries no FP64 figure",
+            "hbm": {"achieved": per[top]["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": per[top]["gbs"] / hbm_peak,
+                    "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
+            "phases": per,
+        }
+
+    # CPU baseline beside it (bounded sample, rank 0, N = 1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        from oracle import orc
+
+        cores = orc.num_threads()
+        n = min(B, 48 * cores)
+        time_cpu(orc, m, w, min(n, 4 * cores), N_ITERS)
+        t = time_cpu(orc, m, w, n, N_ITERS)
+        reps = 1
+        while t < 8.0 and reps < 16:
+            t += time_cpu(orc, m, w, n, N_ITERS)
+            reps += 1
+        cpu = {"value": n * reps / t, "unit": "solves/s", "cores": cores, "kind": "port",
+               "sample": f"{n} of the 4096 problems x {reps} passes ({t:.1f} s), OpenMP one problem per thread; "
+                         "CPU restatement of Crocoddyl FDDP (oracle/agx_oracle.cpp), not Crocoddyl itself"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 1), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "B_per_gpu": B, "T": T_NODES, "dt": DT, "fddp_iters": N_ITERS,
+                   "l2": "inputs_larger_than_L2 (node records 481 MB + gains 161 MB per step vs 126 MB L2)",
+                   "parallelism": f"independent slabs x{world}, NCCL all_gather of cost/iters/status only"},
+        "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps,
+                "returned": "xs, us, K[:,0] (the gain the controller applies), cost, iters, status"},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "latency_b1": lat,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sample", type=int, default=None, help="problems per step of the reference arm")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-latency", action="store_true", help="skip the B=1 latency leg")
+    ap.add_argument("--no-probe", action="store_true", help="skip the FP64 peak probe (profiler runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -143,6 +143,18 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
               double* out_K, double* out_k, double* out_cost, int32_t* out_iters,
               int32_t* out_status, double* out_stop, void* stream);
 
+/* Optional device timing of the solve's three phases (bench evidence, off by default): while enabled,
+ * agx_solve brackets every calc_diff / backward / forward launch with a CUDA event pair on `stream`.
+ * agx_get_timing synchronises on those events, adds the elapsed milliseconds and launch counts per phase
+ * (index 0 = calc_diff, 1 = backward sweep, 2 = forward line search) into out_ms[3] / out_launches[3]
+ * and clears the record (at most 2048 launches are kept between two reads). */
+int agx_set_timing(agx_handle* h, int enable);
+int agx_get_timing(agx_handle* h, double* out_ms, long long* out_launches);
+
+/* Roofline denominator: sustained FP64 FMA throughput of `device` (TFLOP/s, FMA = 2 flops) measured by
+ * a register-only probe kernel run for about `seconds`; out_ms (may be NULL) = device time of the run. */
+int agx_probe_fp64(int device, double seconds, double* out_tflops, double* out_ms);
+
 /* Number of kernel launches the library issued on this handle since creation (bench evidence). */
 long long agx_launch_count(const agx_handle* h);
 

@@ -1,0 +1,107 @@
+"""The shipped CUDA kernels, compiled for the CPU SIMT emulator (tests/emul), against the oracle.
+
+These run on a machine without a GPU: same translation unit as libagx.so (agx_api.cu + the kernels), with
+CUDA threads emulated as fibers.  The GPU twin of this file is tests/test_gpu_parity.py.
+"""
+import numpy as np
+import pytest
+
+from agimus_controller_b200 import PANDA_Q_NOMINAL, _abi, panda_table
+from agimus_controller_b200.workloads import goal_reaching_batch, golden_problem
+from emul import emu
+
+
+def rel(a, b):
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(b).max(), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def m7():
+    return panda_table().to_struct()
+
+
+def _workload(orc, m, B, T, **kw):
+    return goal_reaching_batch(B, T=T, rnea=lambda q, v, a: orc.rnea(m, q, v, a), **kw)
+
+
+def test_rnea_and_integrate(orc, m7):
+    rng = np.random.default_rng(0)
+    q = PANDA_Q_NOMINAL + rng.uniform(-1, 1, (9, 7))
+    v, a = rng.uniform(-1, 1, (9, 7)), rng.uniform(-3, 3, (9, 7))
+    assert rel(emu.rnea(m7, q, v, a), orc.rnea(m7, q, v, a)) < 1e-13
+    x = np.concatenate([q, v], 1)
+    assert rel(emu.integrate(m7, x, a, 0.01), orc.integrate(m7, x, a, 0.01)) < 1e-13
+
+
+@pytest.mark.parametrize("target_R", ["tool_down", "identity"])
+def test_calc_diff_per_node(orc, m7, target_R):
+    B, T = 3, 6
+    kw = {} if target_R == "tool_down" else dict(target_R=np.eye(3))
+    w = _workload(orc, m7, B, T, **kw)
+    rng = np.random.default_rng(1)
+    xs = w["xs_ws"] + rng.uniform(-0.2, 0.2, w["xs_ws"].shape)
+    us = w["us_ws"] + rng.uniform(-2, 2, w["us_ws"].shape)
+    c0, xn0 = orc.calc(m7, w["refs"], w["dts"], xs, us)
+    c1, xn1 = emu.calc(m7, w["refs"], w["dts"], xs, us)
+    assert rel(c1, c0) < 1e-12 and rel(xn1, xn0) < 1e-12
+    o = orc.calc_diff(m7, w["refs"], w["dts"], xs, us)
+    e = emu.calc_diff(m7, w["refs"], w["dts"], xs, us)
+    for k in ("cost", "xnext", "Fx", "Fu", "Lx", "Lu", "Lxx", "Luu"):
+        assert rel(e[k], o[k]) < 1e-9, k
+    assert np.abs(e["Lxu"]).max() == 0.0
+
+
+def test_ragged_dts_and_rollout(orc, m7):
+    """Variable step sizes (DTFactorsNSeq, ocp_param_base.py:67-78): 2 x dt, 2 x 2dt, 1 x 4dt."""
+    B, T = 2, 5
+    w = _workload(orc, m7, B, T)
+    dts = np.array([0.01, 0.01, 0.02, 0.02, 0.04])
+    xs = emu.rollout(m7, w["refs"], dts, w["x0"], w["us_ws"])
+    assert rel(xs, orc.rollout(m7, w["refs"], dts, w["x0"], w["us_ws"])) < 1e-12
+    o = orc.calc_diff(m7, w["refs"], dts, xs, w["us_ws"])
+    e = emu.calc_diff(m7, w["refs"], dts, xs, w["us_ws"])
+    for k in ("Fx", "Fu", "Lx", "Lxx"):
+        assert rel(e[k], o[k]) < 1e-9, k
+
+
+@pytest.mark.parametrize("fixed,iters", [(True, 3), (False, 40)])
+def test_solve_matches_oracle(orc, m7, fixed, iters):
+    B, T = 3, 12
+    w = _workload(orc, m7, B, T)
+    opts = _abi.default_fddp_opts(fixed_iters=fixed)
+    o = orc.solve(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], iters, opts)
+    e = emu.solve(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], iters, opts)
+    np.testing.assert_array_equal(e["iters"], o["iters"])
+    np.testing.assert_array_equal(e["status"], o["status"])
+    for k in ("xs", "us", "cost", "K", "k"):
+        assert rel(e[k], o[k]) < 1e-6, k
+    assert e["launches"] == 3 * iters + 2  # init + (calc_diff, backward, forward) per iteration + finalize
+
+
+def test_solve_golden_problem_shapes(orc):
+    """The reference's golden OCP (T = 9, dt = 1e-3, ill-conditioned Quu): 3 iterations, same iterates."""
+    w = golden_problem()
+    m = w["table"].to_struct()
+    opts = _abi.default_fddp_opts(fixed_iters=True)
+    o = orc.solve(m, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 3, opts)
+    e = emu.solve(m, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 3, opts)
+    assert rel(e["cost"], o["cost"]) < 1e-6
+    assert rel(e["xs"], o["xs"]) < 1e-5
+
+
+def test_regularisation_failure_path(orc, m7):
+    """Zero control weight and zero terminal Hessian make Quu singular: the sweep must raise the
+    regularisation exactly as the oracle does (same final status / reg decisions)."""
+    B, T = 2, 4
+    w = _workload(orc, m7, B, T, w_u=0.0, w_pose=0.0, w_q=0.0, w_v=0.0)
+    opts = _abi.default_fddp_opts(fixed_iters=True)
+    o = orc.solve(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 2, opts)
+    e = emu.solve(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 2, opts)
+    np.testing.assert_array_equal(e["status"], o["status"])
+    np.testing.assert_array_equal(e["iters"], o["iters"])
+
+
+def test_unsupported_models_are_refused():
+    t9 = panda_table(lock_fingers=False)
+    with pytest.raises(RuntimeError, match="only nv = 7"):
+        emu.Handle(t9.to_struct(), np.full(3, 0.01), 1, 3)
