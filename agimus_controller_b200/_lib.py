@@ -15,9 +15,13 @@ _LIB = None
 def lib() -> C.CDLL:
     global _LIB
     if _LIB is None:
-        if not LIB.exists():
+        import os
+        import pathlib
+
+        path = pathlib.Path(os.environ.get("AGX_LIBRARY", LIB))  # tuning hook: another build of the same library
+        if not path.exists():
             raise RuntimeError(
-                f"{LIB} is missing: build it with `python -m agimus_controller_b200.build` "
+                f"{path} is missing: build it with `python -m agimus_controller_b200.build` "
                 "(the solve path has no CPU fallback)")
-        _LIB = _abi.bind(C.CDLL(str(LIB)))
+        _LIB = _abi.bind(C.CDLL(str(path)))
     return _LIB

@@ -59,8 +59,16 @@ inline bool copy_d2d(void* d, const void* s, size_t n, stream_t) { std::memmove(
 inline const char* dev_check() { return nullptr; }
 #endif
 
-constexpr int NODE_CTA = 64;   // threads per CTA of the (problem, node) kernels: 8 octets
-constexpr int SEQ_CTA = 32;    // threads per CTA of the per-problem kernels: 4 octets
+// threads per CTA of the (problem, node) kernels (8 octets) and of the per-problem kernels (4 octets);
+// AGX_NODE_CTA / AGX_SEQ_CTA override them for tuning experiments (multiples of 8)
+int env_cta(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  if (!v) return dflt;
+  const int n = std::atoi(v);
+  return (n >= 8 && n <= 256 && n % 8 == 0) ? n : dflt;
+}
+const int NODE_CTA = env_cta("AGX_NODE_CTA", 64);
+const int SEQ_CTA = env_cta("AGX_SEQ_CTA", 32);
 
 // agx_model -> device table (agx_octet_base.h layout).  Returns false for shapes the kernels do not
 // cover yet: anything but a 7-joint serial chain of revolute-z joints.
@@ -426,7 +434,7 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
     AGX_LAUNCH(h, backward_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * BW_SIZE * opc_s, st, P, W, h->S, O);
     phase_end(h, st);
     phase_begin(h, 2, st);
-    AGX_LAUNCH(h, forward_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * (OCT_BOARD + 16) * opc_s, st, P, W,
+    AGX_LAUNCH(h, forward_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * FW_BOARD * opc_s, st, P, W,
                h->S, O);
     phase_end(h, st);
   }

@@ -72,19 +72,25 @@ AGX_DEV void kin_local(LaneDyn& d, int j, const double* __restrict__ model) {
   }
 }
 AGX_DEV void se3_store(const LaneDyn& d, int j, double* sb) {
+#pragma unroll
   for (int k = 0; k < 9; ++k) sb[j * 14 + k] = d.R[k];
+#pragma unroll
   for (int k = 0; k < 3; ++k) sb[j * 14 + 9 + k] = d.p[k];
 }
 AGX_DEV void se3_combine(LaneDyn& d, int j, int dist, const double* sb) {
   if (j >= dist) {
     const double* o = sb + (j - dist) * 14;
     double Rn[9], pn[3];
+#pragma unroll
     for (int r = 0; r < 3; ++r) {
+#pragma unroll
       for (int c = 0; c < 3; ++c)
         Rn[3 * r + c] = o[3 * r] * d.R[c] + o[3 * r + 1] * d.R[3 + c] + o[3 * r + 2] * d.R[6 + c];
       pn[r] = o[9 + r] + (o[3 * r] * d.p[0] + o[3 * r + 1] * d.p[1] + o[3 * r + 2] * d.p[2]);
     }
+#pragma unroll
     for (int k = 0; k < 9; ++k) d.R[k] = Rn[k];
+#pragma unroll
     for (int k = 0; k < 3; ++k) d.p[k] = pn[k];
   }
 }
@@ -93,33 +99,44 @@ AGX_DEV void kin_axis(LaneDyn& d, int j) {
   double pz[3];
   cross3(d.p, z, pz);
   const double live = (j < NJ) ? 1.0 : 0.0;
+#pragma unroll
   for (int k = 0; k < 3; ++k) {
     d.J[k] = live * pz[k];
     d.J[3 + k] = live * z[k];
   }
+#pragma unroll
   for (int k = 0; k < 6; ++k) d.s[k] = d.J[k] * d.qd;
 }
 
 // exclusive prefix sum of a per-lane 6-vector over the chain (board: [8][6])
 AGX_DEV void vec6_store(const double* x, int j, double* sb) {
+#pragma unroll
   for (int k = 0; k < 6; ++k) sb[j * 6 + k] = x[k];
 }
 AGX_DEV void vec6_prefix_excl(double* out, int j, const double* seed, const double* sb) {
   double acc[6];
+#pragma unroll
   for (int k = 0; k < 6; ++k) acc[k] = seed[k];
+#pragma unroll
   for (int l = 0; l < NJ - 1; ++l)
     if (l < j)
+#pragma unroll
       for (int k = 0; k < 6; ++k) acc[k] += sb[l * 6 + k];
+#pragma unroll
   for (int k = 0; k < 6; ++k) out[k] = acc[k];
 }
 // inclusive suffix sum of a per-lane 6-vector (board: [8][6]); lane 7's slot must hold zeros
 AGX_DEV void vec6_suffix_incl(double* x, int j, const double* sb) {
   if (j < NJ - 1) {
     double acc[6];
+#pragma unroll
     for (int k = 0; k < 6; ++k) acc[k] = sb[(NJ - 1) * 6 + k];
+#pragma unroll
     for (int l = NJ - 2; l >= 0; --l)
       if (l >= j)
+#pragma unroll
         for (int k = 0; k < 6; ++k) acc[k] = sb[l * 6 + k] + acc[k];
+#pragma unroll
     for (int k = 0; k < 6; ++k) x[k] = acc[k];
   }
 }
@@ -128,22 +145,28 @@ AGX_DEV void vec6_suffix_incl(double* x, int j, const double* sb) {
 // with_B: also the Sym block of the B matrix (derivatives only)
 AGX_DEV void body_terms(LaneDyn& d, int j, const double* __restrict__ model, const double* grav_acc, bool with_B) {
   // velocity of this body, dV/dq column, bias acceleration term g = c * qd
+#pragma unroll
   for (int k = 0; k < 6; ++k) d.v[k] = d.vp[k] + d.s[k];
   crm6(d.vp, d.J, d.c);
+#pragma unroll
   for (int k = 0; k < 6; ++k) d.g[k] = d.c[k] * d.qd;
   (void)grav_acc;
   // world-frame inertia about the origin
   double mass = 0, com[3] = {0, 0, 0}, I6[6] = {0, 0, 0, 0, 0, 0};
   if (j < NJ) {
     mass = model[MF_MASS * 8 + j];
+#pragma unroll
     for (int k = 0; k < 3; ++k) com[k] = model[(MF_COM + k) * 8 + j];
+#pragma unroll
     for (int k = 0; k < 6; ++k) I6[k] = model[(MF_INERTIA + k) * 8 + j];
   }
   double cw[3];
   mv3(d.R, com, cw);
+#pragma unroll
   for (int k = 0; k < 3; ++k) cw[k] += d.p[k];
   // Iw = R Ic R^T  (symmetric)
   double RI[9];
+#pragma unroll
   for (int r = 0; r < 3; ++r) {
     RI[3 * r + 0] = d.R[3 * r] * I6[0] + d.R[3 * r + 1] * I6[1] + d.R[3 * r + 2] * I6[2];
     RI[3 * r + 1] = d.R[3 * r] * I6[1] + d.R[3 * r + 1] * I6[3] + d.R[3 * r + 2] * I6[4];
@@ -165,6 +188,7 @@ AGX_DEV void body_terms(LaneDyn& d, int j, const double* __restrict__ model, con
   d.Y[7] = Iw[3] + mass * (cc - cw[1] * cw[1]);
   d.Y[8] = Iw[4] - mass * cw[1] * cw[2];
   d.Y[9] = Iw[5] + mass * (cc - cw[2] * cw[2]);
+#pragma unroll
   for (int k = 0; k < 10; ++k) d.Z[k] = d.Y[k];
   // momentum h = Y v
   inertia_apply(d.Y, d.v, d.Z + 10);
@@ -187,28 +211,36 @@ AGX_DEV void body_terms(LaneDyn& d, int j, const double* __restrict__ model, con
     d.Z[20] = P2[1] + P1[2] - (mc[1] * vl[2] + vl[1] * mc[2]);         // yz
     d.Z[21] = 2.0 * P2[2] - 2.0 * mc[2] * vl[2] + vm2;                 // zz
   } else {
+#pragma unroll
     for (int k = 16; k < 22; ++k) d.Z[k] = 0;
   }
 }
 // bias force with qdd = 0: f0 = Y a0 + v x* h   (after the acceleration scan filled a0p)
 AGX_DEV void body_force(LaneDyn& d) {
   double a0[6], Ya[6], vh[6];
+#pragma unroll
   for (int k = 0; k < 6; ++k) a0[k] = d.a0p[k] + d.g[k];
   inertia_apply(d.Y, a0, Ya);
   crf6(d.v, d.Z + 10, vh);
+#pragma unroll
   for (int k = 0; k < 6; ++k) d.Z[22 + k] = Ya[k] + vh[k];
 }
 // suffix sums of the 28 composites (board: [8][30])
 AGX_DEV void comp_store(const LaneDyn& d, int j, double* sb) {
+#pragma unroll
   for (int k = 0; k < 28; ++k) sb[j * 30 + k] = d.Z[k];
 }
 AGX_DEV void comp_suffix(LaneDyn& d, int j, const double* sb) {
   if (j < NJ - 1) {
     double acc[28];
+#pragma unroll
     for (int k = 0; k < 28; ++k) acc[k] = sb[(NJ - 1) * 30 + k];
+#pragma unroll
     for (int l = NJ - 2; l >= 0; --l)
       if (l >= j)
+#pragma unroll
         for (int k = 0; k < 28; ++k) acc[k] = sb[l * 30 + k] + acc[k];
+#pragma unroll
     for (int k = 0; k < 28; ++k) d.Z[k] = acc[k];
   }
 }
@@ -223,22 +255,28 @@ AGX_DEV void column_terms(LaneDyn& d, int j, double* sbb) {
   cross3(hf, d.J, t1);
   symv3(d.Z + 16, d.J + 3, t2);
   cross3(hn, d.J + 3, t3);
+#pragma unroll
   for (int k = 0; k < 3; ++k) d.BS[k] = 2.0 * t1[k] + t2[k] + t3[k];
   double* o = sbb + j * 18;
+#pragma unroll
   for (int k = 0; k < 6; ++k) { o[k] = d.J[k]; o[6 + k] = d.dFda[k]; }
+#pragma unroll
   for (int k = 0; k < 3; ++k) o[12 + k] = d.BS[k];
   o[15] = d.b;
 }
 // column j of M + armature:  M[i][j] = J_min . dFda_max
 AGX_DEV void mass_column(LaneDyn& d, int j, const double* __restrict__ model, const double* sbb) {
+#pragma unroll
   for (int i = 0; i < NJ; ++i) {
     const double* o = sbb + i * 18;
     const double up = dot6(o, d.dFda);       // i <= j : J_i . dFda_j
     const double lo = dot6(o + 6, d.J);      // i >  j : dFda_i . J_j
     d.Mc[i] = (i <= j) ? up : lo;
   }
-  if (j < NJ) d.Mc[j] += model[MF_ARM * 8 + j];
-  else d.Mc[0] = 1.0;  // lane 7: never read
+  const double arm = model[MF_ARM * 8 + j];  // lane 7's slot holds 0
+#pragma unroll
+  for (int i = 0; i < NJ; ++i)
+    if (i == j) d.Mc[i] += arm;  // static indices only: a dynamic d.Mc[j] would push the lane state to local memory
 }
 
 // ---------------------------------------------------------------- 7x7 Cholesky, lane j owns column j
@@ -249,6 +287,7 @@ AGX_DEV void chol_pivot(double* col, int j, int k, double* sl) {
     const double dkk = col[k];
     const double r = AGX_RSQRT(dkk);
     sl[k * 8 + k] = dkk * r;
+#pragma unroll
     for (int i = k + 1; i < NJ; ++i) sl[k * 8 + i] = col[i] * r;
     sl[k * 8 + 7] = (dkk > 0.0) ? r : -1.0;  // -1 flags failure (also catches NaN)
   }
@@ -256,6 +295,7 @@ AGX_DEV void chol_pivot(double* col, int j, int k, double* sl) {
 AGX_DEV void chol_update(double* col, int j, int k, const double* sl) {
   if (j > k && j < NJ) {
     const double lj = sl[k * 8 + j];
+#pragma unroll
     for (int i = k + 1; i < NJ; ++i)
       if (i >= j) col[i] -= sl[k * 8 + i] * lj;
   }
@@ -264,7 +304,9 @@ AGX_DEV void chol_update(double* col, int j, int k, const double* sl) {
 AGX_DEV bool chol_load(const double* sl, double* L /*28*/, double* rinv /*7*/) {
   bool ok = true;
   int n = 0;
+#pragma unroll
   for (int k = 0; k < NJ; ++k) {
+#pragma unroll
     for (int i = k; i < NJ; ++i) L[n++] = sl[k * 8 + i];
     rinv[k] = sl[k * 8 + 7];
     ok = ok && (rinv[k] > 0.0);
@@ -275,13 +317,17 @@ AGX_DEV bool chol_load(const double* sl, double* L /*28*/, double* rinv /*7*/) {
 AGX_DEV constexpr int lidx(int i, int k) { return k * NJ - (k * (k - 1)) / 2 + (i - k); }
 // solve (L L^T) x = r in place, r has 7 entries
 AGX_DEV void chol_solve7(const double* L, const double* rinv, double* r) {
+#pragma unroll
   for (int i = 0; i < NJ; ++i) {
     double s = r[i];
+#pragma unroll
     for (int m = 0; m < i; ++m) s -= L[lidx(i, m)] * r[m];
     r[i] = s * rinv[i];
   }
+#pragma unroll
   for (int i = NJ - 1; i >= 0; --i) {
     double s = r[i];
+#pragma unroll
     for (int m = i + 1; m < NJ; ++m) s -= L[lidx(m, i)] * r[m];
     r[i] = s * rinv[i];
   }
@@ -293,22 +339,27 @@ AGX_DEV void deriv_columns(LaneDyn& d, int j, const double* dap /*prefix of J qd
                            double* dFdq, double* dFdv) {
   // parent acceleration incl. qdd, dA/dq column
   double ap[6], A[6], t1[6], t2[6];
+#pragma unroll
   for (int k = 0; k < 6; ++k) ap[k] = d.a0p[k] + dap[k];
   crm6(ap, d.J, t1);
   crm6(d.vp, d.c, t2);
+#pragma unroll
   for (int k = 0; k < 6; ++k) A[k] = t1[k] + t2[k];
   // composite force with qdd
   double fc[6];
+#pragma unroll
   for (int k = 0; k < 6; ++k) fc[k] = d.Z[22 + k] + dfc[k];
   const double* hf = d.Z + 10;
   const double* hn = d.Z + 13;
   // dFdv = Yc (2c) + Bc J
   double c2[6], y1[6], bl[3], ba1[3], ba2[3];
+#pragma unroll
   for (int k = 0; k < 6; ++k) c2[k] = 2.0 * d.c[k];
   inertia_apply(d.Z, c2, y1);
   cross3(hf, d.J + 3, bl);
   symv3(d.Z + 16, d.J + 3, ba1);
   cross3(hn, d.J + 3, ba2);
+#pragma unroll
   for (int k = 0; k < 3; ++k) {
     dFdv[k] = y1[k] - 2.0 * bl[k];
     dFdv[3 + k] = y1[3 + k] + ba1[k] - ba2[k];
@@ -320,15 +371,18 @@ AGX_DEV void deriv_columns(LaneDyn& d, int j, const double* dap /*prefix of J qd
   symv3(d.Z + 16, d.c + 3, ba1);
   cross3(hn, d.c + 3, ba2);
   crf6(d.J, fc, jf);
+#pragma unroll
   for (int k = 0; k < 3; ++k) {
     dFdq[k] = y2[k] - 2.0 * bl[k] + jf[k];
     dFdq[3 + k] = y2[3 + k] + ba1[k] - ba2[k] + jf[3 + k];
   }
   // keep A in g for the lower-triangle entries
+#pragma unroll
   for (int k = 0; k < 6; ++k) d.g[k] = A[k];
 }
 // columns j of dtau/dq and dtau/dv (d.g = A_j)
 AGX_DEV void deriv_fill(LaneDyn& d, int j, const double* dFdq, const double* dFdv, const double* sbb) {
+#pragma unroll
   for (int i = 0; i < NJ; ++i) {
     const double* o = sbb + i * 18;  // J_i, dFda_i, BS_i
     const double uq = dot6(o, dFdq);
@@ -380,6 +434,7 @@ AGX_DEV void log6_and_jac(const double* R, const double* p, double* r, double* J
   double wxp[3];
   cross3(w, p, wxp);
   const double wp = dot3(w, p);
+#pragma unroll
   for (int k = 0; k < 3; ++k) {
     r[k] = alpha * p[k] - 0.5 * wxp[k] + (beta * wp) * w[k];
     r[3 + k] = w[k];
@@ -402,22 +457,29 @@ AGX_DEV void log6_and_jac(const double* R, const double* p, double* r, double* J
     bdot = -2.0 * t2inv * t2inv + (1.0 + st * tinv) * t2inv * inv_2_2ct;
   }
   double* A = Jl;
+#pragma unroll
   for (int i = 0; i < 3; ++i)
+#pragma unroll
     for (int c = 0; c < 3; ++c) A[3 * i + c] = a3 * w[i] * w[c];
   A[0] += diag; A[4] += diag; A[8] += diag;
   A[1] -= 0.5 * w[2]; A[2] += 0.5 * w[1];
   A[3] += 0.5 * w[2]; A[5] -= 0.5 * w[0];
   A[6] -= 0.5 * w[1]; A[7] += 0.5 * w[0];
   double v3[3], C[9];
+#pragma unroll
   for (int k = 0; k < 3; ++k) v3[k] = (bdot * wp) * w[k] - (t2 * bdot + 2.0 * beta6) * p[k];
+#pragma unroll
   for (int i = 0; i < 3; ++i)
+#pragma unroll
     for (int c = 0; c < 3; ++c) C[3 * i + c] = v3[i] * w[c] + beta6 * w[i] * p[c];
   C[0] += wp * beta6; C[4] += wp * beta6; C[8] += wp * beta6;
   C[1] -= 0.5 * p[2]; C[2] += 0.5 * p[1];
   C[3] += 0.5 * p[2]; C[5] -= 0.5 * p[0];
   C[6] -= 0.5 * p[1]; C[7] += 0.5 * p[0];
   double* B = Jl + 9;
+#pragma unroll
   for (int i = 0; i < 3; ++i)
+#pragma unroll
     for (int c = 0; c < 3; ++c) B[3 * i + c] = C[3 * i] * A[c] + C[3 * i + 1] * A[3 + c] + C[3 * i + 2] * A[6 + c];
 }
 
@@ -427,13 +489,18 @@ AGX_DEV void frame_residual(const double* R6, const double* p6, const double* __
                             double* r, double* Jl) {
   const double* FR = model + MT_FR;
   const double* FP = model + MT_FP;
+#pragma unroll
   for (int i = 0; i < 3; ++i) {
+#pragma unroll
     for (int c = 0; c < 3; ++c) Rf[3 * i + c] = R6[3 * i] * FR[c] + R6[3 * i + 1] * FR[3 + c] + R6[3 * i + 2] * FR[6 + c];
     pf[i] = p6[i] + (R6[3 * i] * FP[0] + R6[3 * i + 1] * FP[1] + R6[3 * i + 2] * FP[2]);
   }
   double Rr[9], pr[3], dp[3];
+#pragma unroll
   for (int i = 0; i < 3; ++i)
+#pragma unroll
     for (int c = 0; c < 3; ++c) Rr[3 * i + c] = Rref[i] * Rf[c] + Rref[3 + i] * Rf[3 + c] + Rref[6 + i] * Rf[6 + c];
+#pragma unroll
   for (int k = 0; k < 3; ++k) dp[k] = pf[k] - pref[k];
   mtv3(Rref, dp, pr);
   log6_and_jac(Rr, pr, r, Jl);

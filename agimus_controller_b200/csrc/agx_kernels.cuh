@@ -52,7 +52,9 @@ struct Work {
   const double* x0;  // [B][NX]
 };
 
-constexpr int OCT_BOARD = BRD_A + BRD_B;  // doubles of shared memory per octet in the node kernels
+// doubles of shared memory per octet in the node kernels; the odd stride puts the two octets of a
+// half-warp on different banks (64-bit accesses are served per half-warp)
+constexpr int OCT_BOARD = BRD_A + BRD_B + 1;
 
 #define AGX_OCTET_SETUP()                                   \
   const int j = (int)(threadIdx.x & 7u);                    \
@@ -158,7 +160,10 @@ AGX_DEV size_t buf_of(const int32_t* cur, int b, bool other) {
   return (size_t)(other ? (c ^ 1) : c);
 }
 
-__global__ void calc_diff_kernel(Problem P, const double* __restrict__ xs, const double* __restrict__ us,
+#ifndef AGX_CD_MINB
+#define AGX_CD_MINB 4
+#endif
+__global__ void __launch_bounds__(64, AGX_CD_MINB) calc_diff_kernel(Problem P, const double* __restrict__ xs, const double* __restrict__ us,
                                  const int32_t* __restrict__ cur, const int32_t* __restrict__ recalc,
                                  const int32_t* __restrict__ done, double* __restrict__ rec) {
   AGX_SMEM(smem);
@@ -221,6 +226,7 @@ __global__ void expand_kernel(Problem P, const double* __restrict__ rec, double*
   if (out_xnext) out_xnext[n * NX + r] = R[(top ? RK_QN : RK_VN) * 8 + i];
   if (Lx) Lx[n * NX + r] = R[(top ? RK_LQ : RK_LV) * 8 + i];
   if (Lu && top) Lu[n * NJ + i] = R[RK_LU * 8 + i];
+#pragma unroll
   for (int c = 0; c < NJ; ++c) {
     const double aq = R[(RK_AQ + i) * 8 + c], av = R[(RK_AV + i) * 8 + c], mi = R[(RK_MI + i) * 8 + c];
     const double s = top ? h : 1.0;
@@ -245,6 +251,7 @@ __global__ void expand_kernel(Problem P, const double* __restrict__ rec, double*
 // the products collapse to 7-deep ones:  Z = S^T V', Vs = Z S, W = Vs G + [Z_q 0],
 //   Qxx = Lxx + [V'_qq 0; 0 0] + G^T W + [Z_q^T G; 0],  Qux = N^T W,  Quu = Luu + N^T Vs N,
 //   Qx = Lx + [v'_q; 0] + G^T S^T v',  Qu = Lu + N^T S^T v'.
+constexpr int FW_BOARD = OCT_BOARD + 16;  // forward_kernel: node boards + dx[14] (odd stride kept)
 constexpr int BW_VS = 0;      // [7][8]
 constexpr int BW_G = 56;      // [7][16]
 constexpr int BW_ZQ = 168;    // [7][8]
@@ -255,7 +262,7 @@ constexpr int BW_SV = 448;    // [8]
 constexpr int BW_QU = 456;    // [8]
 constexpr int BW_FS = 464;    // [16]
 constexpr int BW_V = 480;     // [14][16]
-constexpr int BW_SIZE = 704;
+constexpr int BW_SIZE = 712;  // 704 used; +8 doubles skews the second octet of a half-warp by 16 banks
 
 __global__ void backward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
   AGX_SMEM(smem);
@@ -557,7 +564,7 @@ __global__ void forward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
   const int b = (int)ent;
   if (b >= P.B) return;
   if (S.done[b]) return;
-  double* sa = smem + oct_in_cta * (OCT_BOARD + 16);
+  double* sa = smem + oct_in_cta * FW_BOARD;
   double* sb = sa + BRD_A;
   double* sdx = sb + BRD_B;  // [14]
   const int T = P.T, T1 = T + 1;

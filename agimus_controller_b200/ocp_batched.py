@@ -69,6 +69,45 @@ def flatten_cost_stack(model_def: dict, terminal: bool) -> dict:
     return {"weights": slots, "names": names}
 
 
+def build_reference_rows(table: RobotTable, running: dict, terminal: dict, horizon: list) -> np.ndarray:
+    """``[T+1, ref_size]`` reference records of one horizon: what ``DifferentialActionModelFreeFwdDynamics.update``
+    (``ocp_croco_generic.py:712-724``) writes into the Crocoddyl residuals / activations of every node, with the
+    CostModelSum weight folded into the activation weights.  The last point feeds the terminal model."""
+    T1 = len(horizon)
+    nv = table.nv
+    rows = np.zeros((T1, _abi.ref_size(nv)))
+    for t, wp in enumerate(horizon):
+        stack = terminal if t == T1 - 1 else running
+        w = stack["weights"]
+        pt, wt = wp.point, wp.weights
+        xref, wx = np.zeros(2 * nv), np.zeros(2 * nv)
+        if w["state"] != 0.0:
+            xref = np.asarray(pt.robot_state, dtype=np.float64)
+            wx = w["state"] * np.asarray(wt.w_robot_state, dtype=np.float64)
+        uref, wu = np.zeros(nv), np.zeros(nv)
+        if w["control"] != 0.0:
+            uref = np.asarray(pt.robot_effort, dtype=np.float64)
+            wu = w["control"] * np.asarray(wt.w_robot_effort, dtype=np.float64)
+        Rref, pref, wpose = np.eye(3), np.zeros(3), np.zeros(6)
+        if w["pose"] != 0.0:
+            assert len(pt.end_effector_poses) == 1, (
+                "ResidualModelFramePlacement requires exactly one end-effector pose, current is "
+                f"{pt.end_effector_poses}.")
+            ee_name, ee_pose = next(iter(pt.end_effector_poses.items()))
+            if ee_name != table.frame_name:
+                raise NotImplementedError(
+                    f"the device tables were built for frame '{table.frame_name}', got '{ee_name}'")
+            Rref = np.asarray(ee_pose.rotation, dtype=np.float64)
+            pref = np.asarray(ee_pose.translation, dtype=np.float64)
+            wpose = w["pose"] * np.asarray(wt.w_end_effector_poses[ee_name], dtype=np.float64)
+        rows[t] = pack_refs(nv, 0, 1, xref, wx, uref, wu, Rref, pref, wpose)[0, 0]
+        if t == T1 - 1:
+            rows[t, 5 * nv: 6 * nv] = 0.0  # the terminal node has no control cost
+        else:
+            rows[t, 5 * nv: 6 * nv] = wu   # pack_refs treats its last node as terminal
+    return rows
+
+
 class OCPBatchedFDDP(OCPBase):
     def __init__(self, robot_table: RobotTable, params: OCPParamsBaseCroco,
                  yaml_file: T.Union[str, dict, T.IO], batch_size: int = 1, device=None,
@@ -113,37 +152,8 @@ class OCPBatchedFDDP(OCPBase):
     # ------------------------------------------------------------------ references
     def reference_table(self, reference_weighted_trajectory: list) -> np.ndarray:
         """``[T+1, ref_size]`` rows from a list of WeightedTrajectoryPoint (one MPC horizon)."""
-        T1 = self.n_controls + 1
-        assert len(reference_weighted_trajectory) == T1
-        nv = self._table.nv
-        rows = np.zeros((T1, _abi.ref_size(nv)))
-        for t, wp in enumerate(reference_weighted_trajectory):
-            stack = self._terminal if t == T1 - 1 else self._running
-            w = stack["weights"]
-            pt, wt = wp.point, wp.weights
-            xref, wx = np.zeros(2 * nv), np.zeros(2 * nv)
-            if w["state"] != 0.0:
-                xref = np.asarray(pt.robot_state, dtype=np.float64)
-                wx = w["state"] * np.asarray(wt.w_robot_state, dtype=np.float64)
-            uref, wu = np.zeros(nv), np.zeros(nv)
-            if w["control"] != 0.0:
-                uref = np.asarray(pt.robot_effort, dtype=np.float64)
-                wu = w["control"] * np.asarray(wt.w_robot_effort, dtype=np.float64)
-            Rref, pref, wpose = np.eye(3), np.zeros(3), np.zeros(6)
-            if w["pose"] != 0.0:
-                assert len(pt.end_effector_poses) == 1, (
-                    "ResidualModelFramePlacement requires exactly one end-effector pose, current is "
-                    f"{pt.end_effector_poses}.")
-                ee_name, ee_pose = next(iter(pt.end_effector_poses.items()))
-                if ee_name != self._table.frame_name:
-                    raise NotImplementedError(
-                        f"the device tables were built for frame '{self._table.frame_name}', got '{ee_name}'")
-                Rref = np.asarray(ee_pose.rotation, dtype=np.float64)
-                pref = np.asarray(ee_pose.translation, dtype=np.float64)
-                wpose = w["pose"] * np.asarray(wt.w_end_effector_poses[ee_name], dtype=np.float64)
-            rows[t] = pack_refs(nv, 0, 1, xref, wx, uref, wu, Rref, pref, wpose)[0, 0]
-        rows[-1, 4 * nv + nv: 4 * nv + 2 * nv] = 0.0
-        return rows
+        assert len(reference_weighted_trajectory) == self.n_controls + 1
+        return build_reference_rows(self._table, self._running, self._terminal, reference_weighted_trajectory)
 
     def set_reference_weighted_trajectory(self, reference_weighted_trajectory: list) -> None:
         """One horizon for every problem of the batch (list of points) or one horizon per problem (list of lists)."""

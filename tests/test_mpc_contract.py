@@ -1,0 +1,108 @@
+"""OCPBatchedFDDP behind an MPC.run-shaped driver (the contract agimus_controller/tests/test_mpc_unicycle.py
+pins with a fake OCP: any OCPBase works under MPC; res.states[0] == x0 and res.states[1] == integrate(x0, u0))."""
+import pathlib
+import time
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from agimus_controller_b200 import PANDA_Q_NOMINAL, panda_table  # noqa: E402
+from agimus_controller_b200.ocp_interface import (DTFactorsNSeq, OCPBase, OCPParamsBaseCroco, SE3,  # noqa: E402
+                                                  TrajectoryPoint, TrajectoryPointWeights, WeightedTrajectoryPoint)
+
+YAML = pathlib.Path(__file__).parent / "golden" / "ocp_goal_reaching.yaml"
+
+
+def _wpoint(i, q, nv=7):
+    return WeightedTrajectoryPoint(
+        point=TrajectoryPoint(id=i, time_ns=i * 10_000_000, robot_configuration=q, robot_velocity=np.zeros(nv),
+                              robot_acceleration=np.zeros(nv), robot_effort=np.zeros(nv),
+                              end_effector_poses={"panda_hand_tcp": SE3(np.diag([1.0, -1.0, -1.0]),
+                                                                        np.array([0.5, 0.2, 0.5]))}),
+        weights=TrajectoryPointWeights(w_robot_configuration=np.full(nv, 1.0), w_robot_velocity=np.full(nv, 0.1),
+                                       w_robot_acceleration=np.zeros(nv), w_robot_effort=np.full(nv, 1e-3),
+                                       w_end_effector_poses={"panda_hand_tcp": np.full(6, 0.1)}))
+
+
+class ShiftWarmStart:
+    """Minimal WarmStartBase stand-in: previous solution shifted by one node (warm_start_shift_previous_solution.py)."""
+
+    def __init__(self):
+        self.prev = None
+
+    def generate(self, x0, T, nv, u_grav):
+        if self.prev is None:
+            return x0, [x0] * (T + 1), [u_grav] * T
+        xs, us = self.prev.states, self.prev.feed_forward_terms
+        return x0, [x0] + list(xs[2:]) + [xs[-1]], list(us[1:]) + [us[-1]]
+
+    def update_previous_solution(self, res):
+        self.prev = res
+
+
+def test_ocp_plugs_into_an_mpc_loop():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from agimus_controller_b200.ocp_batched import OCPBatchedFDDP
+
+    T = 20
+    params = OCPParamsBaseCroco(dt=0.01, solver_iters=10, dt_factor_n_seq=DTFactorsNSeq([1], [T]), horizon_size=T)
+    ocp = OCPBatchedFDDP(panda_table(), params, str(YAML), batch_size=1)
+    assert isinstance(ocp, OCPBase) and ocp.n_controls == T and ocp.dt == 0.01
+    nv = 7
+    # sine-wave configuration-space reference (trajectories/sine_wave_configuration_space.py): amplitude 0.2, period 4 s
+    buffer = [_wpoint(i, PANDA_Q_NOMINAL + 0.2 * np.sin(2 * np.pi * i * 0.01 / 4.0) * np.ones(nv)) for i in range(T + 60)]
+    ws = ShiftWarmStart()
+    x = np.concatenate([PANDA_Q_NOMINAL, np.zeros(nv)])
+    u_grav = ocp.problem.rnea(PANDA_Q_NOMINAL, np.zeros(nv), np.zeros(nv))[0].cpu().numpy()
+    solve_ns = []
+    for tick in range(30):
+        horizon = buffer[: T + 1]
+        ocp.set_reference_weighted_trajectory(horizon)
+        x0, x_init, u_init = ws.generate(x, T, nv, u_grav)
+        assert len(x_init) == ocp.n_controls + 1 and len(u_init) == ocp.n_controls
+        t0 = time.perf_counter_ns()
+        ocp.solve(x0, x_init, u_init)          # MPC.run passes exactly three positional arguments (mpc.py:53)
+        solve_ns.append(time.perf_counter_ns() - t0)
+        res = ocp.ocp_results
+        ws.update_previous_solution(res)
+        buffer.pop(0)
+        assert len(res.states) == T + 1 and len(res.ricatti_gains) == T and len(res.feed_forward_terms) == T
+        assert res.ricatti_gains[0].shape == (nv, 2 * nv)
+        np.testing.assert_allclose(res.states[0], x0, atol=1e-12)
+        nxt = ocp.integrate(x0, res.feed_forward_terms[0])
+        np.testing.assert_allclose(res.states[1], nxt, atol=1e-8)
+        assert ocp.debug_data.nb_iter >= 1 and np.isfinite(ocp.debug_data.kkt_norm)
+        x = nxt
+    # the tracked joint positions follow the reference (weights 1.0 on q): error stays small
+    assert np.abs(x[:nv] - buffer[0].point.robot_configuration).max() < 0.05
+    # first solve without iteration limits (agimus_controller.py:376-381)
+    ocp.solve(x0, x_init, u_init, use_iteration_limits_and_timeout=False)
+    assert ocp.debug_data.problem_solved
+
+
+def test_batched_overload_matches_single_problem():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from agimus_controller_b200.ocp_batched import OCPBatchedFDDP
+
+    T, B, nv = 20, 8, 7
+    params = OCPParamsBaseCroco(dt=0.01, solver_iters=5, dt_factor_n_seq=DTFactorsNSeq([1], [T]), horizon_size=T)
+    horizon = [_wpoint(i, PANDA_Q_NOMINAL) for i in range(T + 1)]
+    rng = np.random.default_rng(0)
+    x0 = np.concatenate([PANDA_Q_NOMINAL + rng.uniform(-0.2, 0.2, (B, nv)), np.zeros((B, nv))], 1)
+    ob = OCPBatchedFDDP(panda_table(), params, str(YAML), batch_size=B)
+    ob.set_reference_weighted_trajectory(horizon)
+    xs = np.repeat(x0[:, None], T + 1, 1)
+    us = np.zeros((B, T, nv))
+    ob.solve(torch.as_tensor(x0, device="cuda"), torch.as_tensor(xs, device="cuda"), torch.as_tensor(us, device="cuda"))
+    rb = ob.ocp_results_batched
+    o1 = OCPBatchedFDDP(panda_table(), params, str(YAML), batch_size=1)
+    o1.set_reference_weighted_trajectory(horizon)
+    for b in (0, 5):
+        o1.solve(x0[b], list(xs[b]), list(us[b]))
+        np.testing.assert_array_equal(np.stack(o1.ocp_results.states), rb["xs"][b].cpu().numpy())
+        np.testing.assert_array_equal(np.stack(o1.ocp_results.ricatti_gains), rb["K"][b].cpu().numpy())
