@@ -49,7 +49,8 @@ struct LaneDyn {
 
 // board sizes (doubles) used by the dynamics phases
 constexpr int BRD_A = 240;  // scratch region A: up to [8][30]
-constexpr int BRD_B = 144;  // region B: [8][18] = J(6) dFda(6) BS(3) b(1), persistent during derivatives
+constexpr int BRD_B = 144;  // region B: [8][18] = J(6) dFda(6) BS(3) b(1) u(1), persistent during derivatives
+constexpr int BRD_C = 64;   // region C: [7][8] mass matrix, then its Cholesky factor (slot 7 of row k = 1/L[k][k])
 
 // ---------------------------------------------------------------- kinematics
 AGX_DEV void kin_local(LaneDyn& d, int j, const double* __restrict__ model) {
@@ -138,6 +139,71 @@ AGX_DEV void vec6_suffix_incl(double* x, int j, const double* sb) {
         for (int k = 0; k < 6; ++k) acc[k] = sb[l * 6 + k] + acc[k];
 #pragma unroll
     for (int k = 0; k < 6; ++k) x[k] = acc[k];
+  }
+}
+
+// ---------------------------------------------------------------- register scans over the octet (warp shuffles)
+// The chain recursions are scans over the 8 lanes; Hillis-Steele with __shfl_up/down of width 8 keeps
+// them in registers (no shared-memory round trip, no barrier).  Lane 7 carries neutral elements.
+template <int N>
+AGX_DEV void scan_prefix_incl(double* x, int j, unsigned omask) {
+#pragma unroll
+  for (int dist = 1; dist < 8; dist <<= 1) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const double t = __shfl_up_sync(omask, x[k], dist, 8);
+      if (j >= dist) x[k] += t;
+    }
+  }
+}
+// out = seed + sum_{l < j} x_l
+template <int N>
+AGX_DEV void scan_prefix_excl(const double* x, double* out, const double* seed, int j, unsigned omask) {
+  double acc[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) acc[k] = x[k];
+  scan_prefix_incl<N>(acc, j, omask);
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const double t = __shfl_up_sync(omask, acc[k], 1, 8);
+    out[k] = seed[k] + ((j >= 1) ? t : 0.0);
+  }
+}
+// x_j <- sum_{l >= j} x_l
+template <int N>
+AGX_DEV void scan_suffix_incl(double* x, int j, unsigned omask) {
+#pragma unroll
+  for (int dist = 1; dist < 8; dist <<= 1) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const double t = __shfl_down_sync(omask, x[k], dist, 8);
+      if (j + dist < 8) x[k] += t;
+    }
+  }
+}
+// world placements: inclusive prefix PRODUCT of the local transforms
+AGX_DEV void scan_se3_prefix(LaneDyn& d, int j, unsigned omask) {
+#pragma unroll
+  for (int dist = 1; dist < 8; dist <<= 1) {
+    double o[12];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) o[k] = __shfl_up_sync(omask, d.R[k], dist, 8);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o[9 + k] = __shfl_up_sync(omask, d.p[k], dist, 8);
+    if (j >= dist) {
+      double Rn[9], pn[3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          Rn[3 * r + c] = o[3 * r] * d.R[c] + o[3 * r + 1] * d.R[3 + c] + o[3 * r + 2] * d.R[6 + c];
+        pn[r] = o[9 + r] + (o[3 * r] * d.p[0] + o[3 * r + 1] * d.p[1] + o[3 * r + 2] * d.p[2]);
+      }
+#pragma unroll
+      for (int k = 0; k < 9; ++k) d.R[k] = Rn[k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) d.p[k] = pn[k];
+    }
   }
 }
 
@@ -245,23 +311,24 @@ AGX_DEV void comp_suffix(LaneDyn& d, int j, const double* sb) {
   }
 }
 // column quantities: nle, dFda, BS; stored on board B as [J(6) dFda(6) BS(3) b(1)] stride 18
+template <bool DERIV>
 AGX_DEV void column_terms(LaneDyn& d, int j, double* sbb) {
   d.b = dot6(d.J, d.Z + 22);
   inertia_apply(d.Z, d.J, d.dFda);
-  // BS = angular part of Bc^T J = 2 hf x J_lin + (Sym + [hn]x) J_ang
-  const double* hf = d.Z + 10;
-  const double* hn = d.Z + 13;
-  double t1[3], t2[3], t3[3];
-  cross3(hf, d.J, t1);
-  symv3(d.Z + 16, d.J + 3, t2);
-  cross3(hn, d.J + 3, t3);
-#pragma unroll
-  for (int k = 0; k < 3; ++k) d.BS[k] = 2.0 * t1[k] + t2[k] + t3[k];
   double* o = sbb + j * 18;
 #pragma unroll
   for (int k = 0; k < 6; ++k) { o[k] = d.J[k]; o[6 + k] = d.dFda[k]; }
+  if (DERIV) {
+    // BS = angular part of Bc^T J = 2 hf x J_lin + (Sym + [hn]x) J_ang
+    const double* hf = d.Z + 10;
+    const double* hn = d.Z + 13;
+    double t1[3], t2[3], t3[3];
+    cross3(hf, d.J, t1);
+    symv3(d.Z + 16, d.J + 3, t2);
+    cross3(hn, d.J + 3, t3);
 #pragma unroll
-  for (int k = 0; k < 3; ++k) o[12 + k] = d.BS[k];
+    for (int k = 0; k < 3; ++k) { d.BS[k] = 2.0 * t1[k] + t2[k] + t3[k]; o[12 + k] = d.BS[k]; }
+  }
   o[15] = d.b;
 }
 // column j of M + armature:  M[i][j] = J_min . dFda_max
@@ -310,6 +377,40 @@ AGX_DEV bool chol_load(const double* sl, double* L /*28*/, double* rinv /*7*/) {
     for (int i = k; i < NJ; ++i) L[n++] = sl[k * 8 + i];
     rinv[k] = sl[k * 8 + 7];
     ok = ok && (rinv[k] > 0.0);
+  }
+  return ok;
+}
+// Redundant in-register factorisation: every lane loads the lower triangle of the 7x7 matrix stored
+// on the board as M[i * 8 + k] and factors it (no barrier inside).  Same arithmetic order as the
+// column-distributed version above.
+AGX_DEV constexpr int lidx_(int i, int k) { return k * NJ - (k * (k - 1)) / 2 + (i - k); }
+AGX_DEV bool chol7_registers(const double* sm_M, double* A /*28*/, double* rinv /*7*/) {
+#pragma unroll
+  for (int k = 0; k < NJ; ++k)
+#pragma unroll
+    for (int i = 0; i < NJ; ++i)
+      if (i >= k) A[lidx_(i, k)] = sm_M[i * 8 + k];
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < NJ; ++k) {
+    double dkk = A[lidx_(k, k)];
+#pragma unroll
+    for (int m = 0; m < NJ; ++m)
+      if (m < k) dkk -= A[lidx_(k, m)] * A[lidx_(k, m)];
+    ok = ok && (dkk > 0.0);
+    const double r = AGX_RSQRT(dkk);
+    A[lidx_(k, k)] = dkk * r;
+    rinv[k] = r;
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) {
+      if (i > k) {
+        double t = A[lidx_(i, k)];
+#pragma unroll
+        for (int m = 0; m < NJ; ++m)
+          if (m < k) t -= A[lidx_(i, m)] * A[lidx_(k, m)];
+        A[lidx_(i, k)] = t * r;
+      }
+    }
   }
   return ok;
 }

@@ -54,7 +54,7 @@ struct Work {
 
 // doubles of shared memory per octet in the node kernels; the odd stride puts the two octets of a
 // half-warp on different banks (64-bit accesses are served per half-warp)
-constexpr int OCT_BOARD = BRD_A + BRD_B + 1;
+constexpr int OCT_BOARD = BRD_B + BRD_C + 1;
 
 #define AGX_OCTET_SETUP()                                   \
   const int j = (int)(threadIdx.x & 7u);                    \
@@ -77,75 +77,78 @@ AGX_DEV void lane_load_state(LaneDyn& d, int j, const double* x, const double* u
 // ---------------------------------------------------------------------------------------------
 // calc + calcDiff of one node; writes the compact record.  Returns the node cost (scaled).
 AGX_DEV double node_calc_diff(LaneDyn& d, int j, unsigned omask, const double* __restrict__ model,
-                              const double* __restrict__ ref, double dt, bool terminal, double* sa, double* sb,
+                              const double* __restrict__ ref, double dt, bool terminal, double* sb, double* sc,
                               double* __restrict__ rec) {
-  node_kinematics(d, j, omask, model, sa);
-  double lq, lv, lu, Lqq[NJ];
-  const double l = node_costs<true>(d, j, omask, model, ref, terminal, sa, &lq, &lv, &lu, Lqq);
+  node_kinematics(d, j, omask, model);
   const bool live = j < NJ;
   const int jj = live ? j : 0;
-  const double wv = live ? ref[NX + NJ + jj] : 0.0;
-  const double wu = (live && !terminal) ? ref[2 * NX + NJ + jj] : 0.0;
+  const double sc_l = terminal ? 1.0 : dt;  // cost scaling of the integrated model (terminal: unscaled)
+  double l;
+  {
+    // cost terms go straight to the record so that their registers are free during the dynamics
+    double lq, lv, lu, Lqq[NJ];
+    l = node_costs<true>(d, j, omask, model, ref, terminal, sb, &lq, &lv, &lu, Lqq);
+    const double wv = live ? ref[NX + NJ + jj] : 0.0;
+    const double wu = (live && !terminal) ? ref[2 * NX + NJ + jj] : 0.0;
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) rec[(RK_LQQ + i) * 8 + j] = sc_l * Lqq[i];
+    rec[RK_LVV * 8 + j] = sc_l * wv;
+    rec[RK_LUU * 8 + j] = sc_l * wu;
+    rec[RK_LQ * 8 + j] = sc_l * lq;
+    rec[RK_LV * 8 + j] = sc_l * lv;
+    rec[RK_LU * 8 + j] = sc_l * lu;
+  }
   if (terminal) {
 #pragma unroll
     for (int i = 0; i < NJ; ++i) {
       rec[(RK_AQ + i) * 8 + j] = 0.0;
       rec[(RK_AV + i) * 8 + j] = 0.0;
       rec[(RK_MI + i) * 8 + j] = 0.0;
-      rec[(RK_LQQ + i) * 8 + j] = Lqq[i];
     }
-    rec[RK_LVV * 8 + j] = wv;
-    rec[RK_LUU * 8 + j] = 0.0;
-    rec[RK_LQ * 8 + j] = lq;
-    rec[RK_LV * 8 + j] = lv;
-    rec[RK_LU * 8 + j] = 0.0;
     rec[RK_QN * 8 + j] = d.q;
     rec[RK_VN * 8 + j] = d.qd;
     rec[RK_COST * 8 + j] = l;
     return l;
   }
-  double L[28], rinv[NJ], qdd[NJ];
-  const bool ok = node_forward_dynamics<true>(d, j, omask, model, sa, sb, L, rinv, qdd);
-  node_rnea_derivatives(d, j, omask, sa, sb);
-  double aq[NJ], av[NJ], mi[NJ], ej[NJ];
-  solve_column(L, rinv, d.tq, -dt, aq);
-  solve_column(L, rinv, d.tv, -dt, av);
-#pragma unroll
-  for (int i = 0; i < NJ; ++i) ej[i] = (i == j) ? 1.0 : 0.0;
-  solve_column(L, rinv, ej, dt, mi);
-  const double cost = ok ? dt * l : nan("");
-#pragma unroll
-  for (int i = 0; i < NJ; ++i) {
-    rec[(RK_AQ + i) * 8 + j] = aq[i];
-    rec[(RK_AV + i) * 8 + j] = av[i];
-    rec[(RK_MI + i) * 8 + j] = mi[i];
-    rec[(RK_LQQ + i) * 8 + j] = dt * Lqq[i];
-  }
-  rec[RK_LVV * 8 + j] = dt * wv;
-  rec[RK_LUU * 8 + j] = dt * wu;
-  rec[RK_LQ * 8 + j] = dt * lq;
-  rec[RK_LV * 8 + j] = dt * lv;
-  rec[RK_LU * 8 + j] = dt * lu;
+  double L[28], rinv[NJ];
+  const bool ok = node_forward_dynamics<true>(d, j, omask, model, sb, sc, L, rinv);
   rec[RK_QN * 8 + j] = d.q + (d.qd * dt + d.qdd * (dt * dt));
   rec[RK_VN * 8 + j] = d.qd + d.qdd * dt;
+  node_rnea_derivatives(d, j, omask, sb);
+  AGX_OSYNC();
+  factor_reload(sc, L, rinv);
+  double col[NJ];
+  solve_column(L, rinv, d.tq, -dt, col);
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) rec[(RK_AQ + i) * 8 + j] = col[i];
+  solve_column(L, rinv, d.tv, -dt, col);
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) rec[(RK_AV + i) * 8 + j] = col[i];
+  double ej[NJ];
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) ej[i] = (i == j) ? 1.0 : 0.0;
+  solve_column(L, rinv, ej, dt, col);
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) rec[(RK_MI + i) * 8 + j] = col[i];
+  const double cost = ok ? dt * l : nan("");
   rec[RK_COST * 8 + j] = cost;
   return cost;
 }
 
 // calc of one node: cost (scaled) and this lane's entries of xnext.  Returns false on failure.
 AGX_DEV bool node_calc(LaneDyn& d, int j, unsigned omask, const double* __restrict__ model,
-                       const double* __restrict__ ref, double dt, bool terminal, double* sa, double* sb, double* cost,
+                       const double* __restrict__ ref, double dt, bool terminal, double* sb, double* sc, double* cost,
                        double* qn, double* vn) {
-  node_kinematics(d, j, omask, model, sa);
-  const double l = node_costs<false>(d, j, omask, model, ref, terminal, sa, nullptr, nullptr, nullptr, nullptr);
+  node_kinematics(d, j, omask, model);
+  const double l = node_costs<false>(d, j, omask, model, ref, terminal, sb, nullptr, nullptr, nullptr, nullptr);
   if (terminal) {
     *cost = l;
     *qn = d.q;
     *vn = d.qd;
     return true;
   }
-  double L[28], rinv[NJ], qdd[NJ];
-  const bool ok = node_forward_dynamics<false>(d, j, omask, model, sa, sb, L, rinv, qdd);
+  double L[28], rinv[NJ];
+  const bool ok = node_forward_dynamics<false>(d, j, omask, model, sb, sc, L, rinv);
   *cost = dt * l;
   *qn = d.q + (d.qd * dt + d.qdd * (dt * dt));
   *vn = d.qd + d.qdd * dt;
@@ -173,16 +176,16 @@ __global__ void __launch_bounds__(64, AGX_CD_MINB) calc_diff_kernel(Problem P, c
   const int b = (int)(ent / T1), t = (int)(ent % T1);
   if (done && done[b]) return;
   if (recalc && !recalc[b]) return;
-  double* sa = smem + oct_in_cta * OCT_BOARD;
-  double* sb = sa + BRD_A;
+  double* sb = smem + oct_in_cta * OCT_BOARD;
+  double* sc = sb + BRD_B;
   const size_t buf = buf_of(cur, b, false);
   const double* x = xs + ((buf * P.B + b) * T1 + t) * NX;
   const bool terminal = t == P.T;
   const double* u = terminal ? nullptr : us + ((buf * P.B + b) * P.T + t) * NJ;
   LaneDyn d;
   lane_load_state(d, j, x, u);
-  node_calc_diff(d, j, omask, model_of(P, b), P.refs + (size_t)ent * REF_SIZE, terminal ? 0.0 : P.dts[t], terminal, sa,
-                 sb, rec + (size_t)ent * REC_SIZE);
+  node_calc_diff(d, j, omask, model_of(P, b), P.refs + (size_t)ent * REF_SIZE, terminal ? 0.0 : P.dts[t], terminal, sb,
+                 sc, rec + (size_t)ent * REC_SIZE);
 }
 
 __global__ void calc_kernel(Problem P, const double* __restrict__ xs, const double* __restrict__ us,
@@ -192,14 +195,14 @@ __global__ void calc_kernel(Problem P, const double* __restrict__ xs, const doub
   const int T1 = P.T + 1;
   if (ent >= (long long)P.B * T1) return;
   const int b = (int)(ent / T1), t = (int)(ent % T1);
-  double* sa = smem + oct_in_cta * OCT_BOARD;
-  double* sb = sa + BRD_A;
+  double* sb = smem + oct_in_cta * OCT_BOARD;
+  double* sc = sb + BRD_B;
   const bool terminal = t == P.T;
   LaneDyn d;
   lane_load_state(d, j, xs + (size_t)ent * NX, terminal ? nullptr : us + ((size_t)b * P.T + t) * NJ);
   double c, qn, vn;
   const bool ok = node_calc(d, j, omask, model_of(P, b), P.refs + (size_t)ent * REF_SIZE, terminal ? 0.0 : P.dts[t],
-                            terminal, sa, sb, &c, &qn, &vn);
+                            terminal, sb, sc, &c, &qn, &vn);
   if (!ok) c = nan("");
   if (out_cost && j == 0) out_cost[ent] = c;
   if (out_xnext && j < NJ) {
@@ -564,9 +567,9 @@ __global__ void forward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
   const int b = (int)ent;
   if (b >= P.B) return;
   if (S.done[b]) return;
-  double* sa = smem + oct_in_cta * FW_BOARD;
-  double* sb = sa + BRD_A;
-  double* sdx = sb + BRD_B;  // [14]
+  double* sb = smem + oct_in_cta * FW_BOARD;
+  double* sc = sb + BRD_B;
+  double* sdx = sc + BRD_C;  // [14]
   const int T = P.T, T1 = T + 1;
   const bool live = j < NJ;
   const int jj = live ? j : 0;
@@ -621,7 +624,7 @@ __global__ void forward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
       }
       double c, qn, vn;
       const bool okn = node_calc(d, j, omask, model, refs + (size_t)t * REF_SIZE, terminal ? 0.0 : P.dts[t], terminal,
-                                 sa, sb, &c, &qn, &vn);
+                                 sb, sc, &c, &qn, &vn);
       ok = ok && okn;
       ctry += c;
       xq = qn; xv = vn;
@@ -683,8 +686,8 @@ __global__ void rollout_kernel(Problem P, const double* __restrict__ x0, const d
   AGX_OCTET_SETUP();
   const int b = (int)ent;
   if (b >= P.B) return;
-  double* sa = smem + oct_in_cta * OCT_BOARD;
-  double* sb = sa + BRD_A;
+  double* sb = smem + oct_in_cta * OCT_BOARD;
+  double* sc = sb + BRD_B;
   const int T = P.T, T1 = T + 1;
   const bool live = j < NJ;
   const int jj = live ? j : 0;
@@ -696,7 +699,7 @@ __global__ void rollout_kernel(Problem P, const double* __restrict__ x0, const d
     d.q = xq; d.qd = xv; d.u = live ? us[((size_t)b * T + t) * NJ + jj] : 0.0;
     double c, qn, vn;
     const bool ok = node_calc(d, j, omask, model_of(P, b), P.refs + ((size_t)b * T1 + t) * REF_SIZE, P.dts[t], false,
-                              sa, sb, &c, &qn, &vn);
+                              sb, sc, &c, &qn, &vn);
     xq = ok ? qn : nan("");
     xv = ok ? vn : nan("");
     if (live) { xo[(t + 1) * NX + j] = xq; xo[(t + 1) * NX + NJ + j] = xv; }
@@ -709,13 +712,13 @@ __global__ void integrate_kernel(const double* __restrict__ model, const double*
   AGX_SMEM(smem);
   AGX_OCTET_SETUP();
   if (ent >= n) return;
-  double* sa = smem + oct_in_cta * OCT_BOARD;
-  double* sb = sa + BRD_A;
+  double* sb = smem + oct_in_cta * OCT_BOARD;
+  double* sc = sb + BRD_B;
   LaneDyn d;
   lane_load_state(d, j, x + (size_t)ent * NX, u + (size_t)ent * NJ);
-  node_kinematics(d, j, omask, model, sa);
-  double L[28], rinv[NJ], qdd[NJ];
-  const bool ok = node_forward_dynamics<false>(d, j, omask, model, sa, sb, L, rinv, qdd);
+  node_kinematics(d, j, omask, model);
+  double L[28], rinv[NJ];
+  const bool ok = node_forward_dynamics<false>(d, j, omask, model, sb, sc, L, rinv);
   if (j < NJ) {
     out[(size_t)ent * NX + j] = ok ? d.q + (d.qd * dt + d.qdd * (dt * dt)) : nan("");
     out[(size_t)ent * NX + NJ + j] = ok ? d.qd + d.qdd * dt : nan("");
@@ -729,8 +732,8 @@ __global__ void rnea_kernel(const double* __restrict__ model, const double* __re
   AGX_SMEM(smem);
   AGX_OCTET_SETUP();
   if (ent >= n) return;
-  double* sa = smem + oct_in_cta * OCT_BOARD;
-  double* sb = sa + BRD_A;
+  double* sb = smem + oct_in_cta * OCT_BOARD;
+  double* sc = sb + BRD_B;
   const bool live = j < NJ;
   const int jj = live ? j : 0;
   LaneDyn d;
@@ -738,26 +741,18 @@ __global__ void rnea_kernel(const double* __restrict__ model, const double* __re
   d.qd = live ? v[(size_t)ent * NJ + jj] : 0.0;
   d.u = 0.0;
   d.qdd = live ? a[(size_t)ent * NJ + jj] : 0.0;
-  node_kinematics(d, j, omask, model, sa);
+  node_kinematics(d, j, omask, model);
   const double zero6[6] = {0, 0, 0, 0, 0, 0};
   const double agrav[6] = {-model[MT_GRAV + 0], -model[MT_GRAV + 1], -model[MT_GRAV + 2], 0, 0, 0};
-  vec6_store(d.s, j, sa);
-  AGX_OSYNC();
-  vec6_prefix_excl(d.vp, j, zero6, sa);
-  AGX_OSYNC();
+  scan_prefix_excl<6>(d.s, d.vp, zero6, j, omask);
   body_terms(d, j, model, nullptr, false);
   // bias acceleration including the joint accelerations: g = c qd + J qdd
 #pragma unroll
   for (int k = 0; k < 6; ++k) d.g[k] += d.J[k] * d.qdd;
-  vec6_store(d.g, j, sa);
-  AGX_OSYNC();
-  vec6_prefix_excl(d.a0p, j, agrav, sa);
-  AGX_OSYNC();
+  scan_prefix_excl<6>(d.g, d.a0p, agrav, j, omask);
   body_force(d);
-  vec6_store(d.Z + 22, j, sa);
-  AGX_OSYNC();
-  vec6_suffix_incl(d.Z + 22, j, sa);
-  (void)sb;
+  scan_suffix_incl<6>(d.Z + 22, j, omask);
+  (void)sb; (void)sc;
   if (live) out_tau[(size_t)ent * NJ + j] = dot6(d.J, d.Z + 22);
 }
 

@@ -21,85 +21,88 @@ AGX_DEV double octet_sum(double x, unsigned omask) {
 }
 
 // forward kinematics: world placements (prefix product over the chain), joint axes, s = J qd
-AGX_DEV void node_kinematics(LaneDyn& d, int j, unsigned omask, const double* __restrict__ model, double* sa) {
+AGX_DEV void node_kinematics(LaneDyn& d, int j, unsigned omask, const double* __restrict__ model) {
   kin_local(d, j, model);
-#pragma unroll
-  for (int dist = 1; dist < 8; dist <<= 1) {
-    se3_store(d, j, sa);
-    AGX_OSYNC();
-    se3_combine(d, j, dist, sa);
-    AGX_OSYNC();
-  }
+  scan_se3_prefix(d, j, omask);
   kin_axis(d, j);
 }
 
 // Forward dynamics a = (M + armature)^-1 (u - nle) in the world-frame formulation.  On exit:
-// d.qdd = this joint's acceleration, qdd_all = all seven, L/rinv = Cholesky factor of M + armature
-// (every lane holds the whole factor), board `sb` = [J dFda BS b u] per lane.  Returns false when the
-// factorisation fails (octet-uniform).
+// d.qdd = this joint's acceleration, L/rinv = Cholesky factor of M + armature (every lane holds the
+// whole factor; also left on board `sc` as L[i][k] at sc[i*8+k], 1/L[k][k] at sc[k*8+7]), board `sb` =
+// [J dFda BS b u] per lane.  Returns false when the factorisation fails (octet-uniform).
 template <bool DERIV>
-AGX_DEV bool node_forward_dynamics(LaneDyn& d, int j, unsigned omask, const double* __restrict__ model, double* sa,
-                                   double* sb, double* L, double* rinv, double* qdd_all) {
+AGX_DEV bool node_forward_dynamics(LaneDyn& d, int j, unsigned omask, const double* __restrict__ model, double* sb,
+                                   double* sc, double* L, double* rinv) {
   const double zero6[6] = {0, 0, 0, 0, 0, 0};
   const double agrav[6] = {-model[MT_GRAV + 0], -model[MT_GRAV + 1], -model[MT_GRAV + 2], 0, 0, 0};
-  vec6_store(d.s, j, sa);
-  AGX_OSYNC();
-  vec6_prefix_excl(d.vp, j, zero6, sa);
-  AGX_OSYNC();
+  scan_prefix_excl<6>(d.s, d.vp, zero6, j, omask);
   body_terms(d, j, model, nullptr, DERIV);
-  vec6_store(d.g, j, sa);
-  AGX_OSYNC();
-  vec6_prefix_excl(d.a0p, j, agrav, sa);
-  AGX_OSYNC();
+  scan_prefix_excl<6>(d.g, d.a0p, agrav, j, omask);
   body_force(d);
-  comp_store(d, j, sa);
-  AGX_OSYNC();
-  comp_suffix(d, j, sa);
-  AGX_OSYNC();
-  column_terms(d, j, sb);
+  if (DERIV) {
+    scan_suffix_incl<28>(d.Z, j, omask);
+  } else {
+    scan_suffix_incl<10>(d.Z, j, omask);       // composite inertia
+    scan_suffix_incl<6>(d.Z + 22, j, omask);   // composite bias force
+  }
+  column_terms<DERIV>(d, j, sb);
   sb[j * 18 + 16] = d.u;
   AGX_OSYNC();
   mass_column(d, j, model, sb);
 #pragma unroll
-  for (int k = 0; k < NJ; ++k) {
-    chol_pivot(d.Mc, j, k, sa);
-    AGX_OSYNC();
-    chol_update(d.Mc, j, k, sa);
-  }
-  const bool ok = chol_load(sa, L, rinv);
+  for (int i = 0; i < NJ; ++i) sc[i * 8 + j] = d.Mc[i];
+  AGX_OSYNC();
+  const bool ok = chol7_registers(sc, L, rinv);
+  double rhs[NJ];
 #pragma unroll
-  for (int i = 0; i < NJ; ++i) qdd_all[i] = sb[i * 18 + 16] - sb[i * 18 + 15];
-  chol_solve7(L, rinv, qdd_all);
+  for (int i = 0; i < NJ; ++i) rhs[i] = sb[i * 18 + 16] - sb[i * 18 + 15];
+  chol_solve7(L, rinv, rhs);
   d.qdd = 0.0;
 #pragma unroll
   for (int i = 0; i < NJ; ++i)
-    if (i == j) d.qdd = qdd_all[i];
-  AGX_OSYNC();  // board A (the factor) may be overwritten from here on
+    if (i == j) d.qdd = rhs[i];
+  if (DERIV) {
+    // park the factor on the board so that its registers are free during the derivative phase
+    AGX_OSYNC();
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) {
+      if (k == j) {
+#pragma unroll
+        for (int i = 0; i < NJ; ++i)
+          if (i >= k) sc[i * 8 + k] = L[lidx(i, k)];
+        sc[k * 8 + 7] = rinv[k];
+      }
+    }
+  }
   return ok;
+}
+// reload the parked factor (after an octet barrier)
+AGX_DEV void factor_reload(const double* sc, double* L, double* rinv) {
+#pragma unroll
+  for (int k = 0; k < NJ; ++k) {
+#pragma unroll
+    for (int i = 0; i < NJ; ++i)
+      if (i >= k) L[lidx(i, k)] = sc[i * 8 + k];
+    rinv[k] = sc[k * 8 + 7];
+  }
 }
 
 // dtau/dq, dtau/dv columns (computeRNEADerivatives at the forward-dynamics acceleration)
-AGX_DEV void node_rnea_derivatives(LaneDyn& d, int j, unsigned omask, double* sa, const double* sb) {
+AGX_DEV void node_rnea_derivatives(LaneDyn& d, int j, unsigned omask, const double* sb) {
   // acceleration added by qdd: da_j = sum_{l<=j} J_l qdd_l ; force added: suffix sum of Y_l da_l
-  double jq[6], dap[6], da[6], yda[6], dfc[6];
+  double jq[6], dap[6], da[6], dfc[6];
   const double zero6[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
   for (int k = 0; k < 6; ++k) jq[k] = d.J[k] * d.qdd;
-  vec6_store(jq, j, sa);
-  AGX_OSYNC();
-  vec6_prefix_excl(dap, j, zero6, sa);
+  scan_prefix_excl<6>(jq, dap, zero6, j, omask);
 #pragma unroll
   for (int k = 0; k < 6; ++k) da[k] = dap[k] + jq[k];
-  inertia_apply(d.Y, da, yda);
-#pragma unroll
-  for (int k = 0; k < 6; ++k) dfc[k] = yda[k];
-  vec6_store(yda, j, sa + 48);
-  AGX_OSYNC();
-  vec6_suffix_incl(dfc, j, sa + 48);
+  inertia_apply(d.Y, da, dfc);
+  scan_suffix_incl<6>(dfc, j, omask);
   double dFdq[6], dFdv[6];
   deriv_columns(d, j, dap, dfc, dFdq, dFdv);
   deriv_fill(d, j, dFdq, dFdv, sb);
-  AGX_OSYNC();
 }
 
 // Weighted-quadratic costs of one node.  pose residual r6 = log6(Mref^-1 oMf); when DERIV the
@@ -107,8 +110,8 @@ AGX_DEV void node_rnea_derivatives(LaneDyn& d, int j, unsigned omask, double* sa
 // Returns the (unscaled) node cost, identical on every lane.
 template <bool DERIV>
 AGX_DEV double node_costs(const LaneDyn& d, int j, unsigned omask, const double* __restrict__ model,
-                          const double* __restrict__ ref, bool terminal, double* sa, double* Lq, double* Lv, double* Lu,
-                          double* Lqq /*7*/) {
+                          const double* __restrict__ ref, bool terminal, double* srq /*[8][6] scratch board*/, double* Lq,
+                          double* Lv, double* Lu, double* Lqq /*7*/) {
   const bool live = j < NJ;
   const int jj = live ? j : 0;
   // state / control regularisation (ResidualModelState, ResidualModelControl; A7, A8)
@@ -117,20 +120,13 @@ AGX_DEV double node_costs(const LaneDyn& d, int j, unsigned omask, const double*
   const double ru = d.u - ref[2 * NX + jj];
   const double wu = (live && !terminal) ? ref[2 * NX + NJ + jj] : 0.0;
   double part = 0.5 * wq * rq * rq + 0.5 * wv * rv * rv + 0.5 * wu * ru * ru;
-  // frame placement (A9): joint frame_parent's world placement is broadcast through the board
+  // frame placement (A9): joint frame_parent's world placement is broadcast to the octet
   const int fpar = (int)model[MT_FP + 3];
-  if (j == fpar) {
-#pragma unroll
-    for (int k = 0; k < 9; ++k) sa[k] = d.R[k];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) sa[9 + k] = d.p[k];
-  }
-  AGX_OSYNC();
   double R6[9], p6[3];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) R6[k] = sa[k];
+  for (int k = 0; k < 9; ++k) R6[k] = __shfl_sync(omask, d.R[k], fpar, 8);
 #pragma unroll
-  for (int k = 0; k < 3; ++k) p6[k] = sa[9 + k];
+  for (int k = 0; k < 3; ++k) p6[k] = __shfl_sync(omask, d.p[k], fpar, 8);
   const double* Rref = ref + 2 * NX + 2 * NJ;
   const double* pref = Rref + 9;
   const double* wp = pref + 3;
@@ -160,7 +156,6 @@ AGX_DEV double node_costs(const LaneDyn& d, int j, unsigned omask, const double*
                Bm[3 * i + 1] * ca[1] + Bm[3 * i + 2] * ca[2];
       rqc[3 + i] = A[3 * i] * ca[0] + A[3 * i + 1] * ca[1] + A[3 * i + 2] * ca[2];
     }
-    double* srq = sa + 16;  // [8][6]
 #pragma unroll
     for (int k = 0; k < 6; ++k) srq[j * 6 + k] = rqc[k];
     AGX_OSYNC();

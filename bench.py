@@ -33,7 +33,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-B_PER_GPU = 4096
+B_PER_GPU = int(os.environ.get("AGX_BENCH_B", "4096"))  # 4096 is the metric's batch; the override is for scaling studies
 T_NODES = 50
 DT = 0.01
 N_ITERS = 10
