@@ -343,6 +343,13 @@ __global__ void backward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
     for (int t = T - 1; ok && t >= 0; --t) {
       const double* R = rec0 + (size_t)t * REC_SIZE;
       const double h = P.dts[t];
+      if (t > 0) {
+        // pull the next node's record (18 x 128 B) towards the SM while this node is processed
+        const double* Rn = R - REC_SIZE;
+        AGX_PREFETCH(Rn + j * 16);
+        AGX_PREFETCH(Rn + 128 + j * 16);
+        if (j < 2) AGX_PREFETCH(Rn + 256 + j * 16);
+      }
       double G0[NJ], G1[NJ], Nc[NJ], Lqq[NJ];
 #pragma unroll
       for (int i = 0; i < NJ; ++i) {
@@ -441,13 +448,11 @@ __global__ void backward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
       }
       sm[BW_QU + j] = qu;
 #pragma unroll
-      for (int k = 0; k < NJ; ++k) {
-        chol_pivot(Quu, j, k, sm + BW_L);
-        AGX_OSYNC();
-        chol_update(Quu, j, k, sm + BW_L);
-      }
+      for (int i = 0; i < NJ; ++i) sm[BW_L + i * 8 + j] = Quu[i];
+      AGX_OSYNC();
+      // computeGains: every lane factors Quu in registers (no barrier inside the factorisation)
       double L[28], rinv[NJ];
-      ok = chol_load(sm + BW_L, L, rinv);
+      ok = chol7_registers(sm + BW_L, L, rinv);
       if (!ok) break;
       // gains
       double K0[NJ], K1[NJ], kk[NJ];
@@ -588,6 +593,31 @@ __global__ void forward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
   const double cost = S.cost[b], dg = S.dg[b], dq = S.dq[b];
   const double x0q = live ? W.x0[(size_t)b * NX + jj] : 0.0, x0v = live ? W.x0[(size_t)b * NX + NJ + jj] : 0.0;
 
+  // per-node inputs: the small per-lane scalars are fetched one node ahead into registers, the gain rows
+  // and the reference record are pulled into L1 one node ahead (prefetch), so that their HBM/L2 latency
+  // hides behind the node's arithmetic
+  struct NodeIn {
+    double us, kff, dt, xsq, xsv, fq, fv, gq, gv;
+  };
+  auto fetch = [&](int t, NodeIn& n) {
+    const bool run = t < T;
+    n.us = (live && run) ? us[t * NJ + jj] : 0.0;
+    n.kff = (live && run) ? kb[t * NJ + jj] : 0.0;
+    n.dt = run ? P.dts[t] : 0.0;
+    n.xsq = live ? xs[t * NX + jj] : 0.0;
+    n.xsv = live ? xs[t * NX + NJ + jj] : 0.0;
+    const bool gaps = live && !feasible;
+    n.fq = gaps ? fsb[t * NX + jj] : 0.0;
+    n.fv = gaps ? fsb[t * NX + NJ + jj] : 0.0;
+    n.gq = gaps ? gvb[t * NX + jj] : 0.0;
+    n.gv = gaps ? gvb[t * NX + NJ + jj] : 0.0;
+    if (run) {
+      AGX_PREFETCH(Kb + (t * NJ + jj) * NX);
+      AGX_PREFETCH(Kb + (t * NJ + jj) * NX + NX - 1);
+    }
+    if (j < 4) AGX_PREFETCH(refs + (size_t)t * REF_SIZE + j * 16);
+  };
+
   double steplength = 1.0, d1 = 0.0, d2 = 0.0, cost_try = 0.0;
   bool accepted = false, have_d = false;
   for (int ia = 0; ia < O.n_alphas; ++ia) {
@@ -596,39 +626,41 @@ __global__ void forward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
     double xq = x0q, xv = x0v;
     double ctry = 0.0, dvp = 0.0;
     bool ok = true;
+    NodeIn cur;
+    fetch(0, cur);
     for (int t = 0; t <= T; ++t) {
+      NodeIn nxt;
+      if (t < T) fetch(t + 1, nxt);
       double tq = xq, tv = xv;
-      if (contract && live) {
-        tq += fsb[t * NX + j] * (steplength - 1.0);
-        tv += fsb[t * NX + NJ + j] * (steplength - 1.0);
+      if (contract) {
+        tq += cur.fq * (steplength - 1.0);
+        tv += cur.fv * (steplength - 1.0);
       }
-      const double dxq = live ? tq - xs[t * NX + jj] : 0.0, dxv = live ? tv - xs[t * NX + NJ + jj] : 0.0;
+      const double dxq = live ? tq - cur.xsq : 0.0, dxv = live ? tv - cur.xsv : 0.0;
       if (live) {
         xt[t * NX + j] = tq;
         xt[t * NX + NJ + j] = tv;
-        if (!feasible) dvp += gvb[t * NX + j] * dxq + gvb[t * NX + NJ + j] * dxv;
       }
+      dvp += cur.gq * dxq + cur.gv * dxv;
       LaneDyn d;
       d.q = tq; d.qd = tv; d.u = 0.0;
       const bool terminal = t == T;
       if (!terminal) {
         if (live) { sdx[j] = dxq; sdx[NJ + j] = dxv; }
         AGX_OSYNC();
-        if (live) {
-          double s = 0.0;
+        double s = 0.0;
 #pragma unroll
-          for (int m = 0; m < NX; ++m) s += Kb[(t * NJ + j) * NX + m] * sdx[m];
-          d.u = us[t * NJ + j] - kb[t * NJ + j] * steplength - s;
-          ut[t * NJ + j] = d.u;
-        }
+        for (int m = 0; m < NX; ++m) s += Kb[(t * NJ + jj) * NX + m] * sdx[m];
+        d.u = cur.us - cur.kff * steplength - s;
+        if (live) ut[t * NJ + j] = d.u;
       }
       double c, qn, vn;
-      const bool okn = node_calc(d, j, omask, model, refs + (size_t)t * REF_SIZE, terminal ? 0.0 : P.dts[t], terminal,
-                                 sb, sc, &c, &qn, &vn);
+      const bool okn = node_calc(d, j, omask, model, refs + (size_t)t * REF_SIZE, cur.dt, terminal, sb, sc, &c, &qn, &vn);
       ok = ok && okn;
       ctry += c;
       xq = qn; xv = vn;
       if (!(ctry - ctry == 0.0)) { ok = false; break; }  // NaN / inf: reject this step length
+      if (t < T) cur = nxt;
     }
     if (!ok) continue;
     cost_try = ctry;

@@ -21,6 +21,7 @@
 #define AGX_RSQRT(x) rsqrt(x)
 #define AGX_SINCOS(x, s, c) sincos((x), (s), (c))
 #define AGX_SMEM(name) extern __shared__ double name[]
+#define AGX_PREFETCH(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
 #else
 #define AGX_GPU 0
 #define AGX_DEV inline
@@ -31,6 +32,7 @@
     *(c) = cos(x);          \
   } while (0)
 #define AGX_SMEM(name) double* name = reinterpret_cast<double*>(simt::g_smem)
+#define AGX_PREFETCH(p) ((void)(p))
 #endif
 
 namespace agx {
