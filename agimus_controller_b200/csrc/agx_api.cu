@@ -313,6 +313,38 @@ int agx_rnea(agx_handle* h, const double* q, const double* v, const double* a, i
   return check_launch(h, "agx_rnea");
 }
 
+int agx_riccati(agx_handle* h, const double* x0, const double* xs, const double* us, double reg, double* out_K,
+                double* out_k, int32_t* out_status, void* stream) {
+  if (!h || !x0 || !xs || !us || !out_K) return AGX_EINVAL;
+  DeviceGuard g(h->device);
+  stream_t st = (stream_t)stream;
+  agx_fddp_opts od;
+  agx_fddp_opts_default(&od);
+  FddpOpts O;
+  O.reg_min = reg; O.reg_max = reg; O.reg_incfactor = od.reg_incfactor; O.reg_decfactor = od.reg_decfactor;
+  O.th_grad = od.th_grad; O.th_stepdec = od.th_stepdec; O.th_stepinc = od.th_stepinc; O.th_acceptstep = od.th_acceptstep;
+  O.th_acceptnegstep = od.th_acceptnegstep; O.th_stop = od.th_stop; O.reg_init = reg; O.fixed_iters = 1; O.n_alphas = 1;
+  const size_t nB = (size_t)h->B, T = (size_t)h->T, T1 = T + 1;
+  Work W = h->W;
+  W.K = out_K;
+  W.x0 = h->d_x0;
+  if (!copy_d2d(h->d_x0, x0, sizeof(double) * nB * NX, st)) return fail(h, AGX_ECUDA, "agx_riccati: x0 copy failed");
+  const Problem P = problem_of(h);
+  const long long n_init = (long long)(nB * T1 * NX);
+  AGX_LAUNCH(h, init_kernel, (n_init + 255) / 256, 256, 0, st, P, W, h->S, O, xs, us);
+  const long long ents = (long long)(nB * T1);
+  const int opc_n = NODE_CTA / 8, opc_s = SEQ_CTA / 8;
+  AGX_LAUNCH(h, calc_diff_kernel, (ents + opc_n - 1) / opc_n, NODE_CTA, sizeof(double) * OCT_BOARD * opc_n, st, P,
+             (const double*)W.xs, (const double*)W.us, (const int32_t*)h->S.cur, (const int32_t*)h->S.recalc,
+             (const int32_t*)h->S.done, W.rec);
+  AGX_LAUNCH(h, backward_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * BW_SIZE * opc_s, st, P, W, h->S, O);
+  bool ok = true;
+  if (out_k) ok = ok && copy_d2d(out_k, W.k, sizeof(double) * nB * T * NJ, st);
+  if (out_status) ok = ok && copy_d2d(out_status, h->S.status, sizeof(int32_t) * nB, st);
+  if (!ok) return fail(h, AGX_ECUDA, "agx_riccati: output copy failed");
+  return check_launch(h, "agx_riccati");
+}
+
 #if AGX_GPU
 namespace {
 // FP64 FMA throughput probe: 8 independent dependent-chains per thread, 2 flops per DFMA

@@ -498,11 +498,14 @@ AGX_DEV void deriv_fill(LaneDyn& d, int j, const double* dFdq, const double* dFd
 // ---------------------------------------------------------------- SE3 logarithms (Pinocchio's formulas and branches)
 #define AGX_TAYLOR_PREC3 1.220703125e-4  /* eps^(1/4) */
 #define AGX_PI 3.14159265358979323846
-AGX_DEV void log3(const double* R, double& theta, double* w) {
+// log3 with its by-products: theta, cos(theta) = (tr R - 1)/2 (clamped) and sin(theta) = sqrt((1-c)(1+c))
+// (theta in [0, pi], so sin >= 0): same functions of R as sin/cos(acos(.)) without the extra sincos.
+AGX_DEV void log3(const double* R, double& theta, double& ct, double& st, double* w) {
   const double tr = R[0] + R[4] + R[8];
-  if (tr >= 3.0) theta = 0.0;
-  else if (tr <= -1.0) theta = AGX_PI;
-  else theta = acos((tr - 1.0) / 2.0);
+  if (tr >= 3.0) { theta = 0.0; ct = 1.0; }
+  else if (tr <= -1.0) { theta = AGX_PI; ct = -1.0; }
+  else { ct = (tr - 1.0) / 2.0; theta = acos(ct); }
+  st = sqrt((1.0 - ct) * (1.0 + ct));
   if (theta >= AGX_PI - 1e-2) {
     const double cphi = -(tr - 1.0) / 2.0;
     const double beta = theta * theta / (1.0 + cphi);
@@ -511,26 +514,30 @@ AGX_DEV void log3(const double* R, double& theta, double* w) {
     w[1] = (R[2] > R[6] ? 1.0 : -1.0) * (t1 > 0.0 ? sqrt(t1) : 0.0);
     w[2] = (R[3] > R[1] ? 1.0 : -1.0) * (t2 > 0.0 ? sqrt(t2) : 0.0);
   } else {
-    const double t = ((theta > AGX_TAYLOR_PREC3) ? theta / sin(theta) : 1.0) / 2.0;
+    const double t = ((theta > AGX_TAYLOR_PREC3) ? theta / st : 1.0) / 2.0;
     w[0] = t * (R[7] - R[5]);
     w[1] = t * (R[2] - R[6]);
     w[2] = t * (R[3] - R[1]);
   }
 }
-// r = log6(R, p) ([lin; ang]); if Jl != nullptr also the blocks of Jlog6 = [[A, B],[0, A]]: Jl[0..8] = A, Jl[9..17] = B
+// r = log6(R, p) ([lin; ang]); if Jl != nullptr also the blocks of Jlog6 = [[A, B],[0, A]]: Jl[0..8] = A, Jl[9..17] = B.
+// Pinocchio's coefficients share sub-expressions: alpha(log6) = diag(Jlog3) = theta sin / (2 (1 - cos)) and
+// beta(log6) = alpha(Jlog3) = beta(Jlog6) = 1/theta^2 - sin / (2 theta (1 - cos)); they are formed once.
 AGX_DEV void log6_and_jac(const double* R, const double* p, double* r, double* Jl) {
-  double t, w[3];
-  log3(R, t, w);
+  double t, ct, st, w[3];
+  log3(R, t, ct, st, w);
   const double t2 = t * t;
-  double st = 0, ct = 1, alpha, beta;
-  const bool small = t < AGX_TAYLOR_PREC3;
-  if (small) {
+  double alpha, beta, bdot;
+  if (t < AGX_TAYLOR_PREC3) {
     alpha = 1.0 - t2 / 12.0 - t2 * t2 / 720.0;
     beta = 1.0 / 12.0 + t2 / 720.0;
+    bdot = 1.0 / 360.0;
   } else {
-    AGX_SINCOS(t, &st, &ct);
-    alpha = t * st / (2.0 * (1.0 - ct));
-    beta = 1.0 / t2 - st / (2.0 * t * (1.0 - ct));
+    const double tinv = 1.0 / t, t2inv = tinv * tinv;
+    const double inv_2_2ct = 0.5 / (1.0 - ct);
+    alpha = t * st * inv_2_2ct;
+    beta = t2inv - st * tinv * inv_2_2ct;
+    bdot = -2.0 * t2inv * t2inv + (1.0 + st * tinv) * t2inv * inv_2_2ct;
   }
   double wxp[3];
   cross3(w, p, wxp);
@@ -541,39 +548,25 @@ AGX_DEV void log6_and_jac(const double* R, const double* p, double* r, double* J
     r[3 + k] = w[k];
   }
   if (!Jl) return;
-  // Jlog3
-  double a3, diag, bdot, beta6;
-  if (small) {
-    a3 = 1.0 / 12.0 + t2 / 720.0;
-    diag = 0.5 * (2.0 - t2 / 6.0);
-    beta6 = 1.0 / 12.0 + t2 / 720.0;
-    bdot = 1.0 / 360.0;
-  } else {
-    const double st_1mct = st / (1.0 - ct);
-    a3 = 1.0 / t2 - st_1mct / (2.0 * t);
-    diag = 0.5 * (t * st_1mct);
-    const double tinv = 1.0 / t, t2inv = tinv * tinv;
-    const double inv_2_2ct = 1.0 / (2.0 * (1.0 - ct));
-    beta6 = t2inv - st * tinv * inv_2_2ct;
-    bdot = -2.0 * t2inv * t2inv + (1.0 + st * tinv) * t2inv * inv_2_2ct;
-  }
+  // Jlog3 = beta w w^T + diag I + 1/2 [w]x   (diag: Taylor branch 1 - theta^2/12, else alpha)
+  const double diag = (t < AGX_TAYLOR_PREC3) ? 0.5 * (2.0 - t2 / 6.0) : alpha;
   double* A = Jl;
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
-    for (int c = 0; c < 3; ++c) A[3 * i + c] = a3 * w[i] * w[c];
+    for (int c = 0; c < 3; ++c) A[3 * i + c] = beta * w[i] * w[c];
   A[0] += diag; A[4] += diag; A[8] += diag;
   A[1] -= 0.5 * w[2]; A[2] += 0.5 * w[1];
   A[3] += 0.5 * w[2]; A[5] -= 0.5 * w[0];
   A[6] -= 0.5 * w[1]; A[7] += 0.5 * w[0];
   double v3[3], C[9];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) v3[k] = (bdot * wp) * w[k] - (t2 * bdot + 2.0 * beta6) * p[k];
+  for (int k = 0; k < 3; ++k) v3[k] = (bdot * wp) * w[k] - (t2 * bdot + 2.0 * beta) * p[k];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
-    for (int c = 0; c < 3; ++c) C[3 * i + c] = v3[i] * w[c] + beta6 * w[i] * p[c];
-  C[0] += wp * beta6; C[4] += wp * beta6; C[8] += wp * beta6;
+    for (int c = 0; c < 3; ++c) C[3 * i + c] = v3[i] * w[c] + beta * w[i] * p[c];
+  C[0] += wp * beta; C[4] += wp * beta; C[8] += wp * beta;
   C[1] -= 0.5 * p[2]; C[2] += 0.5 * p[1];
   C[3] += 0.5 * p[2]; C[5] -= 0.5 * p[0];
   C[6] -= 0.5 * p[1]; C[7] += 0.5 * p[0];

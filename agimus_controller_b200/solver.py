@@ -163,6 +163,19 @@ class BatchedShootingProblem:
         self._check(lib().agx_rnea(self._h, _ptr(q), _ptr(v), _ptr(a), q.shape[0], _ptr(tau), self._stream()))
         return tau
 
+    def riccati(self, x0, xs, us, reg: float = 0.0):
+        """calc + calcDiff at ``(xs, us)`` and one backward sweep with fixed regularisation ``reg`` -> ``K, k, status``
+        (``reg = 1e-6`` = the proximal sigma of the reference's CSQP backward pass)."""
+        x0 = self._t(x0, (self.B, self.nx))
+        xs = self._t(xs, (self.B, self.T + 1, self.nx))
+        us = self._t(us, (self.B, self.T, self.nv))
+        K = self._empty(self.B, self.T, self.nv, self.nx)
+        k = self._empty(self.B, self.T, self.nv)
+        status = self._empty(self.B, dtype=torch.int32)
+        self._check(lib().agx_riccati(self._h, _ptr(x0), _ptr(xs), _ptr(us), float(reg), _ptr(K), _ptr(k),
+                                      _ptr(status), self._stream()))
+        return K, k, status
+
     # ------------------------------------------------------------------ solver.solve
     def alloc_outputs(self, with_k: bool = True) -> dict:
         B, T, nx, nv = self.B, self.T, self.nx, self.nv

@@ -143,6 +143,16 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
               double* out_K, double* out_k, double* out_cost, int32_t* out_iters,
               int32_t* out_status, double* out_stop, void* stream);
 
+/* One calc + calcDiff at (xs, us) followed by ONE backward Riccati sweep with the fixed regularisation `reg`
+ * added to Quu and to the diagonal of every Vxx (no retry on failure).  With reg = 1e-6 this is the backward
+ * pass of the solver the reference instantiates (mim_solvers.SolverCSQP, ocp_base_croco.py:64, unconstrained
+ * case, proximal sigma = 1e-6) and reproduces the gains of the reference's golden file
+ * (agimus_controller/tests/test_ocp_croco_base.py:175-204).  Gaps are x0 - xs_0 and xnext_t - xs_{t+1}.
+ * Out: out_K [B][T][nu][nx], out_k [B][T][nu] (may be NULL), out_status [B] (may be NULL;
+ * AGX_STATUS_REGMAX = the sweep failed). */
+int agx_riccati(agx_handle* h, const double* x0, const double* xs, const double* us, double reg, double* out_K,
+                double* out_k, int32_t* out_status, void* stream);
+
 /* Optional device timing of the solve's three phases (bench evidence, off by default): while enabled,
  * agx_solve brackets every calc_diff / backward / forward launch with a CUDA event pair on `stream`.
  * agx_get_timing synchronises on those events, adds the elapsed milliseconds and launch counts per phase

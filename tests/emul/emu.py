@@ -139,3 +139,14 @@ def solve(models, refs, dts, x0, xs_ws, us_ws, max_iter, opts=None):
         _p(out["K"]), _p(out["k"]), _p(out["cost"]), _p(out["iters"]), _p(out["status"]), _p(out["stop"]), None))
     out["launches"] = lib().agx_launch_count(h.h)
     return out
+
+
+def riccati(m, refs, dts, x0, xs, us, reg):
+    """Single problem, same signature as ``orc.riccati_sigma`` (returns K, k, status)."""
+    xs, us, x0 = _c(xs)[None], _c(us)[None], _c(x0)[None]
+    T, nv = us.shape[1], us.shape[2]
+    h = _handle(m, _c(refs)[None], dts, 1, T)
+    K, k = np.zeros((1, T, nv, 2 * nv)), np.zeros((1, T, nv))
+    status = np.zeros(1, dtype=np.int32)
+    h.check(lib().agx_riccati(h.h, _p(x0), _p(xs), _p(us), float(reg), _p(K), _p(k), _p(status), None))
+    return K[0], k[0], int(status[0])
