@@ -69,6 +69,7 @@ int env_cta(const char* name, int dflt) {
 }
 const int NODE_CTA = env_cta("AGX_NODE_CTA", 64);
 const int SEQ_CTA = env_cta("AGX_SEQ_CTA", 32);
+const int COST_CTA = env_cta("AGX_COST_CTA", 128);  // thread-per-node cost kernel
 
 // agx_model -> device table (agx_octet_base.h layout).  Returns false for shapes the kernels do not
 // cover yet: anything but a 7-joint serial chain of revolute-z joints.
@@ -188,7 +189,7 @@ int agx_destroy(agx_handle* h) {
   {
     DeviceGuard g(h->device);
     dev_free(h->d_model); dev_free(h->d_refs); dev_free(h->d_dts); dev_free(h->d_x0); dev_free(h->d_K_internal);
-    dev_free(h->W.xs); dev_free(h->W.us); dev_free(h->W.rec); dev_free(h->W.fs); dev_free(h->W.gv); dev_free(h->W.k);
+    dev_free(h->W.xs); dev_free(h->W.us); dev_free(h->W.rec); dev_free(h->W.crec); dev_free(h->W.fs); dev_free(h->W.gv); dev_free(h->W.k);
     dev_free(h->state_block);
 #if AGX_GPU
     for (int i = 0; i < h->ev_made; ++i) cudaEventDestroy(h->ev[i]);
@@ -231,18 +232,21 @@ int agx_create(const agx_model* models_host, int n_models, const double* dts_hos
   ok = ok && dev_alloc((void**)&h->W.xs, sizeof(double) * 2 * nB * T1 * NX);
   ok = ok && dev_alloc((void**)&h->W.us, sizeof(double) * 2 * nB * T * NJ);
   ok = ok && dev_alloc((void**)&h->W.rec, sizeof(double) * nB * T1 * REC_SIZE);
+  ok = ok && dev_alloc((void**)&h->W.crec, sizeof(double) * nB * T1 * CREC_SIZE);
   ok = ok && dev_alloc((void**)&h->W.fs, sizeof(double) * nB * T1 * NX);
   ok = ok && dev_alloc((void**)&h->W.gv, sizeof(double) * nB * T1 * NX);
   ok = ok && dev_alloc((void**)&h->W.k, sizeof(double) * nB * T * NJ);
-  // solver state: 5 double arrays + 7 int arrays in one block
-  const size_t state_bytes = nB * (5 * sizeof(double) + 7 * sizeof(int32_t)) + 64;
+  // solver state: 6 double arrays + 10 int arrays in one block
+  const size_t state_bytes = nB * (6 * sizeof(double) + 10 * sizeof(int32_t)) + 64;
   ok = ok && dev_alloc(&h->state_block, state_bytes);
   if (!ok) { std::free(tab); return fail(h, AGX_ENOMEM, "device allocation failed"); }
   double* dp = (double*)h->state_block;
   h->S.xreg = dp; h->S.cost = dp + nB; h->S.dg = dp + 2 * nB; h->S.dq = dp + 3 * nB; h->S.stop = dp + 4 * nB;
-  int32_t* ip = (int32_t*)(dp + 5 * nB);
+  h->S.dv = dp + 5 * nB;
+  int32_t* ip = (int32_t*)(dp + 6 * nB);
   h->S.is_feasible = ip; h->S.was_feasible = ip + nB; h->S.recalc = ip + 2 * nB; h->S.done = ip + 3 * nB;
   h->S.status = ip + 4 * nB; h->S.iters = ip + 5 * nB; h->S.cur = ip + 6 * nB;
+  h->S.recalc_cost = ip + 7 * nB; h->S.pending = ip + 8 * nB; h->S.roll_ok = ip + 9 * nB;
   ok = copy_h2d(h->d_model, tab, sizeof(double) * MODEL_SIZE * n_models, 0) && copy_h2d(h->d_dts, dts_host, sizeof(double) * T, 0);
 #if AGX_GPU
   ok = ok && cudaStreamSynchronize(0) == cudaSuccess;
@@ -278,9 +282,11 @@ int agx_calc_diff(agx_handle* h, const double* xs, const double* us, double* out
   const int opc = NODE_CTA / 8;
   AGX_LAUNCH(h, calc_diff_kernel, (ents + opc - 1) / opc, NODE_CTA, sizeof(double) * OCT_BOARD * opc, (stream_t)stream,
              problem_of(h), xs, us, (const int32_t*)nullptr, (const int32_t*)nullptr, (const int32_t*)nullptr, h->W.rec);
+  AGX_LAUNCH(h, node_cost_kernel<true>, (ents + COST_CTA - 1) / COST_CTA, COST_CTA, 0, (stream_t)stream, problem_of(h), xs,
+             us, (const int32_t*)nullptr, 0, (const int32_t*)nullptr, (const int32_t*)nullptr, h->W.crec, (double*)nullptr);
   const long long rows = ents * NX;
   AGX_LAUNCH(h, expand_kernel, (rows + 127) / 128, 128, 0, (stream_t)stream, problem_of(h), (const double*)h->W.rec,
-             out_cost, out_xnext, Fx, Fu, Lx, Lu, Lxx, Lxu, Luu);
+             (const double*)h->W.crec, out_cost, out_xnext, Fx, Fu, Lx, Lu, Lxx, Lxu, Luu);
   return check_launch(h, "agx_calc_diff");
 }
 
@@ -337,6 +343,9 @@ int agx_riccati(agx_handle* h, const double* x0, const double* xs, const double*
   AGX_LAUNCH(h, calc_diff_kernel, (ents + opc_n - 1) / opc_n, NODE_CTA, sizeof(double) * OCT_BOARD * opc_n, st, P,
              (const double*)W.xs, (const double*)W.us, (const int32_t*)h->S.cur, (const int32_t*)h->S.recalc,
              (const int32_t*)h->S.done, W.rec);
+  AGX_LAUNCH(h, node_cost_kernel<true>, (ents + COST_CTA - 1) / COST_CTA, COST_CTA, 0, st, P, (const double*)W.xs,
+             (const double*)W.us, (const int32_t*)h->S.cur, 0, (const int32_t*)h->S.done,
+             (const int32_t*)h->S.recalc_cost, W.crec, (double*)nullptr);
   AGX_LAUNCH(h, backward_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * BW_SIZE * opc_s, st, P, W, h->S, O);
   bool ok = true;
   if (out_k) ok = ok && copy_d2d(out_k, W.k, sizeof(double) * nB * T * NJ, st);
@@ -456,17 +465,28 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
   AGX_LAUNCH(h, init_kernel, (n_init + 255) / 256, 256, 0, st, P, W, h->S, O, xs_ws, us_ws);
   const long long ents = (long long)(nB * T1);
   const int opc_n = NODE_CTA / 8, opc_s = SEQ_CTA / 8;
+  const long long cost_ctas = (ents + COST_CTA - 1) / COST_CTA;
   for (int it = 0; it < max_iter; ++it) {
+    // problem.calc + calcDiff at the candidate: dynamics records (octets) + cost records (threads); after an
+    // alpha = 1 acceptance the cost records are already there (written for the trial) and that launch is a no-op
     phase_begin(h, 0, st);
     AGX_LAUNCH(h, calc_diff_kernel, (ents + opc_n - 1) / opc_n, NODE_CTA, sizeof(double) * OCT_BOARD * opc_n, st, P,
                (const double*)W.xs, (const double*)W.us, (const int32_t*)h->S.cur, (const int32_t*)h->S.recalc,
                (const int32_t*)h->S.done, W.rec);
+    AGX_LAUNCH(h, node_cost_kernel<true>, cost_ctas, COST_CTA, 0, st, P, (const double*)W.xs, (const double*)W.us,
+               (const int32_t*)h->S.cur, 0, (const int32_t*)h->S.done, (const int32_t*)h->S.recalc_cost, W.crec,
+               (double*)nullptr);
     phase_end(h, st);
     phase_begin(h, 1, st);
     AGX_LAUNCH(h, backward_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * BW_SIZE * opc_s, st, P, W, h->S, O);
     phase_end(h, st);
     phase_begin(h, 2, st);
-    AGX_LAUNCH(h, forward_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * FW_BOARD * opc_s, st, P, W,
+    AGX_LAUNCH(h, rollout_try_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * FW_BOARD * opc_s, st, P, W,
+               h->S);
+    AGX_LAUNCH(h, node_cost_kernel<true>, cost_ctas, COST_CTA, 0, st, P, (const double*)W.xs, (const double*)W.us,
+               (const int32_t*)h->S.cur, 1, (const int32_t*)h->S.done, (const int32_t*)nullptr, W.crec, (double*)nullptr);
+    AGX_LAUNCH(h, accept_kernel, (h->B + 127) / 128, 128, 0, st, P, W, h->S, O);
+    AGX_LAUNCH(h, linesearch_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * FW_BOARD * opc_s, st, P, W,
                h->S, O);
     phase_end(h, st);
   }

@@ -44,7 +44,8 @@ struct FddpOpts {
 struct Work {
   double* xs;    // [2][B][T+1][NX]   candidate / trial, selected per problem by SolverState::cur
   double* us;    // [2][B][T][NJ]
-  double* rec;   // [B][T+1][REC_SIZE]
+  double* rec;   // [B][T+1][REC_SIZE]   dynamics records
+  double* crec;  // [B][T+1][CREC_SIZE]  cost records
   double* fs;    // [B][T+1][NX]      gaps
   double* gv;    // [B][T+1][NX]      Vxx_t fs_t
   double* K;     // [B][T][NJ][NX]
@@ -75,45 +76,15 @@ AGX_DEV void lane_load_state(LaneDyn& d, int j, const double* x, const double* u
 }
 
 // ---------------------------------------------------------------------------------------------
-// calc + calcDiff of one node; writes the compact record.  Returns the node cost (scaled).
-AGX_DEV double node_calc_diff(LaneDyn& d, int j, unsigned omask, const double* __restrict__ model,
-                              const double* __restrict__ ref, double dt, bool terminal, double* sb, double* sc,
-                              double* __restrict__ rec) {
+// Dynamics part of calc + calcDiff of one running node: xnext, dt da/dq, dt da/dv, dt Minv columns
+// into the compact record.  A failed factorisation leaves NaNs (they make the sweep fail).
+AGX_DEV void node_dyn_diff(LaneDyn& d, int j, unsigned omask, const double* __restrict__ model, double dt, double* sb,
+                           double* sc, double* __restrict__ rec) {
   node_kinematics(d, j, omask, model);
-  const bool live = j < NJ;
-  const int jj = live ? j : 0;
-  const double sc_l = terminal ? 1.0 : dt;  // cost scaling of the integrated model (terminal: unscaled)
-  double l;
-  {
-    // cost terms go straight to the record so that their registers are free during the dynamics
-    double lq, lv, lu, Lqq[NJ];
-    l = node_costs<true>(d, j, omask, model, ref, terminal, sb, &lq, &lv, &lu, Lqq);
-    const double wv = live ? ref[NX + NJ + jj] : 0.0;
-    const double wu = (live && !terminal) ? ref[2 * NX + NJ + jj] : 0.0;
-#pragma unroll
-    for (int i = 0; i < NJ; ++i) rec[(RK_LQQ + i) * 8 + j] = sc_l * Lqq[i];
-    rec[RK_LVV * 8 + j] = sc_l * wv;
-    rec[RK_LUU * 8 + j] = sc_l * wu;
-    rec[RK_LQ * 8 + j] = sc_l * lq;
-    rec[RK_LV * 8 + j] = sc_l * lv;
-    rec[RK_LU * 8 + j] = sc_l * lu;
-  }
-  if (terminal) {
-#pragma unroll
-    for (int i = 0; i < NJ; ++i) {
-      rec[(RK_AQ + i) * 8 + j] = 0.0;
-      rec[(RK_AV + i) * 8 + j] = 0.0;
-      rec[(RK_MI + i) * 8 + j] = 0.0;
-    }
-    rec[RK_QN * 8 + j] = d.q;
-    rec[RK_VN * 8 + j] = d.qd;
-    rec[RK_COST * 8 + j] = l;
-    return l;
-  }
   double L[28], rinv[NJ];
   const bool ok = node_forward_dynamics<true>(d, j, omask, model, sb, sc, L, rinv);
-  rec[RK_QN * 8 + j] = d.q + (d.qd * dt + d.qdd * (dt * dt));
-  rec[RK_VN * 8 + j] = d.qd + d.qdd * dt;
+  rec[RK_QN * 8 + j] = ok ? d.q + (d.qd * dt + d.qdd * (dt * dt)) : nan("");
+  rec[RK_VN * 8 + j] = ok ? d.qd + d.qdd * dt : nan("");
   node_rnea_derivatives(d, j, omask, sb);
   AGX_OSYNC();
   factor_reload(sc, L, rinv);
@@ -130,9 +101,6 @@ AGX_DEV double node_calc_diff(LaneDyn& d, int j, unsigned omask, const double* _
   solve_column(L, rinv, ej, dt, col);
 #pragma unroll
   for (int i = 0; i < NJ; ++i) rec[(RK_MI + i) * 8 + j] = col[i];
-  const double cost = ok ? dt * l : nan("");
-  rec[RK_COST * 8 + j] = cost;
-  return cost;
 }
 
 // calc of one node: cost (scaled) and this lane's entries of xnext.  Returns false on failure.
@@ -163,10 +131,8 @@ AGX_DEV size_t buf_of(const int32_t* cur, int b, bool other) {
   return (size_t)(other ? (c ^ 1) : c);
 }
 
-#ifndef AGX_CD_MINB
-#define AGX_CD_MINB 4
-#endif
-__global__ void __launch_bounds__(64, AGX_CD_MINB) calc_diff_kernel(Problem P, const double* __restrict__ xs, const double* __restrict__ us,
+// problem.calcDiff, dynamics part: one octet per (problem, node)
+__global__ void calc_diff_kernel(Problem P, const double* __restrict__ xs, const double* __restrict__ us,
                                  const int32_t* __restrict__ cur, const int32_t* __restrict__ recalc,
                                  const int32_t* __restrict__ done, double* __restrict__ rec) {
   AGX_SMEM(smem);
@@ -180,12 +146,46 @@ __global__ void __launch_bounds__(64, AGX_CD_MINB) calc_diff_kernel(Problem P, c
   double* sc = sb + BRD_B;
   const size_t buf = buf_of(cur, b, false);
   const double* x = xs + ((buf * P.B + b) * T1 + t) * NX;
-  const bool terminal = t == P.T;
-  const double* u = terminal ? nullptr : us + ((buf * P.B + b) * P.T + t) * NJ;
+  double* R = rec + (size_t)ent * REC_SIZE;
+  if (t == P.T) {
+    // terminal model (dt = 0): xnext = x, no dynamics derivatives
+    const bool live = j < NJ;
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) {
+      R[(RK_AQ + i) * 8 + j] = 0.0;
+      R[(RK_AV + i) * 8 + j] = 0.0;
+      R[(RK_MI + i) * 8 + j] = 0.0;
+    }
+    R[RK_QN * 8 + j] = live ? x[j] : 0.0;
+    R[RK_VN * 8 + j] = live ? x[NJ + j] : 0.0;
+    return;
+  }
   LaneDyn d;
-  lane_load_state(d, j, x, u);
-  node_calc_diff(d, j, omask, model_of(P, b), P.refs + (size_t)ent * REF_SIZE, terminal ? 0.0 : P.dts[t], terminal, sb,
-                 sc, rec + (size_t)ent * REC_SIZE);
+  lane_load_state(d, j, x, us + ((buf * P.B + b) * P.T + t) * NJ);
+  node_dyn_diff(d, j, omask, model_of(P, b), P.dts[t], sb, sc, R);
+}
+
+// problem.calc / calcDiff, cost part: ONE THREAD per (problem, node).  `other` selects the trial buffer
+// (the candidate being evaluated by the line search); `gate` (may be null) restricts the work to problems
+// whose flag is non-zero.  DERIV: the cost part of the node record is (re)written.
+template <bool DERIV>
+__global__ void node_cost_kernel(Problem P, const double* __restrict__ xs, const double* __restrict__ us,
+                                 const int32_t* __restrict__ cur, int other, const int32_t* __restrict__ done,
+                                 const int32_t* __restrict__ gate, double* __restrict__ rec,
+                                 double* __restrict__ out_cost) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int T1 = P.T + 1;
+  if (n >= (long long)P.B * T1) return;
+  const int b = (int)(n / T1), t = (int)(n % T1);
+  if (done && done[b]) return;
+  if (gate && !gate[b]) return;
+  const size_t buf = buf_of(cur, b, other != 0);
+  const bool terminal = t == P.T;
+  const double* x = xs + ((buf * P.B + b) * T1 + t) * NX;
+  const double* u = terminal ? nullptr : us + ((buf * P.B + b) * P.T + t) * NJ;
+  const double c = thread_node_cost<DERIV>(model_of(P, b), P.refs + (size_t)n * REF_SIZE, x, u, terminal,
+                                           terminal ? 1.0 : P.dts[t], DERIV ? rec + (size_t)n * CREC_SIZE : nullptr);
+  if (out_cost) out_cost[n] = c;
 }
 
 __global__ void calc_kernel(Problem P, const double* __restrict__ xs, const double* __restrict__ us,
@@ -212,7 +212,8 @@ __global__ void calc_kernel(Problem P, const double* __restrict__ xs, const doub
 }
 
 // dense view of the records (problem.calcDiff data: Fx Fu Lx Lu Lxx Lxu Luu); one thread per (node, row)
-__global__ void expand_kernel(Problem P, const double* __restrict__ rec, double* out_cost, double* out_xnext,
+__global__ void expand_kernel(Problem P, const double* __restrict__ rec, const double* __restrict__ crec,
+                              double* out_cost, double* out_xnext,
                               double* Fx, double* Fu, double* Lx, double* Lu, double* Lxx, double* Lxu, double* Luu) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int T1 = P.T + 1;
@@ -223,12 +224,13 @@ __global__ void expand_kernel(Problem P, const double* __restrict__ rec, double*
   const bool terminal = t == P.T;
   const double h = terminal ? 0.0 : P.dts[t];
   const double* R = rec + (size_t)n * REC_SIZE;
+  const double* C = crec + (size_t)n * CREC_SIZE;
   const int i = r % NJ;        // joint row inside the q / v block
   const bool top = r < NJ;     // q rows
-  if (out_cost && r == 0) out_cost[n] = R[RK_COST * 8];
+  if (out_cost && r == 0) out_cost[n] = C[CK_COST];
   if (out_xnext) out_xnext[n * NX + r] = R[(top ? RK_QN : RK_VN) * 8 + i];
-  if (Lx) Lx[n * NX + r] = R[(top ? RK_LQ : RK_LV) * 8 + i];
-  if (Lu && top) Lu[n * NJ + i] = R[RK_LU * 8 + i];
+  if (Lx) Lx[n * NX + r] = C[(top ? CK_LQ : CK_LV) + i];
+  if (Lu && top) Lu[n * NJ + i] = C[CK_LU + i];
 #pragma unroll
   for (int c = 0; c < NJ; ++c) {
     const double aq = R[(RK_AQ + i) * 8 + c], av = R[(RK_AV + i) * 8 + c], mi = R[(RK_MI + i) * 8 + c];
@@ -240,11 +242,11 @@ __global__ void expand_kernel(Problem P, const double* __restrict__ rec, double*
     }
     if (Fu) Fu[(n * NX + r) * NJ + c] = s * mi;
     if (Lxx) {
-      Lxx[(n * NX + r) * NX + c] = top ? R[(RK_LQQ + i) * 8 + c] : 0.0;
-      Lxx[(n * NX + r) * NX + NJ + c] = (!top && c == i) ? R[RK_LVV * 8 + i] : 0.0;
+      Lxx[(n * NX + r) * NX + c] = top ? C[CK_LQQ + (i >= c ? lidx(i, c) : lidx(c, i))] : 0.0;
+      Lxx[(n * NX + r) * NX + NJ + c] = (!top && c == i) ? C[CK_LVV + i] : 0.0;
     }
     if (Lxu) Lxu[(n * NX + r) * NJ + c] = 0.0;
-    if (Luu && top) Luu[(n * NJ + i) * NJ + c] = (c == i) ? R[RK_LUU * 8 + i] : 0.0;
+    if (Luu && top) Luu[(n * NJ + i) * NJ + c] = (c == i) ? C[CK_LUU + i] : 0.0;
   }
 }
 
@@ -280,6 +282,7 @@ __global__ void backward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
   const size_t buf = buf_of(S.cur, b, false);
   const double* xs = W.xs + (buf * P.B + b) * (size_t)T1 * NX;
   const double* rec0 = W.rec + (size_t)b * T1 * REC_SIZE;
+  const double* crec0 = W.crec + (size_t)b * T1 * CREC_SIZE;
   double* fsb = W.fs + (size_t)b * T1 * NX;
   double* gvb = W.gv + (size_t)b * T1 * NX;
   double* Kb = W.K + (size_t)b * T * NJ * NX;
@@ -289,7 +292,7 @@ __global__ void backward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
 
   // total cost of the candidate and the gaps (SolverAbstract::computeDynamicFeasibility)
   double cost = 0.0;
-  for (int t = 0; t <= T; ++t) cost += rec0[(size_t)t * REC_SIZE + RK_COST * 8];
+  for (int t = 0; t <= T; ++t) cost += crec0[(size_t)t * CREC_SIZE + CK_COST];
   if (!feasible && live) {
     fsb[j] = W.x0[(size_t)b * NX + j] - xs[j];
     fsb[NJ + j] = W.x0[(size_t)b * NX + NJ + j] - xs[NJ + j];
@@ -309,21 +312,21 @@ __global__ void backward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
     double dgp = 0.0, dqp = 0.0;  // per-lane partial sums
     if (ok) {
       // ---- terminal node
-      const double* R = rec0 + (size_t)T * REC_SIZE;
+      const double* C = crec0 + (size_t)T * CREC_SIZE;
 #pragma unroll
       for (int i = 0; i < NJ; ++i) {
-        V0[i] = live ? R[(RK_LQQ + i) * 8 + jj] : 0.0;
+        V0[i] = live ? C[CK_LQQ + (i >= jj ? lidx(i, jj) : lidx(jj, i))] : 0.0;
         V0[NJ + i] = 0.0;
         V1[i] = 0.0;
         V1[NJ + i] = 0.0;
       }
-      const double lvv = live ? R[RK_LVV * 8 + jj] : 0.0;
+      const double lvv = live ? C[CK_LVV + jj] : 0.0;
 #pragma unroll
       for (int i = 0; i < NJ; ++i) {
         if (i == j) { V0[i] += xreg; V1[NJ + i] = lvv + xreg; }
       }
-      vx0 = live ? R[RK_LQ * 8 + jj] : 0.0;
-      vx1 = live ? R[RK_LV * 8 + jj] : 0.0;
+      vx0 = live ? C[CK_LQ + jj] : 0.0;
+      vx1 = live ? C[CK_LV + jj] : 0.0;
       if (!feasible) {
         if (live) { sm[BW_FS + j] = fsb[T * NX + j]; sm[BW_FS + NJ + j] = fsb[T * NX + NJ + j]; }
         AGX_OSYNC();
@@ -342,13 +345,14 @@ __global__ void backward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
     // ---- running nodes
     for (int t = T - 1; ok && t >= 0; --t) {
       const double* R = rec0 + (size_t)t * REC_SIZE;
+      const double* C = crec0 + (size_t)t * CREC_SIZE;
       const double h = P.dts[t];
       if (t > 0) {
-        // pull the next node's record (18 x 128 B) towards the SM while this node is processed
+        // pull the next node's records (1472 + 512 B) towards the SM while this node is processed
         const double* Rn = R - REC_SIZE;
         AGX_PREFETCH(Rn + j * 16);
-        AGX_PREFETCH(Rn + 128 + j * 16);
-        if (j < 2) AGX_PREFETCH(Rn + 256 + j * 16);
+        if (j < 4) AGX_PREFETCH(Rn + 128 + j * 16);
+        if (j < 4) AGX_PREFETCH(C - CREC_SIZE + j * 16);
       }
       double G0[NJ], G1[NJ], Nc[NJ], Lqq[NJ];
 #pragma unroll
@@ -356,11 +360,11 @@ __global__ void backward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
         G0[i] = live ? R[(RK_AQ + i) * 8 + jj] : 0.0;
         G1[i] = (live ? R[(RK_AV + i) * 8 + jj] : 0.0) + ((i == j) ? 1.0 : 0.0);
         Nc[i] = live ? R[(RK_MI + i) * 8 + jj] : 0.0;
-        Lqq[i] = live ? R[(RK_LQQ + i) * 8 + jj] : 0.0;
+        Lqq[i] = live ? C[CK_LQQ + (i >= jj ? lidx(i, jj) : lidx(jj, i))] : 0.0;
       }
-      const double lvv = live ? R[RK_LVV * 8 + jj] : 0.0, luu = live ? R[RK_LUU * 8 + jj] : 0.0;
-      const double lq = live ? R[RK_LQ * 8 + jj] : 0.0, lv = live ? R[RK_LV * 8 + jj] : 0.0;
-      const double lu = live ? R[RK_LU * 8 + jj] : 0.0;
+      const double lvv = live ? C[CK_LVV + jj] : 0.0, luu = live ? C[CK_LUU + jj] : 0.0;
+      const double lq = live ? C[CK_LQ + jj] : 0.0, lv = live ? C[CK_LV + jj] : 0.0;
+      const double lu = live ? C[CK_LU + jj] : 0.0;
       double Z0[NJ], Z1[NJ];
 #pragma unroll
       for (int i = 0; i < NJ; ++i) {
@@ -565,13 +569,166 @@ __global__ void backward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Line search + acceptance + regularisation / stop logic of one FDDP iteration.
-__global__ void forward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
+// Forward pass of one FDDP iteration, split so that the common case costs little:
+//   rollout_try_kernel  (octet per problem)  nonlinear rollout with alpha = 1, dynamics only
+//   node_cost_kernel    (thread per node)    costs (+ their derivatives) of the trial trajectory
+//   accept_kernel       (thread per problem) dV / dVexp acceptance test, buffer flip, reg / stop logic
+//   linesearch_kernel   (octet per problem)  only for problems whose alpha = 1 trial was rejected:
+//                                            alpha = 1/2, 1/4, ... with the costs evaluated in line
+// (SolverFDDP::forwardPass / tryStep / expectedImprovement and the tail of the solve loop).
+
+// end-of-iteration bookkeeping shared by accept_kernel and linesearch_kernel (one thread per problem)
+AGX_DEV void finish_iteration(const SolverState& S, const FddpOpts& O, int b, bool accepted, double steplength,
+                              bool feasible, double cost_try, int obuf, bool fast_path) {
+  bool was_feasible = S.was_feasible[b] != 0;
+  if (accepted) {
+    was_feasible = feasible;
+    S.was_feasible[b] = feasible ? 1 : 0;
+    S.is_feasible[b] = (feasible || steplength == 1.0) ? 1 : 0;
+    S.cost[b] = cost_try;
+    S.cur[b] = (int32_t)obuf;
+    S.recalc[b] = 1;
+    S.recalc_cost[b] = fast_path ? 0 : 1;  // the fast path already wrote the cost records of the new candidate
+  } else {
+    S.recalc[b] = 0;
+    S.recalc_cost[b] = 1;  // the trial's cost records overwrote the candidate's
+  }
+  double xreg = S.xreg[b];
+  int status = 1, done = 0;
+  if (steplength > O.th_stepdec) {
+    xreg /= O.reg_decfactor;
+    if (xreg < O.reg_min) xreg = O.reg_min;
+  }
+  if (steplength <= O.th_stepinc) {
+    xreg *= O.reg_incfactor;
+    if (xreg > O.reg_max) xreg = O.reg_max;
+    if (xreg == O.reg_max) { status = 2; done = 1; }
+  }
+  S.xreg[b] = xreg;
+  S.iters[b] += 1;
+  if (!done && !O.fixed_iters && was_feasible && S.stop[b] < O.th_stop) { status = 0; done = 1; }
+  if (done) { S.status[b] = status; S.done[b] = 1; }
+}
+
+// dV / dVexp test of SolverFDDP::solve
+AGX_DEV bool accept_step(const FddpOpts& O, double dV, double d1, double dVexp) {
+  if (dVexp >= 0.0) return d1 < O.th_grad || dV > O.th_acceptstep * dVexp;
+  return dV > O.th_acceptnegstep * dVexp;
+}
+
+__global__ void rollout_try_kernel(Problem P, Work W, SolverState S) {
   AGX_SMEM(smem);
   AGX_OCTET_SETUP();
   const int b = (int)ent;
   if (b >= P.B) return;
   if (S.done[b]) return;
+  double* sb = smem + oct_in_cta * FW_BOARD;
+  double* sc = sb + BRD_B;
+  double* sdx = sc + BRD_C;  // [14]
+  const int T = P.T, T1 = T + 1;
+  const bool live = j < NJ;
+  const int jj = live ? j : 0;
+  const double* model = model_of(P, b);
+  const size_t buf = buf_of(S.cur, b, false), obuf = buf ^ 1;
+  const double* xs = W.xs + (buf * P.B + b) * (size_t)T1 * NX;
+  const double* us = W.us + (buf * P.B + b) * (size_t)T * NJ;
+  double* xt = W.xs + (obuf * P.B + b) * (size_t)T1 * NX;
+  double* ut = W.us + (obuf * P.B + b) * (size_t)T * NJ;
+  const double* gvb = W.gv + (size_t)b * T1 * NX;
+  const double* Kb = W.K + (size_t)b * T * NJ * NX;
+  const double* kb = W.k + (size_t)b * T * NJ;
+  const bool feasible = S.is_feasible[b] != 0;
+  // per-node inputs are fetched one node ahead (scalars into registers, gain rows into L1)
+  struct NodeIn { double us, kff, dt, xsq, xsv, gq, gv; };
+  auto fetch = [&](int t, NodeIn& n) {
+    const bool run = t < T;
+    n.us = (live && run) ? us[t * NJ + jj] : 0.0;
+    n.kff = (live && run) ? kb[t * NJ + jj] : 0.0;
+    n.dt = run ? P.dts[t] : 0.0;
+    n.xsq = live ? xs[t * NX + jj] : 0.0;
+    n.xsv = live ? xs[t * NX + NJ + jj] : 0.0;
+    const bool gaps = live && !feasible;
+    n.gq = gaps ? gvb[t * NX + jj] : 0.0;
+    n.gv = gaps ? gvb[t * NX + NJ + jj] : 0.0;
+    if (run) {
+      AGX_PREFETCH(Kb + (t * NJ + jj) * NX);
+      AGX_PREFETCH(Kb + (t * NJ + jj) * NX + NX - 1);
+    }
+  };
+  double xq = live ? W.x0[(size_t)b * NX + jj] : 0.0, xv = live ? W.x0[(size_t)b * NX + NJ + jj] : 0.0;
+  double dvp = 0.0;
+  bool ok = true;
+  NodeIn cur;
+  fetch(0, cur);
+  for (int t = 0; t <= T; ++t) {
+    NodeIn nxt;
+    if (t < T) fetch(t + 1, nxt);
+    const double dxq = live ? xq - cur.xsq : 0.0, dxv = live ? xv - cur.xsv : 0.0;
+    if (live) {
+      xt[t * NX + j] = xq;
+      xt[t * NX + NJ + j] = xv;
+    }
+    dvp += cur.gq * dxq + cur.gv * dxv;
+    if (t == T) break;
+    if (live) { sdx[j] = dxq; sdx[NJ + j] = dxv; }
+    AGX_OSYNC();
+    double s = 0.0;
+#pragma unroll
+    for (int m = 0; m < NX; ++m) s += Kb[(t * NJ + jj) * NX + m] * sdx[m];
+    LaneDyn d;
+    d.q = xq; d.qd = xv;
+    d.u = live ? cur.us - cur.kff - s : 0.0;
+    if (live) ut[t * NJ + j] = d.u;
+    node_kinematics(d, j, omask, model);
+    double L[28], rinv[NJ];
+    const bool okn = node_forward_dynamics<false>(d, j, omask, model, sb, sc, L, rinv);
+    ok = ok && okn;
+    xq = d.q + (d.qd * cur.dt + d.qdd * (cur.dt * cur.dt));
+    xv = d.qd + d.qdd * cur.dt;
+    cur = nxt;
+    AGX_OSYNC();
+  }
+  const double dv = feasible ? 0.0 : octet_sum(dvp, omask);
+  if (j == 0) {
+    S.dv[b] = dv;
+    S.roll_ok[b] = ok ? 1 : 0;
+  }
+}
+
+__global__ void accept_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
+  const int b = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (b >= P.B) return;
+  if (S.done[b]) return;
+  const int T1 = P.T + 1;
+  const double* crec0 = W.crec + (size_t)b * T1 * CREC_SIZE;
+  double cost_try = 0.0;
+  for (int t = 0; t < T1; ++t) cost_try += crec0[(size_t)t * CREC_SIZE + CK_COST];
+  const bool finite = S.roll_ok[b] != 0 && (cost_try - cost_try == 0.0);
+  bool accepted = false;
+  const bool feasible = S.is_feasible[b] != 0;
+  if (finite) {
+    const double dv = S.dv[b];
+    const double d1 = S.dg[b] + dv, d2 = S.dq[b] - 2.0 * dv;
+    const double dV = S.cost[b] - cost_try;
+    const double dVexp = d1 + 0.5 * d2;  // steplength = 1
+    S.stop[b] = fabs(d1 + 0.5 * d2);
+    accepted = accept_step(O, dV, d1, dVexp);
+  }
+  if (accepted || O.n_alphas <= 1) {
+    S.pending[b] = 0;
+    finish_iteration(S, O, b, accepted, 1.0, feasible, cost_try, (S.cur[b] & 1) ^ 1, true);
+  } else {
+    S.pending[b] = 1;
+  }
+}
+
+// remaining step lengths alpha = 2^-ia, ia >= 1, for the problems still pending
+__global__ void linesearch_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
+  AGX_SMEM(smem);
+  AGX_OCTET_SETUP();
+  const int b = (int)ent;
+  if (b >= P.B) return;
+  if (S.done[b] || !S.pending[b]) return;
   double* sb = smem + oct_in_cta * FW_BOARD;
   double* sc = sb + BRD_B;
   double* sdx = sc + BRD_C;  // [14]
@@ -593,121 +750,62 @@ __global__ void forward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
   const double cost = S.cost[b], dg = S.dg[b], dq = S.dq[b];
   const double x0q = live ? W.x0[(size_t)b * NX + jj] : 0.0, x0v = live ? W.x0[(size_t)b * NX + NJ + jj] : 0.0;
 
-  // per-node inputs: the small per-lane scalars are fetched one node ahead into registers, the gain rows
-  // and the reference record are pulled into L1 one node ahead (prefetch), so that their HBM/L2 latency
-  // hides behind the node's arithmetic
-  struct NodeIn {
-    double us, kff, dt, xsq, xsv, fq, fv, gq, gv;
-  };
-  auto fetch = [&](int t, NodeIn& n) {
-    const bool run = t < T;
-    n.us = (live && run) ? us[t * NJ + jj] : 0.0;
-    n.kff = (live && run) ? kb[t * NJ + jj] : 0.0;
-    n.dt = run ? P.dts[t] : 0.0;
-    n.xsq = live ? xs[t * NX + jj] : 0.0;
-    n.xsv = live ? xs[t * NX + NJ + jj] : 0.0;
-    const bool gaps = live && !feasible;
-    n.fq = gaps ? fsb[t * NX + jj] : 0.0;
-    n.fv = gaps ? fsb[t * NX + NJ + jj] : 0.0;
-    n.gq = gaps ? gvb[t * NX + jj] : 0.0;
-    n.gv = gaps ? gvb[t * NX + NJ + jj] : 0.0;
-    if (run) {
-      AGX_PREFETCH(Kb + (t * NJ + jj) * NX);
-      AGX_PREFETCH(Kb + (t * NJ + jj) * NX + NX - 1);
-    }
-    if (j < 4) AGX_PREFETCH(refs + (size_t)t * REF_SIZE + j * 16);
-  };
-
-  double steplength = 1.0, d1 = 0.0, d2 = 0.0, cost_try = 0.0;
-  bool accepted = false, have_d = false;
-  for (int ia = 0; ia < O.n_alphas; ++ia) {
+  double steplength = 1.0, cost_try = 0.0, stop = S.stop[b];
+  bool accepted = false;
+  for (int ia = 1; ia < O.n_alphas; ++ia) {
     steplength = ldexp(1.0, -ia);
-    const bool contract = !(feasible || ia == 0);
+    const bool contract = !feasible;
     double xq = x0q, xv = x0v;
     double ctry = 0.0, dvp = 0.0;
     bool ok = true;
-    NodeIn cur;
-    fetch(0, cur);
     for (int t = 0; t <= T; ++t) {
-      NodeIn nxt;
-      if (t < T) fetch(t + 1, nxt);
       double tq = xq, tv = xv;
-      if (contract) {
-        tq += cur.fq * (steplength - 1.0);
-        tv += cur.fv * (steplength - 1.0);
+      if (contract && live) {
+        tq += fsb[t * NX + j] * (steplength - 1.0);
+        tv += fsb[t * NX + NJ + j] * (steplength - 1.0);
       }
-      const double dxq = live ? tq - cur.xsq : 0.0, dxv = live ? tv - cur.xsv : 0.0;
+      const double dxq = live ? tq - xs[t * NX + jj] : 0.0, dxv = live ? tv - xs[t * NX + NJ + jj] : 0.0;
       if (live) {
         xt[t * NX + j] = tq;
         xt[t * NX + NJ + j] = tv;
+        if (!feasible) dvp += gvb[t * NX + j] * dxq + gvb[t * NX + NJ + j] * dxv;
       }
-      dvp += cur.gq * dxq + cur.gv * dxv;
       LaneDyn d;
       d.q = tq; d.qd = tv; d.u = 0.0;
       const bool terminal = t == T;
       if (!terminal) {
         if (live) { sdx[j] = dxq; sdx[NJ + j] = dxv; }
         AGX_OSYNC();
-        double s = 0.0;
+        if (live) {
+          double s = 0.0;
 #pragma unroll
-        for (int m = 0; m < NX; ++m) s += Kb[(t * NJ + jj) * NX + m] * sdx[m];
-        d.u = cur.us - cur.kff * steplength - s;
-        if (live) ut[t * NJ + j] = d.u;
+          for (int m = 0; m < NX; ++m) s += Kb[(t * NJ + j) * NX + m] * sdx[m];
+          d.u = us[t * NJ + j] - kb[t * NJ + j] * steplength - s;
+          ut[t * NJ + j] = d.u;
+        }
       }
       double c, qn, vn;
-      const bool okn = node_calc(d, j, omask, model, refs + (size_t)t * REF_SIZE, cur.dt, terminal, sb, sc, &c, &qn, &vn);
+      const bool okn = node_calc(d, j, omask, model, refs + (size_t)t * REF_SIZE, terminal ? 0.0 : P.dts[t], terminal,
+                                 sb, sc, &c, &qn, &vn);
       ok = ok && okn;
       ctry += c;
       xq = qn; xv = vn;
       if (!(ctry - ctry == 0.0)) { ok = false; break; }  // NaN / inf: reject this step length
-      if (t < T) cur = nxt;
     }
     if (!ok) continue;
     cost_try = ctry;
     const double dv = feasible ? 0.0 : octet_sum(dvp, omask);
     const double dV = cost - cost_try;
-    d1 = dg + dv;
-    d2 = dq - 2.0 * dv;
-    have_d = true;
+    const double d1 = dg + dv, d2 = dq - 2.0 * dv;
+    stop = fabs(d1 + 0.5 * d2);
     const double dVexp = steplength * (d1 + 0.5 * steplength * d2);
-    if (dVexp >= 0.0) {
-      if (d1 < O.th_grad || dV > O.th_acceptstep * dVexp) accepted = true;
-    } else {
-      if (dV > O.th_acceptnegstep * dVexp) accepted = true;
-    }
+    accepted = accept_step(O, dV, d1, dVexp);
     if (accepted) break;
   }
   if (j == 0) {
-    bool was_feasible = S.was_feasible[b] != 0;
-    if (accepted) {
-      was_feasible = feasible;
-      S.was_feasible[b] = feasible ? 1 : 0;
-      S.is_feasible[b] = (feasible || steplength == 1.0) ? 1 : 0;
-      S.cost[b] = cost_try;
-      S.cur[b] = (int32_t)obuf;
-      S.recalc[b] = 1;
-    } else {
-      S.recalc[b] = 0;
-    }
-    double xreg = S.xreg[b];
-    int status = 1, done = 0;
-    if (steplength > O.th_stepdec) {
-      xreg /= O.reg_decfactor;
-      if (xreg < O.reg_min) xreg = O.reg_min;
-    }
-    if (steplength <= O.th_stepinc) {
-      xreg *= O.reg_incfactor;
-      if (xreg > O.reg_max) xreg = O.reg_max;
-      if (xreg == O.reg_max) { status = 2; done = 1; }
-    }
-    S.xreg[b] = xreg;
-    S.iters[b] += 1;
-    if (!done) {
-      const double stop = have_d ? fabs(d1 + 0.5 * d2) : S.stop[b];
-      S.stop[b] = stop;
-      if (!O.fixed_iters && was_feasible && stop < O.th_stop) { status = 0; done = 1; }
-    }
-    if (done) { S.status[b] = status; S.done[b] = 1; }
+    S.stop[b] = stop;
+    S.pending[b] = 0;
+    finish_iteration(S, O, b, accepted, steplength, feasible, cost_try, (int)obuf, false);
   }
 }
 
@@ -802,6 +900,7 @@ __global__ void init_kernel(Problem P, Work W, SolverState S, FddpOpts O, const 
     S.cost[b] = 0.0; S.dg[b] = 0.0; S.dq[b] = 0.0; S.stop[b] = 0.0;
     S.is_feasible[b] = 0; S.was_feasible[b] = 0; S.recalc[b] = 1; S.done[b] = 0;
     S.status[b] = 1; S.iters[b] = 0; S.cur[b] = 0;
+    S.dv[b] = 0.0; S.recalc_cost[b] = 1; S.pending[b] = 0; S.roll_ok[b] = 0;
   }
 }
 

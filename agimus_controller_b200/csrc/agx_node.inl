@@ -180,6 +180,123 @@ AGX_DEV double node_costs(const LaneDyn& d, int j, unsigned omask, const double*
   return cost;
 }
 
+// ---------------------------------------------------------------------------------------------
+// One node's cost terms on ONE THREAD (32 nodes per warp): sequential forward kinematics, frame
+// placement residual r = log6(Mref^-1 oMf) with Pinocchio's branches, Rq = Jlog6 * fJf, weighted-quad
+// Gauss-Newton terms.  The log maps are scalar code: run once per octet they waste 7/8 of the lanes,
+// run one node per thread they do not.  With DERIV the cost record of the node is written
+// (scaled by s = dt, or 1 for the terminal node).  Returns the scaled node cost.
+template <bool DERIV>
+AGX_DEV double thread_node_cost(const double* __restrict__ model, const double* __restrict__ ref,
+                                const double* __restrict__ x, const double* __restrict__ u, bool terminal, double s,
+                                double* __restrict__ rec) {
+  const int fpar = (int)model[MT_FP + 3];
+  // forward kinematics down the chain; world joint axes J_i = [p_i x z_i; z_i]
+  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0};
+  double Rf0[9], pf0[3];
+  double Jw[NJ][6];
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) {
+    double sq, cq;
+    AGX_SINCOS(x[i], &sq, &cq);
+    double Rl[9], pl[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const double a = model[(MF_RP + 3 * r) * 8 + i], b = model[(MF_RP + 3 * r + 1) * 8 + i];
+      Rl[3 * r] = cq * a + sq * b;
+      Rl[3 * r + 1] = cq * b - sq * a;
+      Rl[3 * r + 2] = model[(MF_RP + 3 * r + 2) * 8 + i];
+      pl[r] = model[(MF_PP + r) * 8 + i];
+    }
+    double Rn[9], pn[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) Rn[3 * r + c] = R[3 * r] * Rl[c] + R[3 * r + 1] * Rl[3 + c] + R[3 * r + 2] * Rl[6 + c];
+      pn[r] = p[r] + (R[3 * r] * pl[0] + R[3 * r + 1] * pl[1] + R[3 * r + 2] * pl[2]);
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[k] = Rn[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) p[k] = pn[k];
+    if (DERIV) {
+      const double z[3] = {R[2], R[5], R[8]};
+      double pz[3];
+      cross3(p, z, pz);
+      const double moves = (i <= fpar) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { Jw[i][k] = moves * pz[k]; Jw[i][3 + k] = moves * z[k]; }
+    }
+    if (i == fpar) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) Rf0[k] = R[k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) pf0[k] = p[k];
+    }
+  }
+  const double* Rref = ref + 2 * NX + 2 * NJ;
+  const double* pref = Rref + 9;
+  const double* wp = pref + 3;
+  double Rf[9], pf[3], r6[6], Jl[18];
+  frame_residual(Rf0, pf0, model, Rref, pref, Rf, pf, r6, DERIV ? Jl : nullptr);
+  double cost = 0.0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) cost += 0.5 * wp[k] * r6[k] * r6[k];
+  double wr6[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) wr6[k] = wp[k] * r6[k];
+  // Rq columns (in place over Jw) and the per-joint gradient / diagonal terms
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) {
+    const double rq = x[i] - ref[i], rv = x[NJ + i] - ref[NJ + i];
+    const double wq = ref[NX + i], wv = ref[NX + NJ + i];
+    const double ru = terminal ? 0.0 : u[i] - ref[2 * NX + i];
+    const double wu = terminal ? 0.0 : ref[2 * NX + NJ + i];
+    cost += 0.5 * wq * rq * rq + 0.5 * wv * rv * rv + 0.5 * wu * ru * ru;
+    if (DERIV) {
+      double t[3], pw[3], cl[3], ca[3];
+      cross3(pf, Jw[i] + 3, pw);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) t[k] = Jw[i][k] - pw[k];
+      mtv3(Rf, t, cl);
+      mtv3(Rf, Jw[i] + 3, ca);
+      const double* A = Jl;
+      const double* Bm = Jl + 9;
+      double lq = wq * rq;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        Jw[i][k] = A[3 * k] * cl[0] + A[3 * k + 1] * cl[1] + A[3 * k + 2] * cl[2] + Bm[3 * k] * ca[0] +
+                   Bm[3 * k + 1] * ca[1] + Bm[3 * k + 2] * ca[2];
+        Jw[i][3 + k] = A[3 * k] * ca[0] + A[3 * k + 1] * ca[1] + A[3 * k + 2] * ca[2];
+      }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) lq += Jw[i][k] * wr6[k];
+      rec[CK_LVV + i] = s * wv;
+      rec[CK_LUU + i] = s * wu;
+      rec[CK_LQ + i] = s * lq;
+      rec[CK_LV + i] = s * (wv * rv);
+      rec[CK_LU + i] = s * (wu * ru);
+    }
+  }
+  if (DERIV) {
+    // Lqq = Rq^T diag(w) Rq + diag(wq): symmetric, packed lower triangle
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) {
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) {
+        if (i >= k) {
+          double h = (i == k) ? ref[NX + i] : 0.0;
+#pragma unroll
+          for (int m = 0; m < 6; ++m) h += Jw[i][m] * (wp[m] * Jw[k][m]);
+          rec[CK_LQQ + lidx(i, k)] = s * h;
+        }
+      }
+    }
+    rec[CK_COST] = s * cost;
+  }
+  return s * cost;
+}
+
 // solve (M + armature) X = rhs for this lane's column with the register-resident factor
 AGX_DEV void solve_column(const double* L, const double* rinv, const double* rhs, double scale, double* out) {
   double t[NJ];

@@ -55,22 +55,27 @@ constexpr int MT_FR = MT_GRAV + 3;       // 9 frame rotation
 constexpr int MT_FP = MT_FR + 9;         // 3 frame translation
 constexpr int MODEL_SIZE = MT_FP + 3 + 1;  // 208 doubles
 
-// ---- compact node record written by calc_diff, read by the Riccati sweep.
-// Field-major / lane-minor: record[k * 8 + lane], so an octet's load of field k is one 64-byte line.
-constexpr int REC_FIELDS = 36;
-constexpr int REC_SIZE = 8 * REC_FIELDS;  // 288 doubles (2304 B) instead of 658 dense
+// ---- compact node records written by calc_diff, read by the Riccati sweep (instead of the 658 dense
+// doubles of Fx, Fu, Lx, Lu, Lxx, Lxu, Luu per node).
+// Dynamics record (octet kernel): field-major / lane-minor, rec[k * 8 + lane] — an octet's store of one
+// field is one 64-byte line.
+constexpr int REC_FIELDS = 23;
+constexpr int REC_SIZE = 8 * REC_FIELDS;  // 184 doubles (1472 B)
 constexpr int RK_AQ = 0;     // 7: dt * da/dq [:, j]
 constexpr int RK_AV = 7;     // 7: dt * da/dv [:, j]
 constexpr int RK_MI = 14;    // 7: dt * Minv [:, j]
-constexpr int RK_LQQ = 21;   // 7: s * Lqq [:, j]   (s = dt for running nodes, 1 for the terminal node)
-constexpr int RK_LVV = 28;   // s * wv_j
-constexpr int RK_LUU = 29;   // s * wu_j
-constexpr int RK_LQ = 30;    // s * Lq_j
-constexpr int RK_LV = 31;    // s * Lv_j
-constexpr int RK_LU = 32;    // s * Lu_j
-constexpr int RK_QN = 33;    // xnext (q part)
-constexpr int RK_VN = 34;    // xnext (v part)
-constexpr int RK_COST = 35;  // node cost (every lane holds the same value); NaN flags a failed node
+constexpr int RK_QN = 21;    // xnext (q part)
+constexpr int RK_VN = 22;    // xnext (v part)
+// Cost record (thread-per-node kernel): 64 consecutive doubles per node (512 B), all scaled by
+// s = dt for running nodes and 1 for the terminal node.
+constexpr int CREC_SIZE = 64;
+constexpr int CK_LQQ = 0;    // 28: Lqq, symmetric, packed lower triangle column by column (lidx)
+constexpr int CK_LVV = 28;   // 7: diagonal of Lvv
+constexpr int CK_LUU = 35;   // 7: diagonal of Luu
+constexpr int CK_LQ = 42;    // 7
+constexpr int CK_LV = 49;    // 7
+constexpr int CK_LU = 56;    // 7
+constexpr int CK_COST = 63;  // node cost
 
 // ---- per-problem solver state (SoA arrays, one entry per problem; device memory)
 struct SolverState {
@@ -81,11 +86,15 @@ struct SolverState {
   double* stop;       // |d1 + d2/2|
   int32_t* is_feasible;
   int32_t* was_feasible;
-  int32_t* recalc;    // derivatives must be recomputed (a step was accepted)
+  int32_t* recalc;    // the dynamics part of the node records must be recomputed (a step was accepted)
   int32_t* done;      // problem finished (converged or failed): kernels skip it
   int32_t* status;
   int32_t* iters;
   int32_t* cur;       // which of the two (xs, us) buffers holds the current candidate
+  double* dv;         // gap term of the expected improvement for the alpha = 1 trial
+  int32_t* recalc_cost;  // the cost part of the node records must be recomputed for the candidate
+  int32_t* pending;   // the alpha = 1 trial was rejected: the line search continues with smaller steps
+  int32_t* roll_ok;   // the alpha = 1 rollout met no NaN / failed factorisation
 };
 
 // ---- 3-vector helpers (per-lane, register resident)
