@@ -69,7 +69,8 @@ int env_cta(const char* name, int dflt) {
 }
 const int NODE_CTA = env_cta("AGX_NODE_CTA", 64);
 const int SEQ_CTA = env_cta("AGX_SEQ_CTA", 32);
-const int COST_CTA = env_cta("AGX_COST_CTA", 128);  // thread-per-node cost kernel
+const int COST_CTA = 64;  // thread-per-node cost kernel: 2 warps, 33 KB of staging shared memory
+const size_t COST_SMEM = sizeof(double) * COST_STAGE * (COST_CTA / 32);
 
 // agx_model -> device table (agx_octet_base.h layout).  Returns false for shapes the kernels do not
 // cover yet: anything but a 7-joint serial chain of revolute-z joints.
@@ -281,9 +282,8 @@ int agx_calc_diff(agx_handle* h, const double* xs, const double* us, double* out
   const long long ents = (long long)h->B * (h->T + 1);
   const int opc = NODE_CTA / 8;
   AGX_LAUNCH(h, calc_diff_kernel, (ents + opc - 1) / opc, NODE_CTA, sizeof(double) * OCT_BOARD * opc, (stream_t)stream,
-             problem_of(h), xs, us, (const int32_t*)nullptr, (const int32_t*)nullptr, (const int32_t*)nullptr, h->W.rec);
-  AGX_LAUNCH(h, node_cost_kernel<true>, (ents + COST_CTA - 1) / COST_CTA, COST_CTA, 0, (stream_t)stream, problem_of(h), xs,
-             us, (const int32_t*)nullptr, 0, (const int32_t*)nullptr, (const int32_t*)nullptr, h->W.crec, (double*)nullptr);
+             problem_of(h), xs, us, (const int32_t*)nullptr, (const int32_t*)nullptr, (const int32_t*)nullptr, 1,
+             (const int32_t*)nullptr, h->W.rec, h->W.crec);
   const long long rows = ents * NX;
   AGX_LAUNCH(h, expand_kernel, (rows + 127) / 128, 128, 0, (stream_t)stream, problem_of(h), (const double*)h->W.rec,
              (const double*)h->W.crec, out_cost, out_xnext, Fx, Fu, Lx, Lu, Lxx, Lxu, Luu);
@@ -342,10 +342,7 @@ int agx_riccati(agx_handle* h, const double* x0, const double* xs, const double*
   const int opc_n = NODE_CTA / 8, opc_s = SEQ_CTA / 8;
   AGX_LAUNCH(h, calc_diff_kernel, (ents + opc_n - 1) / opc_n, NODE_CTA, sizeof(double) * OCT_BOARD * opc_n, st, P,
              (const double*)W.xs, (const double*)W.us, (const int32_t*)h->S.cur, (const int32_t*)h->S.recalc,
-             (const int32_t*)h->S.done, W.rec);
-  AGX_LAUNCH(h, node_cost_kernel<true>, (ents + COST_CTA - 1) / COST_CTA, COST_CTA, 0, st, P, (const double*)W.xs,
-             (const double*)W.us, (const int32_t*)h->S.cur, 0, (const int32_t*)h->S.done,
-             (const int32_t*)h->S.recalc_cost, W.crec, (double*)nullptr);
+             (const int32_t*)h->S.recalc_cost, 0, (const int32_t*)h->S.done, W.rec, W.crec);
   AGX_LAUNCH(h, backward_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * BW_SIZE * opc_s, st, P, W, h->S, O);
   bool ok = true;
   if (out_k) ok = ok && copy_d2d(out_k, W.k, sizeof(double) * nB * T * NJ, st);
@@ -467,15 +464,12 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
   const int opc_n = NODE_CTA / 8, opc_s = SEQ_CTA / 8;
   const long long cost_ctas = (ents + COST_CTA - 1) / COST_CTA;
   for (int it = 0; it < max_iter; ++it) {
-    // problem.calc + calcDiff at the candidate: dynamics records (octets) + cost records (threads); after an
-    // alpha = 1 acceptance the cost records are already there (written for the trial) and that launch is a no-op
+    // problem.calc + calcDiff at the candidate: dynamics records, plus the cost records where they are stale
+    // (after an alpha = 1 acceptance they were already written for the trial by node_cost_kernel)
     phase_begin(h, 0, st);
     AGX_LAUNCH(h, calc_diff_kernel, (ents + opc_n - 1) / opc_n, NODE_CTA, sizeof(double) * OCT_BOARD * opc_n, st, P,
                (const double*)W.xs, (const double*)W.us, (const int32_t*)h->S.cur, (const int32_t*)h->S.recalc,
-               (const int32_t*)h->S.done, W.rec);
-    AGX_LAUNCH(h, node_cost_kernel<true>, cost_ctas, COST_CTA, 0, st, P, (const double*)W.xs, (const double*)W.us,
-               (const int32_t*)h->S.cur, 0, (const int32_t*)h->S.done, (const int32_t*)h->S.recalc_cost, W.crec,
-               (double*)nullptr);
+               (const int32_t*)h->S.recalc_cost, 0, (const int32_t*)h->S.done, W.rec, W.crec);
     phase_end(h, st);
     phase_begin(h, 1, st);
     AGX_LAUNCH(h, backward_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * BW_SIZE * opc_s, st, P, W, h->S, O);
@@ -483,10 +477,9 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
     phase_begin(h, 2, st);
     AGX_LAUNCH(h, rollout_try_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * FW_BOARD * opc_s, st, P, W,
                h->S);
-    AGX_LAUNCH(h, node_cost_kernel<true>, cost_ctas, COST_CTA, 0, st, P, (const double*)W.xs, (const double*)W.us,
+    AGX_LAUNCH(h, node_cost_kernel<true>, cost_ctas, COST_CTA, COST_SMEM, st, P, (const double*)W.xs, (const double*)W.us,
                (const int32_t*)h->S.cur, 1, (const int32_t*)h->S.done, (const int32_t*)nullptr, W.crec, (double*)nullptr);
-    AGX_LAUNCH(h, accept_kernel, (h->B + 127) / 128, 128, 0, st, P, W, h->S, O);
-    AGX_LAUNCH(h, linesearch_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * FW_BOARD * opc_s, st, P, W,
+    AGX_LAUNCH(h, accept_linesearch_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * FW_BOARD * opc_s, st, P, W,
                h->S, O);
     phase_end(h, st);
   }

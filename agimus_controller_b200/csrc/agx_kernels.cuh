@@ -131,25 +131,56 @@ AGX_DEV size_t buf_of(const int32_t* cur, int b, bool other) {
   return (size_t)(other ? (c ^ 1) : c);
 }
 
-// problem.calcDiff, dynamics part: one octet per (problem, node)
+// problem.calcDiff: one octet per (problem, node).  Always the dynamics record; the cost record only where
+// `recalc_cost` says so (null = everywhere) — inside a solve the cost records normally come from
+// node_cost_kernel, which evaluated them for the accepted trial already.
 __global__ void calc_diff_kernel(Problem P, const double* __restrict__ xs, const double* __restrict__ us,
                                  const int32_t* __restrict__ cur, const int32_t* __restrict__ recalc,
-                                 const int32_t* __restrict__ done, double* __restrict__ rec) {
+                                 const int32_t* __restrict__ recalc_cost, int cost_everywhere,
+                                 const int32_t* __restrict__ done, double* __restrict__ rec, double* __restrict__ crec) {
   AGX_SMEM(smem);
   AGX_OCTET_SETUP();
   const int T1 = P.T + 1;
   if (ent >= (long long)P.B * T1) return;
   const int b = (int)(ent / T1), t = (int)(ent % T1);
   if (done && done[b]) return;
-  if (recalc && !recalc[b]) return;
+  const bool do_dyn = !recalc || recalc[b];
+  const bool do_cost = cost_everywhere || (recalc_cost && recalc_cost[b]);
+  if (!do_dyn && !do_cost) return;
   double* sb = smem + oct_in_cta * OCT_BOARD;
   double* sc = sb + BRD_B;
   const size_t buf = buf_of(cur, b, false);
   const double* x = xs + ((buf * P.B + b) * T1 + t) * NX;
+  const bool terminal = t == P.T;
+  const bool live = j < NJ;
+  const double* model = model_of(P, b);
   double* R = rec + (size_t)ent * REC_SIZE;
-  if (t == P.T) {
+  LaneDyn d;
+  lane_load_state(d, j, x, terminal ? nullptr : us + ((buf * P.B + b) * P.T + t) * NJ);
+  if (do_cost) {
+    // octet version of the cost record (same numbers as thread_node_cost up to rounding)
+    node_kinematics(d, j, omask, model);
+    const double* ref = P.refs + (size_t)ent * REF_SIZE;
+    double* C = crec + (size_t)ent * CREC_SIZE;
+    const double s = terminal ? 1.0 : P.dts[t];
+    double lq, lv, lu, Lqq[NJ];
+    const double l = node_costs<true>(d, j, omask, model, ref, terminal, sb, &lq, &lv, &lu, Lqq);
+    if (live) {
+#pragma unroll
+      for (int i = 0; i < NJ; ++i)
+        if (i >= j) C[CK_LQQ + lidx(i, j)] = s * Lqq[i];
+      C[CK_LVV + j] = s * ref[NX + NJ + j];
+      C[CK_LUU + j] = terminal ? 0.0 : s * ref[2 * NX + NJ + j];
+      C[CK_LQ + j] = s * lq;
+      C[CK_LV + j] = s * lv;
+      C[CK_LU + j] = s * lu;
+    } else {
+      C[CK_COST] = s * l;
+    }
+  }
+  if (!do_dyn) return;
+  if (terminal) {
     // terminal model (dt = 0): xnext = x, no dynamics derivatives
-    const bool live = j < NJ;
 #pragma unroll
     for (int i = 0; i < NJ; ++i) {
       R[(RK_AQ + i) * 8 + j] = 0.0;
@@ -160,32 +191,48 @@ __global__ void calc_diff_kernel(Problem P, const double* __restrict__ xs, const
     R[RK_VN * 8 + j] = live ? x[NJ + j] : 0.0;
     return;
   }
-  LaneDyn d;
-  lane_load_state(d, j, x, us + ((buf * P.B + b) * P.T + t) * NJ);
-  node_dyn_diff(d, j, omask, model_of(P, b), P.dts[t], sb, sc, R);
+  node_dyn_diff(d, j, omask, model, P.dts[t], sb, sc, R);
 }
 
 // problem.calc / calcDiff, cost part: ONE THREAD per (problem, node).  `other` selects the trial buffer
 // (the candidate being evaluated by the line search); `gate` (may be null) restricts the work to problems
 // whose flag is non-zero.  DERIV: the cost part of the node record is (re)written.
+constexpr int COST_STAGE = 32 * (CREC_SIZE + 1) + 32;  // doubles of shared memory per warp of node_cost_kernel
 template <bool DERIV>
 __global__ void node_cost_kernel(Problem P, const double* __restrict__ xs, const double* __restrict__ us,
                                  const int32_t* __restrict__ cur, int other, const int32_t* __restrict__ done,
-                                 const int32_t* __restrict__ gate, double* __restrict__ rec,
+                                 const int32_t* __restrict__ gate, double* __restrict__ crec,
                                  double* __restrict__ out_cost) {
+  AGX_SMEM(smem);
   const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = (int)(threadIdx.x & 31u), warp = (int)(threadIdx.x >> 5);
   const int T1 = P.T + 1;
-  if (n >= (long long)P.B * T1) return;
-  const int b = (int)(n / T1), t = (int)(n % T1);
-  if (done && done[b]) return;
-  if (gate && !gate[b]) return;
-  const size_t buf = buf_of(cur, b, other != 0);
-  const bool terminal = t == P.T;
-  const double* x = xs + ((buf * P.B + b) * T1 + t) * NX;
-  const double* u = terminal ? nullptr : us + ((buf * P.B + b) * P.T + t) * NJ;
-  const double c = thread_node_cost<DERIV>(model_of(P, b), P.refs + (size_t)n * REF_SIZE, x, u, terminal,
-                                           terminal ? 1.0 : P.dts[t], DERIV ? rec + (size_t)n * CREC_SIZE : nullptr);
-  if (out_cost) out_cost[n] = c;
+  const long long N = (long long)P.B * T1;
+  const int b = (int)((n < N ? n : N - 1) / T1), t = (int)((n < N ? n : N - 1) % T1);
+  const bool active = n < N && !(done && done[b]) && !(gate && !gate[b]);
+  // the 64 outputs of a node are staged in shared memory (row stride 65: conflict-free) and written out by
+  // the whole warp as one contiguous 16 KB block: a thread-per-node store would touch 32 sectors per instruction
+  double* stage = smem + warp * COST_STAGE;
+  if (active) {
+    const size_t buf = buf_of(cur, b, other != 0);
+    const bool terminal = t == P.T;
+    const double* x = xs + ((buf * P.B + b) * T1 + t) * NX;
+    const double* u = terminal ? nullptr : us + ((buf * P.B + b) * P.T + t) * NJ;
+    const double c = thread_node_cost<DERIV>(model_of(P, b), P.refs + (size_t)n * REF_SIZE, x, u, terminal,
+                                             terminal ? 1.0 : P.dts[t], DERIV ? stage + lane * (CREC_SIZE + 1) : nullptr);
+    if (out_cost) out_cost[n] = c;
+  }
+  if (DERIV) {
+    double* flags = stage + 32 * (CREC_SIZE + 1);
+    flags[lane] = active ? 1.0 : 0.0;
+    __syncwarp();
+    const long long n0 = n - lane;
+#pragma unroll 4
+    for (int it = 0; it < CREC_SIZE; ++it) {
+      const int idx = it * 32 + lane, node = idx >> 6, k = idx & (CREC_SIZE - 1);
+      if (flags[node] != 0.0) crec[(size_t)(n0 + node) * CREC_SIZE + k] = stage[node * (CREC_SIZE + 1) + k];
+    }
+  }
 }
 
 __global__ void calc_kernel(Problem P, const double* __restrict__ xs, const double* __restrict__ us,
@@ -572,9 +619,9 @@ __global__ void backward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
 // Forward pass of one FDDP iteration, split so that the common case costs little:
 //   rollout_try_kernel  (octet per problem)  nonlinear rollout with alpha = 1, dynamics only
 //   node_cost_kernel    (thread per node)    costs (+ their derivatives) of the trial trajectory
-//   accept_kernel       (thread per problem) dV / dVexp acceptance test, buffer flip, reg / stop logic
-//   linesearch_kernel   (octet per problem)  only for problems whose alpha = 1 trial was rejected:
-//                                            alpha = 1/2, 1/4, ... with the costs evaluated in line
+//   accept_linesearch_kernel (octet per problem) dV / dVexp acceptance test, buffer flip, reg / stop logic;
+//                                            only if the alpha = 1 trial is rejected: alpha = 1/2, 1/4, ...
+//                                            with the costs evaluated in line
 // (SolverFDDP::forwardPass / tryStep / expectedImprovement and the tail of the solve loop).
 
 // end-of-iteration bookkeeping shared by accept_kernel and linesearch_kernel (one thread per problem)
@@ -695,40 +742,39 @@ __global__ void rollout_try_kernel(Problem P, Work W, SolverState S) {
   }
 }
 
-__global__ void accept_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
-  const int b = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-  if (b >= P.B) return;
-  if (S.done[b]) return;
-  const int T1 = P.T + 1;
-  const double* crec0 = W.crec + (size_t)b * T1 * CREC_SIZE;
-  double cost_try = 0.0;
-  for (int t = 0; t < T1; ++t) cost_try += crec0[(size_t)t * CREC_SIZE + CK_COST];
-  const bool finite = S.roll_ok[b] != 0 && (cost_try - cost_try == 0.0);
-  bool accepted = false;
-  const bool feasible = S.is_feasible[b] != 0;
-  if (finite) {
-    const double dv = S.dv[b];
-    const double d1 = S.dg[b] + dv, d2 = S.dq[b] - 2.0 * dv;
-    const double dV = S.cost[b] - cost_try;
-    const double dVexp = d1 + 0.5 * d2;  // steplength = 1
-    S.stop[b] = fabs(d1 + 0.5 * d2);
-    accepted = accept_step(O, dV, d1, dVexp);
-  }
-  if (accepted || O.n_alphas <= 1) {
-    S.pending[b] = 0;
-    finish_iteration(S, O, b, accepted, 1.0, feasible, cost_try, (S.cur[b] & 1) ^ 1, true);
-  } else {
-    S.pending[b] = 1;
-  }
-}
-
-// remaining step lengths alpha = 2^-ia, ia >= 1, for the problems still pending
-__global__ void linesearch_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
+// Acceptance test of the alpha = 1 trial (its costs come from node_cost_kernel) and, only if it is rejected,
+// the remaining step lengths alpha = 2^-ia, ia >= 1, with the costs evaluated in line.
+__global__ void accept_linesearch_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
   AGX_SMEM(smem);
   AGX_OCTET_SETUP();
   const int b = (int)ent;
   if (b >= P.B) return;
-  if (S.done[b] || !S.pending[b]) return;
+  if (S.done[b]) return;
+  {
+    const double* crec0 = W.crec + (size_t)b * (P.T + 1) * CREC_SIZE;
+    double part = 0.0;
+    for (int t = j; t <= P.T; t += 8) part += crec0[(size_t)t * CREC_SIZE + CK_COST];
+    const double cost1 = octet_sum(part, omask);
+    const bool finite = S.roll_ok[b] != 0 && (cost1 - cost1 == 0.0);
+    bool acc1 = false;
+    double stop1 = S.stop[b];
+    if (finite) {
+      const double dv = S.dv[b];
+      const double d1 = S.dg[b] + dv, d2 = S.dq[b] - 2.0 * dv;
+      stop1 = fabs(d1 + 0.5 * d2);
+      acc1 = accept_step(O, S.cost[b] - cost1, d1, d1 + 0.5 * d2);  // steplength = 1
+    }
+    AGX_OSYNC();  // every lane has read the state before lane 0 updates it
+    if (acc1 || O.n_alphas <= 1) {
+      if (j == 0) {
+        S.stop[b] = stop1;
+        finish_iteration(S, O, b, acc1, 1.0, S.is_feasible[b] != 0, cost1, (S.cur[b] & 1) ^ 1, true);
+      }
+      return;
+    }
+    if (j == 0) S.stop[b] = stop1;
+    AGX_OSYNC();
+  }
   double* sb = smem + oct_in_cta * FW_BOARD;
   double* sc = sb + BRD_B;
   double* sdx = sc + BRD_C;  // [14]
@@ -804,7 +850,6 @@ __global__ void linesearch_kernel(Problem P, Work W, SolverState S, FddpOpts O) 
   }
   if (j == 0) {
     S.stop[b] = stop;
-    S.pending[b] = 0;
     finish_iteration(S, O, b, accepted, steplength, feasible, cost_try, (int)obuf, false);
   }
 }
