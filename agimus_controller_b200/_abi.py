@@ -126,6 +126,10 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.agx_rnea.restype = C.c_int
     lib.agx_solve.argtypes = [H, _P, _P, _P, C.c_int, C.POINTER(AgxFddpOpts)] + [_P] * 9
     lib.agx_solve.restype = C.c_int
+    lib.agx_cost_terms.argtypes = [H, _P, _P, _P, _P]
+    lib.agx_cost_terms.restype = C.c_int
+    lib.agx_shift_warmstart.argtypes = [H, _P, _P, _P, _P, _P]
+    lib.agx_shift_warmstart.restype = C.c_int
     lib.agx_riccati.argtypes = [H, _P, _P, _P, C.c_double, _P, _P, _P, _P]
     lib.agx_riccati.restype = C.c_int
     lib.agx_set_timing.argtypes = [H, C.c_int]
@@ -142,5 +146,5 @@ def bind(lib: C.CDLL) -> C.CDLL:
 EXPORTED_SYMBOLS = (
     "agx_ref_size", "agx_fddp_opts_default", "agx_create", "agx_destroy", "agx_last_error", "agx_set_refs",
     "agx_calc", "agx_calc_diff", "agx_rollout", "agx_integrate", "agx_rnea", "agx_solve", "agx_launch_count",
-    "agx_set_timing", "agx_get_timing", "agx_probe_fp64", "agx_riccati",
+    "agx_set_timing", "agx_get_timing", "agx_probe_fp64", "agx_riccati", "agx_cost_terms", "agx_shift_warmstart",
 )

@@ -290,6 +290,24 @@ int agx_calc_diff(agx_handle* h, const double* xs, const double* us, double* out
   return check_launch(h, "agx_calc_diff");
 }
 
+int agx_cost_terms(agx_handle* h, const double* xs, const double* us, double* out_terms, void* stream) {
+  if (!h || !xs || !us || !out_terms) return AGX_EINVAL;
+  DeviceGuard g(h->device);
+  const long long ents = (long long)h->B * (h->T + 1);
+  AGX_LAUNCH(h, cost_terms_kernel, (ents + 127) / 128, 128, 0, (stream_t)stream, problem_of(h), xs, us, out_terms);
+  return check_launch(h, "agx_cost_terms");
+}
+
+int agx_shift_warmstart(agx_handle* h, const double* xs, const double* us, double* out_xs, double* out_us, void* stream) {
+  if (!h || !xs || !us || !out_xs || !out_us || xs == out_xs || us == out_us) return AGX_EINVAL;
+  DeviceGuard g(h->device);
+  const long long ents = (long long)h->B * (h->T + 1);
+  const int opc = NODE_CTA / 8;
+  AGX_LAUNCH(h, shift_kernel, (ents + opc - 1) / opc, NODE_CTA, sizeof(double) * OCT_BOARD * opc, (stream_t)stream,
+             problem_of(h), xs, us, out_xs, out_us);
+  return check_launch(h, "agx_shift_warmstart");
+}
+
 int agx_rollout(agx_handle* h, const double* x0, const double* us, double* out_xs, void* stream) {
   if (!h || !x0 || !us || !out_xs) return AGX_EINVAL;
   DeviceGuard g(h->device);

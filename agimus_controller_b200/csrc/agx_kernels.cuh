@@ -881,6 +881,63 @@ __global__ void rollout_kernel(Problem P, const double* __restrict__ x0, const d
   }
 }
 
+// per-cost evaluation: one thread per node -> [state_reg, control_reg, goal_tracking, r6(6)] (9 doubles)
+__global__ void cost_terms_kernel(Problem P, const double* __restrict__ xs, const double* __restrict__ us,
+                                  double* __restrict__ out_terms) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int T1 = P.T + 1;
+  if (n >= (long long)P.B * T1) return;
+  const int b = (int)(n / T1), t = (int)(n % T1);
+  const bool terminal = t == P.T;
+  double terms[9];
+  thread_node_cost<false>(model_of(P, b), P.refs + (size_t)n * REF_SIZE, xs + (size_t)n * NX,
+                          terminal ? nullptr : us + ((size_t)b * P.T + t) * NJ, terminal, 1.0, nullptr, terms);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) out_terms[(size_t)n * 9 + k] = terms[k];
+}
+
+// Warm start by shifting the previous solution by the first time step
+// (WarmStartShiftPreviousSolution.shift, warm_start_shift_previous_solution.py:85-104): nodes whose step equals
+// dt0 take the next node's state / control, coarser nodes are re-integrated over dt0 with their own control.
+__global__ void shift_kernel(Problem P, const double* __restrict__ xs, const double* __restrict__ us,
+                             double* __restrict__ out_xs, double* __restrict__ out_us) {
+  AGX_SMEM(smem);
+  AGX_OCTET_SETUP();
+  const int T = P.T, T1 = T + 1;
+  if (ent >= (long long)P.B * T1) return;
+  const int b = (int)(ent / T1), i = (int)(ent % T1);
+  double* sb = smem + oct_in_cta * OCT_BOARD;
+  double* sc = sb + BRD_B;
+  const bool live = j < NJ;
+  const double* xb = xs + (size_t)b * T1 * NX;
+  const double* ub = us + (size_t)b * T * NJ;
+  double* xo = out_xs + ((size_t)b * T1 + i) * NX;
+  if (i == T) {
+    if (live) { xo[j] = xb[T * NX + j]; xo[NJ + j] = xb[T * NX + NJ + j]; }
+    return;
+  }
+  double* uo = out_us + ((size_t)b * T + i) * NJ;
+  const double dt0 = P.dts[0];
+  if (P.dts[i] == dt0) {
+    if (live) {
+      xo[j] = xb[(i + 1) * NX + j];
+      xo[NJ + j] = xb[(i + 1) * NX + NJ + j];
+      uo[j] = ub[(i < T - 1 ? i + 1 : i) * NJ + j];
+    }
+    return;
+  }
+  LaneDyn d;
+  lane_load_state(d, j, xb + (size_t)i * NX, ub + (size_t)i * NJ);
+  node_kinematics(d, j, omask, model_of(P, b));
+  double L[28], rinv[NJ];
+  const bool ok = node_forward_dynamics<false>(d, j, omask, model_of(P, b), sb, sc, L, rinv);
+  if (live) {
+    xo[j] = ok ? d.q + (d.qd * dt0 + d.qdd * (dt0 * dt0)) : nan("");
+    xo[NJ + j] = ok ? d.qd + d.qdd * dt0 : nan("");
+    uo[j] = d.u;
+  }
+}
+
 // IntegratedActionModelEuler.calc -> xnext for n independent (x, u) pairs (costs skipped)
 __global__ void integrate_kernel(const double* __restrict__ model, const double* __restrict__ x,
                                  const double* __restrict__ u, double dt, int n, double* __restrict__ out) {

@@ -189,7 +189,7 @@ AGX_DEV double node_costs(const LaneDyn& d, int j, unsigned omask, const double*
 template <bool DERIV>
 AGX_DEV double thread_node_cost(const double* __restrict__ model, const double* __restrict__ ref,
                                 const double* __restrict__ x, const double* __restrict__ u, bool terminal, double s,
-                                double* __restrict__ rec) {
+                                double* __restrict__ rec, double* __restrict__ terms = nullptr) {
   const int fpar = (int)model[MT_FP + 3];
   // forward kinematics down the chain; world joint axes J_i = [p_i x z_i; z_i]
   double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0};
@@ -242,6 +242,23 @@ AGX_DEV double thread_node_cost(const double* __restrict__ model, const double* 
   double cost = 0.0;
 #pragma unroll
   for (int k = 0; k < 6; ++k) cost += 0.5 * wp[k] * r6[k] * r6[k];
+  if (terms) {
+    // per-cost view (mpc_debugger_node.py:294-323): [state_reg, control_reg, goal_tracking] values and the
+    // frame-placement residual; unscaled (differential) costs
+    double cs = 0.0, cu = 0.0;
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) {
+      const double rq = x[i] - ref[i], rv = x[NJ + i] - ref[NJ + i];
+      cs += 0.5 * ref[NX + i] * rq * rq + 0.5 * ref[NX + NJ + i] * rv * rv;
+      if (!terminal) {
+        const double ru = u[i] - ref[2 * NX + i];
+        cu += 0.5 * ref[2 * NX + NJ + i] * ru * ru;
+      }
+    }
+    terms[0] = cs; terms[1] = cu; terms[2] = cost;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) terms[3 + k] = r6[k];
+  }
   double wr6[6];
 #pragma unroll
   for (int k = 0; k < 6; ++k) wr6[k] = wp[k] * r6[k];

@@ -111,6 +111,30 @@ class RobotTable:
             t.mass[link] += delta
         return t
 
+    def frame_placement(self, q) -> tuple[np.ndarray, np.ndarray]:
+        """World placement ``(R, p)`` of the task frame at configuration ``q`` (host-side forward kinematics,
+        used to build references; the solve path itself never calls it)."""
+        q = np.asarray(q, dtype=np.float64)
+        Rw = [None] * self.nv
+        pw = [None] * self.nv
+        for i in range(self.nv):
+            a = self.axis[i]
+            if self.jtype[i] == _abi.AGX_JOINT_REVOLUTE:
+                K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+                Rj = np.eye(3) + np.sin(q[i]) * K + (1 - np.cos(q[i])) * (K @ K)
+                pj = np.zeros(3)
+            else:
+                Rj, pj = np.eye(3), a * q[i]
+            Rl = self.placement_R[i] @ Rj
+            pl = self.placement_p[i] + self.placement_R[i] @ pj
+            par = int(self.parent[i])
+            if par < 0:
+                Rw[i], pw[i] = Rl, pl
+            else:
+                Rw[i], pw[i] = Rw[par] @ Rl, pw[par] + Rw[par] @ pl
+        fpar, fR, fp = self.frames[self.frame_name]
+        return Rw[fpar] @ np.asarray(fR), pw[fpar] + Rw[fpar] @ np.asarray(fp)
+
     def to_struct(self) -> _abi.AgxModel:
         assert self.nv <= _abi.AGX_MAX_NV
         assert self.frame_name, "select the task frame with with_frame() first"

@@ -163,6 +163,22 @@ class BatchedShootingProblem:
         self._check(lib().agx_rnea(self._h, _ptr(q), _ptr(v), _ptr(a), q.shape[0], _ptr(tau), self._stream()))
         return tau
 
+    def cost_terms(self, xs, us) -> dict:
+        """Per-cost values and the frame-placement residual of every node (debugger view)."""
+        xs = self._t(xs, (self.B, self.T + 1, self.nx))
+        us = self._t(us, (self.B, self.T, self.nv))
+        out = self._empty(self.B, self.T + 1, 9)
+        self._check(lib().agx_cost_terms(self._h, _ptr(xs), _ptr(us), _ptr(out), self._stream()))
+        return dict(state_reg=out[..., 0], control_reg=out[..., 1], goal_tracking=out[..., 2], r_pose=out[..., 3:9])
+
+    def shift_warmstart(self, xs, us):
+        """Previous solution shifted by the first time step (``WarmStartShiftPreviousSolution.shift``)."""
+        xs = self._t(xs, (self.B, self.T + 1, self.nx))
+        us = self._t(us, (self.B, self.T, self.nv))
+        oxs, ous = torch.empty_like(xs), torch.empty_like(us)
+        self._check(lib().agx_shift_warmstart(self._h, _ptr(xs), _ptr(us), _ptr(oxs), _ptr(ous), self._stream()))
+        return oxs, ous
+
     def riccati(self, x0, xs, us, reg: float = 0.0):
         """calc + calcDiff at ``(xs, us)`` and one backward sweep with fixed regularisation ``reg`` -> ``K, k, status``
         (``reg = 1e-6`` = the proximal sigma of the reference's CSQP backward pass)."""

@@ -47,3 +47,51 @@ def golden_problem():
                      np.ones(3), np.ones(6), wpose_terminal=np.full(6, 50.0))
     return dict(table=table, refs=refs, dts=np.full(T, 1e-3), x0=np.zeros((1, 2 * nv)),
                 xs_ws=np.zeros((1, T + 1, 2 * nv)), us_ws=np.zeros((1, T, nv)))
+
+
+def quintic(t, scale_duration):
+    """Quintic ramp 0 -> 1 over ``scale_duration`` (trajectories/quintic_trajectory.py:16-42)."""
+    s = np.clip(np.asarray(t, dtype=np.float64) / scale_duration, 0.0, 1.0)
+    return 10 * s**3 - 15 * s**4 + 6 * s**5
+
+
+def cartesian_sine_batch(B, T=50, dt=0.01, rnea=None, amplitude=(0.2, 0.2, 0.2), period=4.0, scale_duration=1.0,
+                         w_q=1e-2, w_v=1e-2, w_u=1e-4, w_pose=1.0, armature=0.1, t0=1.0):
+    """Config 3: end-effector tracking of a Cartesian sine wave with frame-placement residuals
+    (trajectories/sine_wave_cartesian_space.py:113-142: pose = initial pose + amplitude * quintic(t) * sin(w t)),
+    one phase offset per problem, phi_b = 2 pi b / B.  The horizon starts at time ``t0``.  Joint references stay at the
+    nominal posture with small weights (the reference's per-point IK is an input generator, not part of the solve)."""
+    table = panda_table(lock_fingers=True, armature=armature)
+    nv = table.nv
+    R0, p0 = table.frame_placement(PANDA_Q_NOMINAL)
+    tt = t0 + dt * np.arange(T + 1)
+    w = 2 * np.pi / period
+    phi = 2 * np.pi * np.arange(B) / B
+    amp = np.asarray(amplitude, dtype=np.float64)
+    pref = p0[None, None, :] + amp[None, None, :] * (quintic(tt, scale_duration)[None, :, None]
+                                                      * np.sin(w * tt[None, :, None] + phi[:, None, None]))
+    x_nom = np.concatenate([PANDA_Q_NOMINAL, np.zeros(nv)])
+    z = np.zeros((1, nv))
+    u_grav = np.asarray(rnea(PANDA_Q_NOMINAL[None], z, z)).reshape(nv) if rnea is not None else np.zeros(nv)
+    refs = pack_refs(nv, T, B, x_nom, np.concatenate([np.full(nv, w_q), np.full(nv, w_v)]), u_grav, np.full(nv, w_u),
+                     R0, pref, np.full(6, w_pose))
+    x0 = np.repeat(x_nom[None], B, axis=0)
+    xs_ws = np.repeat(x0[:, None, :], T + 1, axis=1)
+    us_ws = np.repeat(np.broadcast_to(u_grav, (B, 1, nv)), T, axis=1)
+    return dict(table=table, refs=refs, dts=np.full(T, dt), x0=x0, xs_ws=np.ascontiguousarray(xs_ws),
+                us_ws=np.ascontiguousarray(us_ws))
+
+
+# measured (x0, u0) operating points of the model-sensibility study are not redistributed; five synthetic points
+# around the nominal posture stand in for state_and_control_expe_data.yaml
+def model_sensibility_batch(B, T=50, dt=0.01, rnea=None, delta=0.01, seed=5):
+    """Config 5: the cfg-2 problem with one inertial parameter perturbed per problem — 7 links x {6 inertia entries,
+    3 COM coordinates, mass}, ``delta * s`` with ``s ~ U(-1, 1)`` (evaluate_model_sensibility.py:9-49, :71-73).
+    Returns one RobotTable per problem in ``tables``."""
+    w = goal_reaching_batch(B, T=T, dt=dt, seed=seed, rnea=rnea)
+    base = w["table"]
+    rng = np.random.default_rng(seed)
+    s = rng.uniform(-1.0, 1.0, size=B)
+    tables = [base.perturbed((b % 70) // 10, (b % 70) % 10, delta * s[b]) for b in range(B)]
+    w["tables"] = tables
+    return w

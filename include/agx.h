@@ -122,6 +122,17 @@ int agx_calc_diff(agx_handle* h, const double* xs, const double* us, double* out
                   double* out_xnext, double* Fx, double* Fu, double* Lx, double* Lu, double* Lxx,
                   double* Lxu, double* Luu, void* stream);
 
+/* Per-cost evaluation (what mpc_debugger_node.py:294-323 reads off problem.runningDatas): for every node the
+ * unscaled value of each named cost of ocp_goal_reaching.yaml and the frame-placement residual,
+ * out_terms [B][T+1][9] = [state_reg, control_reg, goal_tracking, r6 (lin 3, ang 3)]. */
+int agx_cost_terms(agx_handle* h, const double* xs, const double* us, double* out_terms, void* stream);
+
+/* WarmStartShiftPreviousSolution.shift (warm_start_shift_previous_solution.py:85-104) for the whole batch:
+ * nodes whose time step equals dts[0] take the next node's state and control (the last control is repeated),
+ * coarser nodes are re-integrated over dts[0] with their own control; xs[T] is kept.  Out of place. */
+int agx_shift_warmstart(agx_handle* h, const double* xs, const double* us, double* out_xs, double* out_us,
+                        void* stream);
+
 /* problem.rollout(us): x0 [B][nx], us [B][T][nu] -> out_xs [B][T+1][nx]. */
 int agx_rollout(agx_handle* h, const double* x0, const double* us, double* out_xs, void* stream);
 

@@ -150,3 +150,21 @@ def riccati(m, refs, dts, x0, xs, us, reg):
     status = np.zeros(1, dtype=np.int32)
     h.check(lib().agx_riccati(h.h, _p(x0), _p(xs), _p(us), float(reg), _p(K), _p(k), _p(status), None))
     return K[0], k[0], int(status[0])
+
+
+def cost_terms(models, refs, dts, xs, us):
+    xs, us = _c(xs), _c(us)
+    B, T1, nx = xs.shape
+    h = _handle(models, refs, dts, B, T1 - 1)
+    out = np.zeros((B, T1, 9))
+    h.check(lib().agx_cost_terms(h.h, _p(xs), _p(us), _p(out), None))
+    return out
+
+
+def shift_warmstart(models, refs, dts, xs, us):
+    xs, us = _c(xs), _c(us)
+    B, T1, nx = xs.shape
+    h = _handle(models, refs, dts, B, T1 - 1)
+    oxs, ous = np.zeros_like(xs), np.zeros_like(us)
+    h.check(lib().agx_shift_warmstart(h.h, _p(xs), _p(us), _p(oxs), _p(ous), None))
+    return oxs, ous

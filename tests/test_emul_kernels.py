@@ -124,3 +124,45 @@ def test_golden_gains_through_the_shipped_kernels(orc, golden):
     assert rel(K, Ko) < 1e-6 and rel(k, ko) < 1e-6
     K0, _, _ = emu.riccati(m, p["refs"][0], p["dts"], p["x0"][0], xs, us, 0.0)
     assert np.abs(K0[0] - Kg[0]).max() / np.abs(Kg[0]).max() > 0.5
+
+
+def test_shift_warmstart_matches_the_reference_semantics(orc, m7):
+    """warm_start_shift_previous_solution.py:85-104 and tests/test_warm_start_shift_previous_reference.py:108-117:
+    timesteps (dt, dt, 2dt, 2dt): fine nodes shift, coarse nodes are re-integrated over dt with their own control."""
+    B, T = 2, 4
+    w = _workload(orc, m7, B, T)
+    dts = np.array([0.01, 0.01, 0.02, 0.02])
+    rng = np.random.default_rng(5)
+    us = w["us_ws"] + rng.uniform(-1, 1, w["us_ws"].shape)
+    xs = orc.rollout(m7, w["refs"], dts, w["x0"], us)
+    oxs, ous = emu.shift_warmstart(m7, w["refs"], dts, xs, us)
+    for b in range(B):
+        exp_x, exp_u = xs[b].copy(), us[b].copy()
+        for i, dt in enumerate(dts):
+            if dt == dts[0]:
+                exp_x[i] = xs[b, i + 1]
+                if i < T - 1:
+                    exp_u[i] = us[b, i + 1]
+            else:
+                exp_x[i] = orc.integrate(m7, xs[b, i], us[b, i], dts[0])
+        np.testing.assert_allclose(oxs[b], exp_x, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(ous[b], exp_u, rtol=0, atol=0)
+
+
+def test_cost_terms_add_up(orc, m7):
+    """Per-cost values: sum of the named costs == node cost / dt (terminal: unscaled); residual identities of
+    agimus_controller/tests/test_ocp_croco_generic.py:48-52 (cost == sum 1/2 w r^2)."""
+    B, T = 2, 5
+    w = _workload(orc, m7, B, T)
+    rng = np.random.default_rng(2)
+    xs = w["xs_ws"] + rng.uniform(-0.2, 0.2, w["xs_ws"].shape)
+    us = w["us_ws"] + rng.uniform(-2, 2, w["us_ws"].shape)
+    terms = emu.cost_terms(m7, w["refs"], w["dts"], xs, us)
+    cost, _ = orc.calc(m7, w["refs"], w["dts"], xs, us)
+    scale = np.concatenate([w["dts"], [1.0]])
+    np.testing.assert_allclose(terms[..., :3].sum(-1) * scale, cost, rtol=1e-12)
+    wx = w["refs"][..., 14:28]
+    np.testing.assert_allclose(terms[..., 0], 0.5 * (wx * (xs - w["refs"][..., :14]) ** 2).sum(-1), rtol=1e-12)
+    wp = w["refs"][..., 54:60]
+    np.testing.assert_allclose(terms[..., 2], 0.5 * (wp * terms[..., 3:9] ** 2).sum(-1), rtol=1e-12)
+    assert np.all(terms[:, -1, 1] == 0.0)

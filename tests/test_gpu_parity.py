@@ -202,3 +202,82 @@ def test_reference_golden_file_on_the_gpu(solver_mod, orc, golden):
     assert rel(K, Ko) < 1e-6
     K0, _, _ = p.riccati(w["x0"], xs[None], us[None], 0.0)
     assert np.abs(K0.cpu().numpy()[0, 0] - Kg[0]).max() / np.abs(Kg[0]).max() > 0.5
+
+
+def test_cfg3_cartesian_sine_tracking(solver_mod, orc):
+    """BASELINE config 3: Cartesian sine end-effector tracking (frame-placement residuals, one phase per problem).
+    128 problems against the oracle; the full 16384-problem batch through size-independent properties."""
+    from agimus_controller_b200.workloads import cartesian_sine_batch
+
+    m = panda_table().to_struct()
+    rn = lambda q, v, a: orc.rnea(m, q, v, a)  # noqa: E731
+    opts = _abi.default_fddp_opts(fixed_iters=True)
+    B, T = 128, 50
+    w = cartesian_sine_batch(B, T=T, rnea=rn)
+    o = orc.solve(m, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 10, opts)
+    p = _problem(solver_mod, w, B)
+    g = {k: v.cpu().numpy() for k, v in p.solve(w["x0"], w["xs_ws"], w["us_ws"], 10, opts).items()}
+    np.testing.assert_array_equal(g["iters"], o["iters"])
+    for k in ("xs", "us", "cost"):
+        assert rel(g[k], o[k]) < TRAJ_RTOL, k
+    # the end effector moves towards the moving target along the horizon
+    terms = p.cost_terms(g["xs"], g["us"])
+    err = terms["r_pose"][..., :3].norm(dim=-1)
+    assert float(err[:, -1].mean()) < 0.5 * float(err[:, 0].mean())
+    # full size
+    Bf = 16384
+    wf = cartesian_sine_batch(Bf, T=T, rnea=rn)
+    pf = _problem(solver_mod, wf, Bf)
+    gf = pf.solve(wf["x0"], wf["xs_ws"], wf["us_ws"], 10, opts)
+    assert bool(torch.isfinite(gf["xs"]).all())
+    assert float((pf.rollout(wf["x0"], gf["us"]) - gf["xs"]).abs().max()) < 1e-7
+    cost_nodes, _ = pf.calc(gf["xs"], gf["us"])
+    assert rel(cost_nodes.sum(1).cpu().numpy(), gf["cost"].cpu().numpy()) < 1e-10
+    # problems b and b + B/128 * k ... the 128-problem batch is the stride-128 subsample of the phases
+    idx = np.arange(0, Bf, Bf // B)
+    assert rel(gf["xs"].cpu().numpy()[idx], o["xs"]) < TRAJ_RTOL
+
+
+def test_cfg5_model_sensibility_ensemble(solver_mod, orc):
+    """BASELINE config 5 shape: every problem has its own inertial table (one parameter perturbed by delta * s)."""
+    from agimus_controller_b200.workloads import model_sensibility_batch
+
+    m = panda_table().to_struct()
+    B, T = 280, 50
+    w = model_sensibility_batch(B, T=T, rnea=lambda q, v, a: orc.rnea(m, q, v, a))
+    structs = [t.to_struct() for t in w["tables"]]
+    opts = _abi.default_fddp_opts(fixed_iters=True)
+    o = orc.solve(structs, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 10, opts)
+    p = solver_mod.BatchedShootingProblem(w["tables"], w["dts"], B)
+    p.set_refs(w["refs"])
+    g = {k: v.cpu().numpy() for k, v in p.solve(w["x0"], w["xs_ws"], w["us_ws"], 10, opts).items()}
+    for k in ("xs", "us", "cost"):
+        assert rel(g[k], o[k]) < TRAJ_RTOL, k
+    # the perturbation matters: the same problems with the nominal table give different trajectories
+    p0 = _problem(solver_mod, w, B)
+    g0 = p0.solve(w["x0"], w["xs_ws"], w["us_ws"], 10, opts)
+    assert float((g0["us"] - torch.as_tensor(g["us"], device=g0["us"].device)).abs().max()) > 1e-6
+
+
+def test_cost_terms_and_shift_on_gpu(solver_mod, orc):
+    B, T = 32, 12
+    w, m = _workload(orc, B, T)
+    dts = np.array([0.01] * 6 + [0.02] * 4 + [0.04] * 2)
+    p = solver_mod.BatchedShootingProblem(w["table"], dts, B)
+    p.set_refs(w["refs"])
+    rng = np.random.default_rng(4)
+    us = w["us_ws"] + rng.uniform(-2, 2, w["us_ws"].shape)
+    xs = p.rollout(w["x0"], us)
+    terms = p.cost_terms(xs, us)
+    cost, _ = p.calc(xs, us)
+    scale = torch.as_tensor(np.concatenate([dts, [1.0]]), device=cost.device)
+    tot = (terms["state_reg"] + terms["control_reg"] + terms["goal_tracking"]) * scale
+    assert rel(tot.cpu().numpy(), cost.cpu().numpy()) < 1e-12
+    oxs, ous = p.shift_warmstart(xs, us)
+    xs_h, oxs_h = xs.cpu().numpy(), oxs.cpu().numpy()
+    np.testing.assert_array_equal(oxs_h[:, :6], xs_h[:, 1:7])
+    exp = orc.integrate(m, xs_h[:, 6:12].reshape(-1, 14), us[:, 6:12].reshape(-1, 7), 0.01).reshape(B, 6, 14)
+    np.testing.assert_allclose(oxs_h[:, 6:12], exp, rtol=0, atol=1e-11)
+    np.testing.assert_array_equal(oxs_h[:, 12], xs_h[:, 12])
+    np.testing.assert_array_equal(ous.cpu().numpy()[:, :6], us[:, 1:7])
+    np.testing.assert_array_equal(ous.cpu().numpy()[:, 6:], us[:, 6:])

@@ -106,3 +106,43 @@ def test_batched_overload_matches_single_problem():
         o1.solve(x0[b], list(xs[b]), list(us[b]))
         np.testing.assert_array_equal(np.stack(o1.ocp_results.states), rb["xs"][b].cpu().numpy())
         np.testing.assert_array_equal(np.stack(o1.ocp_results.ricatti_gains), rb["K"][b].cpu().numpy())
+
+
+def test_batched_closed_loop_with_device_warm_starts(orc):
+    """A batch of closed-loop MPCs that never leaves the device between ticks: reference warm start on the first
+    tick (batched RNEA), shifted previous solution afterwards; every tick's warm start equals the reference
+    semantics evaluated on the host with the oracle."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from agimus_controller_b200 import _abi
+    from agimus_controller_b200.solver import BatchedShootingProblem
+    from agimus_controller_b200.warm_start import WarmStartReference, WarmStartShiftPreviousSolution
+    from agimus_controller_b200.workloads import goal_reaching_batch
+
+    B, T, nv = 16, 20, 7
+    m = panda_table().to_struct()
+    w = goal_reaching_batch(B, T=T, rnea=lambda q, v, a: orc.rnea(m, q, v, a))
+    p = BatchedShootingProblem(w["table"], w["dts"], B)
+    p.set_refs(w["refs"])
+    ref_q = np.broadcast_to(PANDA_Q_NOMINAL, (B, T + 1, nv)).copy()
+    zeros = np.zeros((B, T + 1, nv))
+    x0, xs, us = WarmStartReference(p).generate_batched(w["x0"], ref_q, zeros, zeros)
+    # u_init[t] = rnea(q_t, v_t, a_t) exactly as tests/test_warm_start_reference.py:19-75 pins it
+    xs_h = xs.cpu().numpy()
+    np.testing.assert_allclose(us.cpu().numpy().reshape(-1, nv),
+                               orc.rnea(m, xs_h[:, :-1, :nv].reshape(-1, nv), xs_h[:, :-1, nv:].reshape(-1, nv),
+                                        np.zeros((B * T, nv))), rtol=0, atol=1e-10)
+    ws = WarmStartShiftPreviousSolution(p)
+    opts = _abi.default_fddp_opts()
+    x = x0
+    cost_first = None
+    for tick in range(8):
+        out = p.solve(x, xs, us, 10, opts)
+        if cost_first is None:
+            cost_first = out["cost"].clone()
+        ws.update_previous_solution({k: v.clone() for k, v in out.items()})
+        x = p.integrate(x, out["us"][:, 0], 0.01)          # plant = the OCP's own integrator
+        _, xs, us = ws.generate_batched(x)
+        torch.testing.assert_close(xs[:, :-1], out["xs"][:, 1:], rtol=0, atol=0)   # constant dt: pure shift
+        torch.testing.assert_close(xs[:, 0], x, rtol=0, atol=1e-9)                  # the plant follows the plan
+    assert bool((out["cost"] < cost_first).all())
