@@ -134,12 +134,22 @@ AGX_DEV size_t buf_of(const int32_t* cur, int b, bool other) {
 // problem.calcDiff: one octet per (problem, node).  Always the dynamics record; the cost record only where
 // `recalc_cost` says so (null = everywhere) — inside a solve the cost records normally come from
 // node_cost_kernel, which evaluated them for the accepted trial already.
-__global__ void calc_diff_kernel(Problem P, const double* __restrict__ xs, const double* __restrict__ us,
+#ifndef AGX_CD_MINB
+#define AGX_CD_MINB 4
+#endif
+__global__ void __launch_bounds__(64, AGX_CD_MINB)
+calc_diff_kernel(Problem P, const double* __restrict__ xs, const double* __restrict__ us,
                                  const int32_t* __restrict__ cur, const int32_t* __restrict__ recalc,
                                  const int32_t* __restrict__ recalc_cost, int cost_everywhere,
                                  const int32_t* __restrict__ done, double* __restrict__ rec, double* __restrict__ crec) {
   AGX_SMEM(smem);
-  AGX_OCTET_SETUP();
+  const int j = (int)(threadIdx.x & 7u);
+  const int oct_in_cta = (int)(threadIdx.x >> 3);
+  const long long ent = (long long)blockIdx.x * (int)(blockDim.x >> 3) + oct_in_cta;
+  // Whole-warp collectives: the four octets of a warp run the same instruction stream (octets that have nothing
+  // to do EXIT, they never branch around a collective), so shuffles and barriers use the constant full mask and
+  // compile to plain SHFL / WARPSYNC without the divergence-safe MATCH / VOTE prologue of a run-time mask.
+  const unsigned omask = 0xffffffffu;
   const int T1 = P.T + 1;
   if (ent >= (long long)P.B * T1) return;
   const int b = (int)(ent / T1), t = (int)(ent % T1);
@@ -157,25 +167,29 @@ __global__ void calc_diff_kernel(Problem P, const double* __restrict__ xs, const
   double* R = rec + (size_t)ent * REC_SIZE;
   LaneDyn d;
   lane_load_state(d, j, x, terminal ? nullptr : us + ((buf * P.B + b) * P.T + t) * NJ);
-  if (do_cost) {
-    // octet version of the cost record (same numbers as thread_node_cost up to rounding)
-    node_kinematics(d, j, omask, model);
+  if (__any_sync(omask, do_cost)) {
+    // octet version of the cost record (same numbers as thread_node_cost up to rounding); the decision is
+    // warp-uniform, octets that did not ask for it compute and discard
+    LaneDyn dk = d;
+    node_kinematics(dk, j, omask, model);
     const double* ref = P.refs + (size_t)ent * REF_SIZE;
     double* C = crec + (size_t)ent * CREC_SIZE;
     const double s = terminal ? 1.0 : P.dts[t];
     double lq, lv, lu, Lqq[NJ];
-    const double l = node_costs<true>(d, j, omask, model, ref, terminal, sb, &lq, &lv, &lu, Lqq);
-    if (live) {
+    const double l = node_costs<true>(dk, j, omask, model, ref, terminal, sb, &lq, &lv, &lu, Lqq);
+    if (do_cost) {
+      if (live) {
 #pragma unroll
-      for (int i = 0; i < NJ; ++i)
-        if (i >= j) C[CK_LQQ + lidx(i, j)] = s * Lqq[i];
-      C[CK_LVV + j] = s * ref[NX + NJ + j];
-      C[CK_LUU + j] = terminal ? 0.0 : s * ref[2 * NX + NJ + j];
-      C[CK_LQ + j] = s * lq;
-      C[CK_LV + j] = s * lv;
-      C[CK_LU + j] = s * lu;
-    } else {
-      C[CK_COST] = s * l;
+        for (int i = 0; i < NJ; ++i)
+          if (i >= j) C[CK_LQQ + lidx(i, j)] = s * Lqq[i];
+        C[CK_LVV + j] = s * ref[NX + NJ + j];
+        C[CK_LUU + j] = terminal ? 0.0 : s * ref[2 * NX + NJ + j];
+        C[CK_LQ + j] = s * lq;
+        C[CK_LV + j] = s * lv;
+        C[CK_LU + j] = s * lu;
+      } else {
+        C[CK_COST] = s * l;
+      }
     }
   }
   if (!do_dyn) return;
@@ -665,8 +679,12 @@ AGX_DEV bool accept_step(const FddpOpts& O, double dV, double d1, double dVexp) 
 
 __global__ void rollout_try_kernel(Problem P, Work W, SolverState S) {
   AGX_SMEM(smem);
-  AGX_OCTET_SETUP();
-  const int b = (int)ent;
+  const int j = (int)(threadIdx.x & 7u);
+  const int oct_in_cta = (int)(threadIdx.x >> 3);
+  const int b = (int)blockIdx.x * (int)(blockDim.x >> 3) + oct_in_cta;
+  // whole-warp collectives (see calc_diff_kernel): every octet of a warp walks the same T nodes, finished
+  // problems exit before the first collective
+  const unsigned omask = 0xffffffffu;
   if (b >= P.B) return;
   if (S.done[b]) return;
   double* sb = smem + oct_in_cta * FW_BOARD;

@@ -177,6 +177,28 @@ inline double __shfl_up_sync(unsigned mask, double v, int delta, int width = 32)
   const int l = me & (width - 1);
   return __shfl_sync(mask, v, (l - delta >= 0) ? l - delta : l, width);
 }
+inline unsigned __activemask() {
+  simt::Block* b = simt::cur_block();
+  const int warp = b->current >> 5;
+  unsigned m = 0;
+  for (int i = 0; i < 32; ++i) {
+    const int t = warp * 32 + i;
+    if (t < b->nthreads && !b->fibers[t].done) m |= 1u << i;
+  }
+  return m;
+}
+inline int __any_sync(unsigned mask, int pred) {
+  simt::Block* b = simt::cur_block();
+  const int me = b->current;
+  b->fibers[me].shfl_slot = pred ? 1.0 : 0.0;
+  __syncwarp(mask);
+  int any = 0;
+  const int base = me & ~31;
+  for (int i = 0; i < 32; ++i)
+    if (((mask >> i) & 1u) && base + i < b->nthreads && !b->fibers[base + i].done && b->fibers[base + i].shfl_slot != 0.0) any = 1;
+  __syncwarp(mask);
+  return any;
+}
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 inline void sincos(double x, double* s, double* c) { *s = std::sin(x); *c = std::cos(x); }
 inline double __ldg(const double* p) { return *p; }
