@@ -120,10 +120,10 @@ struct agx_handle {
   bool timing = false;
   int n_pairs = 0;
 #if AGX_GPU
-  cudaEvent_t ev[2 * 2048];
+  cudaEvent_t ev[2 * 4096];
   int ev_made = 0;
 #endif
-  int pair_phase[2048];
+  int pair_phase[4096];
 };
 
 namespace {
@@ -138,13 +138,13 @@ int check_launch(agx_handle* h, const char* what) {
 }
 #if AGX_GPU
 inline void phase_begin(agx_handle* h, int phase, cudaStream_t st) {
-  if (!h->timing || h->n_pairs >= 2048) return;
+  if (!h->timing || h->n_pairs >= 4096) return;
   while (h->ev_made < 2 * (h->n_pairs + 1)) cudaEventCreate(&h->ev[h->ev_made++]);
   h->pair_phase[h->n_pairs] = phase;
   cudaEventRecord(h->ev[2 * h->n_pairs], st);
 }
 inline void phase_end(agx_handle* h, cudaStream_t st) {
-  if (!h->timing || h->n_pairs >= 2048) return;
+  if (!h->timing || h->n_pairs >= 4096) return;
   cudaEventRecord(h->ev[2 * h->n_pairs + 1], st);
   ++h->n_pairs;
 }
@@ -436,7 +436,7 @@ int agx_set_timing(agx_handle* h, int enable) {
 
 int agx_get_timing(agx_handle* h, double* out_ms, long long* out_launches) {
   if (!h || !out_ms || !out_launches) return AGX_EINVAL;
-  for (int p = 0; p < 3; ++p) { out_ms[p] = 0.0; out_launches[p] = 0; }
+  for (int p = 0; p < 5; ++p) { out_ms[p] = 0.0; out_launches[p] = 0; }
 #if AGX_GPU
   DeviceGuard g(h->device);
   for (int i = 0; i < h->n_pairs; ++i) {
@@ -495,8 +495,12 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
     phase_begin(h, 2, st);
     AGX_LAUNCH(h, rollout_try_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * FW_BOARD * opc_s, st, P, W,
                h->S);
+    phase_end(h, st);
+    phase_begin(h, 3, st);
     AGX_LAUNCH(h, node_cost_kernel<true>, cost_ctas, COST_CTA, COST_SMEM, st, P, (const double*)W.xs, (const double*)W.us,
                (const int32_t*)h->S.cur, 1, (const int32_t*)h->S.done, (const int32_t*)nullptr, W.crec, (double*)nullptr);
+    phase_end(h, st);
+    phase_begin(h, 4, st);
     AGX_LAUNCH(h, accept_linesearch_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * FW_BOARD * opc_s, st, P, W,
                h->S, O);
     phase_end(h, st);

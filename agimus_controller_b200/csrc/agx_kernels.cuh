@@ -318,17 +318,32 @@ __global__ void expand_kernel(Problem P, const double* __restrict__ rec, const d
 //   Qxx = Lxx + [V'_qq 0; 0 0] + G^T W + [Z_q^T G; 0],  Qux = N^T W,  Quu = Luu + N^T Vs N,
 //   Qx = Lx + [v'_q; 0] + G^T S^T v',  Qu = Lu + N^T S^T v'.
 constexpr int FW_BOARD = OCT_BOARD + 16;  // forward_kernel: node boards + dx[14] (odd stride kept)
-constexpr int BW_VS = 0;      // [7][8]
-constexpr int BW_G = 56;      // [7][16]
+// shared-memory board of one octet (doubles).  Regions that are never live together share storage.
+constexpr int BW_VS = 0;      // [7][8]   Vs ........ later the Quu columns handed to the factorisation
+constexpr int BW_L = 0;
+constexpr int BW_G = 56;      // [7][16]  G ......... later Qux
+constexpr int BW_QUX = 56;
 constexpr int BW_ZQ = 168;    // [7][8]
 constexpr int BW_N = 224;     // [7][8]
-constexpr int BW_QUX = 280;   // [7][16]
-constexpr int BW_L = 392;     // [7][8]
-constexpr int BW_SV = 448;    // [8]
-constexpr int BW_QU = 456;    // [8]
-constexpr int BW_FS = 464;    // [16]
-constexpr int BW_V = 480;     // [14][16]
-constexpr int BW_SIZE = 712;  // 704 used; +8 doubles skews the second octet of a half-warp by 16 banks
+constexpr int BW_SV = 280;    // [8]
+constexpr int BW_QU = 288;    // [8]
+constexpr int BW_FS = 296;    // [16]
+constexpr int BW_V = 312;     // [14][16] Qxx, then the unsymmetrised Vxx
+constexpr int BW_ST = 536;    // staged records of the NEXT node: dynamics [184], cost [64], gap row [16]
+constexpr int ST_REC = BW_ST, ST_CREC = BW_ST + REC_SIZE, ST_FS = BW_ST + REC_SIZE + CREC_SIZE;
+constexpr int BW_SIZE = 536 + REC_SIZE + CREC_SIZE + 16 + 8;  // +8 doubles: octets of a half-warp 16 banks apart
+
+// asynchronous copy of node t's records (and gap row) into the stage buffer: 131 chunks of 16 B over 8 lanes
+AGX_DEV void stage_node(double* sm, const double* __restrict__ rec, const double* __restrict__ crec,
+                        const double* __restrict__ fs, int j) {
+  constexpr int NREC = REC_SIZE / 2, NCREC = CREC_SIZE / 2, NFS = NX / 2;
+  for (int c = j; c < NREC + NCREC + NFS; c += 8) {
+    if (c < NREC) AGX_CP_ASYNC16(sm + ST_REC + 2 * c, rec + 2 * c);
+    else if (c < NREC + NCREC) AGX_CP_ASYNC16(sm + ST_CREC + 2 * (c - NREC), crec + 2 * (c - NREC));
+    else AGX_CP_ASYNC16(sm + ST_FS + 2 * (c - NREC - NCREC), fs + 2 * (c - NREC - NCREC));
+  }
+  AGX_CP_ASYNC_COMMIT();
+}
 
 __global__ void backward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
   AGX_SMEM(smem);
@@ -353,7 +368,11 @@ __global__ void backward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
 
   // total cost of the candidate and the gaps (SolverAbstract::computeDynamicFeasibility)
   double cost = 0.0;
-  for (int t = 0; t <= T; ++t) cost += crec0[(size_t)t * CREC_SIZE + CK_COST];
+  {
+    double part = 0.0;
+    for (int t = j; t <= T; t += 8) part += crec0[(size_t)t * CREC_SIZE + CK_COST];
+    cost = octet_sum(part, omask);
+  }
   if (!feasible && live) {
     fsb[j] = W.x0[(size_t)b * NX + j] - xs[j];
     fsb[NJ + j] = W.x0[(size_t)b * NX + NJ + j] - xs[NJ + j];
@@ -372,6 +391,8 @@ __global__ void backward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
     double V0[NX], V1[NX], vx0, vx1;
     double dgp = 0.0, dqp = 0.0;  // per-lane partial sums
     if (ok) {
+      // the first running node's records start flowing into shared memory while the terminal node is handled
+      stage_node(sm, rec0 + (size_t)(T - 1) * REC_SIZE, crec0 + (size_t)(T - 1) * CREC_SIZE, fsb + (size_t)(T - 1) * NX, j);
       // ---- terminal node
       const double* C = crec0 + (size_t)T * CREC_SIZE;
 #pragma unroll
@@ -405,27 +426,30 @@ __global__ void backward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
     }
     // ---- running nodes
     for (int t = T - 1; ok && t >= 0; --t) {
-      const double* R = rec0 + (size_t)t * REC_SIZE;
-      const double* C = crec0 + (size_t)t * CREC_SIZE;
       const double h = P.dts[t];
-      if (t > 0) {
-        // pull the next node's records (1472 + 512 B) towards the SM while this node is processed
-        const double* Rn = R - REC_SIZE;
-        AGX_PREFETCH(Rn + j * 16);
-        if (j < 4) AGX_PREFETCH(Rn + 128 + j * 16);
-        if (j < 4) AGX_PREFETCH(C - CREC_SIZE + j * 16);
-      }
+      // node t's records were staged during the previous node: wait, copy this lane's slice to registers,
+      // then let the next node's records flow in behind the arithmetic
+      AGX_CP_ASYNC_WAIT_ALL();
+      AGX_OSYNC();
       double G0[NJ], G1[NJ], Nc[NJ], Lqq[NJ];
+      {
+        const double* R = sm + ST_REC;
+        const double* C = sm + ST_CREC;
 #pragma unroll
-      for (int i = 0; i < NJ; ++i) {
-        G0[i] = live ? R[(RK_AQ + i) * 8 + jj] : 0.0;
-        G1[i] = (live ? R[(RK_AV + i) * 8 + jj] : 0.0) + ((i == j) ? 1.0 : 0.0);
-        Nc[i] = live ? R[(RK_MI + i) * 8 + jj] : 0.0;
-        Lqq[i] = live ? C[CK_LQQ + (i >= jj ? lidx(i, jj) : lidx(jj, i))] : 0.0;
+        for (int i = 0; i < NJ; ++i) {
+          G0[i] = live ? R[(RK_AQ + i) * 8 + jj] : 0.0;
+          G1[i] = (live ? R[(RK_AV + i) * 8 + jj] : 0.0) + ((i == j) ? 1.0 : 0.0);
+          Nc[i] = live ? R[(RK_MI + i) * 8 + jj] : 0.0;
+          Lqq[i] = live ? C[CK_LQQ + (i >= jj ? lidx(i, jj) : lidx(jj, i))] : 0.0;
+        }
       }
-      const double lvv = live ? C[CK_LVV + jj] : 0.0, luu = live ? C[CK_LUU + jj] : 0.0;
-      const double lq = live ? C[CK_LQ + jj] : 0.0, lv = live ? C[CK_LV + jj] : 0.0;
-      const double lu = live ? C[CK_LU + jj] : 0.0;
+      const double lvv = live ? sm[ST_CREC + CK_LVV + jj] : 0.0, luu = live ? sm[ST_CREC + CK_LUU + jj] : 0.0;
+      const double lq = live ? sm[ST_CREC + CK_LQ + jj] : 0.0, lv = live ? sm[ST_CREC + CK_LV + jj] : 0.0;
+      const double lu = live ? sm[ST_CREC + CK_LU + jj] : 0.0;
+      const double fs0 = live ? sm[ST_FS + jj] : 0.0, fs1 = live ? sm[ST_FS + NJ + jj] : 0.0;
+      AGX_OSYNC();
+      if (t > 0)
+        stage_node(sm, rec0 + (size_t)(t - 1) * REC_SIZE, crec0 + (size_t)(t - 1) * CREC_SIZE, fsb + (size_t)(t - 1) * NX, j);
       double Z0[NJ], Z1[NJ];
 #pragma unroll
       for (int i = 0; i < NJ; ++i) {
@@ -442,7 +466,7 @@ __global__ void backward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
         sm[BW_N + i * 8 + j] = Nc[i];
       }
       sm[BW_SV + j] = sv;
-      if (!feasible && live) { sm[BW_FS + j] = fsb[t * NX + j]; sm[BW_FS + NJ + j] = fsb[t * NX + NJ + j]; }
+      if (!feasible && live) { sm[BW_FS + j] = fs0; sm[BW_FS + NJ + j] = fs1; }
       AGX_OSYNC();
       // W = Vs G + [Zq 0] ; VN = Vs N
       double W0[NJ], W1[NJ], VN[NJ];
@@ -458,12 +482,11 @@ __global__ void backward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
         }
         W0[i] = a0; W1[i] = a1; VN[i] = a2;
       }
-      // Qxx columns
-      double Q0[NX], Q1[NX];
+      // Qxx columns = Lxx + [V'qq 0; 0 0] + G^T W + [Zq^T G; 0]; parked on the board (their registers are needed
+      // by the factorisation and the gains)
 #pragma unroll
       for (int r = 0; r < NJ; ++r) {
-        double a0 = Lqq[r] + V0[r], a1 = V1[r];  // Lxx + [V'qq 0; 0 0]  (column j+7, q rows: V'[r][j+7]? no: zero)
-        a1 = 0.0;
+        double a0 = Lqq[r] + V0[r], a1 = 0.0;
         double b0 = 0.0, b1 = (r == j) ? lvv : 0.0;
 #pragma unroll
         for (int i = 0; i < NJ; ++i) {
@@ -473,7 +496,10 @@ __global__ void backward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
           b0 += gv * W0[i];
           b1 += gv * W1[i];
         }
-        Q0[r] = a0; Q1[r] = a1; Q0[NJ + r] = b0; Q1[NJ + r] = b1;
+        sm[BW_V + r * 16 + j] = a0;
+        sm[BW_V + r * 16 + 8 + j] = a1;
+        sm[BW_V + (NJ + r) * 16 + j] = b0;
+        sm[BW_V + (NJ + r) * 16 + 8 + j] = b1;
       }
       // Qux columns, Quu column, Qx, Qu
       double U0[NJ], U1[NJ], Quu[NJ];
@@ -502,31 +528,28 @@ __global__ void backward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
 #pragma unroll
         for (int i = 0; i < NJ; ++i) Quu[i] = (i == 0) ? 1.0 : 0.0;
       }
-      double QuuC[NJ];
-#pragma unroll
-      for (int i = 0; i < NJ; ++i) QuuC[i] = Quu[i];
-      AGX_OSYNC();  // all reads of VS/G/ZQ/N done before QUX/L are (re)written
+      AGX_OSYNC();  // all reads of VS / G / ZQ / N done: their storage is reused for Quu and Qux
 #pragma unroll
       for (int i = 0; i < NJ; ++i) {
         sm[BW_QUX + i * 16 + j] = U0[i];
         sm[BW_QUX + i * 16 + 8 + j] = U1[i];
+        sm[BW_L + i * 8 + j] = Quu[i];
       }
       sm[BW_QU + j] = qu;
-#pragma unroll
-      for (int i = 0; i < NJ; ++i) sm[BW_L + i * 8 + j] = Quu[i];
       AGX_OSYNC();
       // computeGains: every lane factors Quu in registers (no barrier inside the factorisation)
-      double L[28], rinv[NJ];
-      ok = chol7_registers(sm + BW_L, L, rinv);
-      if (!ok) break;
-      // gains
       double K0[NJ], K1[NJ], kk[NJ];
+      {
+        double L[28], rinv[NJ];
+        ok = chol7_registers(sm + BW_L, L, rinv);
+        if (!ok) break;
 #pragma unroll
-      for (int i = 0; i < NJ; ++i) { K0[i] = U0[i]; K1[i] = U1[i]; kk[i] = sm[BW_QU + i]; }
-      chol_solve7(L, rinv, K0);
-      chol_solve7(L, rinv, K1);
-      chol_solve7(L, rinv, kk);
-      // value function
+        for (int i = 0; i < NJ; ++i) { K0[i] = U0[i]; K1[i] = U1[i]; kk[i] = sm[BW_QU + i]; }
+        chol_solve7(L, rinv, K0);
+        chol_solve7(L, rinv, K1);
+        chol_solve7(L, rinv, kk);
+      }
+      // value function: Vx = Qx - K^T Qu ; Vxx = Qxx - Qxu K (updated in place on the board)
       double nvx0 = qx0, nvx1 = qx1;
 #pragma unroll
       for (int i = 0; i < NJ; ++i) {
@@ -534,9 +557,11 @@ __global__ void backward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
         nvx0 -= K0[i] * qui;
         nvx1 -= K1[i] * qui;
       }
+      double Q0[NX], Q1[NX];
 #pragma unroll
       for (int r = 0; r < NJ; ++r) {
-        double a0 = Q0[r], a1 = Q1[r], b0 = Q0[NJ + r], b1 = Q1[NJ + r];
+        double a0 = sm[BW_V + r * 16 + j], a1 = sm[BW_V + r * 16 + 8 + j];
+        double b0 = sm[BW_V + (NJ + r) * 16 + j], b1 = sm[BW_V + (NJ + r) * 16 + 8 + j];
 #pragma unroll
         for (int i = 0; i < NJ; ++i) {
           const double xq = sm[BW_QUX + i * 16 + r], xv = sm[BW_QUX + i * 16 + 8 + r];
@@ -572,7 +597,7 @@ __global__ void backward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
       if (live) {
         double quuk = 0.0;
 #pragma unroll
-        for (int i = 0; i < NJ; ++i) quuk += QuuC[i] * kk[i];
+        for (int i = 0; i < NJ; ++i) quuk += sm[BW_L + i * 8 + j] * kk[i];
         double kj = 0.0;
 #pragma unroll
         for (int i = 0; i < NJ; ++i)
@@ -599,6 +624,8 @@ __global__ void backward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
       }
       AGX_OSYNC();
     }
+    AGX_CP_ASYNC_WAIT_ALL();  // nothing may still be in flight when the sweep is abandoned or restarted
+    AGX_OSYNC();
     if (ok) {
       // non-finite value function = failed sweep (SolverDDP::backwardPass raises on NaN)
       double chk = vx0 + vx1;

@@ -14,14 +14,21 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__) && !defined(AGX_EMULATE)
 #define AGX_GPU 1
 #define AGX_DEV __device__ __forceinline__
 #define AGX_RSQRT(x) rsqrt(x)
 #define AGX_SINCOS(x, s, c) sincos((x), (s), (c))
-#define AGX_SMEM(name) extern __shared__ double name[]
+#define AGX_SMEM(name) extern __shared__ __align__(16) double name[]
 #define AGX_PREFETCH(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
+// 16-byte asynchronous copy global -> shared (LDGSTS), no registers involved
+#define AGX_CP_ASYNC16(dst_smem, src_gmem)                                                       \
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), \
+               "l"(src_gmem))
+#define AGX_CP_ASYNC_COMMIT() asm volatile("cp.async.commit_group;")
+#define AGX_CP_ASYNC_WAIT_ALL() asm volatile("cp.async.wait_group 0;")
 #else
 #define AGX_GPU 0
 #define AGX_DEV inline
@@ -33,6 +40,9 @@
   } while (0)
 #define AGX_SMEM(name) double* name = reinterpret_cast<double*>(simt::g_smem)
 #define AGX_PREFETCH(p) ((void)(p))
+#define AGX_CP_ASYNC16(dst_smem, src_gmem) memcpy((dst_smem), (src_gmem), 16)
+#define AGX_CP_ASYNC_COMMIT() ((void)0)
+#define AGX_CP_ASYNC_WAIT_ALL() ((void)0)
 #endif
 
 namespace agx {

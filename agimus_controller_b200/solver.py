@@ -105,10 +105,10 @@ class BatchedShootingProblem:
 
     def get_timing(self) -> dict:
         """Per-phase device time (ms) and launch counts since the last read (synchronises)."""
-        ms = (C.c_double * 3)()
-        n = (C.c_longlong * 3)()
+        ms = (C.c_double * 5)()
+        n = (C.c_longlong * 5)()
         self._check(lib().agx_get_timing(self._h, ms, n))
-        names = ("calc_diff", "backward", "forward")
+        names = ("calc_diff", "backward", "rollout_try", "node_cost", "accept_linesearch")
         return {k: dict(ms=float(ms[i]), launches=int(n[i])) for i, k in enumerate(names)}
 
     # ------------------------------------------------------------------ problem data

@@ -40,11 +40,15 @@ N_ITERS = 10
 METRIC = "OCP solves/sec, Panda T=50 batch 4096, fixed 10 FDDP iterations"
 WORKLOAD = "cfg2: 4096 Panda goal-reaching OCPs per GPU, T=50, dt=0.01, randomised x0, fixed 10 FDDP iterations"
 
-# agreed algorithmic work per node and iteration, FMA = 2 flops
-FLOP_CALC_DIFF = 16000.0
-FLOP_BACKWARD = 23500.0
-FLOP_FORWARD = 3500.0
-REC_BYTES = 288 * 8
+# agreed algorithmic work per node and iteration, FMA = 2 flops.  calc+calcDiff (16 000) is split
+# between the dynamics kernel (ABA 2500 + RNEA derivatives 5500 + Minv 1500 + two Minv products 1400 + Euler
+# scaling 1000 + regs 1000 = 12 900) and the cost kernel (FK / frame Jacobian / log6 / Jlog6 1800 + Gauss-Newton
+# assembly 1300 = 3 100, which also yields the forward pass's cost evaluation, 600); forward (3 500) = rollout
+# (ABA 2500 + K dx / integrate 400 = 2 900) + that cost evaluation.
+FLOP = {"calc_diff": 12900.0, "backward": 23500.0, "rollout_try": 2900.0, "node_cost": 3700.0,
+        "accept_linesearch": 0.0}
+REC_BYTES = 184 * 8    # dynamics record
+CREC_BYTES = 64 * 8    # cost record
 
 
 def build_workload(B, seed, rnea):
@@ -286,18 +290,22 @@ def run_ours(args):
 
     # dominant kernel: algorithmic flops per launch / mean launch duration
     T1 = T_NODES + 1
-    flops = {"calc_diff": FLOP_CALC_DIFF * B * T1, "backward": FLOP_BACKWARD * B * T_NODES,
-             "forward": FLOP_FORWARD * B * T1}
-    bytes_alg = {"calc_diff": B * T1 * (REC_BYTES + (14 + 7 + 60) * 8),
-                 "backward": B * (T1 * REC_BYTES + T_NODES * (98 + 7) * 8 + T1 * (14 * 3) * 8),
-                 "forward": B * T1 * ((14 * 4 + 7 * 3 + 98 + 60) * 8)}
+    flops = {"calc_diff": FLOP["calc_diff"] * B * T_NODES, "backward": FLOP["backward"] * B * T_NODES,
+             "rollout_try": FLOP["rollout_try"] * B * T_NODES, "node_cost": FLOP["node_cost"] * B * T1,
+             "accept_linesearch": 0.0}
+    # algorithmic bytes per launch: what the kernel must read and write once
+    bytes_alg = {"calc_diff": B * T1 * (REC_BYTES + (14 + 7) * 8),
+                 "backward": B * (T1 * (REC_BYTES + CREC_BYTES) + T_NODES * (98 + 7) * 8 + T1 * (14 * 3) * 8),
+                 "rollout_try": B * T1 * ((14 * 3 + 7 * 3 + 98) * 8),
+                 "node_cost": B * T1 * (CREC_BYTES + (14 + 7 + 60) * 8),
+                 "accept_linesearch": B * T1 * 8}
     per = {}
     for k, v in phases.items():
         if v["launches"]:
             mean_ms = v["ms"] / v["launches"]
             per[k] = {"ms_per_launch": mean_ms, "launches": v["launches"], "share_of_step": v["ms"] / ms_total,
                       "tflops": flops[k] / (mean_ms * 1e-3) / 1e12, "gbs": bytes_alg[k] / (mean_ms * 1e-3) / 1e9}
-    top = max(per, key=lambda k: per[k]["ms_per_launch"] * per[k]["launches"]) if per else None
+    top = max((k for k in per if flops[k] > 0), key=lambda k: per[k]["ms_per_launch"] * per[k]["launches"]) if per else None
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

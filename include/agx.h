@@ -164,11 +164,11 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
 int agx_riccati(agx_handle* h, const double* x0, const double* xs, const double* us, double reg, double* out_K,
                 double* out_k, int32_t* out_status, void* stream);
 
-/* Optional device timing of the solve's three phases (bench evidence, off by default): while enabled,
- * agx_solve brackets every calc_diff / backward / forward launch with a CUDA event pair on `stream`.
- * agx_get_timing synchronises on those events, adds the elapsed milliseconds and launch counts per phase
- * (index 0 = calc_diff, 1 = backward sweep, 2 = forward line search) into out_ms[3] / out_launches[3]
- * and clears the record (at most 2048 launches are kept between two reads). */
+/* Optional device timing of the solve's kernels (bench evidence, off by default): while enabled, agx_solve
+ * brackets every launch of an iteration with a CUDA event pair on `stream`.  agx_get_timing synchronises on those
+ * events, adds the elapsed milliseconds and launch counts per kernel into out_ms[5] / out_launches[5]
+ * (0 = calc_diff, 1 = backward sweep, 2 = alpha-1 rollout, 3 = trial cost records, 4 = accept + line search)
+ * and clears the record (at most 4096 launches are kept between two reads). */
 int agx_set_timing(agx_handle* h, int enable);
 int agx_get_timing(agx_handle* h, double* out_ms, long long* out_launches);
 
