@@ -95,3 +95,34 @@ def model_sensibility_batch(B, T=50, dt=0.01, rnea=None, delta=0.01, seed=5):
     tables = [base.perturbed((b % 70) // 10, (b % 70) % 10, delta * s[b]) for b in range(B)]
     w["tables"] = tables
     return w
+
+
+def sine_configuration_reference(n_points, dt=0.01, amplitude=0.2, period=4.0, scale_duration=1.0, rnea=None,
+                                 w_q=1.0, w_v=0.1, w_u=1e-3, w_pose=0.1, armature=0.1):
+    """Config 1 reference stream: sine wave in configuration space around the nominal posture
+    (trajectories/sine_wave_configuration_space.py:41-72, parameters of trajectory_weights_parameters.yaml:27-76):
+    q(t) = q_nom + A quintic(t) sin(w t), its derivatives, u = rnea(q, v, a), end-effector pose = FK(q).
+    Returns the table and per-point reference records ``[n_points, ref_size]`` (running-node form)."""
+    table = panda_table(lock_fingers=True, armature=armature)
+    nv = table.nv
+    t = dt * np.arange(n_points)
+    w = 2 * np.pi / period
+    s = np.clip(t / scale_duration, 0.0, 1.0)
+    p = 10 * s**3 - 15 * s**4 + 6 * s**5
+    dp = np.where(s < 1.0, (30 * s**2 - 60 * s**3 + 30 * s**4) / scale_duration, 0.0)
+    ddp = np.where(s < 1.0, (60 * s - 180 * s**2 + 120 * s**3) / scale_duration**2, 0.0)
+    sn, cs = np.sin(w * t), np.cos(w * t)
+    off = amplitude * p * sn
+    doff = amplitude * (dp * sn + p * w * cs)
+    ddoff = amplitude * (ddp * sn + 2 * dp * w * cs - p * w * w * sn)
+    q = PANDA_Q_NOMINAL[None, :] + off[:, None]
+    v = np.repeat(doff[:, None], nv, axis=1)
+    a = np.repeat(ddoff[:, None], nv, axis=1)
+    u = np.asarray(rnea(q, v, a)).reshape(n_points, nv) if rnea is not None else np.zeros((n_points, nv))
+    rows = np.zeros((n_points, 6 * nv + 18))
+    for i in range(n_points):
+        R, pos = table.frame_placement(q[i])
+        rows[i] = pack_refs(nv, 0, 1, np.concatenate([q[i], v[i]]), np.concatenate([np.full(nv, w_q), np.full(nv, w_v)]),
+                            u[i], np.full(nv, w_u), R, pos, np.full(6, w_pose))[0, 0]
+        rows[i, 5 * nv: 6 * nv] = w_u  # pack_refs zeroes the control weights of its last (terminal) node
+    return table, rows, q, v, u

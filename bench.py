@@ -145,6 +145,52 @@ def run_reference(args):
     return 0
 
 
+def mpc_latency(prob, dev, ticks):
+    """p50 / p99 of one MPC tick's solve (reference: MPCDebugData.duration_ocp_solve_ns, mpc.py:52-64): reference
+    update, warm start, solve, read-back of the control the node publishes (us[0], K[0])."""
+    import torch
+
+    from agimus_controller_b200 import _abi
+    from agimus_controller_b200.solver import BatchedShootingProblem
+    from agimus_controller_b200.workloads import sine_configuration_reference
+
+    T, dt = 20, DT
+    table, rows, q, v, u = sine_configuration_reference(ticks + T + 2, dt=dt,
+                                                        rnea=lambda q_, v_, a_: prob.rnea(q_, v_, a_).cpu().numpy())
+    p1 = BatchedShootingProblem(table, np.full(T, dt), 1, device=dev)
+    nv = table.nv
+    rows_d = torch.as_tensor(rows, device=dev)
+    opts = _abi.default_fddp_opts()
+    out = p1.alloc_outputs()
+    x = torch.as_tensor(np.concatenate([q[0], v[0]])[None], device=dev)
+    xs = torch.cat([torch.as_tensor(q[: T + 1]), torch.as_tensor(v[: T + 1])], dim=1)[None].to(dev).contiguous()
+    us = torch.as_tensor(u[:T][None], device=dev).contiguous()
+    ts, iters = [], []
+    term_mask = torch.ones(rows.shape[1], dtype=torch.float64, device=dev)
+    term_mask[5 * nv: 6 * nv] = 0.0   # the terminal node has no control cost
+    for k in range(ticks):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        refs = rows_d[k: k + T + 1].clone()
+        refs[T] *= term_mask
+        p1.set_refs(refs[None])
+        p1.solve(x, xs, us, N_ITERS, opts, out=out)
+        u0 = out["us"][0, 0].cpu()
+        K0 = out["K"][0, 0].cpu()                                    # what Control(feedback_gain, feedforward) carries
+        ts.append(time.perf_counter() - t0)
+        iters.append(int(out["iters"][0]))
+        x = p1.integrate(x, out["us"][:, 0], dt)                      # plant = the OCP's integrator
+        xs, us = p1.shift_warmstart(out["xs"], out["us"])
+        xs[:, 0] = x
+    del u0, K0
+    ts = np.array(ts[20:]) * 1e3
+    track = float(np.abs(x[0, :nv].cpu().numpy() - q[ticks]).max())
+    return {"p50_ms": float(np.percentile(ts, 50)), "p99_ms": float(np.percentile(ts, 99)), "ticks": int(len(ts)),
+            "mean_iters": float(np.mean(iters[20:])), "final_tracking_error_rad": track,
+            "workload": "cfg1: B=1, T=20, dt=0.01, sine in configuration space (0.2 rad, 4 s), closed loop with shift "
+                        "warm start, <=10 FDDP iterations per tick; host wall clock of set_refs + solve + D2H of us[0], K[0]"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -295,26 +341,11 @@ def run_ours(args):
     # the results that came back are the solver's: same costs as the resident run
     assert torch.equal(slots[0].res["cost"], out["cost"].cpu()), "e2e results differ from the resident run"
 
-    # single-problem MPC latency (cfg 1 shape: B = 1, T = 20, <= 10 iterations), rank 0 only
+    # single-MPC latency (BASELINE config 1): B = 1, T = 20, dt = 0.01, sine wave in configuration space, closed loop
+    # with the shift warm start, <= 10 FDDP iterations per tick (early exit allowed), rank 0 only
     lat = None
     if rank == 0 and not args.no_latency:
-        from agimus_controller_b200.workloads import goal_reaching_batch
-
-        w1 = goal_reaching_batch(1, T=20, dt=DT, seed=0, rnea=lambda q, v, a: prob.rnea(q, v, a).cpu().numpy())
-        p1 = BatchedShootingProblem(w1["table"], w1["dts"], 1, device=dev)
-        p1.set_refs(w1["refs"])
-        o1 = p1.alloc_outputs()
-        a1 = [torch.as_tensor(w1[k], device=dev) for k in ("x0", "xs_ws", "us_ws")]
-        ts = []
-        for i in range(60):
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            p1.solve(*a1, N_ITERS, opts, out=o1)
-            _ = o1["us"][0, 0].cpu()
-            ts.append(time.perf_counter() - t0)
-        ts = np.array(ts[10:]) * 1e3
-        lat = {"p50_ms": float(np.percentile(ts, 50)), "p99_ms": float(np.percentile(ts, 99)),
-               "workload": "cfg1 shape: B=1, T=20, 10 fixed FDDP iterations, host wall clock incl. launch + 1 D2H"}
+        lat = mpc_latency(prob, dev, args.latency_ticks)
 
     if rank != 0:
         if world > 1:
@@ -373,7 +404,9 @@ def run_ours(args):
         while t < 8.0 and reps < 16:
             t += time_cpu(orc, m, w, n, N_ITERS)
             reps += 1
+        t1 = min(time_cpu(orc, m, w, 1, N_ITERS, threads=1) for _ in range(5))
         cpu = {"value": n * reps / t, "unit": "solves/s", "cores": cores, "kind": "port",
+               "single_solve_ms_1thread": 1e3 * t1,
                "sample": f"{n} of the 4096 problems x {reps} passes ({t:.1f} s), OpenMP one problem per thread; "
                          "CPU restatement of Crocoddyl FDDP (oracle/agx_oracle.cpp), not Crocoddyl itself"}
 
@@ -407,6 +440,7 @@ def main():
     ap.add_argument("--sample", type=int, default=None, help="problems per step of the reference arm")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-latency", action="store_true", help="skip the B=1 latency leg")
+    ap.add_argument("--latency-ticks", type=int, default=300, help="MPC ticks of the B=1 latency leg")
     ap.add_argument("--no-probe", action="store_true", help="skip the FP64 peak probe (profiler runs)")
     args = ap.parse_args()
     if args.impl == "reference":
