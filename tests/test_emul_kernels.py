@@ -166,3 +166,55 @@ def test_cost_terms_add_up(orc, m7):
     wp = w["refs"][..., 54:60]
     np.testing.assert_allclose(terms[..., 2], 0.5 * (wp * terms[..., 3:9] ** 2).sum(-1), rtol=1e-12)
     assert np.all(terms[:, -1, 1] == 0.0)
+
+
+def test_edge_shapes_and_error_codes(orc, m7):
+    """Smallest shapes (B = 1, T = 1), a zero iteration budget, and the error paths of the ABI (no exception crosses it:
+    bad arguments come back as AGX_EINVAL with a message)."""
+    import ctypes as C
+
+    w = _workload(orc, m7, 1, 1)
+    opts = _abi.default_fddp_opts(fixed_iters=True)
+    o = orc.solve(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 2, opts)
+    e = emu.solve(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 2, opts)
+    assert rel(e["xs"], o["xs"]) < 1e-9 and rel(e["K"], o["K"]) < 1e-9
+    e0 = emu.solve(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 0, opts)
+    np.testing.assert_array_equal(e0["xs"], w["xs_ws"])   # no iteration: the warm start comes back
+    np.testing.assert_array_equal(e0["iters"], [0])
+    lib = emu.lib()
+    h = C.c_void_p()
+    assert lib.agx_create(None, 1, None, 1, 1, 0, C.byref(h)) == _abi.AGX_EINVAL
+    arr = (_abi.AgxModel * 1)(m7)
+    dts = np.full(3, 0.01)
+    assert lib.agx_create(arr, 2, dts.ctypes.data, 4, 3, 0, C.byref(h)) == _abi.AGX_EINVAL   # n_models must be 1 or B
+    lib.agx_destroy(h)
+    hd = emu.Handle(m7, dts, 2, 3)
+    assert lib.agx_solve(hd.h, None, None, None, 1, None, None, None, None, None, None, None, None, None, None) == _abi.AGX_EINVAL
+    x = np.zeros((2, 4, 14)); u = np.zeros((2, 3, 7))
+    assert lib.agx_shift_warmstart(hd.h, x.ctypes.data, u.ctypes.data, x.ctypes.data, u.ctypes.data, None) == _abi.AGX_EINVAL
+    bad = _abi.default_fddp_opts(); bad.n_alphas = 11
+    out = [np.zeros(s) for s in ((2, 4, 14), (2, 3, 7), (2, 3, 7, 14), (2,))]
+    it = np.zeros(2, np.int32); stt = np.zeros(2, np.int32)
+    rc = lib.agx_solve(hd.h, x[:, 0].copy().ctypes.data, x.ctypes.data, u.ctypes.data, 1, C.byref(bad), out[0].ctypes.data,
+                       out[1].ctypes.data, out[2].ctypes.data, None, out[3].ctypes.data, it.ctypes.data, stt.ctypes.data,
+                       None, None)
+    assert rc == _abi.AGX_EINVAL and b"n_alphas" in lib.agx_last_error(hd.h)
+    assert lib.agx_destroy(None) == _abi.AGX_OK
+
+
+def test_nan_inputs_do_not_poison_neighbours(orc, m7):
+    """A problem with a NaN initial state ends with a failure status; its neighbours are solved as usual."""
+    B, T = 3, 6
+    w = _workload(orc, m7, B, T)
+    opts = _abi.default_fddp_opts(fixed_iters=True)
+    good = emu.solve(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 3, opts)
+    x0 = w["x0"].copy(); xs = w["xs_ws"].copy()
+    x0[1, 3] = np.nan; xs[1, :, 3] = np.nan
+    e = emu.solve(m7, w["refs"], w["dts"], x0, xs, w["us_ws"], 3, opts)
+    assert e["status"][1] == _abi.AGX_STATUS_REGMAX
+    for b in (0, 2):
+        np.testing.assert_array_equal(e["xs"][b], good["xs"][b])
+        assert e["status"][b] == good["status"][b]
+    o = orc.solve(m7, w["refs"], w["dts"], x0, xs, w["us_ws"], 3, opts)
+    np.testing.assert_array_equal(e["status"], o["status"])
+    np.testing.assert_array_equal(e["iters"], o["iters"])
