@@ -118,6 +118,8 @@ def run_reference(args):
         return 0
     from oracle import orc
 
+    # torchrun exports OMP_NUM_THREADS=1: the thread count is passed explicitly so that the reference arm
+    # uses every host core it may run on
     cores = len(os.sched_getaffinity(0))
     n = 64 * cores if args.sample is None else args.sample
     n = min(n, B_PER_GPU)
@@ -126,8 +128,8 @@ def run_reference(args):
     m0 = panda_table().to_struct()
     w, m = build_workload(B_PER_GPU, 0, lambda q, v, a: orc.rnea(m0, q, v, a))
     for _ in range(args.warmup):
-        time_cpu(orc, m, w, n, N_ITERS)
-    t = [time_cpu(orc, m, w, n, N_ITERS) for _ in range(args.steps)]
+        time_cpu(orc, m, w, n, N_ITERS, threads=cores)
+    t = [time_cpu(orc, m, w, n, N_ITERS, threads=cores) for _ in range(args.steps)]
     total = sum(t)
     value = n * args.steps / total
     line = {
@@ -135,7 +137,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": f"first {n} of the 4096 problems per step"},
-        "cpu_baseline": {"value": value, "unit": "solves/s", "cores": orc.num_threads(), "kind": "port",
+        "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port",
                          "sample": f"{n} problems x {args.steps} steps, OpenMP one problem per thread, "
                                    "CPU restatement of Crocoddyl FDDP (oracle/agx_oracle.cpp)"},
         "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -396,13 +398,13 @@ def run_ours(args):
     if world == 1 and not args.no_cpu:
         from oracle import orc
 
-        cores = orc.num_threads()
+        cores = len(os.sched_getaffinity(0))
         n = min(B, 48 * cores)
-        time_cpu(orc, m, w, min(n, 4 * cores), N_ITERS)
-        t = time_cpu(orc, m, w, n, N_ITERS)
+        time_cpu(orc, m, w, min(n, 4 * cores), N_ITERS, threads=cores)
+        t = time_cpu(orc, m, w, n, N_ITERS, threads=cores)
         reps = 1
         while t < 8.0 and reps < 16:
-            t += time_cpu(orc, m, w, n, N_ITERS)
+            t += time_cpu(orc, m, w, n, N_ITERS, threads=cores)
             reps += 1
         t1 = min(time_cpu(orc, m, w, 1, N_ITERS, threads=1) for _ in range(5))
         cpu = {"value": n * reps / t, "unit": "solves/s", "cores": cores, "kind": "port",
