@@ -484,10 +484,18 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
   for (int it = 0; it < max_iter; ++it) {
     // problem.calc + calcDiff at the candidate: dynamics records, plus the cost records where they are stale
     // (after an alpha = 1 acceptance they were already written for the trial by node_cost_kernel)
+    if (it == 0) {
+      // first iteration: every cost record is stale; the thread-per-node kernel is the cheap way to fill them
+      // (later iterations only meet stale cost records after a line search, handled in line by calc_diff_kernel)
+      phase_begin(h, 3, st);
+      AGX_LAUNCH(h, node_cost_kernel<true>, cost_ctas, COST_CTA, COST_SMEM, st, P, (const double*)W.xs, (const double*)W.us,
+                 (const int32_t*)h->S.cur, 0, (const int32_t*)h->S.done, (const int32_t*)nullptr, W.crec, (double*)nullptr);
+      phase_end(h, st);
+    }
     phase_begin(h, 0, st);
     AGX_LAUNCH(h, calc_diff_kernel, (ents + opc_n - 1) / opc_n, NODE_CTA, sizeof(double) * OCT_BOARD * opc_n, st, P,
                (const double*)W.xs, (const double*)W.us, (const int32_t*)h->S.cur, (const int32_t*)h->S.recalc,
-               (const int32_t*)h->S.recalc_cost, 0, (const int32_t*)h->S.done, W.rec, W.crec);
+               (const int32_t*)(it == 0 ? nullptr : h->S.recalc_cost), 0, (const int32_t*)h->S.done, W.rec, W.crec);
     phase_end(h, st);
     phase_begin(h, 1, st);
     AGX_LAUNCH(h, backward_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * BW_SIZE * opc_s, st, P, W, h->S, O);

@@ -75,7 +75,7 @@ def test_solve_matches_oracle(orc, m7, fixed, iters):
     np.testing.assert_array_equal(e["status"], o["status"])
     for k in ("xs", "us", "cost", "K", "k"):
         assert rel(e[k], o[k]) < 1e-6, k
-    assert e["launches"] == 5 * iters + 2  # init + 5 launches per iteration + finalize
+    assert e["launches"] == 5 * iters + 3  # init + first cost records + 5 launches per iteration + finalize
 
 
 def test_solve_golden_problem_shapes(orc):
