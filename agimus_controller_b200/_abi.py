@@ -114,6 +114,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.agx_last_error.restype = C.c_char_p
     lib.agx_set_refs.argtypes = [H, _P, _P]
     lib.agx_set_refs.restype = C.c_int
+    lib.agx_set_refs_window.argtypes = [H, _P, C.c_int, C.c_int, _P, C.c_int, _P]
+    lib.agx_set_refs_window.restype = C.c_int
     lib.agx_calc.argtypes = [H, _P, _P, _P, _P, _P]
     lib.agx_calc.restype = C.c_int
     lib.agx_calc_diff.argtypes = [H] + [_P] * 12
@@ -146,5 +148,5 @@ def bind(lib: C.CDLL) -> C.CDLL:
 EXPORTED_SYMBOLS = (
     "agx_ref_size", "agx_fddp_opts_default", "agx_create", "agx_destroy", "agx_last_error", "agx_set_refs",
     "agx_calc", "agx_calc_diff", "agx_rollout", "agx_integrate", "agx_rnea", "agx_solve", "agx_launch_count",
-    "agx_set_timing", "agx_get_timing", "agx_probe_fp64", "agx_riccati", "agx_cost_terms", "agx_shift_warmstart",
+    "agx_set_timing", "agx_get_timing", "agx_probe_fp64", "agx_riccati", "agx_cost_terms", "agx_shift_warmstart", "agx_set_refs_window",
 )

@@ -111,6 +111,7 @@ struct agx_handle {
   double* d_dts = nullptr;
   double* d_x0 = nullptr;
   double* d_K_internal = nullptr;
+  int32_t* d_hidx = nullptr;  // horizon indexes: cumulative step factors dts[i] / dts[0]
   agx::Work W{};
   agx::SolverState S{};
   void* state_block = nullptr;
@@ -189,7 +190,7 @@ int agx_destroy(agx_handle* h) {
   if (!h) return AGX_OK;
   {
     DeviceGuard g(h->device);
-    dev_free(h->d_model); dev_free(h->d_refs); dev_free(h->d_dts); dev_free(h->d_x0); dev_free(h->d_K_internal);
+    dev_free(h->d_model); dev_free(h->d_refs); dev_free(h->d_dts); dev_free(h->d_x0); dev_free(h->d_K_internal); dev_free(h->d_hidx);
     dev_free(h->W.xs); dev_free(h->W.us); dev_free(h->W.rec); dev_free(h->W.crec); dev_free(h->W.fs); dev_free(h->W.gv); dev_free(h->W.k);
     dev_free(h->state_block);
 #if AGX_GPU
@@ -248,11 +249,23 @@ int agx_create(const agx_model* models_host, int n_models, const double* dts_hos
   h->S.is_feasible = ip; h->S.was_feasible = ip + nB; h->S.recalc = ip + 2 * nB; h->S.done = ip + 3 * nB;
   h->S.status = ip + 4 * nB; h->S.iters = ip + 5 * nB; h->S.cur = ip + 6 * nB;
   h->S.recalc_cost = ip + 7 * nB; h->S.pending = ip + 8 * nB; h->S.roll_ok = ip + 9 * nB;
-  ok = copy_h2d(h->d_model, tab, sizeof(double) * MODEL_SIZE * n_models, 0) && copy_h2d(h->d_dts, dts_host, sizeof(double) * T, 0);
+  // horizon indexes of the reference stream (TrajectoryBuffer.compute_horizon_indexes, trajectory.py:199-215)
+  int32_t* hidx = (int32_t*)std::malloc(sizeof(int32_t) * (T + 1));
+  ok = hidx != nullptr && dev_alloc((void**)&h->d_hidx, sizeof(int32_t) * (T + 1));
+  if (ok) {
+    hidx[0] = 0;
+    for (int i = 0; i < T; ++i) {
+      const double f = dts_host[i] / dts_host[0];
+      hidx[i + 1] = hidx[i] + (int)(f + 0.5);
+    }
+    ok = copy_h2d(h->d_hidx, hidx, sizeof(int32_t) * (T + 1), 0);
+  }
+  ok = ok && copy_h2d(h->d_model, tab, sizeof(double) * MODEL_SIZE * n_models, 0) && copy_h2d(h->d_dts, dts_host, sizeof(double) * T, 0);
 #if AGX_GPU
   ok = ok && cudaStreamSynchronize(0) == cudaSuccess;
 #endif
   std::free(tab);
+  std::free(hidx);
   if (!ok) return fail(h, AGX_ECUDA, "upload of the model tables failed");
   return AGX_OK;
 }
@@ -263,6 +276,16 @@ int agx_set_refs(agx_handle* h, const double* refs, void* stream) {
   if (!copy_d2d(h->d_refs, refs, sizeof(double) * (size_t)h->B * (h->T + 1) * REF_SIZE, (stream_t)stream))
     return fail(h, AGX_ECUDA, "agx_set_refs: copy failed");
   return AGX_OK;
+}
+
+int agx_set_refs_window(agx_handle* h, const double* stream_refs, int n_streams, int n_points, const int32_t* start,
+                        int start0, void* stream) {
+  if (!h || !stream_refs || n_points <= 0 || (n_streams != 1 && n_streams != h->B)) return AGX_EINVAL;
+  DeviceGuard g(h->device);
+  const long long n = (long long)h->B * (h->T + 1) * REF_SIZE;
+  AGX_LAUNCH(h, gather_refs_kernel, (n + 255) / 256, 256, 0, (stream_t)stream, h->B, h->T + 1, stream_refs, n_streams,
+             n_points, start, start0, (const int32_t*)h->d_hidx, h->d_refs);
+  return check_launch(h, "agx_set_refs_window");
 }
 
 int agx_calc(agx_handle* h, const double* xs, const double* us, double* out_cost, double* out_xnext, void* stream) {

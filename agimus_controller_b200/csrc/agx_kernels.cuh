@@ -926,6 +926,23 @@ __global__ void rollout_kernel(Problem P, const double* __restrict__ x0, const d
   }
 }
 
+// Reference window: refs[b][t][:] = stream[b or 0][start_b + horizon_idx[t]][:] — the device-side replacement of the
+// per-tick horizon extraction (TrajectoryBuffer.horizon, trajectory.py:199-222) and of the per-node setter loop /
+// circularAppend of ocp_croco_generic.py:855-892: the whole reference stream stays on the device.
+__global__ void gather_refs_kernel(int B, int T1, const double* __restrict__ stream, int n_streams, int n_points,
+                                   const int32_t* __restrict__ start, int start0, const int32_t* __restrict__ hidx,
+                                   double* __restrict__ refs) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = gid / REF_SIZE;
+  const int k = (int)(gid % REF_SIZE);
+  if (n >= (long long)B * T1) return;
+  const int b = (int)(n / T1), t = (int)(n % T1);
+  int p = (start ? start[b] : start0) + hidx[t];
+  if (p >= n_points) p = n_points - 1;  // buffer under-run: repeat the last point (agimus_controller.py:492-503)
+  if (p < 0) p = 0;
+  refs[gid] = stream[((size_t)(n_streams > 1 ? b : 0) * n_points + p) * REF_SIZE + k];
+}
+
 // per-cost evaluation: one thread per node -> [state_reg, control_reg, goal_tracking, r6(6)] (9 doubles)
 __global__ void cost_terms_kernel(Problem P, const double* __restrict__ xs, const double* __restrict__ us,
                                   double* __restrict__ out_terms) {

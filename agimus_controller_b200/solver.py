@@ -118,6 +118,22 @@ class BatchedShootingProblem:
         self._check(lib().agx_set_refs(self._h, _ptr(r), self._stream()))
         self._refs_set = True
 
+    def set_refs_window(self, stream_refs: torch.Tensor, start) -> None:
+        """Select the horizon window out of a device-resident reference stream ``[n_points, ref_size]`` (shared) or
+        ``[B, n_points, ref_size]``; ``start`` is an int (all problems) or an int32 device tensor ``[B]``."""
+        r = torch.as_tensor(stream_refs, dtype=torch.float64, device=self.device).contiguous()
+        if r.dim() == 2:
+            r = r[None]
+        if r.shape[0] not in (1, self.B) or r.shape[2] != self.ref_size:
+            raise ValueError(f"bad reference stream shape {tuple(r.shape)}")
+        if isinstance(start, torch.Tensor):
+            st = start.to(device=self.device, dtype=torch.int32).contiguous()
+            self._check(lib().agx_set_refs_window(self._h, _ptr(r), r.shape[0], r.shape[1], _ptr(st), 0, self._stream()))
+        else:
+            self._check(lib().agx_set_refs_window(self._h, _ptr(r), r.shape[0], r.shape[1], None, int(start),
+                                                  self._stream()))
+        self._refs_set = True
+
     # ------------------------------------------------------------------ problem.calc / calcDiff / rollout
     def calc(self, xs, us):
         xs = self._t(xs, (self.B, self.T + 1, self.nx))

@@ -109,6 +109,16 @@ const char* agx_last_error(const agx_handle* h);
  * refs: device [B][T+1][ref_size]; copied into the handle (stream ordered). */
 int agx_set_refs(agx_handle* h, const double* refs, void* stream);
 
+/* Device-side reference stream: instead of rebuilding the [B][T+1][ref_size] table on the host every tick, keep the
+ * whole weighted reference trajectory on the device — stream_refs [n_streams][n_points][ref_size], n_streams = 1
+ * (shared by the batch) or B — and select the horizon window: node t of problem b reads point
+ * start_b + hidx[t], hidx = cumulative step factors dts[i]/dts[0] (TrajectoryBuffer.compute_horizon_indexes,
+ * trajectory.py:199-215); indices past the end repeat the last point.  `start` is a device int32 [B] or NULL (then
+ * start0 applies to every problem).  Replaces buffer.horizon + set_reference_weighted_trajectory (mpc.py:40-41,
+ * ocp_croco_generic.py:855-892) and the rolling-buffer circularAppend. */
+int agx_set_refs_window(agx_handle* h, const double* stream_refs, int n_streams, int n_points, const int32_t* start,
+                        int start0, void* stream);
+
 /* problem.calc: xs [B][T+1][nx], us [B][T][nu] -> out_cost [B][T+1] (node costs),
  * out_xnext [B][T+1][nx] (terminal row = xs_T). Either output may be NULL. */
 int agx_calc(agx_handle* h, const double* xs, const double* us, double* out_cost,

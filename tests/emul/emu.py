@@ -168,3 +168,21 @@ def shift_warmstart(models, refs, dts, xs, us):
     oxs, ous = np.zeros_like(xs), np.zeros_like(us)
     h.check(lib().agx_shift_warmstart(h.h, _p(xs), _p(us), _p(oxs), _p(ous), None))
     return oxs, ous
+
+
+def refs_window_cost(models, dts, stream_refs, start, xs, us):
+    """Set the references from a stream window, then problem.calc (exercises agx_set_refs_window)."""
+    xs, us = _c(xs), _c(us)
+    B, T1, nx = xs.shape
+    h = Handle(models, dts, B, T1 - 1)
+    sr = _c(stream_refs)
+    if sr.ndim == 2:
+        sr = sr[None]
+    if np.ndim(start) == 0:
+        h.check(lib().agx_set_refs_window(h.h, _p(sr), sr.shape[0], sr.shape[1], None, int(start), None))
+    else:
+        st = np.ascontiguousarray(start, dtype=np.int32)
+        h.check(lib().agx_set_refs_window(h.h, _p(sr), sr.shape[0], sr.shape[1], st.ctypes.data, 0, None))
+    cost, xnext = np.zeros((B, T1)), np.zeros((B, T1, nx))
+    h.check(lib().agx_calc(h.h, _p(xs), _p(us), _p(cost), _p(xnext), None))
+    return cost

@@ -218,3 +218,25 @@ def test_nan_inputs_do_not_poison_neighbours(orc, m7):
     o = orc.solve(m7, w["refs"], w["dts"], x0, xs, w["us_ws"], 3, opts)
     np.testing.assert_array_equal(e["status"], o["status"])
     np.testing.assert_array_equal(e["iters"], o["iters"])
+
+
+def test_reference_window_follows_the_buffer_horizon_indexes(orc, m7):
+    """agx_set_refs_window == TrajectoryBuffer.horizon (trajectory.py:199-222): with factors [1, 2, 4] x n_steps
+    [2, 2, 1] the horizon reads points start + [0, 1, 2, 4, 6, 10]; past the end the last point repeats
+    (tests/test_buffer.py:82-93 pins the index rule)."""
+    from agimus_controller_b200.workloads import sine_configuration_reference
+
+    table, rows, q, v, u = sine_configuration_reference(40, rnea=lambda q_, v_, a_: orc.rnea(m7, q_, v_, a_))
+    dts = np.array([0.01, 0.01, 0.02, 0.02, 0.04])
+    hidx = np.array([0, 1, 2, 4, 6, 10])
+    B, T = 3, 5
+    rng = np.random.default_rng(0)
+    xs = rng.uniform(-0.3, 0.3, (B, T + 1, 14)) + np.concatenate([q[0], v[0]])
+    us = rng.uniform(-2, 2, (B, T, 7))
+    start = np.array([0, 7, 33])
+    cost = emu.refs_window_cost(m7, dts, rows, start, xs, us)
+    refs = np.stack([rows[np.minimum(s0 + hidx, 39)] for s0 in start])
+    expect, _ = orc.calc(m7, refs, dts, xs, us)
+    np.testing.assert_allclose(cost, expect, rtol=1e-12)
+    cost0 = emu.refs_window_cost(m7, dts, rows, 7, xs, us)
+    np.testing.assert_allclose(cost0[1], cost[1], rtol=0, atol=0)

@@ -281,3 +281,26 @@ def test_cost_terms_and_shift_on_gpu(solver_mod, orc):
     np.testing.assert_array_equal(oxs_h[:, 12], xs_h[:, 12])
     np.testing.assert_array_equal(ous.cpu().numpy()[:, :6], us[:, 1:7])
     np.testing.assert_array_equal(ous.cpu().numpy()[:, 6:], us[:, 6:])
+
+
+def test_reference_window_on_gpu(solver_mod, orc):
+    """agx_set_refs_window gathers the same table the host would build from TrajectoryBuffer.horizon."""
+    from agimus_controller_b200.workloads import sine_configuration_reference
+
+    m = panda_table().to_struct()
+    table, rows, q, v, u = sine_configuration_reference(200, rnea=lambda q_, v_, a_: orc.rnea(m, q_, v_, a_))
+    dts = np.array([0.01] * 6 + [0.02] * 4 + [0.04] * 2)
+    hidx = np.concatenate([[0], np.cumsum(np.round(dts / dts[0]).astype(int))])
+    B, T = 64, 12
+    p = solver_mod.BatchedShootingProblem(table, dts, B)
+    rng = np.random.default_rng(1)
+    xs = rng.uniform(-0.3, 0.3, (B, T + 1, 14)) + np.concatenate([q[0], v[0]])
+    us = rng.uniform(-2, 2, (B, T, 7))
+    start = rng.integers(0, 190, B)
+    p.set_refs_window(torch.as_tensor(rows, device=p.device), torch.as_tensor(start, dtype=torch.int32))
+    c_win, _ = p.calc(xs, us)
+    refs = np.stack([rows[np.minimum(s0 + hidx, 199)] for s0 in start])
+    p.set_refs(refs)
+    c_tab, _ = p.calc(xs, us)
+    assert torch.equal(c_win, c_tab)
+    assert rel(c_win.cpu().numpy(), orc.calc(m, refs, dts, xs, us)[0]) < 1e-12
