@@ -69,6 +69,9 @@ int env_cta(const char* name, int dflt) {
 }
 const int NODE_CTA = env_cta("AGX_NODE_CTA", 64);
 const int SEQ_CTA = env_cta("AGX_SEQ_CTA", 32);
+// backward sweep: "mma" = one warp per problem on the FP64 tensor cores (default), "octet" = 8 lanes per problem
+const bool BW_MMA = !(std::getenv("AGX_BW") && std::string(std::getenv("AGX_BW")) == "octet");
+const int BWM_CTA = env_cta("AGX_BWM_CTA", 32);
 const int COST_CTA = 64;  // thread-per-node cost kernel: 2 warps, 33 KB of staging shared memory
 const size_t COST_SMEM = sizeof(double) * COST_STAGE * (COST_CTA / 32);
 
@@ -168,6 +171,16 @@ struct DeviceGuard {
 #else
 struct DeviceGuard { explicit DeviceGuard(int) {} };
 #endif
+
+void launch_backward(agx_handle* h, const agx::Problem& P, const agx::Work& W, const agx::FddpOpts& O, stream_t st) {
+  if (BW_MMA) {
+    const int wpc = 1;  // one warp per CTA (matches the kernel's __launch_bounds__)
+    AGX_LAUNCH(h, backward_mma_kernel, (h->B + wpc - 1) / wpc, 32 * wpc, sizeof(double) * MB_SIZE * wpc, st, P, W, h->S, O);
+  } else {
+    const int opc_s = SEQ_CTA / 8;
+    AGX_LAUNCH(h, backward_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * BW_SIZE * opc_s, st, P, W, h->S, O);
+  }
+}
 
 }  // namespace
 
@@ -384,7 +397,7 @@ int agx_riccati(agx_handle* h, const double* x0, const double* xs, const double*
   AGX_LAUNCH(h, calc_diff_kernel, (ents + opc_n - 1) / opc_n, NODE_CTA, sizeof(double) * OCT_BOARD * opc_n, st, P,
              (const double*)W.xs, (const double*)W.us, (const int32_t*)h->S.cur, (const int32_t*)h->S.recalc,
              (const int32_t*)h->S.recalc_cost, 0, (const int32_t*)h->S.done, W.rec, W.crec);
-  AGX_LAUNCH(h, backward_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * BW_SIZE * opc_s, st, P, W, h->S, O);
+  launch_backward(h, P, W, O, st);
   bool ok = true;
   if (out_k) ok = ok && copy_d2d(out_k, W.k, sizeof(double) * nB * T * NJ, st);
   if (out_status) ok = ok && copy_d2d(out_status, h->S.status, sizeof(int32_t) * nB, st);
@@ -521,7 +534,7 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
                (const int32_t*)(it == 0 ? nullptr : h->S.recalc_cost), 0, (const int32_t*)h->S.done, W.rec, W.crec);
     phase_end(h, st);
     phase_begin(h, 1, st);
-    AGX_LAUNCH(h, backward_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * BW_SIZE * opc_s, st, P, W, h->S, O);
+    launch_backward(h, P, W, O, st);
     phase_end(h, st);
     phase_begin(h, 2, st);
     AGX_LAUNCH(h, rollout_try_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * FW_BOARD * opc_s, st, P, W,

@@ -657,6 +657,10 @@ __global__ void backward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
 }
 
 // ---------------------------------------------------------------------------------------------
+}  // namespace agx
+#include "agx_riccati_mma.cuh"
+namespace agx {
+
 // Forward pass of one FDDP iteration, split so that the common case costs little:
 //   rollout_try_kernel  (octet per problem)  nonlinear rollout with alpha = 1, dynamics only
 //   node_cost_kernel    (thread per node)    costs (+ their derivatives) of the trial trajectory

@@ -29,6 +29,12 @@
                "l"(src_gmem))
 #define AGX_CP_ASYNC_COMMIT() asm volatile("cp.async.commit_group;")
 #define AGX_CP_ASYNC_WAIT_ALL() asm volatile("cp.async.wait_group 0;")
+// FP64 tensor-core tile product D(8x8) = A(8x4) B(4x8) + C (DMMA): lane T holds a = A[T/4][T%4],
+// b = B[T%4][T/4], c/d = C[T/4][2(T%4) + {0,1}]
+#define AGX_DMMA(d0, d1, a, b, c0, c1)                                                              \
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"      \
+               : "=d"(d0), "=d"(d1)                                                                 \
+               : "d"(a), "d"(b), "d"(c0), "d"(c1))
 #else
 #define AGX_GPU 0
 #define AGX_DEV inline
@@ -43,6 +49,7 @@
 #define AGX_CP_ASYNC16(dst_smem, src_gmem) memcpy((dst_smem), (src_gmem), 16)
 #define AGX_CP_ASYNC_COMMIT() ((void)0)
 #define AGX_CP_ASYNC_WAIT_ALL() ((void)0)
+#define AGX_DMMA(d0, d1, a, b, c0, c1) agx_emul_dmma((d0), (d1), (a), (b), (c0), (c1))
 #endif
 
 namespace agx {

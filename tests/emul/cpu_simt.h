@@ -199,6 +199,25 @@ inline int __any_sync(unsigned mask, int pred) {
   __syncwarp(mask);
   return any;
 }
+// mma.sync.aligned.m8n8k4.row.col.f64: D(8x8) = A(8x4) B(4x8) + C.  Lane T holds a = A[T/4][T%4], b = B[T%4][T/4],
+// c/d = C[T/4][2(T%4) + {0,1}].  All 32 lanes of the warp take part.
+struct simt_mma_slots { double a[32], b[32]; };
+inline simt_mma_slots& simt_mma(int warp) { static simt_mma_slots s[8]; return s[warp]; }
+inline void agx_emul_dmma(double& d0, double& d1, double a, double b, double c0, double c1) {
+  simt::Block* blk = simt::cur_block();
+  const int me = blk->current, lane = me & 31, warp = me >> 5;
+  simt_mma_slots& s = simt_mma(warp);
+  s.a[lane] = a; s.b[lane] = b;
+  __syncwarp();
+  const int g = lane >> 2, q = lane & 3;
+  double r0 = c0, r1 = c1;
+  for (int k = 0; k < 4; ++k) {
+    r0 = std::fma(s.a[g * 4 + k], s.b[(2 * q) * 4 + k], r0);
+    r1 = std::fma(s.a[g * 4 + k], s.b[(2 * q + 1) * 4 + k], r1);
+  }
+  __syncwarp();
+  d0 = r0; d1 = r1;
+}
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 inline void sincos(double x, double* s, double* c) { *s = std::sin(x); *c = std::cos(x); }
 inline double __ldg(const double* p) { return *p; }
