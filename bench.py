@@ -378,11 +378,33 @@ def run_ours(args):
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch, same command line)
+    traffic = None
+    try:
+        import csv
+
+        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r1_ncu_full_final_raw.csv"))))
+        hdr, units = rows[0], rows[1]
+        kname = {"backward": "backward_mma_kernel", "node_cost": "node_cost_kernel"}.get(top, (top or "") + "_kernel")
+        for row in rows[2:]:
+            if kname in row[hdr.index("Kernel Name")]:
+                def _bytes(col):
+                    v, u = float(row[hdr.index(col)]), units[hdr.index(col)]
+                    return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
+                traffic = _bytes("dram__bytes_read.sum") + _bytes("dram__bytes_write.sum")
+                break
+    except Exception:
+        traffic = None
     roofline = None
     if top:
         roofline = {
-            "kernel": top + "_kernel", "bound": "fp64", "achieved": per[top]["tflops"], "peak": fp64_peak,
-            "unit": "TFLOP/s", "frac": per[top]["tflops"] / fp64_peak if fp64_peak else None, "traffic": None,
+            "kernel": {"backward": "backward_mma_kernel" if os.environ.get("AGX_BW", "mma") != "octet" else "backward_kernel",
+                       "node_cost": "node_cost_kernel<true>"}.get(top, top + "_kernel"),
+            "bound": "fp64", "achieved": per[top]["tflops"], "peak": fp64_peak,
+            "unit": "TFLOP/s", "frac": per[top]["tflops"] / fp64_peak if fp64_peak else None, "traffic": traffic,
+            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from "
+                            "profiles/r1_ncu_full_final_raw.csv; algorithmic bytes per launch: "
+                            f"{bytes_alg[top]:.0f}",
             "peak_source": "in-run DFMA probe (agx_probe_fp64); MEASURED_PEAKS.json carries no FP64 figure",
             "hbm": {"achieved": per[top]["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": per[top]["gbs"] / hbm_peak,
                     "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
