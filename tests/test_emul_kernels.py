@@ -10,6 +10,10 @@ from agimus_controller_b200 import PANDA_Q_NOMINAL, _abi, panda_table
 from agimus_controller_b200.workloads import goal_reaching_batch, golden_problem
 from emul import emu
 
+import pathlib
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+
 
 def rel(a, b):
     return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(b).max(), 1e-300))
@@ -240,3 +244,31 @@ def test_reference_window_follows_the_buffer_horizon_indexes(orc, m7):
     np.testing.assert_allclose(cost, expect, rtol=1e-12)
     cost0 = emu.refs_window_cost(m7, dts, rows, 7, xs, us)
     np.testing.assert_allclose(cost0[1], cost[1], rtol=0, atol=0)
+
+
+def test_octet_sweep_still_matches(orc, m7, tmp_path):
+    """The DFMA (octet) Riccati sweep is kept as a cross-check of the tensor-core sweep: AGX_BW=octet selects it at
+    library load, so it runs in a subprocess; both must reproduce the oracle's iterates."""
+    import os
+    import subprocess
+    import sys
+
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from agimus_controller_b200 import _abi, panda_table
+from agimus_controller_b200.workloads import goal_reaching_batch
+from emul import emu
+from oracle import orc
+m = panda_table().to_struct()
+w = goal_reaching_batch(3, T=10, rnea=lambda q, v, a: orc.rnea(m, q, v, a))
+opts = _abi.default_fddp_opts(fixed_iters=True)
+o = orc.solve(m, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 3, opts)
+e = emu.solve(m, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 3, opts)
+for k in ("xs", "us", "K", "cost"):
+    assert np.abs(e[k] - o[k]).max() / np.abs(o[k]).max() < 1e-8, k
+print("octet ok")
+''' % (str(ROOT), str(ROOT / "tests"))
+    env = dict(os.environ, AGX_BW="octet")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "octet ok" in r.stdout, r.stderr[-2000:]
