@@ -153,13 +153,19 @@ calc_diff_kernel(Problem P, const double* __restrict__ xs, const double* __restr
   const int T1 = P.T + 1;
   if (ent >= (long long)P.B * T1) return;
   const int b = (int)(ent / T1), t = (int)(ent % T1);
-  if (done && done[b]) return;
-  const bool do_dyn = !recalc || recalc[b];
-  const bool do_cost = cost_everywhere || (recalc_cost && recalc_cost[b]);
+  // the per-problem flags are independent loads: issue them together, then branch (a chain of dependent
+  // global loads at the start of every octet's work is pure exposed latency at two warps per scheduler)
+  const int f_done = done ? done[b] : 0;
+  const int f_dyn = recalc ? recalc[b] : 1;
+  const int f_cost = recalc_cost ? recalc_cost[b] : 0;
+  const int f_cur = cur ? (cur[b] & 1) : 0;
+  if (f_done) return;
+  const bool do_dyn = f_dyn != 0;
+  const bool do_cost = cost_everywhere || f_cost != 0;
   if (!do_dyn && !do_cost) return;
   double* sb = smem + oct_in_cta * OCT_BOARD;
   double* sc = sb + BRD_B;
-  const size_t buf = buf_of(cur, b, false);
+  const size_t buf = (size_t)f_cur;
   const double* x = xs + ((buf * P.B + b) * T1 + t) * NX;
   const bool terminal = t == P.T;
   const bool live = j < NJ;
@@ -223,12 +229,16 @@ __global__ void node_cost_kernel(Problem P, const double* __restrict__ xs, const
   const int T1 = P.T + 1;
   const long long N = (long long)P.B * T1;
   const int b = (int)((n < N ? n : N - 1) / T1), t = (int)((n < N ? n : N - 1) % T1);
-  const bool active = n < N && !(done && done[b]) && !(gate && !gate[b]);
+  // independent flag loads first (see calc_diff_kernel)
+  const int f_done = done ? done[b] : 0;
+  const int f_gate = gate ? gate[b] : 1;
+  const int f_cur = cur ? (cur[b] & 1) : 0;
+  const bool active = n < N && !f_done && f_gate != 0;
   // the 64 outputs of a node are staged in shared memory (row stride 65: conflict-free) and written out by
   // the whole warp as one contiguous 16 KB block: a thread-per-node store would touch 32 sectors per instruction
   double* stage = smem + warp * COST_STAGE;
   if (active) {
-    const size_t buf = buf_of(cur, b, other != 0);
+    const size_t buf = (size_t)(cur ? (other ? (f_cur ^ 1) : f_cur) : 0);
     const bool terminal = t == P.T;
     const double* x = xs + ((buf * P.B + b) * T1 + t) * NX;
     const double* u = terminal ? nullptr : us + ((buf * P.B + b) * P.T + t) * NJ;
