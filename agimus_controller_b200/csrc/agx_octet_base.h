@@ -27,6 +27,9 @@
 #define AGX_CP_ASYNC16(dst_smem, src_gmem)                                                       \
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), \
                "l"(src_gmem))
+#define AGX_CP_ASYNC8(dst_smem, src_gmem)                                                        \
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), \
+               "l"(src_gmem))
 #define AGX_CP_ASYNC_COMMIT() asm volatile("cp.async.commit_group;")
 #define AGX_CP_ASYNC_WAIT_ALL() asm volatile("cp.async.wait_group 0;")
 // FP64 tensor-core tile product D(8x8) = A(8x4) B(4x8) + C (DMMA): lane T holds a = A[T/4][T%4],
@@ -47,6 +50,7 @@
 #define AGX_SMEM(name) double* name = reinterpret_cast<double*>(simt::g_smem)
 #define AGX_PREFETCH(p) ((void)(p))
 #define AGX_CP_ASYNC16(dst_smem, src_gmem) memcpy((dst_smem), (src_gmem), 16)
+#define AGX_CP_ASYNC8(dst_smem, src_gmem) memcpy((dst_smem), (src_gmem), 8)
 #define AGX_CP_ASYNC_COMMIT() ((void)0)
 #define AGX_CP_ASYNC_WAIT_ALL() ((void)0)
 #define AGX_DMMA(d0, d1, a, b, c0, c1) agx_emul_dmma((d0), (d1), (a), (b), (c0), (c1))

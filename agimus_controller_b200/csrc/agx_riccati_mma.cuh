@@ -31,7 +31,8 @@ constexpr int MB_W = 288;       // [8][20]  W, later K
 constexpr int MB_QUX = 448;     // [8][20]  [Qux | Qu]
 constexpr int MB_V = 608;       // [16][17] unsymmetrised Vxx
 constexpr int MB_FS = 880;      // [16]     gap of the node (padded indexing)
-constexpr int MB_SIZE = 896;
+constexpr int MB_ST = 896;      // [15][32] next node's per-lane operands, staged by cp.async
+constexpr int MB_SIZE = 896 + 15 * 32;
 
 AGX_DEV double warp_sum(double x) {
   x += __shfl_xor_sync(0xffffffffu, x, 16, 32);
@@ -74,7 +75,7 @@ AGX_DEV bool chol7_registers_strided(const double* sm_M, int stride, double* A /
   return ok;
 }
 
-// per-lane operands of one node, fetched one node ahead
+// per-lane operands of one node
 struct MmaNodeIn {
   double gB[2][2];   // G[4 kc + q][8 tc + g]  (tc = 0: dt aq, tc = 1: I + dt av)
   double nB[2];      // N[4 kc + q][g]         (dt Minv)
@@ -84,29 +85,54 @@ struct MmaNodeIn {
   double h;
 };
 
-AGX_DEV void mma_fetch(MmaNodeIn& n, const double* __restrict__ R, const double* __restrict__ C,
-                       const double* __restrict__ fs, double h, bool gaps, int g, int q) {
+// The 15 per-lane operands of a node are copied global -> shared (8-byte
+// cp.async, no registers) while the previous node is processed; every lane reads back only its own slots.
+AGX_DEV void mma_stage(double* st, const double* __restrict__ R, const double* __restrict__ C,
+                       const double* __restrict__ fs, bool gaps, int g, int q, int lane) {
+  const int gg = g < NJ ? g : NJ - 1;
+#pragma unroll
+  for (int kc = 0; kc < 2; ++kc) {
+    const int r = 4 * kc + q, rr = r < NJ ? r : NJ - 1;
+    AGX_CP_ASYNC8(st + (0 + kc) * 32 + lane, R + (RK_AQ + rr) * 8 + gg);
+    AGX_CP_ASYNC8(st + (2 + kc) * 32 + lane, R + (RK_AV + rr) * 8 + gg);
+    AGX_CP_ASYNC8(st + (4 + kc) * 32 + lane, R + (RK_MI + rr) * 8 + gg);
+  }
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int c = 2 * q + e < NJ ? 2 * q + e : NJ - 1;
+    AGX_CP_ASYNC8(st + (6 + e) * 32 + lane, C + CK_LQQ + (gg >= c ? lidx_(gg, c) : lidx_(c, gg)));
+  }
+  AGX_CP_ASYNC8(st + 8 * 32 + lane, C + CK_LVV + gg);
+  AGX_CP_ASYNC8(st + 9 * 32 + lane, C + CK_LUU + gg);
+  AGX_CP_ASYNC8(st + 10 * 32 + lane, C + CK_LQ + gg);
+  AGX_CP_ASYNC8(st + 11 * 32 + lane, C + CK_LV + gg);
+  AGX_CP_ASYNC8(st + 12 * 32 + lane, C + CK_LU + gg);
+  if (gaps) {
+    AGX_CP_ASYNC8(st + 13 * 32 + lane, fs + gg);
+    AGX_CP_ASYNC8(st + 14 * 32 + lane, fs + NJ + gg);
+  }
+  AGX_CP_ASYNC_COMMIT();
+}
+AGX_DEV void mma_unstage(MmaNodeIn& n, const double* st, double h, bool gaps, int g, int q, int lane) {
+  AGX_CP_ASYNC_WAIT_ALL();
   const bool gl = g < NJ;
 #pragma unroll
   for (int kc = 0; kc < 2; ++kc) {
     const int r = 4 * kc + q;
     const bool ok = gl && r < NJ;
-    n.gB[0][kc] = ok ? R[(RK_AQ + r) * 8 + g] : 0.0;
-    n.gB[1][kc] = ok ? R[(RK_AV + r) * 8 + g] + ((r == g) ? 1.0 : 0.0) : 0.0;
-    n.nB[kc] = ok ? R[(RK_MI + r) * 8 + g] : 0.0;
+    n.gB[0][kc] = ok ? st[(0 + kc) * 32 + lane] : 0.0;
+    n.gB[1][kc] = ok ? st[(2 + kc) * 32 + lane] + ((r == g) ? 1.0 : 0.0) : 0.0;
+    n.nB[kc] = ok ? st[(4 + kc) * 32 + lane] : 0.0;
   }
 #pragma unroll
-  for (int e = 0; e < 2; ++e) {
-    const int c = 2 * q + e;
-    n.lqq[e] = (gl && c < NJ) ? C[CK_LQQ + (g >= c ? lidx_(g, c) : lidx_(c, g))] : 0.0;
-  }
-  n.lvv = gl ? C[CK_LVV + g] : 0.0;
-  n.luu = gl ? C[CK_LUU + g] : 0.0;
-  n.lq = gl ? C[CK_LQ + g] : 0.0;
-  n.lv = gl ? C[CK_LV + g] : 0.0;
-  n.lu = gl ? C[CK_LU + g] : 0.0;
-  n.fs0 = (gl && gaps) ? fs[g] : 0.0;
-  n.fs1 = (gl && gaps) ? fs[NJ + g] : 0.0;
+  for (int e = 0; e < 2; ++e) n.lqq[e] = (gl && 2 * q + e < NJ) ? st[(6 + e) * 32 + lane] : 0.0;
+  n.lvv = gl ? st[8 * 32 + lane] : 0.0;
+  n.luu = gl ? st[9 * 32 + lane] : 0.0;
+  n.lq = gl ? st[10 * 32 + lane] : 0.0;
+  n.lv = gl ? st[11 * 32 + lane] : 0.0;
+  n.lu = gl ? st[12 * 32 + lane] : 0.0;
+  n.fs0 = (gl && gaps) ? st[13 * 32 + lane] : 0.0;
+  n.fs1 = (gl && gaps) ? st[14 * 32 + lane] : 0.0;
   n.h = h;
 }
 
@@ -159,8 +185,9 @@ __global__ void __launch_bounds__(32, AGX_BWM_MINB) backward_mma_kernel(Problem 
     double dgp = 0.0, dqp = 0.0;
     MmaNodeIn cur;
     if (ok) {
-      mma_fetch(cur, rec0 + (size_t)(T - 1) * REC_SIZE, crec0 + (size_t)(T - 1) * CREC_SIZE, fsb + (size_t)(T - 1) * NX,
-                P.dts[T - 1], !feasible, g, q);
+      // the first running node's operands start flowing into shared memory while the terminal node is handled
+      mma_stage(sm + MB_ST, rec0 + (size_t)(T - 1) * REC_SIZE, crec0 + (size_t)(T - 1) * CREC_SIZE,
+                fsb + (size_t)(T - 1) * NX, !feasible, g, q, lane);
       // ---- terminal node: Vxx = Lxx (+ xreg), Vx = Lx (+ Vxx fs)
       const double* C = crec0 + (size_t)T * CREC_SIZE;
       const double lvvT = gl ? C[CK_LVV + g] : 0.0;
@@ -203,15 +230,11 @@ __global__ void __launch_bounds__(32, AGX_BWM_MINB) backward_mma_kernel(Problem 
     }
     // ---- running nodes
     for (int t = T - 1; ok && t >= 0; --t) {
-      if (t < T - 1)
-        mma_fetch(cur, rec0 + (size_t)t * REC_SIZE, crec0 + (size_t)t * CREC_SIZE, fsb + (size_t)t * NX, P.dts[t],
-                  !feasible, g, q);
-      if (t > 0) {
-        // pull the next node's records (1472 + 512 B = 16 lines) into L1 behind this node's arithmetic
-        if (lane < 12) AGX_PREFETCH(rec0 + (size_t)(t - 1) * REC_SIZE + lane * 16);
-        else if (lane < 16) AGX_PREFETCH(crec0 + (size_t)(t - 1) * CREC_SIZE + (lane - 12) * 16);
-        else if (lane == 16) AGX_PREFETCH(fsb + (size_t)(t - 1) * NX);
-      }
+      // this node's operands were staged during the previous node; the next node's follow behind the arithmetic
+      mma_unstage(cur, sm + MB_ST, P.dts[t], !feasible, g, q, lane);
+      if (t > 0)
+        mma_stage(sm + MB_ST, rec0 + (size_t)(t - 1) * REC_SIZE, crec0 + (size_t)(t - 1) * CREC_SIZE,
+                  fsb + (size_t)(t - 1) * NX, !feasible, g, q, lane);
       const double h = cur.h;
       // (1) Z = S^T V' (two tiles), Vs = Z S, sv = S^T v'
       double Zt[2][2], Vs[2];
@@ -393,6 +416,7 @@ __global__ void __launch_bounds__(32, AGX_BWM_MINB) backward_mma_kernel(Problem 
       if (!gl) { vx[0] = 0.0; vx[1] = 0.0; }
       __syncwarp();
     }
+    AGX_CP_ASYNC_WAIT_ALL();  // nothing may still be in flight when the sweep is abandoned or restarted
     if (ok) {
       // non-finite value function = failed sweep (SolverDDP::backwardPass raises on NaN)
       double chk = vlane ? vx[0] + vx[1] : 0.0;
