@@ -327,7 +327,7 @@ __global__ void expand_kernel(Problem P, const double* __restrict__ rec, const d
 // the products collapse to 7-deep ones:  Z = S^T V', Vs = Z S, W = Vs G + [Z_q 0],
 //   Qxx = Lxx + [V'_qq 0; 0 0] + G^T W + [Z_q^T G; 0],  Qux = N^T W,  Quu = Luu + N^T Vs N,
 //   Qx = Lx + [v'_q; 0] + G^T S^T v',  Qu = Lu + N^T S^T v'.
-constexpr int FW_BOARD = OCT_BOARD + 16;  // forward_kernel: node boards + dx[14] (odd stride kept)
+constexpr int FW_BOARD = OCT_BOARD + 1 + 16 + 2 * 98;  // forward kernels: node boards + dx[14] + two staged gain blocks (even: 16-byte aligned octet boards)
 // shared-memory board of one octet (doubles).  Regions that are never live together share storage.
 constexpr int BW_VS = 0;      // [7][8]   Vs ........ later the Quu columns handed to the factorisation
 constexpr int BW_L = 0;
@@ -731,6 +731,7 @@ __global__ void rollout_try_kernel(Problem P, Work W, SolverState S) {
   double* sb = smem + oct_in_cta * FW_BOARD;
   double* sc = sb + BRD_B;
   double* sdx = sc + BRD_C;  // [14]
+  double* sK = sdx + 16;     // [2][7][14] gain blocks of the current / next node
   const int T = P.T, T1 = T + 1;
   const bool live = j < NJ;
   const int jj = live ? j : 0;
@@ -756,10 +757,13 @@ __global__ void rollout_try_kernel(Problem P, Work W, SolverState S) {
     const bool gaps = live && !feasible;
     n.gq = gaps ? gvb[t * NX + jj] : 0.0;
     n.gv = gaps ? gvb[t * NX + NJ + jj] : 0.0;
+    // the node's 7x14 gain block (784 B) is copied global -> shared asynchronously: 49 chunks of 16 B over 8 lanes
     if (run) {
-      AGX_PREFETCH(Kb + (t * NJ + jj) * NX);
-      AGX_PREFETCH(Kb + (t * NJ + jj) * NX + NX - 1);
+      double* dst = sK + (t & 1) * 98;
+      const double* srck = Kb + (size_t)t * NJ * NX;
+      for (int c = j; c < 49; c += 8) AGX_CP_ASYNC16(dst + 2 * c, srck + 2 * c);
     }
+    AGX_CP_ASYNC_COMMIT();
   };
   double xq = live ? W.x0[(size_t)b * NX + jj] : 0.0, xv = live ? W.x0[(size_t)b * NX + NJ + jj] : 0.0;
   double dvp = 0.0;
@@ -768,6 +772,7 @@ __global__ void rollout_try_kernel(Problem P, Work W, SolverState S) {
   fetch(0, cur);
   for (int t = 0; t <= T; ++t) {
     NodeIn nxt;
+    AGX_CP_ASYNC_WAIT_ALL();  // node t's gain block has landed (it was issued one node ago)
     if (t < T) fetch(t + 1, nxt);
     const double dxq = live ? xq - cur.xsq : 0.0, dxv = live ? xv - cur.xsv : 0.0;
     if (live) {
@@ -780,7 +785,7 @@ __global__ void rollout_try_kernel(Problem P, Work W, SolverState S) {
     AGX_OSYNC();
     double s = 0.0;
 #pragma unroll
-    for (int m = 0; m < NX; ++m) s += Kb[(t * NJ + jj) * NX + m] * sdx[m];
+    for (int m = 0; m < NX; ++m) s += sK[(t & 1) * 98 + jj * NX + m] * sdx[m];
     LaneDyn d;
     d.q = xq; d.qd = xv;
     d.u = live ? cur.us - cur.kff - s : 0.0;
