@@ -214,7 +214,8 @@ def run_ours(args):
 
     opts = _abi.default_fddp_opts(fixed_iters=True)
     prob = BatchedShootingProblem(panda_table(), np.full(T_NODES, DT), B, device=dev)
-    w, m = build_workload(B, rank, lambda q, v, a: prob.rnea(q, v, a).cpu().numpy())
+    seed = rank + int(os.environ.get("AGX_BENCH_SEED", "0"))  # rank r solves its own slab (seed r)
+    w, m = build_workload(B, seed, lambda q, v, a: prob.rnea(q, v, a).cpu().numpy())
     # resident inputs
     refs_d = torch.as_tensor(w["refs"], device=dev)
     x0_d = torch.as_tensor(w["x0"], device=dev)
