@@ -88,6 +88,8 @@ class BatchedShootingProblem:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _t(self, x, shape) -> torch.Tensor:
+        if isinstance(x, np.ndarray) and not x.flags.writeable:
+            x = x.copy()  # broadcast views are read-only; torch wants a writable buffer
         t = torch.as_tensor(x, dtype=torch.float64, device=self.device).contiguous()
         if tuple(t.shape) != tuple(shape):
             raise ValueError(f"expected shape {tuple(shape)}, got {tuple(t.shape)}")

@@ -146,3 +146,55 @@ def test_batched_closed_loop_with_device_warm_starts(orc):
         torch.testing.assert_close(xs[:, :-1], out["xs"][:, 1:], rtol=0, atol=0)   # constant dt: pure shift
         torch.testing.assert_close(xs[:, 0], x, rtol=0, atol=1e-9)                  # the plant follows the plan
     assert bool((out["cost"] < cost_first).all())
+
+
+def test_pick_and_place_configuration_through_the_ocp_class(orc):
+    """The reference's pick-and-place example configuration (panda_pick_and_place/config: dt 0.01, 60 nodes =
+    30 x dt + 20 x 2dt + 10 x 4dt, max_iter 3, control_reg + state_reg only, terminal weight 0) through
+    OCPBatchedFDDP, against the oracle fed with the same flattened tables."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import yaml
+
+    from agimus_controller_b200 import _abi
+    from agimus_controller_b200.ocp_batched import OCPBatchedFDDP, build_reference_rows, flatten_cost_stack
+    from agimus_controller_b200.workloads import quintic
+
+    nv = 7
+    params = OCPParamsBaseCroco(dt=0.01, solver_iters=3, dt_factor_n_seq=DTFactorsNSeq([1, 2, 4], [30, 20, 10]),
+                                horizon_size=60)
+    assert abs(params.total_time - 1.1) < 1e-12
+    yml = pathlib.Path(__file__).parent / "golden" / "ocp_pick_and_place.yaml"
+    table = panda_table()
+    ocp = OCPBatchedFDDP(table, params, str(yml), batch_size=1)
+    # quintic joint-space move q_init -> q_nom over 1 s, sampled at the horizon indexes of the trajectory buffer
+    q_init = PANDA_Q_NOMINAL + np.array([0.3, -0.2, 0.25, 0.3, -0.3, 0.2, 0.1])
+    hidx = np.concatenate([[0], np.cumsum([1] * 30 + [2] * 20 + [4] * 10)])
+    horizon = []
+    for i in hidx:
+        s = float(quintic(0.01 * i, 1.0))
+        q = q_init + s * (PANDA_Q_NOMINAL - q_init)
+        horizon.append(WeightedTrajectoryPoint(
+            point=TrajectoryPoint(id=int(i), robot_configuration=q, robot_velocity=np.zeros(nv),
+                                  robot_acceleration=np.zeros(nv), robot_effort=np.zeros(nv),
+                                  end_effector_poses={"panda_hand_tcp": SE3()}),
+            weights=TrajectoryPointWeights(w_robot_configuration=np.full(nv, 3.0), w_robot_velocity=np.full(nv, 0.12),
+                                           w_robot_acceleration=np.zeros(nv), w_robot_effort=np.full(nv, 8e-4),
+                                           w_end_effector_poses={"panda_hand_tcp": np.zeros(6)})))
+    ocp.set_reference_weighted_trajectory(horizon)
+    x0 = np.concatenate([q_init, np.zeros(nv)])
+    u_grav = ocp.problem.rnea(q_init, np.zeros(nv), np.zeros(nv))[0].cpu().numpy()
+    ocp.solve(x0, [x0] * 61, [u_grav] * 60)
+    res = ocp.ocp_results
+    # oracle on the same flattened problem
+    data = yaml.safe_load(yml.read_text())
+    rows = build_reference_rows(table, flatten_cost_stack(data["running_model"], False),
+                                flatten_cost_stack(data["terminal_model"], True), horizon)
+    assert np.all(rows[-1, 14:28] == 0.0)  # terminal CostModelSum weight 0
+    m = table.to_struct()
+    o = orc.solve(m, rows[None], np.asarray(params.timesteps), x0[None], np.repeat(x0[None, None], 61, 1),
+                  np.repeat(u_grav[None, None], 60, 1), 3, _abi.default_fddp_opts())
+    assert np.abs(np.stack(res.states) - o["xs"][0]).max() / np.abs(o["xs"]).max() < 1e-6
+    assert np.abs(np.stack(res.feed_forward_terms) - o["us"][0]).max() / np.abs(o["us"]).max() < 1e-6
+    assert np.abs(np.stack(res.ricatti_gains) - o["K"][0]).max() / np.abs(o["K"]).max() < 1e-5
+    assert ocp.debug_data.nb_iter == int(o["iters"][0])
