@@ -18,8 +18,8 @@
 //   B = [[0, -2[hf]x], [0, Sym - [hn]x]]   (composite momentum (hf,hn) + a symmetric 3x3),
 // see DESIGN.md "calc_diff".
 //
-// Every phase is a plain inline function of ONE lane's state; phases that exchange data are split
-// into a store half and a load half with an octet barrier between them (agx_octet_base.h).
+// Every phase is a plain inline function of ONE lane's state.  The scans run in registers (width-8 warp
+// shuffles); the column phases read the other lanes' 6-vectors from a small shared-memory board.
 
 namespace agx {
 
@@ -48,7 +48,6 @@ struct LaneDyn {
 };
 
 // board sizes (doubles) used by the dynamics phases
-constexpr int BRD_A = 240;  // scratch region A: up to [8][30]
 constexpr int BRD_B = 144;  // region B: [8][18] = J(6) dFda(6) BS(3) b(1) u(1), persistent during derivatives
 constexpr int BRD_C = 64;   // region C: [7][8] mass matrix, then its Cholesky factor (slot 7 of row k = 1/L[k][k])
 
@@ -72,29 +71,6 @@ AGX_DEV void kin_local(LaneDyn& d, int j, const double* __restrict__ model) {
     d.p[0] = d.p[1] = d.p[2] = 0;
   }
 }
-AGX_DEV void se3_store(const LaneDyn& d, int j, double* sb) {
-#pragma unroll
-  for (int k = 0; k < 9; ++k) sb[j * 14 + k] = d.R[k];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) sb[j * 14 + 9 + k] = d.p[k];
-}
-AGX_DEV void se3_combine(LaneDyn& d, int j, int dist, const double* sb) {
-  if (j >= dist) {
-    const double* o = sb + (j - dist) * 14;
-    double Rn[9], pn[3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c)
-        Rn[3 * r + c] = o[3 * r] * d.R[c] + o[3 * r + 1] * d.R[3 + c] + o[3 * r + 2] * d.R[6 + c];
-      pn[r] = o[9 + r] + (o[3 * r] * d.p[0] + o[3 * r + 1] * d.p[1] + o[3 * r + 2] * d.p[2]);
-    }
-#pragma unroll
-    for (int k = 0; k < 9; ++k) d.R[k] = Rn[k];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) d.p[k] = pn[k];
-  }
-}
 AGX_DEV void kin_axis(LaneDyn& d, int j) {
   const double z[3] = {d.R[2], d.R[5], d.R[8]};
   double pz[3];
@@ -107,39 +83,6 @@ AGX_DEV void kin_axis(LaneDyn& d, int j) {
   }
 #pragma unroll
   for (int k = 0; k < 6; ++k) d.s[k] = d.J[k] * d.qd;
-}
-
-// exclusive prefix sum of a per-lane 6-vector over the chain (board: [8][6])
-AGX_DEV void vec6_store(const double* x, int j, double* sb) {
-#pragma unroll
-  for (int k = 0; k < 6; ++k) sb[j * 6 + k] = x[k];
-}
-AGX_DEV void vec6_prefix_excl(double* out, int j, const double* seed, const double* sb) {
-  double acc[6];
-#pragma unroll
-  for (int k = 0; k < 6; ++k) acc[k] = seed[k];
-#pragma unroll
-  for (int l = 0; l < NJ - 1; ++l)
-    if (l < j)
-#pragma unroll
-      for (int k = 0; k < 6; ++k) acc[k] += sb[l * 6 + k];
-#pragma unroll
-  for (int k = 0; k < 6; ++k) out[k] = acc[k];
-}
-// inclusive suffix sum of a per-lane 6-vector (board: [8][6]); lane 7's slot must hold zeros
-AGX_DEV void vec6_suffix_incl(double* x, int j, const double* sb) {
-  if (j < NJ - 1) {
-    double acc[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) acc[k] = sb[(NJ - 1) * 6 + k];
-#pragma unroll
-    for (int l = NJ - 2; l >= 0; --l)
-      if (l >= j)
-#pragma unroll
-        for (int k = 0; k < 6; ++k) acc[k] = sb[l * 6 + k] + acc[k];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) x[k] = acc[k];
-  }
 }
 
 // ---------------------------------------------------------------- register scans over the octet (warp shuffles)
@@ -291,25 +234,6 @@ AGX_DEV void body_force(LaneDyn& d) {
 #pragma unroll
   for (int k = 0; k < 6; ++k) d.Z[22 + k] = Ya[k] + vh[k];
 }
-// suffix sums of the 28 composites (board: [8][30])
-AGX_DEV void comp_store(const LaneDyn& d, int j, double* sb) {
-#pragma unroll
-  for (int k = 0; k < 28; ++k) sb[j * 30 + k] = d.Z[k];
-}
-AGX_DEV void comp_suffix(LaneDyn& d, int j, const double* sb) {
-  if (j < NJ - 1) {
-    double acc[28];
-#pragma unroll
-    for (int k = 0; k < 28; ++k) acc[k] = sb[(NJ - 1) * 30 + k];
-#pragma unroll
-    for (int l = NJ - 2; l >= 0; --l)
-      if (l >= j)
-#pragma unroll
-        for (int k = 0; k < 28; ++k) acc[k] = sb[l * 30 + k] + acc[k];
-#pragma unroll
-    for (int k = 0; k < 28; ++k) d.Z[k] = acc[k];
-  }
-}
 // column quantities: nle, dFda, BS; stored on board B as [J(6) dFda(6) BS(3) b(1)] stride 18
 template <bool DERIV>
 AGX_DEV void column_terms(LaneDyn& d, int j, double* sbb) {
@@ -346,43 +270,10 @@ AGX_DEV void mass_column(LaneDyn& d, int j, const double* __restrict__ model, co
     if (i == j) d.Mc[i] += arm;  // static indices only: a dynamic d.Mc[j] would push the lane state to local memory
 }
 
-// ---------------------------------------------------------------- 7x7 Cholesky, lane j owns column j
-// board: L stored as [k][8]: column k entries i = k..6, slot 7 = 1/L[k][k].  Returns false on a
-// non-positive pivot (octet-uniform because every lane reads the same pivot record).
-AGX_DEV void chol_pivot(double* col, int j, int k, double* sl) {
-  if (j == k) {
-    const double dkk = col[k];
-    const double r = AGX_RSQRT(dkk);
-    sl[k * 8 + k] = dkk * r;
-#pragma unroll
-    for (int i = k + 1; i < NJ; ++i) sl[k * 8 + i] = col[i] * r;
-    sl[k * 8 + 7] = (dkk > 0.0) ? r : -1.0;  // -1 flags failure (also catches NaN)
-  }
-}
-AGX_DEV void chol_update(double* col, int j, int k, const double* sl) {
-  if (j > k && j < NJ) {
-    const double lj = sl[k * 8 + j];
-#pragma unroll
-    for (int i = k + 1; i < NJ; ++i)
-      if (i >= j) col[i] -= sl[k * 8 + i] * lj;
-  }
-}
-// load the whole factor into registers: L[i][k] (i >= k) packed, rinv[7]; returns false if any pivot failed
-AGX_DEV bool chol_load(const double* sl, double* L /*28*/, double* rinv /*7*/) {
-  bool ok = true;
-  int n = 0;
-#pragma unroll
-  for (int k = 0; k < NJ; ++k) {
-#pragma unroll
-    for (int i = k; i < NJ; ++i) L[n++] = sl[k * 8 + i];
-    rinv[k] = sl[k * 8 + 7];
-    ok = ok && (rinv[k] > 0.0);
-  }
-  return ok;
-}
+// ---------------------------------------------------------------- 7x7 Cholesky
 // Redundant in-register factorisation: every lane loads the lower triangle of the 7x7 matrix stored
 // on the board as M[i * 8 + k] and factors it (no barrier inside).  Same arithmetic order as the
-// column-distributed version above.
+// oracle's column loop.
 AGX_DEV constexpr int lidx_(int i, int k) { return k * NJ - (k * (k - 1)) / 2 + (i - k); }
 AGX_DEV bool chol7_registers(const double* sm_M, double* A /*28*/, double* rinv /*7*/) {
 #pragma unroll

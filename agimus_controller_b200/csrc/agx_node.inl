@@ -6,8 +6,8 @@
 // evaluates through problem.calc / problem.calcDiff (ocp_base_croco.py:172,
 // agimus_controller_ros/agimus_controller_ros/mpc_debugger_node.py:300-301).
 //
-// Built from the lane phases of agx_dynamics.inl; `sa` (BRD_A doubles) and `sb` (BRD_B doubles) are
-// this octet's shared-memory boards.
+// Built from the lane phases of agx_dynamics.inl; `sb` (BRD_B doubles) and `sc` (BRD_C doubles) are this
+// octet's shared-memory boards; the chain recursions themselves run as register scans (warp shuffles).
 
 namespace agx {
 
