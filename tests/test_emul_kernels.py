@@ -272,3 +272,19 @@ print("octet ok")
     env = dict(os.environ, AGX_BW="octet")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0 and "octet ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_converged_fddp_on_the_shipped_kernels_lands_on_the_golden_solution(orc, golden):
+    """KAT-8 on the product kernels (emulated): zero warm start, run to convergence -> the reference's golden
+    states / controls within 3e-3 / 0.15, same iteration count and iterates as the oracle."""
+    w = golden_problem()
+    m = w["table"].to_struct()
+    opts = _abi.default_fddp_opts()
+    e = emu.solve(m, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 60, opts)
+    o = orc.solve(m, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 60, opts)
+    assert e["status"][0] == _abi.AGX_STATUS_CONVERGED
+    assert np.abs(e["xs"][0] - golden["states"]).max() < 3e-3
+    assert np.abs(e["us"][0] - golden["feed_forward_terms"]).max() < 0.15
+    assert abs(e["cost"][0] - 202.6215) < 1e-3
+    assert abs(int(e["iters"][0]) - int(o["iters"][0])) <= 2
+    assert rel(e["xs"], o["xs"]) < 1e-6 and rel(e["cost"], o["cost"]) < 1e-9

@@ -304,3 +304,16 @@ def test_reference_window_on_gpu(solver_mod, orc):
     c_tab, _ = p.calc(xs, us)
     assert torch.equal(c_win, c_tab)
     assert rel(c_win.cpu().numpy(), orc.calc(m, refs, dts, xs, us)[0]) < 1e-12
+
+
+def test_converged_fddp_on_the_gpu_lands_on_the_golden_solution(solver_mod, golden):
+    """KAT-8 on the GPU: the FDDP solve of the reference's golden OCP (tests/test_ocp_croco_base.py), zero warm start,
+    run to convergence, lands on the reference's golden states / controls (3e-3 / 0.15: the golden file is an
+    unconverged iterate of the reference's CSQP) at cost 202.6215."""
+    w = golden_problem()
+    p = _problem(solver_mod, w, 1)
+    g = {k: v.cpu().numpy() for k, v in p.solve(w["x0"], w["xs_ws"], w["us_ws"], 100, _abi.default_fddp_opts()).items()}
+    assert g["status"][0] == _abi.AGX_STATUS_CONVERGED and g["iters"][0] < 100
+    assert np.abs(g["xs"][0] - golden["states"]).max() < 3e-3
+    assert np.abs(g["us"][0] - golden["feed_forward_terms"]).max() < 0.15
+    assert abs(g["cost"][0] - 202.6215) < 1e-3

@@ -100,3 +100,18 @@ def test_appendix_c_check_values(orc):
     a, _ = orc.forward_dynamics(m1, qn, v, np.arange(1.0, 8.0))
     np.testing.assert_allclose(a, [-3.2985189959, -6.4305935203, 3.2042919333, -27.5839018674, 34.4103255304,
                                    46.1667931284, 65.8594064759], atol=1e-8)
+
+
+def test_kat8_converged_fddp_lands_on_the_golden_solution(orc, golden):
+    """KAT-8: the golden file is an (unconverged) iterate of the reference's solver on the OCP of
+    tests/test_ocp_croco_base.py; any exact DDP-type solver run to convergence on that OCP must land within 3e-3
+    (states) / 0.15 (controls, values up to 1.4e4, i.e. 1e-5 relative) of it, at cost 202.6215."""
+    from agimus_controller_b200 import _abi
+
+    w = golden_problem()
+    m = w["table"].to_struct()
+    o = orc.solve(m, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 1000, _abi.default_fddp_opts())
+    assert o["status"][0] == _abi.AGX_STATUS_CONVERGED and o["iters"][0] < 100
+    assert np.abs(o["xs"][0] - golden["states"]).max() < 3e-3
+    assert np.abs(o["us"][0] - golden["feed_forward_terms"]).max() < 0.15
+    assert abs(o["cost"][0] - 202.6215) < 1e-3
