@@ -114,7 +114,8 @@ struct agx_handle {
   double* d_dts = nullptr;
   double* d_x0 = nullptr;
   double* d_K_internal = nullptr;
-  int32_t* d_hidx = nullptr;  // horizon indexes: cumulative step factors dts[i] / dts[0]
+  int32_t* d_hidx = nullptr;
+  int32_t* d_live = nullptr;  // device counter of unfinished problems  // horizon indexes: cumulative step factors dts[i] / dts[0]
   agx::Work W{};
   agx::SolverState S{};
   void* state_block = nullptr;
@@ -203,7 +204,7 @@ int agx_destroy(agx_handle* h) {
   if (!h) return AGX_OK;
   {
     DeviceGuard g(h->device);
-    dev_free(h->d_model); dev_free(h->d_refs); dev_free(h->d_dts); dev_free(h->d_x0); dev_free(h->d_K_internal); dev_free(h->d_hidx);
+    dev_free(h->d_model); dev_free(h->d_refs); dev_free(h->d_dts); dev_free(h->d_x0); dev_free(h->d_K_internal); dev_free(h->d_hidx); dev_free(h->d_live);
     dev_free(h->W.xs); dev_free(h->W.us); dev_free(h->W.rec); dev_free(h->W.crec); dev_free(h->W.fs); dev_free(h->W.gv); dev_free(h->W.k);
     dev_free(h->state_block);
 #if AGX_GPU
@@ -264,7 +265,7 @@ int agx_create(const agx_model* models_host, int n_models, const double* dts_hos
   h->S.recalc_cost = ip + 7 * nB; h->S.pending = ip + 8 * nB; h->S.roll_ok = ip + 9 * nB;
   // horizon indexes of the reference stream (TrajectoryBuffer.compute_horizon_indexes, trajectory.py:199-215)
   int32_t* hidx = (int32_t*)std::malloc(sizeof(int32_t) * (T + 1));
-  ok = hidx != nullptr && dev_alloc((void**)&h->d_hidx, sizeof(int32_t) * (T + 1));
+  ok = hidx != nullptr && dev_alloc((void**)&h->d_hidx, sizeof(int32_t) * (T + 1)) && dev_alloc((void**)&h->d_live, 64);
   if (ok) {
     hidx[0] = 0;
     for (int i = 0; i < T; ++i) {
@@ -548,6 +549,23 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
     AGX_LAUNCH(h, accept_linesearch_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * FW_BOARD * opc_s, st, P, W,
                h->S, O);
     phase_end(h, st);
+    // Long budgets (the controller's first solve runs with max_iter = 1000, agimus_controller.py:376-381): once in a
+    // while ask the device whether anything is still running, instead of queueing hundreds of empty launches.  Budgets
+    // up to 32 iterations (every MPC tick) never synchronise.
+    if (!opts->fixed_iters && max_iter > 32 && (it % 16) == 15 && it + 1 < max_iter) {
+      int32_t live = 1;
+#if AGX_GPU
+      cudaMemsetAsync(h->d_live, 0, sizeof(int32_t), st);
+      AGX_LAUNCH(h, count_live_kernel, (h->B + 255) / 256, 256, 0, st, h->B, (const int32_t*)h->S.done, h->d_live);
+      cudaMemcpyAsync(&live, h->d_live, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+      cudaStreamSynchronize(st);
+#else
+      *h->d_live = 0;
+      AGX_LAUNCH(h, count_live_kernel, (h->B + 255) / 256, 256, 0, st, h->B, (const int32_t*)h->S.done, h->d_live);
+      live = *h->d_live;
+#endif
+      if (live == 0) break;
+    }
   }
   const long long n_fin = (long long)(nB * T * NJ * NX);
   AGX_LAUNCH(h, finalize_kernel, (n_fin + 255) / 256, 256, 0, st, P, W, h->S, out_xs, out_us, out_K, out_k, out_cost,

@@ -1069,6 +1069,12 @@ __global__ void rnea_kernel(const double* __restrict__ model, const double* __re
   if (live) out_tau[(size_t)ent * NJ + j] = dot6(d.J, d.Z + 22);
 }
 
+// number of problems still running (early-exit check of long iteration budgets)
+__global__ void count_live_kernel(int B, const int32_t* __restrict__ done, int32_t* __restrict__ out) {
+  const int b = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (b < B && !done[b]) atomicAdd(out, 1);
+}
+
 // ---------------------------------------------------------------------------------------------
 __global__ void init_kernel(Problem P, Work W, SolverState S, FddpOpts O, const double* __restrict__ xs_ws,
                             const double* __restrict__ us_ws) {

@@ -158,7 +158,9 @@ int agx_rnea(agx_handle* h, const double* q, const double* v, const double* a, i
 /* solver.solve(xs, us, max_iter) with problem.x0 = x0 (ocp_base_croco.py:158, :172).
  * In:  x0 [B][nx], xs_ws [B][T+1][nx], us_ws [B][T][nu].
  * Out: out_xs [B][T+1][nx], out_us [B][T][nu], out_K [B][T][nu][nx], out_k [B][T][nu] (may be NULL),
- *      out_cost [B], out_iters [B] (int32), out_status [B] (int32), out_stop [B] (may be NULL). */
+ *      out_cost [B], out_iters [B] (int32), out_status [B] (int32), out_stop [B] (may be NULL).
+ * Stream-ordered and asynchronous for max_iter <= 32 or opts->fixed_iters; with a larger budget the call
+ * synchronises `stream` every 16 iterations to stop as soon as every problem has finished. */
 int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double* us_ws,
               int max_iter, const agx_fddp_opts* opts, double* out_xs, double* out_us,
               double* out_K, double* out_k, double* out_cost, int32_t* out_iters,

@@ -218,6 +218,7 @@ inline void agx_emul_dmma(double& d0, double& d1, double a, double b, double c0,
   __syncwarp();
   d0 = r0; d1 = r1;
 }
+inline int atomicAdd(int* p, int v) { const int o = *p; *p = o + v; return o; }
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 inline void sincos(double x, double* s, double* c) { *s = std::sin(x); *c = std::cos(x); }
 inline double __ldg(const double* p) { return *p; }
