@@ -61,17 +61,16 @@ inline const char* dev_check() { return nullptr; }
 
 // threads per CTA of the (problem, node) kernels (8 octets) and of the per-problem kernels (4 octets);
 // AGX_NODE_CTA / AGX_SEQ_CTA override them for tuning experiments (multiples of 8)
-int env_cta(const char* name, int dflt) {
+int env_cta(const char* name, int dflt, int max_threads) {
   const char* v = std::getenv(name);
   if (!v) return dflt;
   const int n = std::atoi(v);
-  return (n >= 8 && n <= 256 && n % 8 == 0) ? n : dflt;
+  return (n >= 8 && n <= max_threads && n % 8 == 0) ? n : dflt;
 }
-const int NODE_CTA = env_cta("AGX_NODE_CTA", 64);
-const int SEQ_CTA = env_cta("AGX_SEQ_CTA", 32);
+const int NODE_CTA = env_cta("AGX_NODE_CTA", 64, 64);   // calc_diff_kernel is bounded to 64 threads
+const int SEQ_CTA = env_cta("AGX_SEQ_CTA", 32, 128);
 // backward sweep: "mma" = one warp per problem on the FP64 tensor cores (default), "octet" = 8 lanes per problem
 const bool BW_MMA = !(std::getenv("AGX_BW") && std::string(std::getenv("AGX_BW")) == "octet");
-const int BWM_CTA = env_cta("AGX_BWM_CTA", 32);
 const int COST_CTA = 64;  // thread-per-node cost kernel: 2 warps, 33 KB of staging shared memory
 const size_t COST_SMEM = sizeof(double) * COST_STAGE * (COST_CTA / 32);
 
