@@ -7,6 +7,8 @@ import ctypes as C
 import numpy as np
 
 AGX_MAX_NV = 16
+AGX_MAX_CAPSULES = 4
+AGX_MAX_COLLISION_PAIRS = 2
 AGX_JOINT_REVOLUTE = 0
 AGX_JOINT_PRISMATIC = 1
 
@@ -43,6 +45,15 @@ class AgxModel(C.Structure):
         ("gravity", _D * 3),
         ("frame_R", _D * 9),
         ("frame_p", _D * 3),
+        ("cap_a0", (_D * 3) * AGX_MAX_CAPSULES),
+        ("cap_a1", (_D * 3) * AGX_MAX_CAPSULES),
+        ("cap_radius", _D * AGX_MAX_CAPSULES),
+        ("col_alpha", _D),
+        ("n_capsules", _I),
+        ("cap_parent", _I * AGX_MAX_CAPSULES),
+        ("n_pairs", _I),
+        ("pair_a", _I * AGX_MAX_COLLISION_PAIRS),
+        ("pair_b", _I * AGX_MAX_COLLISION_PAIRS),
     ]
 
 
@@ -67,8 +78,8 @@ class AgxFddpOpts(C.Structure):
 
 
 def ref_size(nv: int) -> int:
-    """Doubles per node reference record: [xref nx][wx nx][uref nu][wu nu][Rref 9][pref 3][wpose 6]."""
-    return 6 * nv + 18
+    """Doubles per node reference record: [xref nx][wx nx][uref nu][wu nu][Rref 9][pref 3][wpose 6][wcol 2]."""
+    return 6 * nv + 20
 
 
 def default_fddp_opts(fixed_iters: bool = False) -> AgxFddpOpts:

@@ -186,7 +186,7 @@ void launch_backward(agx_handle* h, const agx::Problem& P, const agx::Work& W, c
 
 extern "C" {
 
-int agx_ref_size(int nv) { return 6 * nv + 18; }
+int agx_ref_size(int nv) { return 6 * nv + 20; }
 
 void agx_fddp_opts_default(agx_fddp_opts* o) {
   o->reg_min = 1e-9; o->reg_max = 1e9; o->reg_incfactor = 10.0; o->reg_decfactor = 10.0;

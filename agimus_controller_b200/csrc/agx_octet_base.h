@@ -60,7 +60,7 @@ namespace agx {
 
 constexpr int NJ = 7;            // joints handled by one octet
 constexpr int NX = 2 * NJ;       // state dimension
-constexpr int REF_SIZE = 6 * NJ + 18;
+constexpr int REF_SIZE = 6 * NJ + 20;  // [xref 14][wx 14][uref 7][wu 7][Rref 9][pref 3][wpose 6][wcol 2]
 
 // ---- device model table (doubles): joint fields are stored field-major / joint-minor so that
 // lane j reads model[f * 8 + j]; tail holds gravity and the task frame.

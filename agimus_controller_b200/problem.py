@@ -3,8 +3,8 @@
 This is the flattened form of what ``OCPCrocoGeneric.set_reference_weighted_trajectory``
 (``agimus_controller/agimus_controller/ocp/ocp_croco_generic.py:855-892``) writes into Crocoddyl
 objects one Boost.Python attribute at a time.  Record layout (``include/agx.h``):
-``[xref nx][wx nx][uref nu][wu nu][Rref 9][pref 3][wpose 6]`` with the CostModelSum weight folded
-into the activation weights.
+``[xref nx][wx nx][uref nu][wu nu][Rref 9][pref 3][wpose 6][wcol 2]`` with the CostModelSum weight folded
+into the activation weights; ``wcol`` are the scalar weights of the (up to two) collision pairs.
 """
 from __future__ import annotations
 
@@ -13,7 +13,7 @@ import numpy as np
 from ._abi import ref_size
 
 
-def pack_refs(nv, T, B, xref, wx, uref, wu, Rref, pref, wpose, wpose_terminal=None, wx_terminal=None):
+def pack_refs(nv, T, B, xref, wx, uref, wu, Rref, pref, wpose, wpose_terminal=None, wx_terminal=None, wcol=None):
     """Broadcast the given references/weights to ``[B, T+1, ref_size]`` (float64, C order).
 
     Every argument broadcasts against ``[B, T+1, n]``; ``*_terminal`` overrides the last node.
@@ -32,6 +32,8 @@ def pack_refs(nv, T, B, xref, wx, uref, wu, Rref, pref, wpose, wpose_terminal=No
                                          (B, T + 1, 9))
     r[..., o + 9 : o + 12] = np.broadcast_to(np.asarray(pref, dtype=np.float64), (B, T + 1, 3))
     r[..., o + 12 : o + 18] = np.broadcast_to(np.asarray(wpose, dtype=np.float64), (B, T + 1, 6))
+    if wcol is not None:
+        r[..., o + 18 : o + 20] = np.broadcast_to(np.asarray(wcol, dtype=np.float64), (B, T + 1, 2))
     if wpose_terminal is not None:
         r[:, T, o + 12 : o + 18] = np.broadcast_to(np.asarray(wpose_terminal, dtype=np.float64), (B, 6))
     if wx_terminal is not None:

@@ -72,6 +72,10 @@ class RobotTable:
     gravity: np.ndarray  # [3]
     frames: dict[str, tuple[int, np.ndarray, np.ndarray]]  # name -> (parent joint, R, p)
     frame_name: str = ""
+    # collision geometry: name -> (parent joint or -1 = world, a0, a1, radius), segment endpoints in the parent frame
+    capsules: dict = dataclasses.field(default_factory=dict)
+    collision_pairs: list = dataclasses.field(default_factory=list)  # [(capsule name, capsule name)], at most two
+    collision_alpha: float = 1e-4  # ActivationModelQuadExp alpha (ocp_traj_tracking_collision_avoidance.yaml:44)
 
     @property
     def nv(self) -> int:
@@ -92,6 +96,24 @@ class RobotTable:
     def with_armature(self, armature) -> "RobotTable":
         a = np.broadcast_to(np.asarray(armature, dtype=np.float64), (self.nv,)).copy()
         return dataclasses.replace(self, armature=a)
+
+    def with_capsules(self, capsules: dict, pairs: list, alpha: float = 1e-4) -> "RobotTable":
+        """Attach collision capsules ``{name: (parent joint name or index or None, a0, a1, radius)}`` and the pairs whose
+        distance feeds ``ResidualDistanceCollision`` (``factory/robot_model.py:261-330`` builds the reference's capsules
+        from the URDF cylinders; the solve path only needs this flat table)."""
+        caps = {}
+        for name, (parent, a0, a1, radius) in capsules.items():
+            if parent is None:
+                pi = -1
+            elif isinstance(parent, str):
+                pi = self.joint_names.index(parent)
+            else:
+                pi = int(parent)
+            caps[name] = (pi, np.asarray(a0, dtype=np.float64), np.asarray(a1, dtype=np.float64), float(radius))
+        assert len(caps) <= _abi.AGX_MAX_CAPSULES and len(pairs) <= _abi.AGX_MAX_COLLISION_PAIRS
+        for a, b in pairs:
+            assert a in caps and b in caps, f"Geometry object '{a if a not in caps else b}' not found."
+        return dataclasses.replace(self, capsules=caps, collision_pairs=list(pairs), collision_alpha=float(alpha))
 
     def perturbed(self, link: int, param: int, delta: float) -> "RobotTable":
         """One inertial parameter of body ``link`` shifted by ``delta``: ``param`` 0-5 = inertia
@@ -162,6 +184,20 @@ class RobotTable:
             m.frame_p[k] = float(fp[k])
         for k in range(9):
             m.frame_R[k] = float(np.asarray(fR).reshape(9)[k])
+        names = list(self.capsules)
+        m.n_capsules = len(names)
+        for c, name in enumerate(names):
+            pi, a0, a1, radius = self.capsules[name]
+            m.cap_parent[c] = int(pi)
+            m.cap_radius[c] = float(radius)
+            for k in range(3):
+                m.cap_a0[c][k] = float(a0[k])
+                m.cap_a1[c][k] = float(a1[k])
+        m.n_pairs = len(self.collision_pairs)
+        for k, (a, b) in enumerate(self.collision_pairs):
+            m.pair_a[k] = names.index(a)
+            m.pair_b[k] = names.index(b)
+        m.col_alpha = float(self.collision_alpha)
         return m
 
     @staticmethod
@@ -301,6 +337,17 @@ def panda_links() -> list[Link]:
 
 PANDA_FRAMES = {"panda_hand_tcp": ("panda_hand", (0, 0, 0.1034), (0, 0, 0))}
 PANDA_Q_NOMINAL = np.array([0.0, -0.78, 0.0, -2.35, 0.0, 1.57, 0.78])  # dummy_mpc_test.py:89
+
+
+# Synthetic capsule table (the reference's `fer_link*_sc_capsule_*` geometry comes from franka_description, which is
+# not in the tree): one capsule on link 3, one on link 7 / hand, one obstacle in the world
+# (agimus_controller/tests/resources/environment.xacro:23-24: direction x, radius 0.1, length 0.4, moved into reach).
+PANDA_CAPSULES = {
+    "link3_capsule": ("panda_joint3", (0.0, 0.0, -0.12), (0.0, 0.0, -0.02), 0.07),
+    "link7_capsule": ("panda_joint7", (0.0, 0.0, 0.06), (0.0, 0.0, 0.20), 0.06),
+    "obstacle_capsule": (None, (0.35, -0.2, 0.30), (0.35, 0.2, 0.30), 0.05),
+}
+PANDA_COLLISION_PAIRS = [("link7_capsule", "link3_capsule"), ("link7_capsule", "obstacle_capsule")]
 
 
 def panda_table(

@@ -119,7 +119,7 @@ def sine_configuration_reference(n_points, dt=0.01, amplitude=0.2, period=4.0, s
     v = np.repeat(doff[:, None], nv, axis=1)
     a = np.repeat(ddoff[:, None], nv, axis=1)
     u = np.asarray(rnea(q, v, a)).reshape(n_points, nv) if rnea is not None else np.zeros((n_points, nv))
-    rows = np.zeros((n_points, 6 * nv + 18))
+    rows = np.zeros((n_points, 6 * nv + 20))
     for i in range(n_points):
         R, pos = table.frame_placement(q[i])
         rows[i] = pack_refs(nv, 0, 1, np.concatenate([q[i], v[i]]), np.concatenate([np.full(nv, w_q), np.full(nv, w_v)]),

@@ -367,7 +367,7 @@ def run_ours(args):
     bytes_alg = {"calc_diff": B * T1 * (REC_BYTES + (14 + 7) * 8),
                  "backward": B * (T1 * (REC_BYTES + CREC_BYTES) + T_NODES * (98 + 7) * 8 + T1 * (14 * 3) * 8),
                  "rollout_try": B * T1 * ((14 * 3 + 7 * 3 + 98) * 8),
-                 "node_cost": B * T1 * (CREC_BYTES + (14 + 7 + 60) * 8),
+                 "node_cost": B * T1 * (CREC_BYTES + (14 + 7 + 62) * 8),
                  "accept_linesearch": B * T1 * 8}
     per = {}
     for k, v in phases.items():

@@ -32,6 +32,8 @@ extern "C" {
 #endif
 
 #define AGX_MAX_NV 16
+#define AGX_MAX_CAPSULES 4
+#define AGX_MAX_COLLISION_PAIRS 2
 
 /* joint types */
 #define AGX_JOINT_REVOLUTE 0
@@ -72,6 +74,20 @@ typedef struct agx_model {
   double gravity[3];
   double frame_R[9];
   double frame_p[3];
+  /* Collision geometry for ResidualDistanceCollision (ocp_croco_generic.py:495-533; capsules as built by
+   * factory/robot_model.py:261-302): a capsule is a segment [a0, a1] with a radius, given in the frame of the body
+   * it is attached to (cap_parent >= 0) or in the world frame (cap_parent = -1).  A pair (pair_a[k], pair_b[k])
+   * contributes the residual r = distance between the two capsule surfaces, with the activation exp(-r^2 / alpha)
+   * (ActivationModelQuadExp, ocp_croco_generic.py:117-143) and a per-node weight (reference record, below). */
+  double cap_a0[AGX_MAX_CAPSULES][3];
+  double cap_a1[AGX_MAX_CAPSULES][3];
+  double cap_radius[AGX_MAX_CAPSULES];
+  double col_alpha;
+  int32_t n_capsules;
+  int32_t cap_parent[AGX_MAX_CAPSULES];
+  int32_t n_pairs;
+  int32_t pair_a[AGX_MAX_COLLISION_PAIRS];
+  int32_t pair_b[AGX_MAX_COLLISION_PAIRS];
 } agx_model;
 
 /*
@@ -89,9 +105,10 @@ typedef struct agx_fddp_opts {
 typedef struct agx_handle agx_handle;
 
 /* Size in doubles of one node's reference record:
- *   [xref nx][wx nx][uref nu][wu nu][Rref 9][pref 3][wpose 6]
+ *   [xref nx][wx nx][uref nu][wu nu][Rref 9][pref 3][wpose 6][wcol 2]
  * wx/wu/wpose are the activation weights already multiplied by the CostModelSum weight
- * (ocp_croco_generic.py:577-585, :688-691); an inactive cost has zero weights.  The terminal
+ * (ocp_croco_generic.py:577-585, :688-691); an inactive cost has zero weights; wcol[k] is the scalar weight of
+ * collision pair k (w_collision_avoidance, ocp_croco_generic.py:718-719), 0 when unused.  The terminal
  * node (t = T) ignores uref/wu.  Layout of `refs`: [B][T+1][agx_ref_size(nv)]. */
 int agx_ref_size(int nv);
 

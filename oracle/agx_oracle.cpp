@@ -565,13 +565,13 @@ void Jlog6(const SE3& M, double* J /* 6x6 row-major */) {
 
 // ----------------------------------------------------------------------------- node (action) model
 struct NodeRef {  // view into one reference record
-  const double *xref, *wx, *uref, *wu, *Rref, *pref, *wpose;
+  const double *xref, *wx, *uref, *wu, *Rref, *pref, *wpose, *wcol;
 };
 inline NodeRef make_ref(const double* r, int nv) {
   const int nx = 2 * nv;
   NodeRef o;
   o.xref = r; o.wx = r + nx; o.uref = r + 2 * nx; o.wu = r + 2 * nx + nv;
-  o.Rref = r + 2 * nx + 2 * nv; o.pref = o.Rref + 9; o.wpose = o.pref + 3;
+  o.Rref = r + 2 * nx + 2 * nv; o.pref = o.Rref + 9; o.wpose = o.pref + 3; o.wcol = o.wpose + 6;
   return o;
 }
 
@@ -1067,7 +1067,7 @@ inline const agx_model& model_of(const agx_model* models, int n_models, int b) {
 // ============================================================================= C entry points
 extern "C" {
 
-int agx_ref_size(int nv) { return 6 * nv + 18; }
+int agx_ref_size(int nv) { return 6 * nv + 20; }
 
 void agx_fddp_opts_default(agx_fddp_opts* o) {
   o->reg_min = 1e-9; o->reg_max = 1e9; o->reg_incfactor = 10.0; o->reg_decfactor = 10.0;

@@ -25,7 +25,7 @@ def test_library_builds_and_exports_every_symbol():
     for name in declared_symbols():
         assert hasattr(lib, name), name
     _abi.bind(lib)
-    assert lib.agx_ref_size(7) == _abi.ref_size(7) == 60
+    assert lib.agx_ref_size(7) == _abi.ref_size(7) == 62
     o = _abi.AgxFddpOpts()
     lib.agx_fddp_opts_default(ctypes.byref(o))
     d = _abi.default_fddp_opts()
@@ -36,8 +36,8 @@ def test_library_builds_and_exports_every_symbol():
 
 def test_struct_sizes_match_the_header():
     # agx_model: 2 + 16 + 16 ints, then doubles (8-byte aligned)
-    n_d = 16 * 3 + 16 * 9 + 16 * 3 + 16 + 16 * 3 + 16 * 6 + 16 + 3 + 9 + 3
-    assert ctypes.sizeof(_abi.AgxModel) == 34 * 4 + n_d * 8
+    n_d = 16 * 3 + 16 * 9 + 16 * 3 + 16 + 16 * 3 + 16 * 6 + 16 + 3 + 9 + 3 + 4 * 3 + 4 * 3 + 4 + 1
+    assert ctypes.sizeof(_abi.AgxModel) == 34 * 4 + n_d * 8 + 10 * 4
     assert ctypes.sizeof(_abi.AgxFddpOpts) == 11 * 8 + 2 * 4
 
 
