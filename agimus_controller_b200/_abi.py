@@ -9,6 +9,7 @@ import numpy as np
 AGX_MAX_NV = 16
 AGX_MAX_CAPSULES = 4
 AGX_MAX_COLLISION_PAIRS = 2
+AGX_N_COST_TERMS = 13
 AGX_JOINT_REVOLUTE = 0
 AGX_JOINT_PRISMATIC = 1
 

@@ -59,6 +59,20 @@ inline bool copy_d2d(void* d, const void* s, size_t n, stream_t) { std::memmove(
 inline const char* dev_check() { return nullptr; }
 #endif
 
+// kernels templated on COL (collision pairs present in some model): pick the instantiation per handle
+#define AGX_LAUNCH_COL(h, kernel, ...)                        \
+  do {                                                        \
+    if ((h)->col) AGX_LAUNCH(h, kernel<true>, __VA_ARGS__);   \
+    else AGX_LAUNCH(h, kernel<false>, __VA_ARGS__);           \
+  } while (0)
+#define AGX_NODE_COST_COL node_cost_kernel<true, true>
+#define AGX_NODE_COST_PLAIN node_cost_kernel<true, false>
+#define AGX_LAUNCH_NODE_COST(h, ...)                              \
+  do {                                                            \
+    if ((h)->col) AGX_LAUNCH(h, AGX_NODE_COST_COL, __VA_ARGS__);  \
+    else AGX_LAUNCH(h, AGX_NODE_COST_PLAIN, __VA_ARGS__);         \
+  } while (0)
+
 // threads per CTA of the (problem, node) kernels (8 octets) and of the per-problem kernels (4 octets);
 // AGX_NODE_CTA / AGX_SEQ_CTA override them for tuning experiments (multiples of 8)
 int env_cta(const char* name, int dflt, int max_threads) {
@@ -101,6 +115,29 @@ bool flatten_model(const agx_model& m, double* out, std::string& why) {
   for (int k = 0; k < 9; ++k) out[MT_FR + k] = m.frame_R[k];
   for (int k = 0; k < 3; ++k) out[MT_FP + k] = m.frame_p[k];
   out[MT_FP + 3] = (double)m.frame_parent;
+  // collision capsules and pairs (A10)
+  if (m.n_capsules < 0 || m.n_capsules > AGX_MAX_CAPSULES || m.n_pairs < 0 || m.n_pairs > AGX_MAX_COLLISION_PAIRS) {
+    why = "capsule / collision pair count out of range";
+    return false;
+  }
+  for (int c = 0; c < MAX_CAPS; ++c) out[MT_CAP + 8 * c + 7] = -1.0;
+  for (int c = 0; c < m.n_capsules; ++c) {
+    if (m.cap_parent[c] < -1 || m.cap_parent[c] >= NJ) { why = "capsule parent joint out of range"; return false; }
+    for (int k = 0; k < 3; ++k) { out[MT_CAP + 8 * c + k] = m.cap_a0[c][k]; out[MT_CAP + 8 * c + 3 + k] = m.cap_a1[c][k]; }
+    out[MT_CAP + 8 * c + 6] = m.cap_radius[c];
+    out[MT_CAP + 8 * c + 7] = (double)m.cap_parent[c];
+  }
+  out[MT_COL] = (double)m.n_pairs;
+  out[MT_COL + 1] = m.n_pairs > 0 ? m.col_alpha : 1.0;
+  if (m.n_pairs > 0 && !(m.col_alpha > 0.0)) { why = "col_alpha must be positive"; return false; }
+  for (int k = 0; k < m.n_pairs; ++k) {
+    if (m.pair_a[k] < 0 || m.pair_a[k] >= m.n_capsules || m.pair_b[k] < 0 || m.pair_b[k] >= m.n_capsules) {
+      why = "collision pair refers to a capsule that does not exist";
+      return false;
+    }
+    out[MT_COL + 2 + 2 * k] = (double)m.pair_a[k];
+    out[MT_COL + 3 + 2 * k] = (double)m.pair_b[k];
+  }
   return true;
 }
 
@@ -108,6 +145,7 @@ bool flatten_model(const agx_model& m, double* out, std::string& why) {
 
 struct agx_handle {
   int B = 0, T = 0, device = 0, n_models = 0;
+  bool col = false;  // some model carries collision pairs: the COL kernel instantiations run
   double* d_model = nullptr;
   double* d_refs = nullptr;
   double* d_dts = nullptr;
@@ -231,6 +269,7 @@ int agx_create(const agx_model* models_host, int n_models, const double* dts_hos
       std::free(tab);
       return fail(h, AGX_EUNSUPPORTED, why);
     }
+    if (models_host[i].n_pairs > 0) h->col = true;
   }
 #if AGX_GPU
   if (cudaSetDevice(device) != cudaSuccess) {
@@ -306,7 +345,7 @@ int agx_calc(agx_handle* h, const double* xs, const double* us, double* out_cost
   DeviceGuard g(h->device);
   const long long ents = (long long)h->B * (h->T + 1);
   const int opc = NODE_CTA / 8;
-  AGX_LAUNCH(h, calc_kernel, (ents + opc - 1) / opc, NODE_CTA, sizeof(double) * OCT_BOARD * opc, (stream_t)stream,
+  AGX_LAUNCH_COL(h, calc_kernel, (ents + opc - 1) / opc, NODE_CTA, sizeof(double) * OCT_BOARD * opc, (stream_t)stream,
              problem_of(h), xs, us, out_cost, out_xnext);
   return check_launch(h, "agx_calc");
 }
@@ -317,7 +356,7 @@ int agx_calc_diff(agx_handle* h, const double* xs, const double* us, double* out
   DeviceGuard g(h->device);
   const long long ents = (long long)h->B * (h->T + 1);
   const int opc = NODE_CTA / 8;
-  AGX_LAUNCH(h, calc_diff_kernel, (ents + opc - 1) / opc, NODE_CTA, sizeof(double) * OCT_BOARD * opc, (stream_t)stream,
+  AGX_LAUNCH_COL(h, calc_diff_kernel, (ents + opc - 1) / opc, NODE_CTA, sizeof(double) * OCT_BOARD * opc, (stream_t)stream,
              problem_of(h), xs, us, (const int32_t*)nullptr, (const int32_t*)nullptr, (const int32_t*)nullptr, 1,
              (const int32_t*)nullptr, h->W.rec, h->W.crec);
   const long long rows = ents * NX;
@@ -330,7 +369,7 @@ int agx_cost_terms(agx_handle* h, const double* xs, const double* us, double* ou
   if (!h || !xs || !us || !out_terms) return AGX_EINVAL;
   DeviceGuard g(h->device);
   const long long ents = (long long)h->B * (h->T + 1);
-  AGX_LAUNCH(h, cost_terms_kernel, (ents + 127) / 128, 128, 0, (stream_t)stream, problem_of(h), xs, us, out_terms);
+  AGX_LAUNCH_COL(h, cost_terms_kernel, (ents + 127) / 128, 128, 0, (stream_t)stream, problem_of(h), xs, us, out_terms);
   return check_launch(h, "agx_cost_terms");
 }
 
@@ -394,7 +433,7 @@ int agx_riccati(agx_handle* h, const double* x0, const double* xs, const double*
   AGX_LAUNCH(h, init_kernel, (n_init + 255) / 256, 256, 0, st, P, W, h->S, O, xs, us);
   const long long ents = (long long)(nB * T1);
   const int opc_n = NODE_CTA / 8, opc_s = SEQ_CTA / 8;
-  AGX_LAUNCH(h, calc_diff_kernel, (ents + opc_n - 1) / opc_n, NODE_CTA, sizeof(double) * OCT_BOARD * opc_n, st, P,
+  AGX_LAUNCH_COL(h, calc_diff_kernel, (ents + opc_n - 1) / opc_n, NODE_CTA, sizeof(double) * OCT_BOARD * opc_n, st, P,
              (const double*)W.xs, (const double*)W.us, (const int32_t*)h->S.cur, (const int32_t*)h->S.recalc,
              (const int32_t*)h->S.recalc_cost, 0, (const int32_t*)h->S.done, W.rec, W.crec);
   launch_backward(h, P, W, O, st);
@@ -524,12 +563,12 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
       // first iteration: every cost record is stale; the thread-per-node kernel is the cheap way to fill them
       // (later iterations only meet stale cost records after a line search, handled in line by calc_diff_kernel)
       phase_begin(h, 3, st);
-      AGX_LAUNCH(h, node_cost_kernel<true>, cost_ctas, COST_CTA, COST_SMEM, st, P, (const double*)W.xs, (const double*)W.us,
+      AGX_LAUNCH_NODE_COST(h, cost_ctas, COST_CTA, COST_SMEM, st, P, (const double*)W.xs, (const double*)W.us,
                  (const int32_t*)h->S.cur, 0, (const int32_t*)h->S.done, (const int32_t*)nullptr, W.crec, (double*)nullptr);
       phase_end(h, st);
     }
     phase_begin(h, 0, st);
-    AGX_LAUNCH(h, calc_diff_kernel, (ents + opc_n - 1) / opc_n, NODE_CTA, sizeof(double) * OCT_BOARD * opc_n, st, P,
+    AGX_LAUNCH_COL(h, calc_diff_kernel, (ents + opc_n - 1) / opc_n, NODE_CTA, sizeof(double) * OCT_BOARD * opc_n, st, P,
                (const double*)W.xs, (const double*)W.us, (const int32_t*)h->S.cur, (const int32_t*)h->S.recalc,
                (const int32_t*)(it == 0 ? nullptr : h->S.recalc_cost), 0, (const int32_t*)h->S.done, W.rec, W.crec);
     phase_end(h, st);
@@ -541,11 +580,11 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
                h->S);
     phase_end(h, st);
     phase_begin(h, 3, st);
-    AGX_LAUNCH(h, node_cost_kernel<true>, cost_ctas, COST_CTA, COST_SMEM, st, P, (const double*)W.xs, (const double*)W.us,
+    AGX_LAUNCH_NODE_COST(h, cost_ctas, COST_CTA, COST_SMEM, st, P, (const double*)W.xs, (const double*)W.us,
                (const int32_t*)h->S.cur, 1, (const int32_t*)h->S.done, (const int32_t*)nullptr, W.crec, (double*)nullptr);
     phase_end(h, st);
     phase_begin(h, 4, st);
-    AGX_LAUNCH(h, accept_linesearch_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * FW_BOARD * opc_s, st, P, W,
+    AGX_LAUNCH_COL(h, accept_linesearch_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * FW_BOARD * opc_s, st, P, W,
                h->S, O);
     phase_end(h, st);
     // Long budgets (the controller's first solve runs with max_iter = 1000, agimus_controller.py:376-381): once in a

@@ -491,4 +491,53 @@ AGX_DEV void frame_residual(const double* R6, const double* p6, const double* __
   log6_and_jac(Rr, pr, r, Jl);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Collision residual (A10): colmpc::ResidualDistanceCollision on a capsule pair + ActivationModelQuadExp
+// (ocp/ocp_croco_generic.py:119-147, :499-535; ocp_traj_tracking_collision_avoidance.yaml:36-46).
+AGX_DEV double clamp01(double v) { return v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v); }
+
+// Closest points of the segments [a0,a1] and [b0,b1] (world frame): ca, cb, the unit direction n = (ca-cb)/|ca-cb|;
+// returns |ca - cb|.  Degenerate (point-like) segments and the parallel case take the first end point.
+AGX_DEV double segment_pair(const double* a0, const double* a1, const double* b0, const double* b1, double* ca,
+                            double* cb, double* n) {
+  const double eps = 1e-12;
+  double d1[3], d2[3], r[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { d1[k] = a1[k] - a0[k]; d2[k] = b1[k] - b0[k]; r[k] = a0[k] - b0[k]; }
+  const double a = dot3(d1, d1), e = dot3(d2, d2), f = dot3(d2, r);
+  double s = 0.0, t = 0.0;
+  if (a <= eps && e <= eps) {
+    s = t = 0.0;
+  } else if (a <= eps) {
+    t = clamp01(f / e);
+  } else {
+    const double c = dot3(d1, r);
+    if (e <= eps) {
+      s = clamp01(-c / a);
+    } else {
+      const double b = dot3(d1, d2), denom = a * e - b * b;
+      s = (denom > eps * a * e) ? clamp01((b * f - c * e) / denom) : 0.0;
+      t = (b * s + f) / e;
+      if (t < 0.0) { t = 0.0; s = clamp01(-c / a); }
+      else if (t > 1.0) { t = 1.0; s = clamp01((b - c) / a); }
+    }
+  }
+  double dd[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { ca[k] = a0[k] + s * d1[k]; cb[k] = b0[k] + t * d2[k]; dd[k] = ca[k] - cb[k]; }
+  const double len = sqrt(dot3(dd, dd));
+  const double inv = len > 1e-14 ? 1.0 / len : 0.0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) n[k] = dd[k] * inv;
+  return len;
+}
+
+// a = exp(-r^2/alpha) with its first two derivatives in r
+AGX_DEV void quadexp(double r, double alpha, double& a, double& ar, double& arr) {
+  const double ia = 1.0 / alpha;
+  a = exp(-r * r * ia);
+  ar = -2.0 * r * ia * a;
+  arr = (4.0 * r * r * ia * ia - 2.0 * ia) * a;
+}
+
 }  // namespace agx

@@ -104,11 +104,12 @@ AGX_DEV void node_dyn_diff(LaneDyn& d, int j, unsigned omask, const double* __re
 }
 
 // calc of one node: cost (scaled) and this lane's entries of xnext.  Returns false on failure.
+template <bool COL = false>
 AGX_DEV bool node_calc(LaneDyn& d, int j, unsigned omask, const double* __restrict__ model,
                        const double* __restrict__ ref, double dt, bool terminal, double* sb, double* sc, double* cost,
                        double* qn, double* vn) {
   node_kinematics(d, j, omask, model);
-  const double l = node_costs<false>(d, j, omask, model, ref, terminal, sb, nullptr, nullptr, nullptr, nullptr);
+  const double l = node_costs<false, COL>(d, j, omask, model, ref, terminal, sb, nullptr, nullptr, nullptr, nullptr);
   if (terminal) {
     *cost = l;
     *qn = d.q;
@@ -137,6 +138,8 @@ AGX_DEV size_t buf_of(const int32_t* cur, int b, bool other) {
 #ifndef AGX_CD_MINB
 #define AGX_CD_MINB 4
 #endif
+// COL: the models carry collision pairs (A10); the plain instantiation is the one every benchmark runs.
+template <bool COL>
 __global__ void __launch_bounds__(64, AGX_CD_MINB)
 calc_diff_kernel(Problem P, const double* __restrict__ xs, const double* __restrict__ us,
                                  const int32_t* __restrict__ cur, const int32_t* __restrict__ recalc,
@@ -182,7 +185,7 @@ calc_diff_kernel(Problem P, const double* __restrict__ xs, const double* __restr
     double* C = crec + (size_t)ent * CREC_SIZE;
     const double s = terminal ? 1.0 : P.dts[t];
     double lq, lv, lu, Lqq[NJ];
-    const double l = node_costs<true>(dk, j, omask, model, ref, terminal, sb, &lq, &lv, &lu, Lqq);
+    const double l = node_costs<true, COL>(dk, j, omask, model, ref, terminal, sb, &lq, &lv, &lu, Lqq);
     if (do_cost) {
       if (live) {
 #pragma unroll
@@ -218,7 +221,7 @@ calc_diff_kernel(Problem P, const double* __restrict__ xs, const double* __restr
 // (the candidate being evaluated by the line search); `gate` (may be null) restricts the work to problems
 // whose flag is non-zero.  DERIV: the cost part of the node record is (re)written.
 constexpr int COST_STAGE = 32 * (CREC_SIZE + 1) + 32;  // doubles of shared memory per warp of node_cost_kernel
-template <bool DERIV>
+template <bool DERIV, bool COL>
 __global__ void node_cost_kernel(Problem P, const double* __restrict__ xs, const double* __restrict__ us,
                                  const int32_t* __restrict__ cur, int other, const int32_t* __restrict__ done,
                                  const int32_t* __restrict__ gate, double* __restrict__ crec,
@@ -242,8 +245,9 @@ __global__ void node_cost_kernel(Problem P, const double* __restrict__ xs, const
     const bool terminal = t == P.T;
     const double* x = xs + ((buf * P.B + b) * T1 + t) * NX;
     const double* u = terminal ? nullptr : us + ((buf * P.B + b) * P.T + t) * NJ;
-    const double c = thread_node_cost<DERIV>(model_of(P, b), P.refs + (size_t)n * REF_SIZE, x, u, terminal,
-                                             terminal ? 1.0 : P.dts[t], DERIV ? stage + lane * (CREC_SIZE + 1) : nullptr);
+    const double c = thread_node_cost<DERIV, COL>(model_of(P, b), P.refs + (size_t)n * REF_SIZE, x, u, terminal,
+                                                  terminal ? 1.0 : P.dts[t],
+                                                  DERIV ? stage + lane * (CREC_SIZE + 1) : nullptr);
     if (out_cost) out_cost[n] = c;
   }
   if (DERIV) {
@@ -259,6 +263,7 @@ __global__ void node_cost_kernel(Problem P, const double* __restrict__ xs, const
   }
 }
 
+template <bool COL>
 __global__ void calc_kernel(Problem P, const double* __restrict__ xs, const double* __restrict__ us,
                             double* __restrict__ out_cost, double* __restrict__ out_xnext) {
   AGX_SMEM(smem);
@@ -272,8 +277,8 @@ __global__ void calc_kernel(Problem P, const double* __restrict__ xs, const doub
   LaneDyn d;
   lane_load_state(d, j, xs + (size_t)ent * NX, terminal ? nullptr : us + ((size_t)b * P.T + t) * NJ);
   double c, qn, vn;
-  const bool ok = node_calc(d, j, omask, model_of(P, b), P.refs + (size_t)ent * REF_SIZE, terminal ? 0.0 : P.dts[t],
-                            terminal, sb, sc, &c, &qn, &vn);
+  const bool ok = node_calc<COL>(d, j, omask, model_of(P, b), P.refs + (size_t)ent * REF_SIZE,
+                                 terminal ? 0.0 : P.dts[t], terminal, sb, sc, &c, &qn, &vn);
   if (!ok) c = nan("");
   if (out_cost && j == 0) out_cost[ent] = c;
   if (out_xnext && j < NJ) {
@@ -808,6 +813,7 @@ __global__ void rollout_try_kernel(Problem P, Work W, SolverState S) {
 
 // Acceptance test of the alpha = 1 trial (its costs come from node_cost_kernel) and, only if it is rejected,
 // the remaining step lengths alpha = 2^-ia, ia >= 1, with the costs evaluated in line.
+template <bool COL>
 __global__ void accept_linesearch_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
   AGX_SMEM(smem);
   AGX_OCTET_SETUP();
@@ -895,8 +901,8 @@ __global__ void accept_linesearch_kernel(Problem P, Work W, SolverState S, FddpO
         }
       }
       double c, qn, vn;
-      const bool okn = node_calc(d, j, omask, model, refs + (size_t)t * REF_SIZE, terminal ? 0.0 : P.dts[t], terminal,
-                                 sb, sc, &c, &qn, &vn);
+      const bool okn = node_calc<COL>(d, j, omask, model, refs + (size_t)t * REF_SIZE, terminal ? 0.0 : P.dts[t],
+                                      terminal, sb, sc, &c, &qn, &vn);
       ok = ok && okn;
       ctry += c;
       xq = qn; xv = vn;
@@ -962,7 +968,9 @@ __global__ void gather_refs_kernel(int B, int T1, const double* __restrict__ str
   refs[gid] = stream[((size_t)(n_streams > 1 ? b : 0) * n_points + p) * REF_SIZE + k];
 }
 
-// per-cost evaluation: one thread per node -> [state_reg, control_reg, goal_tracking, r6(6)] (9 doubles)
+// per-cost evaluation: one thread per node -> [state_reg, control_reg, goal_tracking, r6(6), collision cost (2),
+// collision distance (2)] (N_COST_TERMS doubles)
+template <bool COL>
 __global__ void cost_terms_kernel(Problem P, const double* __restrict__ xs, const double* __restrict__ us,
                                   double* __restrict__ out_terms) {
   const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -970,11 +978,11 @@ __global__ void cost_terms_kernel(Problem P, const double* __restrict__ xs, cons
   if (n >= (long long)P.B * T1) return;
   const int b = (int)(n / T1), t = (int)(n % T1);
   const bool terminal = t == P.T;
-  double terms[9];
-  thread_node_cost<false>(model_of(P, b), P.refs + (size_t)n * REF_SIZE, xs + (size_t)n * NX,
+  double terms[N_COST_TERMS];
+  thread_node_cost<false, COL>(model_of(P, b), P.refs + (size_t)n * REF_SIZE, xs + (size_t)n * NX,
                           terminal ? nullptr : us + ((size_t)b * P.T + t) * NJ, terminal, 1.0, nullptr, terms);
 #pragma unroll
-  for (int k = 0; k < 9; ++k) out_terms[(size_t)n * 9 + k] = terms[k];
+  for (int k = 0; k < N_COST_TERMS; ++k) out_terms[(size_t)n * N_COST_TERMS + k] = terms[k];
 }
 
 // Warm start by shifting the previous solution by the first time step

@@ -108,7 +108,7 @@ AGX_DEV void node_rnea_derivatives(LaneDyn& d, int j, unsigned omask, const doub
 // Weighted-quadratic costs of one node.  pose residual r6 = log6(Mref^-1 oMf); when DERIV the
 // Gauss-Newton terms Lq_j (this lane's entry) and Lqq[:, j] are produced as well.
 // Returns the (unscaled) node cost, identical on every lane.
-template <bool DERIV>
+template <bool DERIV, bool COL = false>
 AGX_DEV double node_costs(const LaneDyn& d, int j, unsigned omask, const double* __restrict__ model,
                           const double* __restrict__ ref, bool terminal, double* srq /*[8][6] scratch board*/, double* Lq,
                           double* Lv, double* Lu, double* Lqq /*7*/) {
@@ -135,7 +135,60 @@ AGX_DEV double node_costs(const LaneDyn& d, int j, unsigned omask, const double*
   double cpose = 0.0;
 #pragma unroll
   for (int k = 0; k < 6; ++k) cpose += 0.5 * wp[k] * r6[k] * r6[k];
-  const double cost = octet_sum(part, omask) + cpose;
+  double cost = octet_sum(part, omask) + cpose;
+  // collision pairs (A10): lane j holds its own entry of each gradient row; the closest points are computed
+  // redundantly on every lane from capsule end points broadcast by the parent joint's lane
+  double crq[MAX_PAIRS] = {0, 0}, g1[MAX_PAIRS] = {0, 0}, g2[MAX_PAIRS] = {0, 0};
+  if (COL) {
+    const int npairs = (int)model[MT_COL];
+    const double alpha = model[MT_COL + 1];
+    const double* wc = wp + 6;
+#pragma unroll
+    for (int k = 0; k < MAX_PAIRS; ++k) {
+      // the broadcasts run unconditionally: octets that share a warp may carry different models
+      double e[2][6];
+      int jpar[2];
+      double rad = 0.0;
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        const int ic = (int)model[MT_COL + 2 + 2 * k + side];
+        const double* a = model + MT_CAP + 8 * ic;
+        const int par = (int)a[7];
+        jpar[side] = par;
+        rad += a[6];
+        double w[6];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          w[r] = d.p[r] + (d.R[3 * r] * a[0] + d.R[3 * r + 1] * a[1] + d.R[3 * r + 2] * a[2]);
+          w[3 + r] = d.p[r] + (d.R[3 * r] * a[3] + d.R[3 * r + 1] * a[4] + d.R[3 * r + 2] * a[5]);
+        }
+#pragma unroll
+        for (int m = 0; m < 6; ++m) {
+          const double v = __shfl_sync(omask, w[m], par < 0 ? 0 : par, 8);
+          e[side][m] = par < 0 ? a[m] : v;
+        }
+      }
+      if (k < npairs) {
+        double ca[3], cb[3], nn[3];
+        const double len = segment_pair(e[0], e[0] + 3, e[1], e[1] + 3, ca, cb, nn);
+        const double r = len - rad;
+        double a, ar, arr;
+        quadexp(r, alpha, a, ar, arr);
+        cost += wc[k] * a;
+        if (DERIV) {
+          g1[k] = wc[k] * ar;
+          g2[k] = wc[k] * arr;
+          double wa[3], wb[3];
+          cross3(d.J + 3, ca, wa);
+          cross3(d.J + 3, cb, wb);
+          double da = 0.0, db = 0.0;
+#pragma unroll
+          for (int m = 0; m < 3; ++m) { da += nn[m] * (wa[m] + d.J[m]); db += nn[m] * (wb[m] + d.J[m]); }
+          crq[k] = ((j <= jpar[0]) ? da : 0.0) - ((j <= jpar[1]) ? db : 0.0);
+        }
+      }
+    }
+  }
   if (DERIV) {
     // column j of the LOCAL frame Jacobian: oMf^-1 acting on the world axis J_j (zero for joints
     // that do not move the frame), then Rq[:, j] = Jlog6 * that
@@ -165,6 +218,10 @@ AGX_DEV double node_costs(const LaneDyn& d, int j, unsigned omask, const double*
     double lq = wq * rq;
 #pragma unroll
     for (int k = 0; k < 6; ++k) lq += rqc[k] * (wp[k] * r6[k]);
+    if (COL) {
+#pragma unroll
+      for (int k = 0; k < MAX_PAIRS; ++k) lq += g1[k] * crq[k];
+    }
     *Lq = lq;
     *Lv = wv * rv;
     *Lu = wu * ru;
@@ -174,6 +231,14 @@ AGX_DEV double node_costs(const LaneDyn& d, int j, unsigned omask, const double*
 #pragma unroll
       for (int k = 0; k < 6; ++k) h += srq[i * 6 + k] * wr[k];
       Lqq[i] = h + ((i == j) ? wq : 0.0);
+    }
+    if (COL) {
+#pragma unroll
+      for (int k = 0; k < MAX_PAIRS; ++k) {
+        const double gk = g2[k] * crq[k];
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) Lqq[i] += __shfl_sync(omask, crq[k], i, 8) * gk;
+      }
     }
   }
   AGX_OSYNC();
@@ -186,7 +251,9 @@ AGX_DEV double node_costs(const LaneDyn& d, int j, unsigned omask, const double*
 // Gauss-Newton terms.  The log maps are scalar code: run once per octet they waste 7/8 of the lanes,
 // run one node per thread they do not.  With DERIV the cost record of the node is written
 // (scaled by s = dt, or 1 for the terminal node).  Returns the scaled node cost.
-template <bool DERIV>
+// With COL the capsule pairs of the model table add w a(r) per pair (a = QuadExp of the signed distance r) and its
+// Gauss-Newton terms w a' Rq, w a'' Rq Rq^T.
+template <bool DERIV, bool COL = false>
 AGX_DEV double thread_node_cost(const double* __restrict__ model, const double* __restrict__ ref,
                                 const double* __restrict__ x, const double* __restrict__ u, bool terminal, double s,
                                 double* __restrict__ rec, double* __restrict__ terms = nullptr) {
@@ -195,6 +262,13 @@ AGX_DEV double thread_node_cost(const double* __restrict__ model, const double* 
   double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0};
   double Rf0[9], pf0[3];
   double Jw[NJ][6];
+  double cw[COL ? MAX_CAPS : 1][6];  // capsule end points in the world
+  if (COL) {
+#pragma unroll
+    for (int c = 0; c < MAX_CAPS; ++c)
+#pragma unroll
+      for (int k = 0; k < 6; ++k) cw[c][k] = model[MT_CAP + 8 * c + k];  // world-fixed capsules stay as they are
+  }
 #pragma unroll
   for (int i = 0; i < NJ; ++i) {
     double sq, cq;
@@ -223,9 +297,21 @@ AGX_DEV double thread_node_cost(const double* __restrict__ model, const double* 
       const double z[3] = {R[2], R[5], R[8]};
       double pz[3];
       cross3(p, z, pz);
-      const double moves = (i <= fpar) ? 1.0 : 0.0;
+      const double moves = (COL || i <= fpar) ? 1.0 : 0.0;  // COL keeps every axis and masks at the point of use
 #pragma unroll
       for (int k = 0; k < 3; ++k) { Jw[i][k] = moves * pz[k]; Jw[i][3 + k] = moves * z[k]; }
+    }
+    if (COL) {
+#pragma unroll
+      for (int c = 0; c < MAX_CAPS; ++c)
+        if ((int)model[MT_CAP + 8 * c + 7] == i) {
+          const double* a = model + MT_CAP + 8 * c;
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            cw[c][r] = p[r] + (R[3 * r] * a[0] + R[3 * r + 1] * a[1] + R[3 * r + 2] * a[2]);
+            cw[c][3 + r] = p[r] + (R[3 * r] * a[3] + R[3 * r + 1] * a[4] + R[3 * r + 2] * a[5]);
+          }
+        }
     }
     if (i == fpar) {
 #pragma unroll
@@ -242,6 +328,58 @@ AGX_DEV double thread_node_cost(const double* __restrict__ model, const double* 
   double cost = 0.0;
 #pragma unroll
   for (int k = 0; k < 6; ++k) cost += 0.5 * wp[k] * r6[k] * r6[k];
+  // collision pairs: gradient rows crq, gains g1 = w a', g2 = w a''
+  double crq[COL ? MAX_PAIRS : 1][NJ], g1[MAX_PAIRS] = {0, 0}, g2[MAX_PAIRS] = {0, 0}, ccost[MAX_PAIRS] = {0, 0},
+                                       cdist[MAX_PAIRS] = {0, 0};
+  if (COL) {
+    const int npairs = (int)model[MT_COL];
+    const double alpha = model[MT_COL + 1];
+    const double* wc = wp + 6;
+#pragma unroll
+    for (int k = 0; k < MAX_PAIRS; ++k) {
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) crq[k][i] = 0.0;
+      if (k < npairs) {
+        const int ia = (int)model[MT_COL + 2 + 2 * k], ib = (int)model[MT_COL + 3 + 2 * k];
+        double ea[6], eb[6];
+#pragma unroll
+        for (int c = 0; c < MAX_CAPS; ++c) {  // static indexing keeps cw in registers
+          if (c == ia) {
+#pragma unroll
+            for (int m = 0; m < 6; ++m) ea[m] = cw[c][m];
+          }
+          if (c == ib) {
+#pragma unroll
+            for (int m = 0; m < 6; ++m) eb[m] = cw[c][m];
+          }
+        }
+        double ca[3], cb[3], nn[3];
+        const double len = segment_pair(ea, ea + 3, eb, eb + 3, ca, cb, nn);
+        const double r = len - model[MT_CAP + 8 * ia + 6] - model[MT_CAP + 8 * ib + 6];
+        double a, ar, arr;
+        quadexp(r, alpha, a, ar, arr);
+        ccost[k] = wc[k] * a;
+        cdist[k] = r;
+        cost += ccost[k];
+        if (DERIV) {
+          g1[k] = wc[k] * ar;
+          g2[k] = wc[k] * arr;
+          const int ja = (int)model[MT_CAP + 8 * ia + 7], jb = (int)model[MT_CAP + 8 * ib + 7];
+          // d r / d q_i = n . (z_i x (ca - p_i)) [i <= ja] - n . (z_i x (cb - p_i)) [i <= jb]
+#pragma unroll
+          for (int i = 0; i < NJ; ++i) {
+            double wa[3], wb[3];
+            cross3(Jw[i] + 3, ca, wa);
+            cross3(Jw[i] + 3, cb, wb);
+            double da = 0.0, db = 0.0;
+#pragma unroll
+            for (int m = 0; m < 3; ++m) { da += nn[m] * (wa[m] + Jw[i][m]); db += nn[m] * (wb[m] + Jw[i][m]); }
+            crq[k][i] = ((i <= ja) ? da : 0.0) - ((i <= jb) ? db : 0.0);
+          }
+        }
+      }
+    }
+  }
   if (terms) {
     // per-cost view (mpc_debugger_node.py:294-323): [state_reg, control_reg, goal_tracking] values and the
     // frame-placement residual; unscaled (differential) costs
@@ -255,9 +393,11 @@ AGX_DEV double thread_node_cost(const double* __restrict__ model, const double* 
         cu += 0.5 * ref[2 * NX + NJ + i] * ru * ru;
       }
     }
-    terms[0] = cs; terms[1] = cu; terms[2] = cost;
+    terms[0] = cs; terms[1] = cu; terms[2] = cost - (ccost[0] + ccost[1]);
 #pragma unroll
     for (int k = 0; k < 6; ++k) terms[3 + k] = r6[k];
+#pragma unroll
+    for (int k = 0; k < MAX_PAIRS; ++k) { terms[9 + k] = ccost[k]; terms[9 + MAX_PAIRS + k] = cdist[k]; }
   }
   double wr6[6];
 #pragma unroll
@@ -272,6 +412,10 @@ AGX_DEV double thread_node_cost(const double* __restrict__ model, const double* 
     cost += 0.5 * wq * rq * rq + 0.5 * wv * rv * rv + 0.5 * wu * ru * ru;
     if (DERIV) {
       double t[3], pw[3], cl[3], ca[3];
+      if (COL && i > fpar) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) Jw[i][k] = 0.0;
+      }
       cross3(pf, Jw[i] + 3, pw);
 #pragma unroll
       for (int k = 0; k < 3; ++k) t[k] = Jw[i][k] - pw[k];
@@ -288,6 +432,10 @@ AGX_DEV double thread_node_cost(const double* __restrict__ model, const double* 
       }
 #pragma unroll
       for (int k = 0; k < 6; ++k) lq += Jw[i][k] * wr6[k];
+      if (COL) {
+#pragma unroll
+        for (int k = 0; k < MAX_PAIRS; ++k) lq += g1[k] * crq[k][i];
+      }
       rec[CK_LVV + i] = s * wv;
       rec[CK_LUU + i] = s * wu;
       rec[CK_LQ + i] = s * lq;
@@ -305,6 +453,10 @@ AGX_DEV double thread_node_cost(const double* __restrict__ model, const double* 
           double h = (i == k) ? ref[NX + i] : 0.0;
 #pragma unroll
           for (int m = 0; m < 6; ++m) h += Jw[i][m] * (wp[m] * Jw[k][m]);
+          if (COL) {
+#pragma unroll
+            for (int m = 0; m < MAX_PAIRS; ++m) h += g2[m] * crq[m][i] * crq[m][k];
+          }
           rec[CK_LQQ + lidx(i, k)] = s * h;
         }
       }

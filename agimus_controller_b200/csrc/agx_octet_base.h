@@ -74,7 +74,14 @@ constexpr int MF_NFIELDS = 24;
 constexpr int MT_GRAV = MF_NFIELDS * 8;  // 3
 constexpr int MT_FR = MT_GRAV + 3;       // 9 frame rotation
 constexpr int MT_FP = MT_FR + 9;         // 3 frame translation
-constexpr int MODEL_SIZE = MT_FP + 3 + 1;  // 208 doubles
+// collision geometry (A10): capsule c = [a0 3][a1 3][radius][parent joint or -1] in the parent frame, then
+// [n_pairs][alpha][pair0 a][pair0 b][pair1 a][pair1 b]
+constexpr int MAX_CAPS = 4;
+constexpr int MAX_PAIRS = 2;
+constexpr int MT_CAP = MT_FP + 3 + 1;           // 208
+constexpr int MT_COL = MT_CAP + 8 * MAX_CAPS;   // 240
+constexpr int MODEL_SIZE = MT_COL + 8;          // 248 doubles
+constexpr int N_COST_TERMS = 13;  // agx_cost_terms row: [state, control, goal, r6 (6), collision cost (2), distance (2)]
 
 // ---- compact node records written by calc_diff, read by the Riccati sweep (instead of the 658 dense
 // doubles of Fx, Fu, Lx, Lu, Lxx, Lxu, Luu per node).

@@ -30,7 +30,8 @@ from .problem import pack_refs
 from .robot_model import RobotTable
 from .solver import BatchedShootingProblem
 
-_SUPPORTED_RESIDUALS = ("ResidualModelState", "ResidualModelControl", "ResidualModelFramePlacement")
+_SUPPORTED_RESIDUALS = ("ResidualModelState", "ResidualModelControl", "ResidualModelFramePlacement",
+                        "ResidualDistanceCollision")
 
 
 def flatten_cost_stack(model_def: dict, terminal: bool) -> dict:
@@ -48,16 +49,30 @@ def flatten_cost_stack(model_def: dict, terminal: bool) -> dict:
         raise NotImplementedError("constraints need the CSQP solver mode (SURVEY.md 8f N1): not on the FDDP device path")
     slots = {"state": 0.0, "control": 0.0, "pose": 0.0}
     names = {}
+    collisions = []
     for item in diff.get("costs", []):
         cost = item["cost"]
         if cost.get("class") != "CostModelResidual":
             raise NotImplementedError(f"cost class {cost.get('class')}")
         act = cost.get("activation")
-        if act is not None and act.get("class") != "ActivationModelWeightedQuad":
-            raise NotImplementedError(f"activation {act.get('class')} is not supported on the device path")
         rcls = cost["residual"].get("class")
         if rcls not in _SUPPORTED_RESIDUALS:
             raise NotImplementedError(f"residual {rcls} is not supported on the device path")
+        if rcls == "ResidualDistanceCollision":
+            # colmpc distance residual under the squared-exponential activation
+            # (ocp_croco_generic.py:119-147, :499-535; ocp_traj_tracking_collision_avoidance.yaml:36-46)
+            acls = (act or {}).get("class")
+            quad_exp = acls == "ActivationModelQuadExp" or (acls == "ActivationModelExp" and int(act.get("exponent", 1)) == 2)
+            if not quad_exp:
+                raise NotImplementedError(f"activation {acls} on a collision residual is not supported on the device path")
+            res = cost["residual"]
+            pair = tuple(res["collision_pair"]) if "collision_pair" in res else int(res.get("collision_pair_id", 0))
+            collisions.append(dict(name=item["name"], pair=pair, alpha=float(act.get("alpha", 1.0)),
+                                   weight=float(item.get("weight", 1.0)) if item.get("active", True) else 0.0,
+                                   update=bool(item.get("update", False))))
+            continue
+        if act is not None and act.get("class") != "ActivationModelWeightedQuad":
+            raise NotImplementedError(f"activation {act.get('class')} is not supported on the device path")
         slot = {"ResidualModelState": "state", "ResidualModelControl": "control",
                 "ResidualModelFramePlacement": "pose"}[rcls]
         if slot == "control" and terminal:
@@ -66,7 +81,36 @@ def flatten_cost_stack(model_def: dict, terminal: bool) -> dict:
             raise NotImplementedError(f"two costs on the {slot} residual")
         names[slot] = item["name"]
         slots[slot] = float(item.get("weight", 1.0)) if item.get("active", True) else 0.0
-    return {"weights": slots, "names": names}
+    return {"weights": slots, "names": names, "collisions": collisions}
+
+
+def resolve_collision_pairs(table: RobotTable, running: dict, terminal: dict) -> RobotTable:
+    """Table whose collision pairs / alpha are the ones the cost stacks name (``_collision_pair_id``,
+    ``ocp_croco_generic.py:504-521``: a pair is added to the geometry model when a residual asks for it); each
+    stack's collision entries get the ``slot`` of their pair in the reference record."""
+    pairs: list = []
+    alphas = set()
+    for stack in (running, terminal):
+        for col in stack.get("collisions", []):
+            pair = col["pair"]
+            if isinstance(pair, int):
+                if not 0 <= pair < len(table.collision_pairs):
+                    raise ValueError(f"collision_pair_id {pair}: the model has {len(table.collision_pairs)} pairs")
+                pair = tuple(table.collision_pairs[pair])
+            for name in pair:
+                if name not in table.capsules:
+                    raise ValueError(f"Geometry object '{name}' not found.")
+            if pair not in pairs:
+                pairs.append(pair)
+            col["slot"] = pairs.index(pair)
+            alphas.add(col["alpha"])
+    if not pairs:
+        return table
+    if len(pairs) > _abi.AGX_MAX_COLLISION_PAIRS:
+        raise NotImplementedError(f"{len(pairs)} collision pairs: the device records hold {_abi.AGX_MAX_COLLISION_PAIRS}")
+    if len(alphas) != 1:
+        raise NotImplementedError("collision costs with different activation alphas are not supported on the device path")
+    return table.with_capsules({n: c for n, c in table.capsules.items()}, pairs, alphas.pop())
 
 
 def build_reference_rows(table: RobotTable, running: dict, terminal: dict, horizon: list) -> np.ndarray:
@@ -100,7 +144,12 @@ def build_reference_rows(table: RobotTable, running: dict, terminal: dict, horiz
             Rref = np.asarray(ee_pose.rotation, dtype=np.float64)
             pref = np.asarray(ee_pose.translation, dtype=np.float64)
             wpose = w["pose"] * np.asarray(wt.w_end_effector_poses[ee_name], dtype=np.float64)
-        rows[t] = pack_refs(nv, 0, 1, xref, wx, uref, wu, Rref, pref, wpose)[0, 0]
+        wcol = np.zeros(_abi.AGX_MAX_COLLISION_PAIRS)
+        for col in stack.get("collisions", []):
+            # the collision activation has no weight vector: update() sets the scalar CostModelSum weight
+            # (ocp_croco_generic.py:714-719)
+            wcol[col["slot"]] += float(wt.w_collision_avoidance) if col["update"] else col["weight"]
+        rows[t] = pack_refs(nv, 0, 1, xref, wx, uref, wu, Rref, pref, wpose, wcol=wcol)[0, 0]
         if t == T1 - 1:
             rows[t, 5 * nv: 6 * nv] = 0.0  # the terminal node has no control cost
         else:
@@ -121,6 +170,7 @@ class OCPBatchedFDDP(OCPBase):
                 data = yaml.safe_load(f)
         self._running = flatten_cost_stack(data["running_model"], terminal=False)
         self._terminal = flatten_cost_stack(data["terminal_model"], terminal=True)
+        robot_table = resolve_collision_pairs(robot_table, self._running, self._terminal)
         self._table = robot_table
         self._ocp_params = params
         self._B = int(batch_size)

@@ -185,9 +185,10 @@ class BatchedShootingProblem:
         """Per-cost values and the frame-placement residual of every node (debugger view)."""
         xs = self._t(xs, (self.B, self.T + 1, self.nx))
         us = self._t(us, (self.B, self.T, self.nv))
-        out = self._empty(self.B, self.T + 1, 9)
+        out = self._empty(self.B, self.T + 1, _abi.AGX_N_COST_TERMS)
         self._check(lib().agx_cost_terms(self._h, _ptr(xs), _ptr(us), _ptr(out), self._stream()))
-        return dict(state_reg=out[..., 0], control_reg=out[..., 1], goal_tracking=out[..., 2], r_pose=out[..., 3:9])
+        return dict(state_reg=out[..., 0], control_reg=out[..., 1], goal_tracking=out[..., 2], r_pose=out[..., 3:9],
+                    collision=out[..., 9:11], collision_distance=out[..., 11:13])
 
     def shift_warmstart(self, xs, us):
         """Previous solution shifted by the first time step (``WarmStartShiftPreviousSolution.shift``)."""

@@ -10,7 +10,7 @@ from __future__ import annotations
 import numpy as np
 
 from .problem import pack_refs
-from .robot_model import PANDA_Q_NOMINAL, panda_table
+from .robot_model import PANDA_CAPSULES, PANDA_COLLISION_PAIRS, PANDA_Q_NOMINAL, panda_table
 
 TOOL_DOWN = np.diag([1.0, -1.0, -1.0])  # quaternion x = 1 (dummy_mpc_test.py:104-107)
 
@@ -95,6 +95,44 @@ def model_sensibility_batch(B, T=50, dt=0.01, rnea=None, delta=0.01, seed=5):
     tables = [base.perturbed((b % 70) // 10, (b % 70) % 10, delta * s[b]) for b in range(B)]
     w["tables"] = tables
     return w
+
+
+# start posture of the reference's pick-and-place example (panda_pick_and_place/main.py:81-91), arm joints only
+PICK_AND_PLACE_Q_INIT = np.array([-0.3619834760502907, -1.3575006398318104, 0.969610481368033, -2.6028532848927295,
+                                  0.2040785081450368, 1.9436352693107668, 0.6423896937386857])
+
+
+def pick_and_place_collision_batch(B, T=100, dt=0.01, rnea=None, seed=4, alpha=1e-4, w_col=(10.0, 10.0), w_q=3.0,
+                                   w_v=0.12, w_u=8e-4, armature=0.1, move_duration=1.0, q_spread=0.05,
+                                   capsules=None, pairs=None):
+    """Config 4: joint-space quintic move ``q_init -> q_nominal`` over ``move_duration`` (generic_trajectory.py with
+    the weights of panda_pick_and_place/config/trajectory_weigths_params.yaml:4-9) with ``ResidualDistanceCollision`` +
+    ``ActivationModelQuadExp(alpha)`` costs on the link7/link3 and link7/obstacle capsule pairs
+    (config/agimus_controller_params.yaml:16-20, tests/resources/environment.xacro:23-24).  Fingers locked (nv = 7:
+    the kernels cover the 7-joint arm); capsule geometry is the synthetic table of robot_model.PANDA_CAPSULES.
+    Initial states are ``q_init`` plus a per-problem offset."""
+    table = panda_table(lock_fingers=True, armature=armature).with_capsules(
+        PANDA_CAPSULES if capsules is None else capsules, PANDA_COLLISION_PAIRS if pairs is None else pairs, alpha)
+    nv = table.nv
+    rng = np.random.default_rng(seed)
+    off = rng.uniform(-q_spread, q_spread, size=(B, nv))
+    tt = dt * np.arange(T + 1)
+    s = np.clip(tt / move_duration, 0.0, 1.0)
+    p = 10 * s**3 - 15 * s**4 + 6 * s**5
+    dp = np.where(s < 1.0, (30 * s**2 - 60 * s**3 + 30 * s**4) / move_duration, 0.0)
+    ddp = np.where(s < 1.0, (60 * s - 180 * s**2 + 120 * s**3) / move_duration**2, 0.0)
+    dq = (PANDA_Q_NOMINAL - PICK_AND_PLACE_Q_INIT)[None, None, :]
+    q = PICK_AND_PLACE_Q_INIT[None, None, :] + off[:, None, :] * (1.0 - p)[None, :, None] + dq * p[None, :, None]
+    v = (dq - off[:, None, :]) * dp[None, :, None]
+    a = (dq - off[:, None, :]) * ddp[None, :, None]
+    u = (np.asarray(rnea(q.reshape(-1, nv), v.reshape(-1, nv), a.reshape(-1, nv))).reshape(B, T + 1, nv)
+         if rnea is not None else np.zeros((B, T + 1, nv)))
+    xref = np.concatenate([q, v], axis=2)
+    wx = np.concatenate([np.full(nv, w_q), np.full(nv, w_v)])
+    refs = pack_refs(nv, T, B, xref, wx, u, np.full(nv, w_u), np.eye(3), np.zeros(3), np.zeros(6), wcol=np.asarray(w_col))
+    x0 = np.ascontiguousarray(xref[:, 0, :])
+    return dict(table=table, refs=refs, dts=np.full(T, dt), x0=x0, xs_ws=np.ascontiguousarray(xref),
+                us_ws=np.ascontiguousarray(u[:, :T, :]))
 
 
 def sine_configuration_reference(n_points, dt=0.01, amplitude=0.2, period=4.0, scale_duration=1.0, rnea=None,

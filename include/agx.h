@@ -151,7 +151,9 @@ int agx_calc_diff(agx_handle* h, const double* xs, const double* us, double* out
 
 /* Per-cost evaluation (what mpc_debugger_node.py:294-323 reads off problem.runningDatas): for every node the
  * unscaled value of each named cost of ocp_goal_reaching.yaml and the frame-placement residual,
- * out_terms [B][T+1][9] = [state_reg, control_reg, goal_tracking, r6 (lin 3, ang 3)]. */
+ * out_terms [B][T+1][AGX_N_COST_TERMS] = [state_reg, control_reg, goal_tracking, r6 (lin 3, ang 3),
+ * collision cost of pair 0 / 1, signed distance of pair 0 / 1 (plots/plots_utils.py:160-208)]. */
+#define AGX_N_COST_TERMS 13
 int agx_cost_terms(agx_handle* h, const double* xs, const double* us, double* out_terms, void* stream);
 
 /* WarmStartShiftPreviousSolution.shift (warm_start_shift_previous_solution.py:85-104) for the whole batch:

@@ -580,7 +580,7 @@ struct NodeData {
   double Fx[MAXX * MAXX], Fu[MAXX * MAXV];
   double Lx[MAXX], Lu[MAXV], Lxx[MAXX * MAXX], Lxu[MAXX * MAXV], Luu[MAXV * MAXV];
   // intermediate (kept for the per-cost API / debugging)
-  double a[MAXV], Minv[MAXV * MAXV], rpose[6];
+  double a[MAXV], Minv[MAXV * MAXV], rpose[6], rcol[AGX_MAX_COLLISION_PAIRS];
 };
 
 // frame-placement residual r = log6(Mref^-1 oMf) and its Jacobian Rq = Jlog6 * fJf (6 x nv)
@@ -603,6 +603,95 @@ void pose_residual(const agx_model& m, const Kin& kin, const NodeRef& ref, doubl
         Rq[i * nv + j] = s;
       }
   }
+}
+
+// ----------------------------------------------------------------------------- collision residual (A10)
+// colmpc::ResidualDistanceCollision on a capsule pair, followed by colmpc::ActivationModelQuadExp
+// (ocp/ocp_croco_generic.py:119-147, :499-535; ocp/ocp_traj_tracking_collision_avoidance.yaml:36-46).  colmpc is a
+// third-party dependency that is not in the reference tree, so this restates its published formulas:
+//   r(q)   = dist(shape_a, shape_b)           (coal signed distance; capsule pair = segment distance - r_a - r_b)
+//   dr/dq  = n^T (J_a(c_a) - J_b(c_b))        n = (c_a - c_b)/|c_a - c_b|, J(c) the world linear Jacobian of the
+//                                             point c rigidly attached to the capsule's parent joint
+//   a(r)   = exp(-r^2/alpha), a' = -2 r/alpha a, a'' = (4 r^2/alpha^2 - 2/alpha) a
+// PARITY UNPINNED for this row: no golden vector of the reference exercises it.
+struct CapsuleHit {
+  double dist;       // signed distance between the capsules
+  double ca[3], cb[3], n[3];  // closest points on the two axes (world), unit direction cb -> ca
+};
+inline double clamp01(double v) { return v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v); }
+// closest points of two segments [a0,a1], [b0,b1] (Ericson, Real-Time Collision Detection, 5.1.9)
+void capsule_pair(const double* a0, const double* a1, double ra, const double* b0, const double* b1, double rb,
+                  CapsuleHit& h) {
+  const double eps = 1e-12;
+  double d1[3], d2[3], r[3];
+  for (int k = 0; k < 3; ++k) { d1[k] = a1[k] - a0[k]; d2[k] = b1[k] - b0[k]; r[k] = a0[k] - b0[k]; }
+  const double a = dot3(d1, d1), e = dot3(d2, d2), f = dot3(d2, r);
+  double s = 0.0, t = 0.0;
+  if (a <= eps && e <= eps) {
+    s = t = 0.0;
+  } else if (a <= eps) {
+    t = clamp01(f / e);
+  } else {
+    const double c = dot3(d1, r);
+    if (e <= eps) {
+      s = clamp01(-c / a);
+    } else {
+      const double b = dot3(d1, d2), denom = a * e - b * b;
+      s = (denom > eps * a * e) ? clamp01((b * f - c * e) / denom) : 0.0;
+      t = (b * s + f) / e;
+      if (t < 0.0) { t = 0.0; s = clamp01(-c / a); }
+      else if (t > 1.0) { t = 1.0; s = clamp01((b - c) / a); }
+    }
+  }
+  double dd[3];
+  for (int k = 0; k < 3; ++k) { h.ca[k] = a0[k] + s * d1[k]; h.cb[k] = b0[k] + t * d2[k]; dd[k] = h.ca[k] - h.cb[k]; }
+  const double len = std::sqrt(dot3(dd, dd));
+  const double inv = len > 1e-14 ? 1.0 / len : 0.0;
+  for (int k = 0; k < 3; ++k) h.n[k] = dd[k] * inv;
+  h.dist = len - ra - rb;
+}
+// world end points of capsule c
+inline void capsule_world(const agx_model& m, const Kin& kin, int c, double* a0, double* a1) {
+  const int par = m.cap_parent[c];
+  if (par < 0) {
+    for (int k = 0; k < 3; ++k) { a0[k] = m.cap_a0[c][k]; a1[k] = m.cap_a1[c][k]; }
+    return;
+  }
+  double t0[3], t1[3];
+  mv3(kin.oMi[par].R, m.cap_a0[c], t0);
+  mv3(kin.oMi[par].R, m.cap_a1[c], t1);
+  for (int k = 0; k < 3; ++k) { a0[k] = kin.oMi[par].p[k] + t0[k]; a1[k] = kin.oMi[par].p[k] + t1[k]; }
+}
+// distance of pair k and (optionally) its gradient Rq[nv]
+double collision_residual(const agx_model& m, const Kin& kin, int k, double* Rq) {
+  const int ia = m.pair_a[k], ib = m.pair_b[k];
+  double a0[3], a1[3], b0[3], b1[3];
+  capsule_world(m, kin, ia, a0, a1);
+  capsule_world(m, kin, ib, b0, b1);
+  CapsuleHit h;
+  capsule_pair(a0, a1, m.cap_radius[ia], b0, b1, m.cap_radius[ib], h);
+  if (Rq) {
+    for (int j = 0; j < m.nv; ++j) Rq[j] = 0.0;
+    // world linear velocity of a point c attached to joint `par` due to joint j: z_j x (c - p_j) = w x c + v,
+    // with the world axis J_j = [v; w] of forward_kinematics
+    for (int side = 0; side < 2; ++side) {
+      const double* c = side == 0 ? h.ca : h.cb;
+      const double sgn = side == 0 ? 1.0 : -1.0;
+      for (int j = m.cap_parent[side == 0 ? ia : ib]; j >= 0; j = m.parent[j]) {
+        double wxc[3];
+        cross3(kin.J[j] + 3, c, wxc);
+        double vel[3] = {wxc[0] + kin.J[j][0], wxc[1] + kin.J[j][1], wxc[2] + kin.J[j][2]};
+        Rq[j] += sgn * dot3(h.n, vel);
+      }
+    }
+  }
+  return h.dist;
+}
+// QuadExp activation of a scalar residual
+inline void quadexp(double r, double alpha, double& a, double& ar, double& arr) {
+  a = std::exp(-r * r / alpha);
+  ar = -2.0 * r / alpha * a;
+  arr = (4.0 * r * r / (alpha * alpha) - 2.0 / alpha) * a;
 }
 
 // DifferentialActionModelFreeFwdDynamics::calc (armature path): a = (M + diag(arm))^-1 (u - nle)
@@ -647,6 +736,11 @@ double node_cost(const agx_model& m, const NodeRef& ref, const double* x, const 
   pose_residual(m, kin, ref, r6, nullptr);
   for (int i = 0; i < 6; ++i) c += 0.5 * ref.wpose[i] * r6[i] * r6[i];
   if (rpose_out) std::memcpy(rpose_out, r6, sizeof r6);
+  for (int k = 0; k < m.n_pairs; ++k) {
+    double a, ar, arr;
+    quadexp(collision_residual(m, kin, k, nullptr), m.col_alpha, a, ar, arr);
+    c += ref.wcol[k] * a;
+  }
   return c;
 }
 
@@ -715,6 +809,17 @@ bool node_calc_diff(const agx_model& m, const double* refrec, double dt, bool te
       double h = 0;
       for (int k = 0; k < 6; ++k) h += Rq[k * nv + i] * ref.wpose[k] * Rq[k * nv + j];
       d.Lxx[i * nx + j] += h;
+    }
+  }
+  for (int k = 0; k < m.n_pairs; ++k) {
+    double Cq[MAXV], a, ar, arr;
+    const double r = collision_residual(m, kin, k, Cq);
+    quadexp(r, m.col_alpha, a, ar, arr);
+    d.rcol[k] = r;
+    l += ref.wcol[k] * a;
+    for (int i = 0; i < nv; ++i) {
+      Lx[i] += ref.wcol[k] * ar * Cq[i];
+      for (int j = 0; j < nv; ++j) d.Lxx[i * nx + j] += ref.wcol[k] * arr * Cq[i] * Cq[j];
     }
   }
   if (terminal) {
@@ -1097,6 +1202,13 @@ void orc_frame_placement(const agx_model* m, const double* q, double* R, double*
   frame_placement(*m, kin, f);
   std::memcpy(R, f.R, sizeof f.R);
   std::memcpy(p, f.p, sizeof f.p);
+}
+// collision pair k: signed distance, its gradient [nv] and the QuadExp activation (a, a', a'')
+void orc_collision(const agx_model* m, const double* q, int k, double* dist, double* Rq, double* act) {
+  Kin kin;
+  forward_kinematics(*m, q, kin);
+  *dist = collision_residual(*m, kin, k, Rq);
+  if (act) quadexp(*dist, m->col_alpha, act[0], act[1], act[2]);
 }
 // frame Jacobians: LOCAL (6 x nv) and LOCAL_WORLD_ALIGNED (6 x nv)
 void orc_frame_jacobian(const agx_model* m, const double* q, double* J_local, double* J_lwa) {

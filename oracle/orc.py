@@ -89,6 +89,13 @@ def frame_jacobian(m, q):
     return Jl, Jw
 
 
+def collision(m, q, k=0):
+    """Signed capsule distance of collision pair k, its gradient and the QuadExp activation (a, a', a'')."""
+    d, Rq, act = np.zeros(1), np.zeros(m.nv), np.zeros(3)
+    lib().orc_collision(C.byref(m), _p(_c(q)), int(k), _p(d), _p(Rq), _p(act))
+    return float(d[0]), Rq, act
+
+
 def log6(R, p):
     out = np.zeros(6)
     lib().orc_log6(_p(_c(R)), _p(_c(p)), _p(out))

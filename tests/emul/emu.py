@@ -156,7 +156,7 @@ def cost_terms(models, refs, dts, xs, us):
     xs, us = _c(xs), _c(us)
     B, T1, nx = xs.shape
     h = _handle(models, refs, dts, B, T1 - 1)
-    out = np.zeros((B, T1, 9))
+    out = np.zeros((B, T1, 13))
     h.check(lib().agx_cost_terms(h.h, _p(xs), _p(us), _p(out), None))
     return out
 

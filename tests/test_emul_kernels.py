@@ -303,3 +303,113 @@ def test_long_budget_stops_early(orc, m7):
     np.testing.assert_array_equal(e["status"], o["status"])
     assert rel(e["xs"], o["xs"]) < 1e-6
     assert e["launches"] < 5 * (int(o["iters"].max()) + 16) + 20
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Collision-distance residuals: capsule pairs + ActivationModelQuadExp.  Parity is against the CPU
+# restatement only (colmpc / coal are absent from the reference tree: "parity unpinned" for this row).
+@pytest.fixture(scope="module")
+def col_case(orc, m7):
+    from agimus_controller_b200.robot_model import PANDA_CAPSULES, PANDA_COLLISION_PAIRS
+    table = panda_table().with_capsules(PANDA_CAPSULES, PANDA_COLLISION_PAIRS, alpha=0.02)
+    B, T = 3, 8
+    w = _workload(orc, m7, B, T)
+    refs = w["refs"].copy()
+    refs[..., 60] = 30.0
+    refs[..., 61] = 50.0
+    refs[:, T, 60:62] = [0.0, 20.0]   # per-node weights: the terminal node keeps one pair only
+    rng = np.random.default_rng(11)
+    xs = w["xs_ws"] + rng.uniform(-0.2, 0.2, w["xs_ws"].shape)
+    us = w["us_ws"] + rng.uniform(-2, 2, w["us_ws"].shape)
+    return dict(w, m=table.to_struct(), refs=refs, xs=xs, us=us, refs_plain=w["refs"])
+
+
+def test_collision_calc_diff_per_node(orc, col_case):
+    c = col_case
+    m = c["m"]
+    c0, xn0 = orc.calc(m, c["refs"], c["dts"], c["xs"], c["us"])
+    c1, xn1 = emu.calc(m, c["refs"], c["dts"], c["xs"], c["us"])
+    assert rel(c1, c0) < 1e-12 and rel(xn1, xn0) < 1e-12
+    o = orc.calc_diff(m, c["refs"], c["dts"], c["xs"], c["us"])
+    e = emu.calc_diff(m, c["refs"], c["dts"], c["xs"], c["us"])
+    for k in ("cost", "xnext", "Fx", "Fu", "Lx", "Lu", "Lxx", "Luu"):
+        assert rel(e[k], o[k]) < 1e-9, k
+    # the collision terms are really there: they change cost, gradient and Hessian, not the dynamics
+    z = orc.calc_diff(m, c["refs_plain"], c["dts"], c["xs"], c["us"])
+    assert rel(z["Lx"], o["Lx"]) > 1e-3 and rel(z["Lxx"], o["Lxx"]) > 1e-3 and rel(z["Fx"], o["Fx"]) == 0.0
+
+
+def test_collision_gradient_is_the_distance_derivative(orc, col_case):
+    """Rq of the restatement against central differences of its own distance (the oracle's only pin for A10)."""
+    m = col_case["m"]
+    rng = np.random.default_rng(3)
+    for _ in range(6):
+        q = PANDA_Q_NOMINAL + rng.uniform(-1.0, 1.0, 7)
+        for k in range(2):
+            d, Rq, act = orc.collision(m, q, k)
+            fd = np.array([(orc.collision(m, q + h, k)[0] - orc.collision(m, q - h, k)[0]) / 2e-6
+                           for h in 1e-6 * np.eye(7)])
+            assert np.abs(fd - Rq).max() < 1e-8
+            a = np.exp(-d * d / m.col_alpha)
+            np.testing.assert_allclose(act, [a, -2 * d / m.col_alpha * a, (4 * d * d / m.col_alpha**2 - 2 / m.col_alpha) * a],
+                                       rtol=1e-13)
+
+
+def test_collision_cost_terms(orc, col_case):
+    c = col_case
+    m = c["m"]
+    terms = emu.cost_terms(m, c["refs"], c["dts"], c["xs"], c["us"])
+    for b in range(2):
+        for t in (0, 3, 8):
+            for k in range(2):
+                d, _, act = orc.collision(m, c["xs"][b, t, :7], k)
+                assert abs(terms[b, t, 11 + k] - d) < 1e-13
+                assert abs(terms[b, t, 9 + k] - c["refs"][b, t, 60 + k] * act[0]) < 1e-12 * max(1.0, act[0])
+    cost, _ = orc.calc(m, c["refs"], c["dts"], c["xs"], c["us"])
+    scale = np.concatenate([c["dts"], [1.0]])
+    total = (terms[..., 0] + terms[..., 1] + terms[..., 2] + terms[..., 9] + terms[..., 10]) * scale
+    assert rel(total, cost) < 1e-12
+
+
+@pytest.mark.parametrize("fixed,iters", [(True, 3), (False, 40)])
+def test_collision_solve_matches_oracle(orc, col_case, fixed, iters):
+    c = col_case
+    m = c["m"]
+    opts = _abi.default_fddp_opts(fixed_iters=fixed)
+    o = orc.solve(m, c["refs"], c["dts"], c["x0"], c["xs_ws"], c["us_ws"], iters, opts)
+    e = emu.solve(m, c["refs"], c["dts"], c["x0"], c["xs_ws"], c["us_ws"], iters, opts)
+    np.testing.assert_array_equal(e["iters"], o["iters"])
+    np.testing.assert_array_equal(e["status"], o["status"])
+    for k in ("xs", "us", "cost", "K", "k"):
+        assert rel(e[k], o[k]) < 1e-6, k
+    z = orc.solve(m, c["refs_plain"], c["dts"], c["x0"], c["xs_ws"], c["us_ws"], iters, opts)
+    assert rel(z["xs"], o["xs"]) > 1e-3  # the obstacle changes the plan
+
+
+def test_collision_mixed_models_in_one_batch(orc, col_case):
+    """One model per problem, only some with collision pairs: the COL kernels run for the whole batch and the
+    pair-free problems must come out exactly as without them."""
+    c = col_case
+    plain = panda_table().to_struct()
+    models = [c["m"], plain, c["m"]]
+    o = orc.calc_diff(models, c["refs"], c["dts"], c["xs"], c["us"])
+    e = emu.calc_diff(models, c["refs"], c["dts"], c["xs"], c["us"])
+    for k in ("cost", "Lx", "Lxx", "Fx"):
+        assert rel(e[k], o[k]) < 1e-9, k
+    z = emu.calc_diff(plain, c["refs"], c["dts"], c["xs"], c["us"])
+    np.testing.assert_allclose(e["Lxx"][1], z["Lxx"][1], rtol=0, atol=1e-12 * np.abs(z["Lxx"]).max())
+
+
+def test_collision_model_errors(m7):
+    import copy
+    from agimus_controller_b200.robot_model import PANDA_CAPSULES, PANDA_COLLISION_PAIRS
+    table = panda_table().with_capsules(PANDA_CAPSULES, PANDA_COLLISION_PAIRS)
+    bad = table.to_struct()
+    bad.pair_b[1] = 3  # capsule 3 does not exist
+    w = goal_reaching_batch(1, T=2)
+    with pytest.raises(RuntimeError, match="capsule that does not exist"):
+        emu.calc(bad, w["refs"], w["dts"], w["xs_ws"], w["us_ws"])
+    bad = table.to_struct()
+    bad.col_alpha = 0.0
+    with pytest.raises(RuntimeError, match="col_alpha"):
+        emu.calc(bad, w["refs"], w["dts"], w["xs_ws"], w["us_ws"])

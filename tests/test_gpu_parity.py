@@ -321,3 +321,62 @@ def test_converged_fddp_on_the_gpu_lands_on_the_golden_solution(solver_mod, gold
     assert np.abs(g["xs"][0] - golden["states"]).max() < 3e-3
     assert np.abs(g["us"][0] - golden["feed_forward_terms"]).max() < 0.15
     assert abs(g["cost"][0] - 202.6215) < 1e-3
+
+
+def test_cfg4_collision_avoidance(solver_mod, orc):
+    """BASELINE config 4 shape (T = 100, pick-and-place joint move, capsule-pair distance residuals under QuadExp;
+    fingers locked): per-node derivatives and the solve against the CPU restatement, then the full 4096-problem batch
+    through size-independent properties.  A10 is "parity unpinned": the restatement is the only oracle."""
+    from agimus_controller_b200.workloads import pick_and_place_collision_batch
+
+    m0 = panda_table().to_struct()
+    rn = lambda q, v, a: orc.rnea(m0, q, v, a)  # noqa: E731
+    B, T = 96, 100
+    w = pick_and_place_collision_batch(B, T=T, rnea=rn, alpha=1e-3, w_col=(20.0, 20.0))
+    m = w["table"].to_struct()
+    p = _problem(solver_mod, w, B)
+    rng = np.random.default_rng(5)
+    xs = w["xs_ws"] + rng.uniform(-0.1, 0.1, w["xs_ws"].shape)
+    us = w["us_ws"] + rng.uniform(-2, 2, w["us_ws"].shape)
+    o = orc.calc_diff(m, w["refs"], w["dts"], xs, us)
+    g = p.calc_diff(xs, us)
+    for k in ("cost", "xnext", "Fx", "Fu", "Lx", "Lu", "Lxx", "Luu"):
+        assert rel(g[k].cpu().numpy(), o[k]) < DERIV_RTOL, k
+    cost, _ = p.calc(xs, us)
+    assert rel(cost.cpu().numpy(), o["cost"]) < DERIV_RTOL
+    # per-cost view: distances and activations of both pairs
+    terms = p.cost_terms(xs, us)
+    for b, t in ((0, 0), (5, 40), (95, 100)):
+        for k in range(2):
+            d, _, act = orc.collision(m, xs[b, t, :7], k)
+            assert abs(float(terms["collision_distance"][b, t, k]) - d) < 1e-12
+            assert abs(float(terms["collision"][b, t, k]) - w["refs"][b, t, 60 + k] * act[0]) < 1e-12
+    for fixed, iters in ((True, 3), (False, 60)):
+        opts = _abi.default_fddp_opts(fixed_iters=fixed)
+        so = orc.solve(m, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], iters, opts)
+        sg = {k: v.cpu().numpy() for k, v in p.solve(w["x0"], w["xs_ws"], w["us_ws"], iters, opts).items()}
+        np.testing.assert_array_equal(sg["iters"], so["iters"])
+        np.testing.assert_array_equal(sg["status"], so["status"])
+        for k in ("xs", "us", "cost"):
+            assert rel(sg[k], so[k]) < TRAJ_RTOL, k
+    # the collision cost moves the arm away from the obstacle: larger clearance than the plan without it
+    w0 = dict(w, refs=w["refs"].copy())
+    w0["refs"][..., 60:62] = 0.0
+    p0 = _problem(solver_mod, w0, B)
+    opts = _abi.default_fddp_opts()
+    s1 = p.solve(w["x0"], w["xs_ws"], w["us_ws"], 60, opts)
+    s0 = p0.solve(w["x0"], w["xs_ws"], w["us_ws"], 60, opts)
+    d1 = p.cost_terms(s1["xs"], s1["us"])["collision_distance"][..., 1]
+    d0 = p.cost_terms(s0["xs"], s0["us"])["collision_distance"][..., 1]
+    assert float(d1[:, 5:30].min(1).values.mean()) > float(d0[:, 5:30].min(1).values.mean()) + 1e-3
+    # full size
+    Bf = 4096
+    wf = pick_and_place_collision_batch(Bf, T=T, rnea=rn, alpha=1e-3, w_col=(20.0, 20.0))
+    pf = _problem(solver_mod, wf, Bf)
+    gf = pf.solve(wf["x0"], wf["xs_ws"], wf["us_ws"], 3, _abi.default_fddp_opts(fixed_iters=True))
+    assert bool(torch.isfinite(gf["xs"]).all())
+    assert float((pf.rollout(wf["x0"], gf["us"]) - gf["xs"]).abs().max()) < 1e-7
+    cost_nodes, _ = pf.calc(gf["xs"], gf["us"])
+    assert rel(cost_nodes.sum(1).cpu().numpy(), gf["cost"].cpu().numpy()) < 1e-10
+    np.testing.assert_allclose(gf["xs"].cpu().numpy()[:B], pf.solve(wf["x0"], wf["xs_ws"], wf["us_ws"], 3,
+                               _abi.default_fddp_opts(fixed_iters=True))["xs"].cpu().numpy()[:B], rtol=0, atol=0)

@@ -11,11 +11,13 @@ import pytest
 import yaml
 
 from agimus_controller_b200 import PANDA_Q_NOMINAL, _abi, panda_table
-from agimus_controller_b200.ocp_batched import build_reference_rows, flatten_cost_stack
+from agimus_controller_b200.ocp_batched import build_reference_rows, flatten_cost_stack, resolve_collision_pairs
+from agimus_controller_b200.robot_model import PANDA_CAPSULES
 from agimus_controller_b200.ocp_interface import (DTFactorsNSeq, OCPParamsBaseCroco, SE3, TrajectoryPoint,
                                                   TrajectoryPointWeights, WeightedTrajectoryPoint)
 
 GOAL_REACHING = pathlib.Path(__file__).parent / "golden" / "ocp_goal_reaching.yaml"
+COLLISION = pathlib.Path(__file__).parent / "golden" / "ocp_collision_avoidance.yaml"
 
 
 def _point(nv, q, v, u, R, p, wq, wv, wu, wpose, name="panda_hand_tcp"):
@@ -104,3 +106,55 @@ def test_wrong_frame_is_refused():
     pt = _point(7, np.zeros(7), np.zeros(7), np.zeros(7), np.eye(3), np.zeros(3), 1, 1, 1, 1, name="other_frame")
     with pytest.raises(NotImplementedError):
         build_reference_rows(table, run, term, [pt, pt])
+
+
+def test_collision_costs_are_flattened_into_pair_slots(orc):
+    """ResidualDistanceCollision + QuadExp costs (ocp_croco_generic.py:119-147, :499-535): pairs are registered on the
+    table, `update: true` takes the point's scalar w_collision_avoidance (:714-719), `update: false` keeps the
+    CostModelSum weight of the YAML; the terminal stack of the fixture has no collision cost."""
+    data = yaml.safe_load(COLLISION.read_text())
+    run = flatten_cost_stack(data["running_model"], terminal=False)
+    term = flatten_cost_stack(data["terminal_model"], terminal=True)
+    assert [c["name"] for c in run["collisions"]] == ["avoid_collision_obstacle", "avoid_collision_self"]
+    assert term["collisions"] == []
+    table = resolve_collision_pairs(panda_table().with_capsules(PANDA_CAPSULES, []), run, term)
+    assert table.collision_pairs == [("link7_capsule", "obstacle_capsule"), ("link7_capsule", "link3_capsule")]
+    assert table.collision_alpha == 1e-2
+    m = table.to_struct()
+    nv, T = 7, 2
+    R = np.diag([1.0, -1.0, -1.0])
+    horizon = [_point(nv, PANDA_Q_NOMINAL, np.zeros(nv), np.zeros(nv), R, np.array([0.5, 0.2, 0.5]), 1.0, 1.0, 1.0, 1.0)
+               for _ in range(T + 1)]
+    for k, pt in enumerate(horizon):
+        pt.weights.w_collision_avoidance = 4.0 + k
+    rows = build_reference_rows(table, run, term, horizon)
+    np.testing.assert_array_equal(rows[:, 60:62], [[4.0, 2.5], [5.0, 2.5], [0.0, 0.0]])
+    # cost identity through the records: w a(r) on top of the weighted-quad terms
+    q = PANDA_Q_NOMINAL + 0.3
+    xs = np.tile(np.concatenate([q, np.zeros(nv)]), (1, T + 1, 1))
+    us = np.zeros((1, T, nv))
+    dts = np.full(T, 0.01)
+    with_col, _ = orc.calc(m, rows[None], dts, xs, us)
+    rows0 = rows.copy()
+    rows0[:, 60:62] = 0.0
+    without, _ = orc.calc(m, rows0[None], dts, xs, us)
+    a = [np.exp(-orc.collision(m, q, k)[0] ** 2 / 1e-2) for k in range(2)]
+    assert abs((with_col - without)[0, 0] - dts[0] * (4.0 * a[0] + 2.5 * a[1])) < 1e-14
+    assert (with_col - without)[0, T] == 0.0
+
+
+def test_collision_flattening_errors():
+    data = yaml.safe_load(COLLISION.read_text())
+    run = flatten_cost_stack(data["running_model"], terminal=False)
+    term = flatten_cost_stack(data["terminal_model"], terminal=True)
+    with pytest.raises(ValueError, match="Geometry object 'link7_capsule' not found"):
+        resolve_collision_pairs(panda_table(), run, term)  # a table without capsules
+    bad = yaml.safe_load(COLLISION.read_text())
+    bad["running_model"]["differential"]["costs"][3]["cost"]["activation"] = {"class": "ActivationModelExp", "alpha": 1.0}
+    with pytest.raises(NotImplementedError, match="ActivationModelExp"):
+        flatten_cost_stack(bad["running_model"], terminal=False)  # exponent 1 is not on the device path
+    bad = yaml.safe_load(COLLISION.read_text())
+    bad["running_model"]["differential"]["costs"][4]["cost"]["activation"]["alpha"] = 0.5
+    with pytest.raises(NotImplementedError, match="different activation alphas"):
+        resolve_collision_pairs(panda_table().with_capsules(PANDA_CAPSULES, []),
+                                flatten_cost_stack(bad["running_model"], terminal=False), term)
