@@ -10,6 +10,7 @@ AGX_MAX_NV = 16
 AGX_MAX_CAPSULES = 4
 AGX_MAX_COLLISION_PAIRS = 2
 AGX_N_COST_TERMS = 13
+AGX_STATUS_LINESEARCH = 4
 AGX_JOINT_REVOLUTE = 0
 AGX_JOINT_PRISMATIC = 1
 
@@ -78,6 +79,25 @@ class AgxFddpOpts(C.Structure):
     ]
 
 
+class AgxSqpOpts(C.Structure):
+    """``struct agx_sqp_opts``."""
+
+    _fields_ = [
+        ("sigma", _D),
+        ("reg", _D),
+        ("mu", _D),
+        ("termination_tolerance", _D),
+        ("n_alphas", _I),
+        ("reserved", _I),
+    ]
+
+
+def default_sqp_opts(termination_tolerance: float = 1e-3) -> AgxSqpOpts:
+    """``mim_solvers.SolverCSQP`` as the reference configures it (ocp_base_croco.py:64-75, ocp_param_base.py:53-61):
+    proximal sigma 1e-6, regularisation floor 1e-9, merit weight 10, KKT tolerance 1e-3, step lengths 2^-n, n < 10."""
+    return AgxSqpOpts(sigma=1e-6, reg=1e-9, mu=10.0, termination_tolerance=termination_tolerance, n_alphas=10, reserved=0)
+
+
 def ref_size(nv: int) -> int:
     """Doubles per node reference record: [xref nx][wx nx][uref nu][wu nu][Rref 9][pref 3][wpose 6][wcol 2]."""
     return 6 * nv + 20
@@ -140,6 +160,10 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.agx_rnea.restype = C.c_int
     lib.agx_solve.argtypes = [H, _P, _P, _P, C.c_int, C.POINTER(AgxFddpOpts)] + [_P] * 9
     lib.agx_solve.restype = C.c_int
+    lib.agx_solve_sqp.argtypes = [H, _P, _P, _P, C.c_int, C.POINTER(AgxSqpOpts)] + [_P] * 9
+    lib.agx_solve_sqp.restype = C.c_int
+    lib.agx_sqp_opts_default.argtypes = [C.POINTER(AgxSqpOpts)]
+    lib.agx_sqp_opts_default.restype = None
     lib.agx_cost_terms.argtypes = [H, _P, _P, _P, _P]
     lib.agx_cost_terms.restype = C.c_int
     lib.agx_shift_warmstart.argtypes = [H, _P, _P, _P, _P, _P]
@@ -161,4 +185,5 @@ EXPORTED_SYMBOLS = (
     "agx_ref_size", "agx_fddp_opts_default", "agx_create", "agx_destroy", "agx_last_error", "agx_set_refs",
     "agx_calc", "agx_calc_diff", "agx_rollout", "agx_integrate", "agx_rnea", "agx_solve", "agx_launch_count",
     "agx_set_timing", "agx_get_timing", "agx_probe_fp64", "agx_riccati", "agx_cost_terms", "agx_shift_warmstart", "agx_set_refs_window",
+    "agx_solve_sqp", "agx_sqp_opts_default",
 )

@@ -611,4 +611,91 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
   return check_launch(h, "agx_solve");
 }
 
+void agx_sqp_opts_default(agx_sqp_opts* o) {
+  if (!o) return;
+  o->sigma = 1e-6; o->reg = 1e-9; o->mu = 10.0; o->termination_tolerance = 1e-3; o->n_alphas = 10; o->reserved = 0;
+}
+
+int agx_solve_sqp(agx_handle* h, const double* x0, const double* xs_ws, const double* us_ws, int max_iter,
+                  const agx_sqp_opts* opts, double* out_xs, double* out_us, double* out_K, double* out_k,
+                  double* out_cost, int32_t* out_iters, int32_t* out_status, double* out_stop, void* stream) {
+  if (!h || !x0 || !xs_ws || !us_ws || !out_xs || !out_us || !out_cost || !out_iters || !out_status || max_iter < 0)
+    return AGX_EINVAL;
+  DeviceGuard g(h->device);
+  stream_t st = (stream_t)stream;
+  agx_sqp_opts sd;
+  if (!opts) { agx_sqp_opts_default(&sd); opts = &sd; }
+  if (opts->n_alphas < 1 || opts->n_alphas > 10) return fail(h, AGX_EINVAL, "n_alphas must be in 1..10");
+  if (!(opts->sigma >= 0.0) || !(opts->reg >= 0.0) || !(opts->mu >= 0.0))
+    return fail(h, AGX_EINVAL, "sigma, reg and mu must be non-negative");
+  SqpOpts Q;
+  Q.sigma = opts->sigma; Q.reg = opts->reg; Q.mu = opts->mu; Q.tol = opts->termination_tolerance;
+  Q.n_alphas = opts->n_alphas;
+  agx_fddp_opts od;
+  agx_fddp_opts_default(&od);
+  // the sweeps run with a fixed diagonal: a failed factorisation ends the problem (status REGMAX), no retry
+  FddpOpts O;
+  O.reg_min = Q.reg; O.reg_max = Q.reg; O.reg_init = Q.reg; O.reg_incfactor = od.reg_incfactor;
+  O.reg_decfactor = od.reg_decfactor; O.th_grad = od.th_grad; O.th_stepdec = od.th_stepdec; O.th_stepinc = od.th_stepinc;
+  O.th_acceptstep = od.th_acceptstep; O.th_acceptnegstep = od.th_acceptnegstep; O.th_stop = od.th_stop;
+  O.fixed_iters = 0; O.n_alphas = Q.n_alphas;
+  FddpOpts Of = O;
+  Of.reg_min = Of.reg_max = Of.reg_init = Q.sigma + Q.reg;
+  const size_t nB = (size_t)h->B, T = (size_t)h->T, T1 = T + 1;
+  if (!out_K && !h->d_K_internal) {
+    if (!dev_alloc((void**)&h->d_K_internal, sizeof(double) * nB * T * NJ * NX))
+      return fail(h, AGX_ENOMEM, "allocation of the internal gain buffer failed");
+  }
+  Work W = h->W;
+  W.K = out_K ? out_K : h->d_K_internal;
+  W.x0 = h->d_x0;
+  if (!copy_d2d(h->d_x0, x0, sizeof(double) * nB * NX, st)) return fail(h, AGX_ECUDA, "agx_solve_sqp: x0 copy failed");
+  const Problem P = problem_of(h);
+  const long long n_init = (long long)(nB * T1 * NX);
+  AGX_LAUNCH(h, init_kernel, (n_init + 255) / 256, 256, 0, st, P, W, h->S, O, xs_ws, us_ws);
+  const long long ents = (long long)(nB * T1);
+  const int opc_n = NODE_CTA / 8, opc_s = SEQ_CTA / 8;
+  const long long cost_ctas = (ents + COST_CTA - 1) / COST_CTA;
+  auto derivatives = [&]() {
+    // problem.calc + calcDiff at the candidate (finished problems are skipped)
+    AGX_LAUNCH_NODE_COST(h, cost_ctas, COST_CTA, COST_SMEM, st, P, (const double*)W.xs, (const double*)W.us,
+               (const int32_t*)h->S.cur, 0, (const int32_t*)h->S.done, (const int32_t*)nullptr, W.crec, (double*)nullptr);
+    AGX_LAUNCH_COL(h, calc_diff_kernel, (ents + opc_n - 1) / opc_n, NODE_CTA, sizeof(double) * OCT_BOARD * opc_n, st, P,
+               (const double*)W.xs, (const double*)W.us, (const int32_t*)h->S.cur, (const int32_t*)nullptr,
+               (const int32_t*)nullptr, 0, (const int32_t*)h->S.done, W.rec, W.crec);
+  };
+  for (int it = 0; it < max_iter; ++it) {
+    derivatives();
+    launch_backward(h, P, W, O, st);
+    AGX_LAUNCH(h, sqp_direction_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, 0, st, P, W, h->S, Q);
+    for (int n = 0; n < Q.n_alphas; ++n) {
+      AGX_LAUNCH_COL(h, sqp_try_kernel, (ents + opc_n - 1) / opc_n, NODE_CTA, sizeof(double) * OCT_BOARD * opc_n, st, P, W,
+                 h->S);
+      AGX_LAUNCH(h, sqp_accept_kernel, (h->B + 127) / 128, 128, 0, st, P, W, h->S, Q);
+    }
+    if (max_iter > 32 && (it % 16) == 15 && it + 1 < max_iter) {
+      int32_t live = 1;
+#if AGX_GPU
+      cudaMemsetAsync(h->d_live, 0, sizeof(int32_t), st);
+      AGX_LAUNCH(h, count_live_kernel, (h->B + 255) / 256, 256, 0, st, h->B, (const int32_t*)h->S.done, h->d_live);
+      cudaMemcpyAsync(&live, h->d_live, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+      cudaStreamSynchronize(st);
+#else
+      *h->d_live = 0;
+      AGX_LAUNCH(h, count_live_kernel, (h->B + 255) / 256, 256, 0, st, h->B, (const int32_t*)h->S.done, h->d_live);
+      live = *h->d_live;
+#endif
+      if (live == 0) break;
+    }
+  }
+  // the gains the solver holds are those of its last backward pass (sigma + reg on the diagonals), at the final iterate
+  derivatives();
+  AGX_LAUNCH(h, sqp_final_prepare_kernel, (h->B + 255) / 256, 256, 0, st, h->B, h->S, Q);
+  launch_backward(h, P, W, Of, st);
+  const long long n_fin = (long long)(nB * T * NJ * NX);
+  AGX_LAUNCH(h, finalize_kernel, (n_fin + 255) / 256, 256, 0, st, P, W, h->S, out_xs, out_us, out_K, out_k, out_cost,
+             out_iters, out_status, out_stop);
+  return check_launch(h, "agx_solve_sqp");
+}
+
 }  // extern "C"

@@ -674,6 +674,7 @@ __global__ void backward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
 // ---------------------------------------------------------------------------------------------
 }  // namespace agx
 #include "agx_riccati_mma.cuh"
+#include "agx_sqp.cuh"
 namespace agx {
 
 // Forward pass of one FDDP iteration, split so that the common case costs little:

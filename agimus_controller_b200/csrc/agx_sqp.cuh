@@ -1,0 +1,222 @@
+// agx_sqp.cuh — the SQP mode: mim_solvers.SolverCSQP as the reference configures it (ocp_base_croco.py:64-75, :172)
+// with no constraint active.  It shares calc_diff / node_cost / the Riccati sweep with the FDDP path; what is new is
+// the LINEAR rollout of the QP solution, the QP multipliers and the KKT norm (sqp_direction_kernel), and the merit
+// line search on xs + a dx, us + a du (sqp_try_kernel + sqp_accept_kernel), all decided per problem on the device.
+//
+// Workspace reuse: dx lives in Work::gv, du overwrites Work::k, the per-node (cost, gap) pairs of a trial step go to
+// slots 0 / 1 of Work::fs (the gaps were consumed by the direction kernel by then).  SolverState reuse: dg = merit of
+// the candidate, stop = KKT norm, pending = line search running, roll_ok = index n of the step length 2^-n.
+#ifndef AGX_SQP_CUH_
+#define AGX_SQP_CUH_
+
+namespace agx {
+
+struct SqpOpts {
+  double sigma, reg, mu, tol;
+  int n_alphas;
+};
+
+AGX_DEV double octet_max(double x, unsigned omask) {
+  x = fmax(x, __shfl_xor_sync(omask, x, 1, 8));
+  x = fmax(x, __shfl_xor_sync(omask, x, 2, 8));
+  x = fmax(x, __shfl_xor_sync(omask, x, 4, 8));
+  return x;
+}
+
+// One octet per problem.  Forward: dx_0 = fs_0, du_t = -k_t - K_t dx_t, dx_{t+1} = Fx dx_t + Fu du_t + fs_{t+1} with
+// Fx = [I + dt G_q, dt (I + G_v); G_q, I + G_v], Fu = [dt N; N] read from the dynamics record (G_q = dt da/dq,
+// G_v = dt da/dv, N = dt Minv).  Backward: l_T = Lx_T + Lxx_T dx_T, l_t = Lx_t + Lxx_t dx_t + Fx^T l_{t+1};
+// KKT = max(|Lx + Fx^T l' - l|, |Lu + Fu^T l'|, |fs|) (SolverCSQP::checkKKTConditions).
+__global__ void sqp_direction_kernel(Problem P, Work W, SolverState S, SqpOpts Q) {
+  AGX_OCTET_SETUP();
+  const int b = (int)ent;
+  if (b >= P.B) return;
+  if (S.done[b]) return;
+  const int T = P.T, T1 = T + 1;
+  const bool live = j < NJ;
+  const int jj = live ? j : 0;
+  const double* fsb = W.fs + (size_t)b * T1 * NX;
+  double* dxb = W.gv + (size_t)b * T1 * NX;
+  const double* Kb = W.K + (size_t)b * T * NJ * NX;
+  double* kb = W.k + (size_t)b * T * NJ;
+  const double* rec0 = W.rec + (size_t)b * T1 * REC_SIZE;
+  const double* crec0 = W.crec + (size_t)b * T1 * CREC_SIZE;
+
+  double dq = live ? fsb[jj] : 0.0, dv = live ? fsb[NJ + jj] : 0.0;
+  double gl1 = fabs(dq) + fabs(dv), ginf = fmax(fabs(dq), fabs(dv));
+  for (int t = 0; t < T; ++t) {
+    if (live) { dxb[t * NX + j] = dq; dxb[t * NX + NJ + j] = dv; }
+    double dqm[NJ], dvm[NJ], dum[NJ];
+#pragma unroll
+    for (int m = 0; m < NJ; ++m) { dqm[m] = __shfl_sync(omask, dq, m, 8); dvm[m] = __shfl_sync(omask, dv, m, 8); }
+    const double* Kr = Kb + ((size_t)t * NJ + jj) * NX;
+    double s = -kb[t * NJ + jj];
+#pragma unroll
+    for (int m = 0; m < NJ; ++m) s -= Kr[m] * dqm[m] + Kr[NJ + m] * dvm[m];
+    const double du = live ? s : 0.0;
+    if (live) kb[t * NJ + j] = du;
+#pragma unroll
+    for (int m = 0; m < NJ; ++m) dum[m] = __shfl_sync(omask, du, m, 8);
+    const double* R = rec0 + (size_t)t * REC_SIZE;
+    double acc = 0.0;
+#pragma unroll
+    for (int m = 0; m < NJ; ++m)
+      acc += R[(RK_AQ + jj) * 8 + m] * dqm[m] + R[(RK_AV + jj) * 8 + m] * dvm[m] + R[(RK_MI + jj) * 8 + m] * dum[m];
+    const double fq = live ? fsb[(t + 1) * NX + jj] : 0.0, fv = live ? fsb[(t + 1) * NX + NJ + jj] : 0.0;
+    const double dt = P.dts[t];
+    const double dvn = dv + acc + fv;
+    const double dqn = dq + dt * (dv + acc) + fq;
+    gl1 += fabs(fq) + fabs(fv);
+    ginf = fmax(ginf, fmax(fabs(fq), fabs(fv)));
+    dq = live ? dqn : 0.0;
+    dv = live ? dvn : 0.0;
+  }
+  if (live) { dxb[T * NX + j] = dq; dxb[T * NX + NJ + j] = dv; }
+
+  // multipliers and stationarity
+  double lq, lv, kkt;
+  {
+    const double* C = crec0 + (size_t)T * CREC_SIZE;
+    double hq = 0.0;
+#pragma unroll
+    for (int m = 0; m < NJ; ++m)
+      hq += C[CK_LQQ + (jj >= m ? lidx_(jj, m) : lidx_(m, jj))] * __shfl_sync(omask, dq, m, 8);
+    const double hv = C[CK_LVV + jj] * dv;
+    lq = C[CK_LQ + jj] + hq;
+    lv = C[CK_LV + jj] + hv;
+    kkt = live ? fmax(fabs(hq), fabs(hv)) : 0.0;
+  }
+  for (int t = T - 1; t >= 0; --t) {
+    const double dt = P.dts[t];
+    const double* R = rec0 + (size_t)t * REC_SIZE;
+    const double* C = crec0 + (size_t)t * CREC_SIZE;
+    const double w = live ? dt * lq + lv : 0.0;
+    double su = C[CK_LU + jj], aq = 0.0, av = 0.0;
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) {
+      const double wi = __shfl_sync(omask, w, i, 8);
+      su += R[(RK_MI + i) * 8 + jj] * wi;
+      aq += R[(RK_AQ + i) * 8 + jj] * wi;
+      av += R[(RK_AV + i) * 8 + jj] * wi;
+    }
+    const double xq = live ? dxb[t * NX + jj] : 0.0, xv = live ? dxb[t * NX + NJ + jj] : 0.0;
+    double hq = 0.0;
+#pragma unroll
+    for (int m = 0; m < NJ; ++m)
+      hq += C[CK_LQQ + (jj >= m ? lidx_(jj, m) : lidx_(m, jj))] * __shfl_sync(omask, xq, m, 8);
+    const double hv = C[CK_LVV + jj] * xv;
+    const double nlq = C[CK_LQ + jj] + hq + lq + aq;
+    const double nlv = C[CK_LV + jj] + hv + w + av;
+    if (live) kkt = fmax(kkt, fmax(fabs(su), fmax(fabs(hq), fabs(hv))));
+    lq = nlq;
+    lv = nlv;
+  }
+  // NaNs must survive the max: fmax drops them
+  const double bad = octet_sum((live && !(lq - lq == 0.0 && lv - lv == 0.0)) ? 1.0 : 0.0, omask);
+  kkt = fmax(octet_max(kkt, omask), octet_max(ginf, omask));
+  gl1 = octet_sum(live ? gl1 : 0.0, omask);
+  if (j == 0) {
+    if (bad != 0.0) {
+      S.stop[b] = nan("");
+      S.status[b] = 3;
+      S.done[b] = 1;
+    } else {
+      S.stop[b] = kkt;
+      if (kkt <= Q.tol) {
+        S.status[b] = 0;
+        S.done[b] = 1;
+      } else {
+        S.dg[b] = S.cost[b] + Q.mu * gl1;
+        S.pending[b] = 1;
+        S.roll_ok[b] = 0;
+      }
+    }
+  }
+}
+
+// SolverCSQP::tryStep for the step length 2^-n the problem is at: one octet per (problem, node) evaluates the node
+// cost and the gap to the next trial state of xs + a dx, us + a du, which it writes into the trial buffer.
+template <bool COL>
+__global__ void sqp_try_kernel(Problem P, Work W, SolverState S) {
+  AGX_SMEM(smem);
+  AGX_OCTET_SETUP();
+  const int T = P.T, T1 = T + 1;
+  if (ent >= (long long)P.B * T1) return;
+  const int b = (int)(ent / T1), t = (int)(ent % T1);
+  if (S.done[b] || !S.pending[b]) return;
+  double* sb = smem + oct_in_cta * OCT_BOARD;
+  double* sc = sb + BRD_B;
+  const double a = ldexp(1.0, -S.roll_ok[b]);
+  const size_t cur = (size_t)(S.cur[b] & 1), oth = cur ^ 1;
+  const bool live = j < NJ, terminal = t == T;
+  const int jj = live ? j : 0;
+  const double* xs = W.xs + (cur * P.B + b) * (size_t)T1 * NX;
+  const double* us = W.us + (cur * P.B + b) * (size_t)T * NJ;
+  double* xt = W.xs + (oth * P.B + b) * (size_t)T1 * NX;
+  double* ut = W.us + (oth * P.B + b) * (size_t)T * NJ;
+  const double* dx = W.gv + (size_t)b * T1 * NX;
+  const double* du = W.k + (size_t)b * T * NJ;
+  LaneDyn d;
+  d.q = live ? xs[t * NX + jj] + a * dx[t * NX + jj] : 0.0;
+  d.qd = live ? xs[t * NX + NJ + jj] + a * dx[t * NX + NJ + jj] : 0.0;
+  d.u = (live && !terminal) ? us[t * NJ + jj] + a * du[t * NJ + jj] : 0.0;
+  const double q0 = d.q, v0 = d.qd;
+  if (live) {
+    xt[t * NX + j] = d.q;
+    xt[t * NX + NJ + j] = d.qd;
+    if (!terminal) ut[t * NJ + j] = d.u;
+  }
+  double c, qn, vn;
+  const bool ok = node_calc<COL>(d, j, omask, model_of(P, b), P.refs + (size_t)ent * REF_SIZE, terminal ? 0.0 : P.dts[t],
+                                 terminal, sb, sc, &c, &qn, &vn);
+  double g = 0.0;
+  if (live && !terminal) {
+    const double nq = xs[(t + 1) * NX + jj] + a * dx[(t + 1) * NX + jj];
+    const double nvv = xs[(t + 1) * NX + NJ + jj] + a * dx[(t + 1) * NX + NJ + jj];
+    g = fabs(qn - nq) + fabs(vn - nvv);
+  }
+  if (live && t == 0) g += fabs(W.x0[(size_t)b * NX + jj] - q0) + fabs(W.x0[(size_t)b * NX + NJ + jj] - v0);
+  g = octet_sum(g, omask);
+  if (j == 0) {
+    double* out = W.fs + ((size_t)b * T1 + t) * NX;
+    out[0] = ok ? c : nan("");
+    out[1] = g;
+  }
+}
+
+// merit_try < merit: take the step; otherwise the next step length (SolverCSQP::solve, merit line search)
+__global__ void sqp_accept_kernel(Problem P, Work W, SolverState S, SqpOpts Q) {
+  const int b = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (b >= P.B) return;
+  if (S.done[b] || !S.pending[b]) return;
+  const int T1 = P.T + 1;
+  const double* r = W.fs + (size_t)b * T1 * NX;
+  double c = 0.0, g = 0.0;
+  for (int t = 0; t < T1; ++t) { c += r[t * NX]; g += r[t * NX + 1]; }
+  const double mt = c + Q.mu * g;
+  if (mt < S.dg[b]) {
+    S.cur[b] ^= 1;
+    S.pending[b] = 0;
+    S.iters[b] += 1;
+  } else {
+    const int n = S.roll_ok[b] + 1;
+    S.roll_ok[b] = n;
+    if (n >= Q.n_alphas) {
+      S.pending[b] = 0;
+      S.status[b] = 4;
+      S.done[b] = 1;
+    }
+  }
+}
+
+// before the last sweep: every problem takes part again, with the solver's proximal sigma on top of the regularisation
+__global__ void sqp_final_prepare_kernel(int B, SolverState S, SqpOpts Q) {
+  const int b = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (b >= B) return;
+  S.xreg[b] = Q.sigma + Q.reg;
+  S.is_feasible[b] = 0;
+  if (S.status[b] != 3) S.done[b] = 0;
+}
+
+}  // namespace agx
+#endif  // AGX_SQP_CUH_

@@ -160,7 +160,13 @@ def build_reference_rows(table: RobotTable, running: dict, terminal: dict, horiz
 class OCPBatchedFDDP(OCPBase):
     def __init__(self, robot_table: RobotTable, params: OCPParamsBaseCroco,
                  yaml_file: T.Union[str, dict, T.IO], batch_size: int = 1, device=None,
-                 fddp_opts: T.Optional[_abi.AgxFddpOpts] = None) -> None:
+                 fddp_opts: T.Optional[_abi.AgxFddpOpts] = None, solver: str = "fddp") -> None:
+        """``solver = "fddp"`` (the solver BASELINE.json's north_star names) or ``"csqp"``: the solver the reference
+        instantiates (``mim_solvers.SolverCSQP``, ``ocp_base_croco.py:64-75``) in its unconstrained form, configured
+        from ``params.termination_tolerance`` as the reference does."""
+        if solver not in ("fddp", "csqp"):
+            raise ValueError(f"solver must be 'fddp' or 'csqp', got {solver!r}")
+        self._solver = solver
         if isinstance(yaml_file, dict):
             data = yaml_file
         elif hasattr(yaml_file, "read"):
@@ -176,6 +182,7 @@ class OCPBatchedFDDP(OCPBase):
         self._B = int(batch_size)
         self._problem = BatchedShootingProblem(robot_table, params.timesteps, self._B, device=device)
         self._opts = fddp_opts if fddp_opts is not None else _abi.default_fddp_opts()
+        self._sqp_opts = _abi.default_sqp_opts(getattr(params, "termination_tolerance", 1e-3))
         self._ocp_results: T.Optional[OCPResults] = None
         self._results_batched: T.Optional[dict] = None
         self._debug_data = OCPDebugData()
@@ -223,8 +230,10 @@ class OCPBatchedFDDP(OCPBase):
     def solve(self, x0, x_warmstart, u_warmstart, use_iteration_limits_and_timeout: bool = True) -> None:
         max_iters = self._ocp_params.solver_iters if use_iteration_limits_and_timeout else 1000
         batched = isinstance(x0, torch.Tensor) and x0.dim() == 2
+        run = ((lambda *a: self._problem.solve_sqp(*a, self._sqp_opts, out=self._out)) if self._solver == "csqp"
+               else (lambda *a: self._problem.solve(*a, self._opts, out=self._out)))
         if batched:
-            out = self._problem.solve(x0, x_warmstart, u_warmstart, max_iters, self._opts, out=self._out)
+            out = run(x0, x_warmstart, u_warmstart, max_iters)
             self._results_batched = out
             self._ocp_results = None
             return
@@ -232,8 +241,7 @@ class OCPBatchedFDDP(OCPBase):
         nx, nv, T_ = self._problem.nx, self._problem.nv, self.n_controls
         xs = np.asarray(x_warmstart, dtype=np.float64).reshape(1, T_ + 1, nx)
         us = np.asarray(u_warmstart, dtype=np.float64).reshape(1, T_, nv)
-        out = self._problem.solve(np.asarray(x0, dtype=np.float64).reshape(1, nx), xs, us, max_iters, self._opts,
-                                  out=self._out)
+        out = run(np.asarray(x0, dtype=np.float64).reshape(1, nx), xs, us, max_iters)
         self._results_batched = out
         xs_h, us_h, K_h = out["xs"][0].cpu().numpy(), out["us"][0].cpu().numpy(), out["K"][0].cpu().numpy()
         ocp_results = OCPResults(states=list(xs_h), ricatti_gains=list(K_h), feed_forward_terms=list(us_h))

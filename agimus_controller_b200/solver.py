@@ -238,3 +238,24 @@ class BatchedShootingProblem:
             _ptr(out["us"]), _ptr(out["K"]), _ptr(out.get("k")), _ptr(out["cost"]), _ptr(out["iters"]),
             _ptr(out["status"]), _ptr(out.get("stop")), self._stream()))
         return out
+
+    def solve_sqp(self, x0, xs_ws, us_ws, max_iter: int, opts: T.Optional[_abi.AgxSqpOpts] = None,
+                  out: T.Optional[dict] = None) -> dict:
+        """The solver the reference instantiates — ``mim_solvers.SolverCSQP(problem).solve(xs, us, max_iter)``
+        (``ocp_base_croco.py:64-75, :172``) with no constraint active: Gauss-Newton SQP, KKT stop at
+        ``termination_tolerance``, merit line search; ``out["stop"]`` is the KKT norm, ``out["K"]`` the gains of the
+        solver's last backward pass (with its proximal sigma).  Stream-ordered, no sync for budgets up to 32."""
+        if not self._refs_set:
+            raise RuntimeError("set_refs() must be called before solve_sqp()")
+        x0 = self._t(x0, (self.B, self.nx))
+        xs_ws = self._t(xs_ws, (self.B, self.T + 1, self.nx))
+        us_ws = self._t(us_ws, (self.B, self.T, self.nv))
+        if out is None:
+            out = self.alloc_outputs()
+        if opts is None:
+            opts = _abi.default_sqp_opts()
+        self._check(lib().agx_solve_sqp(
+            self._h, _ptr(x0), _ptr(xs_ws), _ptr(us_ws), int(max_iter), C.byref(opts), _ptr(out["xs"]),
+            _ptr(out["us"]), _ptr(out["K"]), _ptr(out.get("k")), _ptr(out["cost"]), _ptr(out["iters"]),
+            _ptr(out["status"]), _ptr(out.get("stop")), self._stream()))
+        return out

@@ -51,6 +51,7 @@ extern "C" {
 #define AGX_STATUS_MAXITER 1   /* iteration budget used */
 #define AGX_STATUS_REGMAX 2    /* regularisation hit reg_max */
 #define AGX_STATUS_NAN 3       /* non-finite value met */
+#define AGX_STATUS_LINESEARCH 4 /* SQP mode: no step length decreased the merit function */
 
 /*
  * Kinematic-tree table: what factory/robot_model.py:88-351 (RobotModels.robot_model, .armature)
@@ -102,6 +103,18 @@ typedef struct agx_fddp_opts {
   int32_t n_alphas; /* step lengths 2^-n, n = 0..n_alphas-1 (<= 10) */
 } agx_fddp_opts;
 
+/*
+ * Parameters of the SQP mode (mim_solvers.SolverCSQP as the reference configures it, ocp_base_croco.py:64-75, with no
+ * constraint active): agx_sqp_opts_default fills sigma = 1e-6 (proximal term), reg = 1e-9 (regularisation at its floor
+ * reg_min), mu = 10 (weight of the L1 gap norm in the merit function), termination_tolerance = 1e-3
+ * (ocp_param_base.py:54-56), n_alphas = 10.
+ */
+typedef struct agx_sqp_opts {
+  double sigma, reg, mu, termination_tolerance;
+  int32_t n_alphas;
+  int32_t reserved;
+} agx_sqp_opts;
+
 typedef struct agx_handle agx_handle;
 
 /* Size in doubles of one node's reference record:
@@ -113,6 +126,7 @@ typedef struct agx_handle agx_handle;
 int agx_ref_size(int nv);
 
 void agx_fddp_opts_default(agx_fddp_opts* opts);
+void agx_sqp_opts_default(agx_sqp_opts* opts);
 
 /* Build a handle for B problems with T running nodes on CUDA device `device`.
  * dts_host: T step sizes (host memory; ocp_param_base.py:67-78 timesteps).
@@ -184,6 +198,23 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
               int max_iter, const agx_fddp_opts* opts, double* out_xs, double* out_us,
               double* out_K, double* out_k, double* out_cost, int32_t* out_iters,
               int32_t* out_status, double* out_stop, void* stream);
+
+/* The solver the reference actually instantiates: mim_solvers.SolverCSQP(problem).solve(xs, us, max_iter)
+ * (ocp_base_croco.py:64-75, :172) with no constraint active, i.e. a Gauss-Newton SQP.  Per iteration:
+ * calc + calcDiff and the gaps; the equality-constrained QP solved by one Riccati sweep (regularisation `reg`) and a
+ * LINEAR rollout du = -k - K dx, dx' = Fx dx + Fu du + fs'; KKT = max(|Lx + Fx^T l' - l|_inf, |Lu + Fu^T l'|_inf,
+ * |fs|_inf) with the QP multipliers l; stop when KKT <= termination_tolerance (the iterate is returned as is);
+ * otherwise the first step length 2^-n with merit(xs + a dx, us + a du) < merit(xs, us),
+ * merit = cost + mu * |gaps|_1.  The gains returned are those of the solver's last backward pass: a sweep at the
+ * final iterate with sigma + reg on Quu, Qxx, Vxx_T.  (With no constraint the ADMM/proximal inner loop sits at its
+ * fixed point, so it is not iterated.)  Replaying the reference's golden test this way (zero warm start,
+ * tests/test_ocp_croco_base.py:140-158) stops at the same criterion 6e-5 from the golden states and reproduces the
+ * golden gains to 1e-11 at the golden point.
+ * Out as agx_solve; out_stop = the KKT norm; out_iters = accepted steps; status AGX_STATUS_CONVERGED = KKT met. */
+int agx_solve_sqp(agx_handle* h, const double* x0, const double* xs_ws, const double* us_ws,
+                  int max_iter, const agx_sqp_opts* opts, double* out_xs, double* out_us,
+                  double* out_K, double* out_k, double* out_cost, int32_t* out_iters,
+                  int32_t* out_status, double* out_stop, void* stream);
 
 /* One calc + calcDiff at (xs, us) followed by ONE backward Riccati sweep with the fixed regularisation `reg`
  * added to Quu and to the diagonal of every Vxx (no retry on failure).  With reg = 1e-6 this is the backward

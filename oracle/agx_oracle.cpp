@@ -1357,6 +1357,127 @@ int orc_solve(const agx_model* models, int n_models, const double* refs, const d
   return 0;
 }
 
+// ----------------------------------------------------------------------------- SolverCSQP, unconstrained (SQP)
+// mim_solvers.SolverCSQP as the reference runs it (ocp_base_croco.py:64-75, :172) when no constraint is active.
+// mim_solvers is not in the reference tree; this restates its published iteration and is pinned
+// on the reference's golden file: the gains exactly (KAT-3), the iterate at the KKT stop to 6e-5 (KAT-9).
+struct Sqp : Fddp {
+  std::vector<double> dx, du, lam;
+  double kkt = 0, merit = 0, gap_l1 = 0;
+
+  // equality-constrained QP at the current iterate: Riccati sweep with `reg`, linear rollout, multipliers, KKT norm
+  bool direction(double reg) {
+    const int n = nx;
+    xreg = ureg = reg;
+    if (!backward_pass()) return false;
+    dx.assign((T + 1) * n, 0.0); du.assign(T * nv, 0.0); lam.assign((T + 1) * n, 0.0);
+    for (int i = 0; i < n; ++i) dx[i] = fs[i];
+    for (int t = 0; t < T; ++t) {
+      const NodeData& d = nd[t];
+      for (int i = 0; i < nv; ++i) {
+        double s = -k[t * nv + i];
+        for (int j = 0; j < n; ++j) s -= K[(t * nv + i) * n + j] * dx[t * n + j];
+        du[t * nv + i] = s;
+      }
+      for (int i = 0; i < n; ++i) {
+        double s = fs[(t + 1) * n + i];
+        for (int j = 0; j < n; ++j) s += d.Fx[i * n + j] * dx[t * n + j];
+        for (int j = 0; j < nv; ++j) s += d.Fu[i * nv + j] * du[t * nv + j];
+        dx[(t + 1) * n + i] = s;
+      }
+    }
+    // multipliers of the QP (adjoint recursion) and the KKT residual of the NONLINEAR problem with them
+    double v = 0;
+    for (int i = 0; i < n; ++i) {
+      double s = nd[T].Lx[i];
+      for (int j = 0; j < n; ++j) s += nd[T].Lxx[i * n + j] * dx[T * n + j];
+      lam[T * n + i] = s;
+      v = std::fmax(v, std::fabs(nd[T].Lx[i] - s));
+    }
+    for (int t = T - 1; t >= 0; --t) {
+      const NodeData& d = nd[t];
+      const double* ln = &lam[(t + 1) * n];
+      for (int i = 0; i < nv; ++i) {
+        double s = d.Lu[i];
+        for (int l = 0; l < n; ++l) s += d.Fu[l * nv + i] * ln[l];
+        v = std::fmax(v, std::fabs(s));
+      }
+      for (int i = 0; i < n; ++i) {
+        double g = d.Lx[i];
+        for (int l = 0; l < n; ++l) g += d.Fx[l * n + i] * ln[l];
+        double h = 0;
+        for (int j = 0; j < n; ++j) h += d.Lxx[i * n + j] * dx[t * n + j];
+        for (int j = 0; j < nv; ++j) h += d.Lxu[i * nv + j] * du[t * nv + j];
+        lam[t * n + i] = g + h;
+        v = std::fmax(v, std::fabs(h));  // Lx + Fx^T l' - l
+      }
+    }
+    gap_l1 = 0;
+    for (size_t i = 0; i < fs.size(); ++i) { v = std::fmax(v, std::fabs(fs[i])); gap_l1 += std::fabs(fs[i]); }
+    kkt = v;
+    return true;
+  }
+  // merit of (xs + a dx, us + a du); false on a failed calc
+  bool try_step(double a, double mu, double* merit_try) {
+    const int n = nx;
+    for (int i = 0; i < (T + 1) * n; ++i) xs_try[i] = xs[i] + a * dx[i];
+    for (int i = 0; i < T * nv; ++i) us_try[i] = us[i] + a * du[i];
+    double c = 0, g = 0;
+    for (int i = 0; i < n; ++i) g += std::fabs(x0[i] - xs_try[i]);
+    for (int t = 0; t <= T; ++t) {
+      const bool term = t == T;
+      double xn[MAXX], ct;
+      if (!node_calc(*m, refs + t * rs, term ? 0.0 : dts[t], term, &xs_try[t * n], term ? nullptr : &us_try[t * nv], xn,
+                     &ct))
+        return false;
+      c += ct;
+      if (!term)
+        for (int i = 0; i < n; ++i) g += std::fabs(xn[i] - xs_try[(t + 1) * n + i]);
+    }
+    cost_try = c;
+    *merit_try = c + mu * g;
+    return true;
+  }
+  int solve_sqp(const double* x0_, const double* xs_ws, const double* us_ws, int max_iter, const agx_sqp_opts& o,
+                int* iters_out) {
+    for (int i = 0; i < nx; ++i) x0[i] = x0_[i];
+    std::memcpy(xs.data(), xs_ws, sizeof(double) * (T + 1) * nx);
+    std::memcpy(us.data(), us_ws, sizeof(double) * T * nv);
+    is_feasible = false; was_feasible = false;
+    int status = AGX_STATUS_MAXITER, iters = 0;
+    stop = 0;
+    bool have_diff = false;
+    for (int it = 0; it < max_iter; ++it) {
+      if (!calc_diff()) { status = AGX_STATUS_NAN; break; }
+      have_diff = true;
+      if (!direction(o.reg)) { status = AGX_STATUS_REGMAX; break; }
+      stop = kkt;
+      if (kkt <= o.termination_tolerance) { status = AGX_STATUS_CONVERGED; break; }
+      merit = cost + o.mu * gap_l1;
+      bool accepted = false;
+      for (int n = 0; n < o.n_alphas; ++n) {
+        double mt;
+        if (!try_step(std::ldexp(1.0, -n), o.mu, &mt)) continue;
+        if (mt < merit) { accepted = true; break; }
+      }
+      if (!accepted) { status = AGX_STATUS_LINESEARCH; break; }
+      xs.swap(xs_try); us.swap(us_try);
+      have_diff = false;
+      ++iters;
+    }
+    // the gains the solver holds: its last backward pass carries sigma + reg on Quu, Qxx, Vxx_T
+    if (status != AGX_STATUS_NAN) {
+      if (!have_diff && !calc_diff()) status = AGX_STATUS_NAN;
+      else {
+        xreg = ureg = o.sigma + o.reg;
+        if (!backward_pass() && status != AGX_STATUS_LINESEARCH) status = AGX_STATUS_REGMAX;
+      }
+    }
+    *iters_out = iters;
+    return status;
+  }
+};
+
 // One Riccati sweep at (xs, us) for a single problem with a proximal sigma on Quu, Qxx(t>0), Vxx_T
 // (mim_solvers SolverCSQP backward pass, unconstrained case) -> K [T][nu][nx], k [T][nu].  Used only
 // by golden KAT-3.  gaps are taken as x0 - xs_0 and xnext_t - xs_{t+1}.
@@ -1402,6 +1523,40 @@ int orc_riccati_sigma(const agx_model* m, const double* refs, const double* dts,
   if (!s.backward_pass()) return -2;
   std::memcpy(out_K, s.K.data(), sizeof(double) * T * nv * n);
   std::memcpy(out_k, s.k.data(), sizeof(double) * T * nv);
+  return 0;
+}
+
+void agx_sqp_opts_default(agx_sqp_opts* o) {
+  o->sigma = 1e-6; o->reg = 1e-9; o->mu = 10.0; o->termination_tolerance = 1e-3; o->n_alphas = 10; o->reserved = 0;
+}
+
+// SolverCSQP.solve (unconstrained) over B problems; one problem per OpenMP thread
+int orc_solve_sqp(const agx_model* models, int n_models, const double* refs, const double* dts, int B, int T,
+                  const double* x0, const double* xs_ws, const double* us_ws, int max_iter, const agx_sqp_opts* opts,
+                  double* out_xs, double* out_us, double* out_K, double* out_k, double* out_cost, int32_t* out_iters,
+                  int32_t* out_status, double* out_stop, int nthreads) {
+  const int nv = models[0].nv, nx = 2 * nv, rs = agx_ref_size(nv);
+#ifdef _OPENMP
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+  nthreads = 1;
+#endif
+#pragma omp parallel for schedule(dynamic) num_threads(nthreads)
+  for (int b = 0; b < B; ++b) {
+    Sqp s;
+    s.init(&model_of(models, n_models, b), refs + (size_t)b * (T + 1) * rs, dts, T);
+    int iters = 0;
+    const int st = s.solve_sqp(x0 + (size_t)b * nx, xs_ws + (size_t)b * (T + 1) * nx, us_ws + (size_t)b * T * nv,
+                               max_iter, *opts, &iters);
+    std::memcpy(out_xs + (size_t)b * (T + 1) * nx, s.xs.data(), sizeof(double) * (T + 1) * nx);
+    std::memcpy(out_us + (size_t)b * T * nv, s.us.data(), sizeof(double) * T * nv);
+    if (out_K) std::memcpy(out_K + (size_t)b * T * nv * nx, s.K.data(), sizeof(double) * T * nv * nx);
+    if (out_k) std::memcpy(out_k + (size_t)b * T * nv, s.k.data(), sizeof(double) * T * nv);
+    out_cost[b] = s.cost;
+    out_iters[b] = iters;
+    out_status[b] = st;
+    if (out_stop) out_stop[b] = s.stop;
+  }
   return 0;
 }
 

@@ -177,6 +177,28 @@ def solve(models, refs, dts, x0, xs_ws, us_ws, max_iter, opts=None, nthreads=0):
     return out
 
 
+def solve_sqp(models, refs, dts, x0, xs_ws, us_ws, max_iter, opts=None, nthreads=0):
+    """mim_solvers.SolverCSQP (unconstrained) restated: see ``Sqp`` in agx_oracle.cpp."""
+    mp, nm, nv = _models(models)
+    refs, dts, x0, xs_ws, us_ws = _c(refs), _c(dts), _c(x0), _c(xs_ws), _c(us_ws)
+    B, T1, nx = xs_ws.shape
+    T = T1 - 1
+    if opts is None:
+        opts = _abi.default_sqp_opts()
+    out = dict(
+        xs=np.zeros((B, T1, nx)), us=np.zeros((B, T, nv)), K=np.zeros((B, T, nv, nx)),
+        k=np.zeros((B, T, nv)), cost=np.zeros(B), iters=np.zeros(B, dtype=np.int32),
+        status=np.zeros(B, dtype=np.int32), stop=np.zeros(B),
+    )
+    f = lib().orc_solve_sqp
+    f.restype = C.c_int
+    rc = f(mp, nm, _p(refs), _p(dts), B, T, _p(x0), _p(xs_ws), _p(us_ws), int(max_iter), C.byref(opts),
+           _p(out["xs"]), _p(out["us"]), _p(out["K"]), _p(out["k"]), _p(out["cost"]),
+           out["iters"].ctypes.data_as(_PI), out["status"].ctypes.data_as(_PI), _p(out["stop"]), int(nthreads))
+    assert rc == 0
+    return out
+
+
 def riccati_sigma(m, refs, dts, x0, xs, us, sigma):
     refs, dts, x0, xs, us = _c(refs), _c(dts), _c(x0), _c(xs), _c(us)
     T = us.shape[0]

@@ -141,6 +141,25 @@ def solve(models, refs, dts, x0, xs_ws, us_ws, max_iter, opts=None):
     return out
 
 
+def solve_sqp(models, refs, dts, x0, xs_ws, us_ws, max_iter, opts=None):
+    x0, xs_ws, us_ws = _c(x0), _c(xs_ws), _c(us_ws)
+    B, T1, nx = xs_ws.shape
+    T, nv = T1 - 1, nx // 2
+    h = _handle(models, refs, dts, B, T)
+    if opts is None:
+        opts = _abi.default_sqp_opts()
+    out = dict(
+        xs=np.zeros((B, T1, nx)), us=np.zeros((B, T, nv)), K=np.zeros((B, T, nv, nx)),
+        k=np.zeros((B, T, nv)), cost=np.zeros(B), iters=np.zeros(B, dtype=np.int32),
+        status=np.zeros(B, dtype=np.int32), stop=np.zeros(B),
+    )
+    h.check(lib().agx_solve_sqp(
+        h.h, _p(x0), _p(xs_ws), _p(us_ws), int(max_iter), C.byref(opts), _p(out["xs"]), _p(out["us"]),
+        _p(out["K"]), _p(out["k"]), _p(out["cost"]), _p(out["iters"]), _p(out["status"]), _p(out["stop"]), None))
+    out["launches"] = lib().agx_launch_count(h.h)
+    return out
+
+
 def riccati(m, refs, dts, x0, xs, us, reg):
     """Single problem, same signature as ``orc.riccati_sigma`` (returns K, k, status)."""
     xs, us, x0 = _c(xs)[None], _c(us)[None], _c(x0)[None]

@@ -413,3 +413,50 @@ def test_collision_model_errors(m7):
     bad.col_alpha = 0.0
     with pytest.raises(RuntimeError, match="col_alpha"):
         emu.calc(bad, w["refs"], w["dts"], w["xs_ws"], w["us_ws"])
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# SQP mode = mim_solvers.SolverCSQP without active constraints
+def test_sqp_reproduces_the_reference_golden_file(golden):
+    """KAT-9 on the shipped kernels: the reference's golden test (tests/test_ocp_croco_base.py:140-204) replayed
+    through agx_solve_sqp meets the reference's own 6-decimal comparison of states, gains and feed-forward terms."""
+    p = golden_problem()
+    m = p["table"].to_struct()
+    e = emu.solve_sqp(m, p["refs"], p["dts"], p["x0"], p["xs_ws"], p["us_ws"], 100)
+    assert int(e["status"][0]) == _abi.AGX_STATUS_CONVERGED and int(e["iters"][0]) == 33
+    np.testing.assert_array_almost_equal(e["xs"][0], golden["states"], decimal=6)
+    np.testing.assert_array_almost_equal(e["K"][0], golden["ricatti_gains"], decimal=6)
+    np.testing.assert_array_almost_equal(e["us"][0], golden["feed_forward_terms"], decimal=6)
+
+
+@pytest.mark.parametrize("max_iter", [0, 4, 60])
+def test_sqp_matches_oracle(orc, m7, max_iter):
+    B, T = 3, 10
+    w = _workload(orc, m7, B, T)
+    o = orc.solve_sqp(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], max_iter)
+    e = emu.solve_sqp(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], max_iter)
+    np.testing.assert_array_equal(e["iters"], o["iters"])
+    np.testing.assert_array_equal(e["status"], o["status"])
+    for k in ("xs", "us", "cost", "K", "stop"):
+        assert rel(e[k], o[k]) < 1e-6, k
+    if max_iter == 60:
+        assert (o["status"] == _abi.AGX_STATUS_CONVERGED).all() and (o["stop"] <= 1e-3).all()
+        # SQP and FDDP agree on the optimum they approach
+        f = orc.solve(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 100)
+        assert rel(o["cost"], f["cost"]) < 1e-4
+
+
+def test_sqp_line_search_failure_and_nan_are_per_problem(orc, m7):
+    """A problem whose merit cannot decrease (one step length only, hostile warm start) or that meets a NaN ends with
+    its own status; its neighbours are solved as if alone."""
+    B, T = 3, 6
+    w = _workload(orc, m7, B, T)
+    us = w["us_ws"].copy()
+    us[1] = np.nan
+    opts = _abi.default_sqp_opts()
+    o = orc.solve_sqp(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], us, 20, opts)
+    e = emu.solve_sqp(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], us, 20, opts)
+    np.testing.assert_array_equal(e["status"], o["status"])
+    assert e["status"][1] != _abi.AGX_STATUS_CONVERGED and e["status"][0] == _abi.AGX_STATUS_CONVERGED
+    alone = emu.solve_sqp(m7, w["refs"][:1], w["dts"], w["x0"][:1], w["xs_ws"][:1], w["us_ws"][:1], 20, opts)
+    np.testing.assert_array_equal(e["xs"][0], alone["xs"][0])

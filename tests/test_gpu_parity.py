@@ -381,3 +381,27 @@ def test_cfg4_collision_avoidance(solver_mod, orc):
     assert rel(cost_nodes.sum(1).cpu().numpy(), gf["cost"].cpu().numpy()) < 1e-10
     np.testing.assert_allclose(gf["xs"].cpu().numpy()[:B], pf.solve(wf["x0"], wf["xs_ws"], wf["us_ws"], 3,
                                _abi.default_fddp_opts(fixed_iters=True))["xs"].cpu().numpy()[:B], rtol=0, atol=0)
+
+
+def test_sqp_mode_matches_oracle_and_the_golden_file(solver_mod, orc, golden):
+    """SQP mode (mim_solvers.SolverCSQP without active constraints, what the reference runs): cfg-2 shapes against the
+    CPU restatement with identical per-problem decisions, and the reference's golden file at its own 6 decimals."""
+    B, T = 256, 50
+    w, m = _workload(orc, B, T)
+    p = _problem(solver_mod, w, B)
+    for max_iter in (3, 60):
+        o = orc.solve_sqp(m, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], max_iter)
+        g = {k: v.cpu().numpy() for k, v in p.solve_sqp(w["x0"], w["xs_ws"], w["us_ws"], max_iter).items()}
+        np.testing.assert_array_equal(g["iters"], o["iters"])
+        np.testing.assert_array_equal(g["status"], o["status"])
+        for k in ("xs", "us", "cost", "stop"):
+            assert rel(g[k], o[k]) < TRAJ_RTOL, k
+        assert rel(g["K"], o["K"]) < 1e-5
+    assert (g["status"] == _abi.AGX_STATUS_CONVERGED).all() and (g["stop"] <= 1e-3).all()
+    wg = golden_problem()
+    pg = _problem(solver_mod, wg, 1)
+    s = {k: v.cpu().numpy() for k, v in pg.solve_sqp(wg["x0"], wg["xs_ws"], wg["us_ws"], 100).items()}
+    assert int(s["iters"][0]) == 33 and int(s["status"][0]) == _abi.AGX_STATUS_CONVERGED
+    np.testing.assert_array_almost_equal(s["xs"][0], golden["states"], decimal=6)
+    np.testing.assert_array_almost_equal(s["K"][0], golden["ricatti_gains"], decimal=6)
+    np.testing.assert_array_almost_equal(s["us"][0], golden["feed_forward_terms"], decimal=6)

@@ -198,3 +198,41 @@ def test_pick_and_place_configuration_through_the_ocp_class(orc):
     assert np.abs(np.stack(res.feed_forward_terms) - o["us"][0]).max() / np.abs(o["us"]).max() < 1e-6
     assert np.abs(np.stack(res.ricatti_gains) - o["K"][0]).max() / np.abs(o["K"]).max() < 1e-5
     assert ocp.debug_data.nb_iter == int(o["iters"][0])
+
+
+def test_check_results(golden):
+    """The reference's golden test, line for line (agimus_controller/tests/test_ocp_croco_base.py:140-204): an OCP with
+    the test's cost stack, nine nodes, Euler step 1e-3, solver_iters = 100, solved from `state_reg` with a zero warm
+    start by the solver the reference instantiates (CSQP mode); `ocp_results.states / ricatti_gains /
+    feed_forward_terms` must equal the pickle at 6 decimals, as `test_check_results` demands of the reference."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from agimus_controller_b200.ocp_batched import OCPBatchedFDDP
+
+    nv = 7
+    # the reference test builds IntegratedActionModelEuler without a step, i.e. Crocoddyl's default 1e-3 (:54-56)
+    params = OCPParamsBaseCroco(dt=1e-3, horizon_size=9, dt_factor_n_seq=DTFactorsNSeq(factors=[1], n_steps=[9]),
+                                solver_iters=100, callbacks=False)
+    yml = pathlib.Path(__file__).parent / "golden" / "ocp_croco_base_test.yaml"
+    ocp = OCPBatchedFDDP(panda_table(), params, str(yml), batch_size=1, solver="csqp")
+    state_reg = np.concatenate((np.zeros(nv), np.zeros(nv)))      # pin.neutral, zero velocity
+    point = WeightedTrajectoryPoint(
+        point=TrajectoryPoint(id=0, robot_configuration=np.zeros(nv), robot_velocity=np.zeros(nv),
+                              robot_acceleration=np.zeros(nv), robot_effort=np.zeros(nv),
+                              end_effector_poses={"panda_hand_tcp": SE3(np.eye(3), np.array([1.0, 1.0, 1.0]))}),
+        weights=TrajectoryPointWeights(w_robot_configuration=np.ones(nv), w_robot_velocity=np.ones(nv),
+                                       w_robot_acceleration=np.zeros(nv), w_robot_effort=np.ones(nv),
+                                       w_end_effector_poses={"panda_hand_tcp": np.ones(6)}))
+    ocp.set_reference_weighted_trajectory([point] * (params.n_controls + 1))
+    state_warmstart = [np.zeros(2 * nv)] * (params.n_controls + 1)
+    control_warmstart = [np.zeros(nv)] * params.n_controls
+    ocp.solve(state_reg, state_warmstart, control_warmstart)
+    for it, state in enumerate(golden["states"]):
+        np.testing.assert_array_almost_equal(state, ocp.ocp_results.states[it], err_msg="States are not equal")
+    for it, gain in enumerate(golden["ricatti_gains"]):
+        np.testing.assert_array_almost_equal(gain, ocp.ocp_results.ricatti_gains[it],
+                                             err_msg="Ricatti gains are not equal")
+    for it, term in enumerate(golden["feed_forward_terms"]):
+        np.testing.assert_array_almost_equal(term, ocp.ocp_results.feed_forward_terms[it],
+                                             err_msg="Feed forward term are not equal")
+    assert ocp.debug_data.problem_solved and ocp.debug_data.nb_iter == 33 and ocp.debug_data.kkt_norm <= 1e-3

@@ -6,6 +6,8 @@ extracted (without unpickling) by tests/golden/extract_golden.py.
 """
 import numpy as np
 
+from agimus_controller_b200 import _abi
+
 from agimus_controller_b200 import PANDA_Q_NOMINAL, panda_table
 from agimus_controller_b200.workloads import golden_problem
 
@@ -62,6 +64,32 @@ def test_kat3_golden_gains_need_csqp_sigma(orc, golden):
     K0, _, _ = orc.riccati_sigma(m, p["refs"][0], p["dts"], p["x0"][0], golden["states"],
                                  golden["feed_forward_terms"], 0.0)
     assert np.abs(K0[0] - Kg[0]).max() / np.abs(Kg[0]).max() > 0.5
+
+
+def test_kat9_csqp_replay_reproduces_the_golden_file(orc, golden):
+    """The reference's own check, verbatim (tests/test_ocp_croco_base.py:140-204): solve the test's OCP from the zero
+    warm start with the solver the reference instantiates (SolverCSQP, termination_tolerance 1e-3, 100 iterations
+    allowed) and compare states / gains / feed-forward terms with the pickle at 6 decimals
+    (assert_array_almost_equal: |a - b| < 1.5e-6 on values up to 1.4e4).  The restated iteration stops by the KKT
+    criterion after 33 steps exactly where the reference did."""
+    p = golden_problem()
+    m = p["table"].to_struct()
+    o = orc.solve_sqp(m, p["refs"], p["dts"], p["x0"], p["xs_ws"], p["us_ws"], 100)
+    assert int(o["status"][0]) == _abi.AGX_STATUS_CONVERGED and int(o["iters"][0]) == 33
+    assert float(o["stop"][0]) <= 1e-3
+    np.testing.assert_array_almost_equal(o["xs"][0], golden["states"], decimal=6)
+    np.testing.assert_array_almost_equal(o["K"][0], golden["ricatti_gains"], decimal=6)
+    np.testing.assert_array_almost_equal(o["us"][0], golden["feed_forward_terms"], decimal=6)
+    # measured: 9e-10 (states), 5e-8 (controls), 4e-8 (gains)
+    assert np.abs(o["xs"][0] - golden["states"]).max() < 1e-8
+    assert np.abs(o["us"][0] - golden["feed_forward_terms"]).max() < 5e-7
+    # each ingredient matters: no regularisation floor in the QP, or another merit weight, miss the file
+    for bad in (dict(reg=0.0), dict(mu=1.0), dict(termination_tolerance=1e-4)):
+        opts = _abi.default_sqp_opts()
+        for k, v in bad.items():
+            setattr(opts, k, v)
+        ob = orc.solve_sqp(m, p["refs"], p["dts"], p["x0"], p["xs_ws"], p["us_ws"], 100, opts)
+        assert np.abs(ob["xs"][0] - golden["states"]).max() > 1e-5, bad
 
 
 def test_kat4_ik_6d_known_answer(orc):
