@@ -16,13 +16,18 @@
 //                 SolverFDDP                              (built at
 //                 agimus_controller/agimus_controller/ocp/ocp_croco_generic.py:687-745, :798-812 and
 //                 agimus_controller/agimus_controller/ocp_base_croco.py:36-80; solve at :142-182)
-//   * mim_solvers SolverCSQP backward pass with proximal sigma (the solver the reference really
-//                 instantiates, ocp_base_croco.py:64) — only its Riccati gains, for golden KAT-3.
+//   * mim_solvers SolverCSQP (the solver the reference really instantiates, ocp_base_croco.py:64-75) in the form it
+//                 takes with no active constraint: Gauss-Newton SQP with a regularised Riccati QP solve, KKT stop,
+//                 L1 merit line search, gains from a last sweep with the proximal sigma (struct Sqp).
+//   * colmpc      ResidualDistanceCollision on capsule pairs + ActivationModelQuadExp (PARITY UNPINNED: no source,
+//                 no golden vector).
 //
-// Parity pinning: the Panda table, forward dynamics, cost stack and stationarity are pinned by the
-// reference's golden file agimus_controller/tests/resources/simple_ocp_croco_results.pkl
-// (tests/test_oracle_golden.py: KAT-1/2/3) and by test_sin_wave_cartesian_space.py:190-218 (KAT-4).
-// FDDP iterates themselves are "parity unpinned": no reference test stores an FDDP result.
+// Parity pinning: the reference's golden file agimus_controller/tests/resources/simple_ocp_croco_results.pkl pins
+// the Panda table, forward dynamics and the cost stack (KAT-1/2), the Riccati gains to 1e-11 (KAT-3) and — through
+// the SQP mode replaying the reference's own test — the whole solve at the reference test's 6 decimals (KAT-9,
+// tests/test_oracle_golden.py); test_sin_wave_cartesian_space.py:190-218 pins the kinematics (KAT-4).
+// What stays "parity unpinned": the FDDP-specific decisions (no reference test stores an FDDP result) and the
+// collision residuals.
 //
 // Build: see oracle/Makefile (g++ -O3 -march=x86-64-v3 -fopenmp -ffp-contract=off).
 #include <cmath>
