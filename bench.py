@@ -349,6 +349,29 @@ def run_ours(args):
     if rank == 0 and not args.no_latency:
         lat = mpc_latency(prob, dev, args.latency_ticks)
 
+    # the reference's own solver mode on the same workload (secondary figure, rank 0, N = 1): SQP = SolverCSQP without
+    # active constraints, same budget of 10 iterations, per-problem KKT stop at the reference's tolerance 1e-3
+    sqp = None
+    if rank == 0 and world == 1 and not args.no_sqp:
+        sq_out = prob.alloc_outputs()
+        for _ in range(2):
+            prob.solve_sqp(x0_d, xs_d, us_d, N_ITERS, None, out=sq_out)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_sq = max(3, min(args.steps, 10))
+        e0.record()
+        for _ in range(n_sq):
+            prob.solve_sqp(x0_d, xs_d, us_d, N_ITERS, None, out=sq_out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_sq = e0.elapsed_time(e1) / n_sq
+        sqp = {"value": B / (ms_sq * 1e-3), "unit": "solves/s", "ms_per_step": ms_sq, "steps": n_sq,
+               "max_iter": N_ITERS, "mean_iters": float(sq_out["iters"].double().mean()),
+               "converged_frac": float((sq_out["status"] == 0).double().mean()),
+               "kkt_median": float(sq_out["stop"].median()),
+               "what": "agx_solve_sqp (mim_solvers.SolverCSQP, unconstrained form, termination_tolerance 1e-3) on the "
+                       "cfg-2 batch, inputs resident; includes the final sigma sweep for the reported gains"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -447,7 +470,7 @@ def run_ours(args):
                 "pipelining": "copies of step i+1 (H2D) and i-1 (D2H) overlap the solve of step i on separate streams; "
                               "the host waits for step i-1's results before issuing step i+1"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-        "latency_b1": lat,
+        "latency_b1": lat, "sqp_mode": sqp,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -466,6 +489,7 @@ def main():
     ap.add_argument("--no-latency", action="store_true", help="skip the B=1 latency leg")
     ap.add_argument("--latency-ticks", type=int, default=300, help="MPC ticks of the B=1 latency leg")
     ap.add_argument("--no-probe", action="store_true", help="skip the FP64 peak probe (profiler runs)")
+    ap.add_argument("--no-sqp", action="store_true", help="skip the SQP-mode leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
