@@ -658,21 +658,41 @@ int agx_solve_sqp(agx_handle* h, const double* x0, const double* xs_ws, const do
   const long long cost_ctas = (ents + COST_CTA - 1) / COST_CTA;
   auto derivatives = [&]() {
     // problem.calc + calcDiff at the candidate (finished problems are skipped)
+    phase_begin(h, 3, st);
     AGX_LAUNCH_NODE_COST(h, cost_ctas, COST_CTA, COST_SMEM, st, P, (const double*)W.xs, (const double*)W.us,
                (const int32_t*)h->S.cur, 0, (const int32_t*)h->S.done, (const int32_t*)nullptr, W.crec, (double*)nullptr);
+    phase_end(h, st);
+    phase_begin(h, 0, st);
     AGX_LAUNCH_COL(h, calc_diff_kernel, (ents + opc_n - 1) / opc_n, NODE_CTA, sizeof(double) * OCT_BOARD * opc_n, st, P,
                (const double*)W.xs, (const double*)W.us, (const int32_t*)h->S.cur, (const int32_t*)nullptr,
                (const int32_t*)nullptr, 0, (const int32_t*)h->S.done, W.rec, W.crec);
+    phase_end(h, st);
   };
+  // timing phases (agx_set_timing): 0 calc_diff, 1 Riccati sweep, 2 QP direction / KKT, 3 cost records, 4 line search
   for (int it = 0; it < max_iter; ++it) {
     derivatives();
+    phase_begin(h, 1, st);
     launch_backward(h, P, W, O, st);
-    AGX_LAUNCH(h, sqp_direction_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, 0, st, P, W, h->S, Q);
+    phase_end(h, st);
+    phase_begin(h, 2, st);
+    // d_live[1 + n] = problems entering step length n (see sqp_direction_kernel)
+    int32_t* pend = h->d_live + 1;
+#if AGX_GPU
+    cudaMemsetAsync(pend, 0, sizeof(int32_t) * 12, st);
+#else
+    std::memset(pend, 0, sizeof(int32_t) * 12);
+#endif
+    AGX_LAUNCH(h, sqp_direction_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, 0, st, P, W, h->S, Q, pend);
+    phase_end(h, st);
+    phase_begin(h, 4, st);
     for (int n = 0; n < Q.n_alphas; ++n) {
-      AGX_LAUNCH_COL(h, sqp_try_kernel, (ents + opc_n - 1) / opc_n, NODE_CTA, sizeof(double) * OCT_BOARD * opc_n, st, P, W,
-                 h->S);
-      AGX_LAUNCH(h, sqp_accept_kernel, (h->B + 127) / 128, 128, 0, st, P, W, h->S, Q);
+      // the first step lengths meet most problems: one octet per entry; the later ones meet few and stride
+      const long long try_ctas = n < 3 ? (ents + opc_n - 1) / opc_n : std::min<long long>((ents + opc_n - 1) / opc_n, 148 * 8);
+      AGX_LAUNCH_COL(h, sqp_try_kernel, try_ctas, NODE_CTA, sizeof(double) * OCT_BOARD * opc_n, st, P, W,
+                 h->S, (const int32_t*)(pend + n));
+      AGX_LAUNCH(h, sqp_accept_kernel, (h->B + 127) / 128, 128, 0, st, P, W, h->S, Q, pend + n);
     }
+    phase_end(h, st);
     if (max_iter > 32 && (it % 16) == 15 && it + 1 < max_iter) {
       int32_t live = 1;
 #if AGX_GPU

@@ -27,7 +27,9 @@ AGX_DEV double octet_max(double x, unsigned omask) {
 // Fx = [I + dt G_q, dt (I + G_v); G_q, I + G_v], Fu = [dt N; N] read from the dynamics record (G_q = dt da/dq,
 // G_v = dt da/dv, N = dt Minv).  Backward: l_T = Lx_T + Lxx_T dx_T, l_t = Lx_t + Lxx_t dx_t + Fx^T l_{t+1};
 // KKT = max(|Lx + Fx^T l' - l|, |Lu + Fu^T l'|, |fs|) (SolverCSQP::checkKKTConditions).
-__global__ void sqp_direction_kernel(Problem P, Work W, SolverState S, SqpOpts Q) {
+// `pend` counts the problems that enter step length n of the line search (pend[0] is written here, pend[n + 1] by
+// sqp_accept_kernel): a try / accept launch that finds its counter at zero returns at once.
+__global__ void sqp_direction_kernel(Problem P, Work W, SolverState S, SqpOpts Q, int32_t* __restrict__ pend) {
   AGX_OCTET_SETUP();
   const int b = (int)ent;
   if (b >= P.B) return;
@@ -44,26 +46,43 @@ __global__ void sqp_direction_kernel(Problem P, Work W, SolverState S, SqpOpts Q
 
   double dq = live ? fsb[jj] : 0.0, dv = live ? fsb[NJ + jj] : 0.0;
   double gl1 = fabs(dq) + fabs(dv), ginf = fmax(fabs(dq), fabs(dv));
+  // the sweep is one dependent chain per node; its operands do not depend on it, so node t + 1's are fetched into
+  // registers before node t's chain starts (row jj of K, G_q, G_v, N; k; the gap)
+  struct FwdIn { double Kq[NJ], Kv[NJ], aq[NJ], av[NJ], mi[NJ], k, fq, fv, dt; };
+  auto fetch_fwd = [&](int t, FwdIn& o) {
+    const double* Kr = Kb + ((size_t)t * NJ + jj) * NX;
+    const double* R = rec0 + (size_t)t * REC_SIZE;
+#pragma unroll
+    for (int m = 0; m < NJ; ++m) {
+      o.Kq[m] = Kr[m]; o.Kv[m] = Kr[NJ + m];
+      o.aq[m] = R[(RK_AQ + jj) * 8 + m]; o.av[m] = R[(RK_AV + jj) * 8 + m]; o.mi[m] = R[(RK_MI + jj) * 8 + m];
+    }
+    o.k = kb[t * NJ + jj];
+    o.fq = live ? fsb[(t + 1) * NX + jj] : 0.0;
+    o.fv = live ? fsb[(t + 1) * NX + NJ + jj] : 0.0;
+    o.dt = P.dts[t];
+  };
+  FwdIn in;
+  if (T > 0) fetch_fwd(0, in);
   for (int t = 0; t < T; ++t) {
+    const FwdIn c = in;
+    if (t + 1 < T) fetch_fwd(t + 1, in);
     if (live) { dxb[t * NX + j] = dq; dxb[t * NX + NJ + j] = dv; }
     double dqm[NJ], dvm[NJ], dum[NJ];
 #pragma unroll
     for (int m = 0; m < NJ; ++m) { dqm[m] = __shfl_sync(omask, dq, m, 8); dvm[m] = __shfl_sync(omask, dv, m, 8); }
-    const double* Kr = Kb + ((size_t)t * NJ + jj) * NX;
-    double s = -kb[t * NJ + jj];
+    double s = -c.k;
 #pragma unroll
-    for (int m = 0; m < NJ; ++m) s -= Kr[m] * dqm[m] + Kr[NJ + m] * dvm[m];
+    for (int m = 0; m < NJ; ++m) s -= c.Kq[m] * dqm[m] + c.Kv[m] * dvm[m];
     const double du = live ? s : 0.0;
     if (live) kb[t * NJ + j] = du;
 #pragma unroll
     for (int m = 0; m < NJ; ++m) dum[m] = __shfl_sync(omask, du, m, 8);
-    const double* R = rec0 + (size_t)t * REC_SIZE;
     double acc = 0.0;
 #pragma unroll
-    for (int m = 0; m < NJ; ++m)
-      acc += R[(RK_AQ + jj) * 8 + m] * dqm[m] + R[(RK_AV + jj) * 8 + m] * dvm[m] + R[(RK_MI + jj) * 8 + m] * dum[m];
-    const double fq = live ? fsb[(t + 1) * NX + jj] : 0.0, fv = live ? fsb[(t + 1) * NX + NJ + jj] : 0.0;
-    const double dt = P.dts[t];
+    for (int m = 0; m < NJ; ++m) acc += c.aq[m] * dqm[m] + c.av[m] * dvm[m] + c.mi[m] * dum[m];
+    const double fq = c.fq, fv = c.fv;
+    const double dt = c.dt;
     const double dvn = dv + acc + fv;
     const double dqn = dq + dt * (dv + acc) + fq;
     gl1 += fabs(fq) + fabs(fv);
@@ -86,27 +105,43 @@ __global__ void sqp_direction_kernel(Problem P, Work W, SolverState S, SqpOpts Q
     lv = C[CK_LV + jj] + hv;
     kkt = live ? fmax(fabs(hq), fabs(hv)) : 0.0;
   }
-  for (int t = T - 1; t >= 0; --t) {
-    const double dt = P.dts[t];
+  // adjoint sweep, same prefetching (column jj of G_q, G_v, N; row jj of Lqq; the node's dx)
+  struct BwdIn { double aq[NJ], av[NJ], mi[NJ], lqq[NJ], lvv, lq, lv, lu, xq, xv, dt; };
+  auto fetch_bwd = [&](int t, BwdIn& o) {
     const double* R = rec0 + (size_t)t * REC_SIZE;
     const double* C = crec0 + (size_t)t * CREC_SIZE;
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) {
+      o.aq[i] = R[(RK_AQ + i) * 8 + jj]; o.av[i] = R[(RK_AV + i) * 8 + jj]; o.mi[i] = R[(RK_MI + i) * 8 + jj];
+      o.lqq[i] = C[CK_LQQ + (jj >= i ? lidx_(jj, i) : lidx_(i, jj))];
+    }
+    o.lvv = C[CK_LVV + jj]; o.lq = C[CK_LQ + jj]; o.lv = C[CK_LV + jj]; o.lu = C[CK_LU + jj];
+    o.xq = live ? dxb[t * NX + jj] : 0.0;
+    o.xv = live ? dxb[t * NX + NJ + jj] : 0.0;
+    o.dt = P.dts[t];
+  };
+  BwdIn bin;
+  if (T > 0) fetch_bwd(T - 1, bin);
+  for (int t = T - 1; t >= 0; --t) {
+    const BwdIn c = bin;
+    if (t > 0) fetch_bwd(t - 1, bin);
+    const double dt = c.dt;
     const double w = live ? dt * lq + lv : 0.0;
-    double su = C[CK_LU + jj], aq = 0.0, av = 0.0;
+    double su = c.lu, aq = 0.0, av = 0.0;
 #pragma unroll
     for (int i = 0; i < NJ; ++i) {
       const double wi = __shfl_sync(omask, w, i, 8);
-      su += R[(RK_MI + i) * 8 + jj] * wi;
-      aq += R[(RK_AQ + i) * 8 + jj] * wi;
-      av += R[(RK_AV + i) * 8 + jj] * wi;
+      su += c.mi[i] * wi;
+      aq += c.aq[i] * wi;
+      av += c.av[i] * wi;
     }
-    const double xq = live ? dxb[t * NX + jj] : 0.0, xv = live ? dxb[t * NX + NJ + jj] : 0.0;
+    const double xq = c.xq, xv = c.xv;
     double hq = 0.0;
 #pragma unroll
-    for (int m = 0; m < NJ; ++m)
-      hq += C[CK_LQQ + (jj >= m ? lidx_(jj, m) : lidx_(m, jj))] * __shfl_sync(omask, xq, m, 8);
-    const double hv = C[CK_LVV + jj] * xv;
-    const double nlq = C[CK_LQ + jj] + hq + lq + aq;
-    const double nlv = C[CK_LV + jj] + hv + w + av;
+    for (int m = 0; m < NJ; ++m) hq += c.lqq[m] * __shfl_sync(omask, xq, m, 8);
+    const double hv = c.lvv * xv;
+    const double nlq = c.lq + hq + lq + aq;
+    const double nlv = c.lv + hv + w + av;
     if (live) kkt = fmax(kkt, fmax(fabs(su), fmax(fabs(hq), fabs(hv))));
     lq = nlq;
     lv = nlv;
@@ -129,6 +164,7 @@ __global__ void sqp_direction_kernel(Problem P, Work W, SolverState S, SqpOpts Q
         S.dg[b] = S.cost[b] + Q.mu * gl1;
         S.pending[b] = 1;
         S.roll_ok[b] = 0;
+        atomicAdd(pend, 1);
       }
     }
   }
@@ -137,15 +173,19 @@ __global__ void sqp_direction_kernel(Problem P, Work W, SolverState S, SqpOpts Q
 // SolverCSQP::tryStep for the step length 2^-n the problem is at: one octet per (problem, node) evaluates the node
 // cost and the gap to the next trial state of xs + a dx, us + a du, which it writes into the trial buffer.
 template <bool COL>
-__global__ void sqp_try_kernel(Problem P, Work W, SolverState S) {
+__global__ void sqp_try_kernel(Problem P, Work W, SolverState S, const int32_t* __restrict__ pend) {
+  if (*pend == 0) return;
   AGX_SMEM(smem);
   AGX_OCTET_SETUP();
   const int T = P.T, T1 = T + 1;
-  if (ent >= (long long)P.B * T1) return;
-  const int b = (int)(ent / T1), t = (int)(ent % T1);
-  if (S.done[b] || !S.pending[b]) return;
   double* sb = smem + oct_in_cta * OCT_BOARD;
   double* sc = sb + BRD_B;
+  // grid-stride over the (problem, node) entries: after the first step length most problems have accepted, and a
+  // launch that finds nothing to do must cost next to nothing
+  const long long total = (long long)P.B * T1, stride = (long long)gridDim.x * octs_per_cta;
+  for (long long e = ent; e < total; e += stride) {
+  const int b = (int)(e / T1), t = (int)(e % T1);
+  if (S.done[b] || !S.pending[b]) continue;
   const double a = ldexp(1.0, -S.roll_ok[b]);
   const size_t cur = (size_t)(S.cur[b] & 1), oth = cur ^ 1;
   const bool live = j < NJ, terminal = t == T;
@@ -167,7 +207,7 @@ __global__ void sqp_try_kernel(Problem P, Work W, SolverState S) {
     if (!terminal) ut[t * NJ + j] = d.u;
   }
   double c, qn, vn;
-  const bool ok = node_calc<COL>(d, j, omask, model_of(P, b), P.refs + (size_t)ent * REF_SIZE, terminal ? 0.0 : P.dts[t],
+  const bool ok = node_calc<COL>(d, j, omask, model_of(P, b), P.refs + (size_t)e * REF_SIZE, terminal ? 0.0 : P.dts[t],
                                  terminal, sb, sc, &c, &qn, &vn);
   double g = 0.0;
   if (live && !terminal) {
@@ -182,10 +222,13 @@ __global__ void sqp_try_kernel(Problem P, Work W, SolverState S) {
     out[0] = ok ? c : nan("");
     out[1] = g;
   }
+  AGX_OSYNC();  // the boards are reused by the next entry
+  }
 }
 
 // merit_try < merit: take the step; otherwise the next step length (SolverCSQP::solve, merit line search)
-__global__ void sqp_accept_kernel(Problem P, Work W, SolverState S, SqpOpts Q) {
+__global__ void sqp_accept_kernel(Problem P, Work W, SolverState S, SqpOpts Q, int32_t* __restrict__ pend) {
+  if (*pend == 0) return;
   const int b = (int)(blockIdx.x * blockDim.x + threadIdx.x);
   if (b >= P.B) return;
   if (S.done[b] || !S.pending[b]) return;
@@ -205,6 +248,8 @@ __global__ void sqp_accept_kernel(Problem P, Work W, SolverState S, SqpOpts Q) {
       S.pending[b] = 0;
       S.status[b] = 4;
       S.done[b] = 1;
+    } else {
+      atomicAdd(pend + 1, 1);
     }
   }
 }
