@@ -43,14 +43,16 @@ class ShiftWarmStart:
         self.prev = res
 
 
-def test_ocp_plugs_into_an_mpc_loop():
+@pytest.mark.parametrize("solver", ["fddp", "csqp"])
+def test_ocp_plugs_into_an_mpc_loop(solver):
+    """Both solver modes: FDDP (north_star) and the reference's own CSQP in its unconstrained form."""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     from agimus_controller_b200.ocp_batched import OCPBatchedFDDP
 
     T = 20
     params = OCPParamsBaseCroco(dt=0.01, solver_iters=10, dt_factor_n_seq=DTFactorsNSeq([1], [T]), horizon_size=T)
-    ocp = OCPBatchedFDDP(panda_table(), params, str(YAML), batch_size=1)
+    ocp = OCPBatchedFDDP(panda_table(), params, str(YAML), batch_size=1, solver=solver)
     assert isinstance(ocp, OCPBase) and ocp.n_controls == T and ocp.dt == 0.01
     nv = 7
     # sine-wave configuration-space reference (trajectories/sine_wave_configuration_space.py): amplitude 0.2, period 4 s
@@ -74,8 +76,9 @@ def test_ocp_plugs_into_an_mpc_loop():
         assert res.ricatti_gains[0].shape == (nv, 2 * nv)
         np.testing.assert_allclose(res.states[0], x0, atol=1e-12)
         nxt = ocp.integrate(x0, res.feed_forward_terms[0])
-        np.testing.assert_allclose(res.states[1], nxt, atol=1e-8)
-        assert ocp.debug_data.nb_iter >= 1 and np.isfinite(ocp.debug_data.kkt_norm)
+        # FDDP iterates are rollouts; SQP iterates are feasible up to the KKT tolerance (gaps <= 1e-3)
+        np.testing.assert_allclose(res.states[1], nxt, atol=1e-8 if solver == "fddp" else 2e-3)
+        assert ocp.debug_data.nb_iter >= (1 if solver == "fddp" else 0) and np.isfinite(ocp.debug_data.kkt_norm)
         x = nxt
     # the tracked joint positions follow the reference (weights 1.0 on q): error stays small
     assert np.abs(x[:nv] - buffer[0].point.robot_configuration).max() < 0.05
