@@ -76,6 +76,8 @@ class AgxFddpOpts(C.Structure):
         ("reg_init", _D),
         ("fixed_iters", _I),
         ("n_alphas", _I),
+        ("eager_exit", _I),
+        ("reserved", _I),
     ]
 
 
@@ -88,14 +90,15 @@ class AgxSqpOpts(C.Structure):
         ("mu", _D),
         ("termination_tolerance", _D),
         ("n_alphas", _I),
-        ("reserved", _I),
+        ("eager_exit", _I),
     ]
 
 
 def default_sqp_opts(termination_tolerance: float = 1e-3) -> AgxSqpOpts:
     """``mim_solvers.SolverCSQP`` as the reference configures it (ocp_base_croco.py:64-75, ocp_param_base.py:53-61):
     proximal sigma 1e-6, regularisation floor 1e-9, merit weight 10, KKT tolerance 1e-3, step lengths 2^-n, n < 10."""
-    return AgxSqpOpts(sigma=1e-6, reg=1e-9, mu=10.0, termination_tolerance=termination_tolerance, n_alphas=10, reserved=0)
+    return AgxSqpOpts(sigma=1e-6, reg=1e-9, mu=10.0, termination_tolerance=termination_tolerance, n_alphas=10,
+                      eager_exit=0)
 
 
 def ref_size(nv: int) -> int:
@@ -119,6 +122,8 @@ def default_fddp_opts(fixed_iters: bool = False) -> AgxFddpOpts:
         reg_init=float("nan"),
         fixed_iters=1 if fixed_iters else 0,
         n_alphas=10,
+        eager_exit=0,
+        reserved=0,
     )
 
 

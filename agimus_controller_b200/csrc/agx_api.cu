@@ -152,6 +152,7 @@ struct agx_handle {
   double* d_x0 = nullptr;
   double* d_K_internal = nullptr;
   int32_t* d_hidx = nullptr;
+  int32_t* h_done = nullptr;  // pinned host copy of the completion flags (eager_exit)
   int32_t* d_live = nullptr;  // device counter of unfinished problems  // horizon indexes: cumulative step factors dts[i] / dts[0]
   agx::Work W{};
   agx::SolverState S{};
@@ -169,6 +170,25 @@ struct agx_handle {
 };
 
 namespace {
+
+// eager_exit: read the completion flags of a small batch back and report whether every problem has finished
+bool all_done_sync(agx_handle* h, stream_t st) {
+  const int n = h->B;
+#if AGX_GPU
+  if (!h->h_done) {
+    if (cudaMallocHost((void**)&h->h_done, sizeof(int32_t) * 64) != cudaSuccess) { h->h_done = nullptr; cudaGetLastError(); return false; }
+  }
+  if (cudaMemcpyAsync(h->h_done, h->S.done, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st) != cudaSuccess) return false;
+  if (cudaStreamSynchronize(st) != cudaSuccess) return false;
+  const int32_t* d = h->h_done;
+#else
+  (void)st;
+  const int32_t* d = h->S.done;
+#endif
+  for (int i = 0; i < n; ++i)
+    if (!d[i]) return false;
+  return true;
+}
 
 int fail(agx_handle* h, int code, const std::string& msg) {
   if (h) h->err = msg;
@@ -231,7 +251,7 @@ void agx_fddp_opts_default(agx_fddp_opts* o) {
   o->th_grad = 1e-12; o->th_stepdec = 0.5; o->th_stepinc = 0.01; o->th_acceptstep = 0.1;
   o->th_acceptnegstep = 2.0; o->th_stop = 1e-9;
   o->reg_init = nan("");
-  o->fixed_iters = 0; o->n_alphas = 10;
+  o->fixed_iters = 0; o->n_alphas = 10; o->eager_exit = 0; o->reserved = 0;
 }
 
 const char* agx_last_error(const agx_handle* h) { return h ? h->err.c_str() : "null handle"; }
@@ -242,6 +262,9 @@ int agx_destroy(agx_handle* h) {
   {
     DeviceGuard g(h->device);
     dev_free(h->d_model); dev_free(h->d_refs); dev_free(h->d_dts); dev_free(h->d_x0); dev_free(h->d_K_internal); dev_free(h->d_hidx); dev_free(h->d_live);
+#if AGX_GPU
+    if (h->h_done) cudaFreeHost(h->h_done);
+#endif
     dev_free(h->W.xs); dev_free(h->W.us); dev_free(h->W.rec); dev_free(h->W.crec); dev_free(h->W.fs); dev_free(h->W.gv); dev_free(h->W.k);
     dev_free(h->state_block);
 #if AGX_GPU
@@ -590,7 +613,9 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
     // Long budgets (the controller's first solve runs with max_iter = 1000, agimus_controller.py:376-381): once in a
     // while ask the device whether anything is still running, instead of queueing hundreds of empty launches.  Budgets
     // up to 32 iterations (every MPC tick) never synchronise.
-    if (!opts->fixed_iters && max_iter > 32 && (it % 16) == 15 && it + 1 < max_iter) {
+    if (opts->eager_exit && !opts->fixed_iters && h->B <= 64 && !h->timing && it + 1 < max_iter) {
+      if (all_done_sync(h, st)) break;
+    } else if (!opts->fixed_iters && max_iter > 32 && (it % 16) == 15 && it + 1 < max_iter) {
       int32_t live = 1;
 #if AGX_GPU
       cudaMemsetAsync(h->d_live, 0, sizeof(int32_t), st);
@@ -613,7 +638,7 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
 
 void agx_sqp_opts_default(agx_sqp_opts* o) {
   if (!o) return;
-  o->sigma = 1e-6; o->reg = 1e-9; o->mu = 10.0; o->termination_tolerance = 1e-3; o->n_alphas = 10; o->reserved = 0;
+  o->sigma = 1e-6; o->reg = 1e-9; o->mu = 10.0; o->termination_tolerance = 1e-3; o->n_alphas = 10; o->eager_exit = 0;
 }
 
 int agx_solve_sqp(agx_handle* h, const double* x0, const double* xs_ws, const double* us_ws, int max_iter,
@@ -693,7 +718,9 @@ int agx_solve_sqp(agx_handle* h, const double* x0, const double* xs_ws, const do
       AGX_LAUNCH(h, sqp_accept_kernel, (h->B + 127) / 128, 128, 0, st, P, W, h->S, Q, pend + n);
     }
     phase_end(h, st);
-    if (max_iter > 32 && (it % 16) == 15 && it + 1 < max_iter) {
+    if (opts->eager_exit && h->B <= 64 && !h->timing && it + 1 < max_iter) {
+      if (all_done_sync(h, st)) break;
+    } else if (max_iter > 32 && (it % 16) == 15 && it + 1 < max_iter) {
       int32_t live = 1;
 #if AGX_GPU
       cudaMemsetAsync(h->d_live, 0, sizeof(int32_t), st);

@@ -183,6 +183,11 @@ class OCPBatchedFDDP(OCPBase):
         self._problem = BatchedShootingProblem(robot_table, params.timesteps, self._B, device=device)
         self._opts = fddp_opts if fddp_opts is not None else _abi.default_fddp_opts()
         self._sqp_opts = _abi.default_sqp_opts(getattr(params, "termination_tolerance", 1e-3))
+        if self._B == 1:
+            # a single MPC tick waits for its result: stop queueing iterations as soon as the problem has finished
+            if fddp_opts is None:
+                self._opts.eager_exit = 1
+            self._sqp_opts.eager_exit = 1
         self._ocp_results: T.Optional[OCPResults] = None
         self._results_batched: T.Optional[dict] = None
         self._debug_data = OCPDebugData()

@@ -94,6 +94,10 @@ typedef struct agx_model {
 /*
  * FDDP parameters (Crocoddyl SolverFDDP defaults are what agx_fddp_opts_default fills).
  * fixed_iters != 0: run exactly max_iter iterations, no early exit (benchmark mode).
+ * eager_exit != 0 (and not fixed_iters): after every iteration the per-problem completion flags are read back and
+ * the call returns as soon as every problem has finished — one small device-to-host copy and a stream
+ * synchronisation per iteration instead of queueing the whole budget.  Meant for the latency-bound single-problem MPC
+ * tick (B <= 64; ignored for larger batches), where the host waits for the result anyway.
  */
 typedef struct agx_fddp_opts {
   double reg_min, reg_max, reg_incfactor, reg_decfactor;
@@ -101,6 +105,8 @@ typedef struct agx_fddp_opts {
   double reg_init; /* NaN -> reg_min */
   int32_t fixed_iters;
   int32_t n_alphas; /* step lengths 2^-n, n = 0..n_alphas-1 (<= 10) */
+  int32_t eager_exit;
+  int32_t reserved;
 } agx_fddp_opts;
 
 /*
@@ -112,7 +118,7 @@ typedef struct agx_fddp_opts {
 typedef struct agx_sqp_opts {
   double sigma, reg, mu, termination_tolerance;
   int32_t n_alphas;
-  int32_t reserved;
+  int32_t eager_exit; /* as in agx_fddp_opts */
 } agx_sqp_opts;
 
 typedef struct agx_handle agx_handle;

@@ -15,7 +15,8 @@ out = p1.alloc_outputs()
 x = torch.as_tensor(np.concatenate([q[0], v[0]])[None], device=dev)
 xs = torch.cat([torch.as_tensor(q[: T + 1]), torch.as_tensor(v[: T + 1])], dim=1)[None].to(dev).contiguous()
 us = torch.as_tensor(u[:T][None], device=dev).contiguous()
-for mode, opts, iters in (("fddp", _abi.default_fddp_opts(), 10), ("fddp3", _abi.default_fddp_opts(), 3)):
+eo = _abi.default_fddp_opts(); eo.eager_exit = 1
+for mode, opts, iters in (("fddp", _abi.default_fddp_opts(), 10), ("fddp_eager", eo, 10)):
     acc = {k: [] for k in ("refs", "solve_call", "sync", "d2h")}
     for k in range(200):
         torch.cuda.synchronize()

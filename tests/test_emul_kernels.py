@@ -460,3 +460,24 @@ def test_sqp_line_search_failure_and_nan_are_per_problem(orc, m7):
     assert e["status"][1] != _abi.AGX_STATUS_CONVERGED and e["status"][0] == _abi.AGX_STATUS_CONVERGED
     alone = emu.solve_sqp(m7, w["refs"][:1], w["dts"], w["x0"][:1], w["xs_ws"][:1], w["us_ws"][:1], 20, opts)
     np.testing.assert_array_equal(e["xs"][0], alone["xs"][0])
+
+
+def test_eager_exit_gives_the_same_results_with_fewer_launches(orc, m7):
+    """eager_exit (the latency mode of a single MPC tick): same iterates and statuses, the launches of the unused part
+    of the budget are not queued."""
+    B, T = 2, 8
+    w = _workload(orc, m7, B, T)
+    ref = emu.solve(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 30, _abi.default_fddp_opts())
+    opts = _abi.default_fddp_opts()
+    opts.eager_exit = 1
+    e = emu.solve(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 30, opts)
+    for k in ("xs", "us", "K", "cost", "iters", "status"):
+        np.testing.assert_array_equal(e[k], ref[k])
+    assert int(ref["iters"].max()) < 30 and e["launches"] == 5 * int(ref["iters"].max()) + 3 < ref["launches"]
+    so = _abi.default_sqp_opts()
+    sref = emu.solve_sqp(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 30, so)
+    so.eager_exit = 1
+    se = emu.solve_sqp(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 30, so)
+    for k in ("xs", "us", "K", "iters", "status"):
+        np.testing.assert_array_equal(se[k], sref[k])
+    assert se["launches"] < sref["launches"]
