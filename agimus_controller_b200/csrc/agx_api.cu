@@ -446,6 +446,7 @@ int agx_riccati(agx_handle* h, const double* x0, const double* xs, const double*
   O.reg_min = reg; O.reg_max = reg; O.reg_incfactor = od.reg_incfactor; O.reg_decfactor = od.reg_decfactor;
   O.th_grad = od.th_grad; O.th_stepdec = od.th_stepdec; O.th_stepinc = od.th_stepinc; O.th_acceptstep = od.th_acceptstep;
   O.th_acceptnegstep = od.th_acceptnegstep; O.th_stop = od.th_stop; O.reg_init = reg; O.fixed_iters = 1; O.n_alphas = 1;
+  O.max_iter = 1; O.defer = 0;
   const size_t nB = (size_t)h->B, T = (size_t)h->T, T1 = T + 1;
   Work W = h->W;
   W.K = out_K;
@@ -564,6 +565,12 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
   O.reg_decfactor = opts->reg_decfactor; O.th_grad = opts->th_grad; O.th_stepdec = opts->th_stepdec;
   O.th_stepinc = opts->th_stepinc; O.th_acceptstep = opts->th_acceptstep; O.th_acceptnegstep = opts->th_acceptnegstep;
   O.th_stop = opts->th_stop; O.reg_init = opts->reg_init; O.fixed_iters = opts->fixed_iters; O.n_alphas = opts->n_alphas;
+  O.max_iter = max_iter;
+  // deferred line search (accept_linesearch_kernel): on unless AGX_LS=inline asks for the in-line search only
+  static const bool ls_inline = [] { const char* e = std::getenv("AGX_LS"); return e && std::strcmp(e, "inline") == 0; }();
+  O.defer = (!ls_inline && O.n_alphas > 1) ? 1 : 0;
+  // a problem that deferred once is one round behind: one more round lets it use its whole budget
+  const int rounds = max_iter + ((O.defer && max_iter > 0) ? 1 : 0);
   const size_t nB = (size_t)h->B, T = (size_t)h->T, T1 = T + 1;
   if (!out_K && !h->d_K_internal) {
     if (!dev_alloc((void**)&h->d_K_internal, sizeof(double) * nB * T * NJ * NX))
@@ -579,7 +586,7 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
   const long long ents = (long long)(nB * T1);
   const int opc_n = NODE_CTA / 8, opc_s = SEQ_CTA / 8;
   const long long cost_ctas = (ents + COST_CTA - 1) / COST_CTA;
-  for (int it = 0; it < max_iter; ++it) {
+  for (int it = 0; it < rounds; ++it) {
     // problem.calc + calcDiff at the candidate: dynamics records, plus the cost records where they are stale
     // (after an alpha = 1 acceptance they were already written for the trial by node_cost_kernel)
     if (it == 0) {
@@ -608,14 +615,14 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
     phase_end(h, st);
     phase_begin(h, 4, st);
     AGX_LAUNCH_COL(h, accept_linesearch_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * FW_BOARD * opc_s, st, P, W,
-               h->S, O);
+               h->S, O, it);
     phase_end(h, st);
     // Long budgets (the controller's first solve runs with max_iter = 1000, agimus_controller.py:376-381): once in a
     // while ask the device whether anything is still running, instead of queueing hundreds of empty launches.  Budgets
     // up to 32 iterations (every MPC tick) never synchronise.
-    if (opts->eager_exit && !opts->fixed_iters && h->B <= 64 && !h->timing && it + 1 < max_iter) {
+    if (opts->eager_exit && h->B <= 64 && !h->timing && it + 1 < rounds) {
       if (all_done_sync(h, st)) break;
-    } else if (!opts->fixed_iters && max_iter > 32 && (it % 16) == 15 && it + 1 < max_iter) {
+    } else if (!opts->fixed_iters && max_iter > 32 && (it % 16) == 15 && it + 1 < rounds) {
       int32_t live = 1;
 #if AGX_GPU
       cudaMemsetAsync(h->d_live, 0, sizeof(int32_t), st);
@@ -663,7 +670,7 @@ int agx_solve_sqp(agx_handle* h, const double* x0, const double* xs_ws, const do
   O.reg_min = Q.reg; O.reg_max = Q.reg; O.reg_init = Q.reg; O.reg_incfactor = od.reg_incfactor;
   O.reg_decfactor = od.reg_decfactor; O.th_grad = od.th_grad; O.th_stepdec = od.th_stepdec; O.th_stepinc = od.th_stepinc;
   O.th_acceptstep = od.th_acceptstep; O.th_acceptnegstep = od.th_acceptnegstep; O.th_stop = od.th_stop;
-  O.fixed_iters = 0; O.n_alphas = Q.n_alphas;
+  O.fixed_iters = 0; O.n_alphas = Q.n_alphas; O.max_iter = max_iter; O.defer = 0;
   FddpOpts Of = O;
   Of.reg_min = Of.reg_max = Of.reg_init = Q.sigma + Q.reg;
   const size_t nB = (size_t)h->B, T = (size_t)h->T, T1 = T + 1;

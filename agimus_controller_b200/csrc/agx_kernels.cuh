@@ -38,6 +38,8 @@ struct FddpOpts {
   double th_grad, th_stepdec, th_stepinc, th_acceptstep, th_acceptnegstep, th_stop;
   double reg_init;
   int fixed_iters, n_alphas;
+  int max_iter;  // iteration budget of every problem (a problem whose search was deferred finishes a round later)
+  int defer;     // a rejected alpha = 1 trial tries alpha = 1/2 in the next round's forward pass (see accept_linesearch_kernel)
 };
 
 // workspace of a solve (device pointers owned by the handle)
@@ -365,7 +367,7 @@ __global__ void backward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
   AGX_OCTET_SETUP();
   const int b = (int)ent;
   if (b >= P.B) return;
-  if (S.done[b]) return;
+  if (S.done[b] || S.pending[b]) return;  // pending: the candidate did not change, its sweep is still valid
   double* sm = smem + oct_in_cta * BW_SIZE;
   const int T = P.T, T1 = T + 1;
   const bool live = j < NJ;
@@ -715,6 +717,7 @@ AGX_DEV void finish_iteration(const SolverState& S, const FddpOpts& O, int b, bo
   S.xreg[b] = xreg;
   S.iters[b] += 1;
   if (!done && !O.fixed_iters && was_feasible && S.stop[b] < O.th_stop) { status = 0; done = 1; }
+  if (!done && S.iters[b] >= O.max_iter) done = 1;  // budget used (status stays MAXITER)
   if (done) { S.status[b] = status; S.done[b] = 1; }
 }
 
@@ -751,8 +754,11 @@ __global__ void rollout_try_kernel(Problem P, Work W, SolverState S) {
   const double* Kb = W.K + (size_t)b * T * NJ * NX;
   const double* kb = W.k + (size_t)b * T * NJ;
   const bool feasible = S.is_feasible[b] != 0;
+  // a problem whose alpha = 1 trial was rejected in the previous round tries alpha = 1/2 here (deferred line search)
+  const double alpha = S.pending[b] ? 0.5 : 1.0;
+  const double* fsb = W.fs + (size_t)b * T1 * NX;
   // per-node inputs are fetched one node ahead (scalars into registers, gain rows into L1)
-  struct NodeIn { double us, kff, dt, xsq, xsv, gq, gv; };
+  struct NodeIn { double us, kff, dt, xsq, xsv, gq, gv, fq, fv; };
   auto fetch = [&](int t, NodeIn& n) {
     const bool run = t < T;
     n.us = (live && run) ? us[t * NJ + jj] : 0.0;
@@ -763,6 +769,9 @@ __global__ void rollout_try_kernel(Problem P, Work W, SolverState S) {
     const bool gaps = live && !feasible;
     n.gq = gaps ? gvb[t * NX + jj] : 0.0;
     n.gv = gaps ? gvb[t * NX + NJ + jj] : 0.0;
+    const bool contract = gaps && alpha != 1.0;  // xs_try = xhat + (alpha - 1) fs
+    n.fq = contract ? fsb[t * NX + jj] : 0.0;
+    n.fv = contract ? fsb[t * NX + NJ + jj] : 0.0;
     // the node's 7x14 gain block (784 B) is copied global -> shared asynchronously: 49 chunks of 16 B over 8 lanes
     if (run) {
       double* dst = sK + (t & 1) * 98;
@@ -780,6 +789,10 @@ __global__ void rollout_try_kernel(Problem P, Work W, SolverState S) {
     NodeIn nxt;
     AGX_CP_ASYNC_WAIT_ALL();  // node t's gain block has landed (it was issued one node ago)
     if (t < T) fetch(t + 1, nxt);
+    if (alpha != 1.0) {
+      xq += cur.fq * (alpha - 1.0);
+      xv += cur.fv * (alpha - 1.0);
+    }
     const double dxq = live ? xq - cur.xsq : 0.0, dxv = live ? xv - cur.xsv : 0.0;
     if (live) {
       xt[t * NX + j] = xq;
@@ -794,7 +807,7 @@ __global__ void rollout_try_kernel(Problem P, Work W, SolverState S) {
     for (int m = 0; m < NX; ++m) s += sK[(t & 1) * 98 + jj * NX + m] * sdx[m];
     LaneDyn d;
     d.q = xq; d.qd = xv;
-    d.u = live ? cur.us - cur.kff - s : 0.0;
+    d.u = live ? cur.us - cur.kff * alpha - s : 0.0;
     if (live) ut[t * NJ + j] = d.u;
     node_kinematics(d, j, omask, model);
     double L[28], rinv[NJ];
@@ -814,13 +827,22 @@ __global__ void rollout_try_kernel(Problem P, Work W, SolverState S) {
 
 // Acceptance test of the alpha = 1 trial (its costs come from node_cost_kernel) and, only if it is rejected,
 // the remaining step lengths alpha = 2^-ia, ia >= 1, with the costs evaluated in line.
+//
+// Deferred search (O.defer): a rejected alpha = 1 trial does not start the in-line search — a whole-horizon rollout
+// that every other problem of the batch would wait for.  The problem is marked `pending` instead: it sits out the
+// next round's calc_diff and sweep (its candidate did not change) and its alpha = 1/2 trial goes through the next
+// round's rollout_try / node_cost launches together with everybody else's alpha = 1 trial.  The sequence of operations
+// of the problem is SolverFDDP's; only the round in which its alpha = 1/2 trial runs moves.  A problem defers once
+// (round - iterations < 1), so one extra round after the budget lets every problem finish its max_iter iterations.
 template <bool COL>
-__global__ void accept_linesearch_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
+__global__ void accept_linesearch_kernel(Problem P, Work W, SolverState S, FddpOpts O, int round) {
   AGX_SMEM(smem);
   AGX_OCTET_SETUP();
   const int b = (int)ent;
   if (b >= P.B) return;
   if (S.done[b]) return;
+  const bool was_pending = S.pending[b] != 0;
+  const double a1 = was_pending ? 0.5 : 1.0;  // the step length the fast path evaluated this round
   {
     const double* crec0 = W.crec + (size_t)b * (P.T + 1) * CREC_SIZE;
     double part = 0.0;
@@ -833,17 +855,29 @@ __global__ void accept_linesearch_kernel(Problem P, Work W, SolverState S, FddpO
       const double dv = S.dv[b];
       const double d1 = S.dg[b] + dv, d2 = S.dq[b] - 2.0 * dv;
       stop1 = fabs(d1 + 0.5 * d2);
-      acc1 = accept_step(O, S.cost[b] - cost1, d1, d1 + 0.5 * d2);  // steplength = 1
+      acc1 = accept_step(O, S.cost[b] - cost1, d1, a1 * (d1 + 0.5 * a1 * d2));
     }
+    const bool last_alpha = O.n_alphas <= (was_pending ? 2 : 1);
+    const bool defer = !acc1 && !last_alpha && !was_pending && O.defer && round - S.iters[b] < 1;
     AGX_OSYNC();  // every lane has read the state before lane 0 updates it
-    if (acc1 || O.n_alphas <= 1) {
+    if (acc1 || last_alpha) {
       if (j == 0) {
         S.stop[b] = stop1;
-        finish_iteration(S, O, b, acc1, 1.0, S.is_feasible[b] != 0, cost1, (S.cur[b] & 1) ^ 1, true);
+        S.pending[b] = 0;
+        finish_iteration(S, O, b, acc1, a1, S.is_feasible[b] != 0, cost1, (S.cur[b] & 1) ^ 1, true);
       }
       return;
     }
-    if (j == 0) S.stop[b] = stop1;
+    if (defer) {
+      if (j == 0) {
+        S.stop[b] = stop1;
+        S.pending[b] = 1;
+        S.recalc[b] = 0;       // same candidate: its dynamics records stay valid ...
+        S.recalc_cost[b] = 0;  // ... and its cost records are not needed before the search ends
+      }
+      return;
+    }
+    if (j == 0) { S.stop[b] = stop1; S.pending[b] = 0; }
     AGX_OSYNC();
   }
   double* sb = smem + oct_in_cta * FW_BOARD;
@@ -869,7 +903,7 @@ __global__ void accept_linesearch_kernel(Problem P, Work W, SolverState S, FddpO
 
   double steplength = 1.0, cost_try = 0.0, stop = S.stop[b];
   bool accepted = false;
-  for (int ia = 1; ia < O.n_alphas; ++ia) {
+  for (int ia = was_pending ? 2 : 1; ia < O.n_alphas; ++ia) {
     steplength = ldexp(1.0, -ia);
     const bool contract = !feasible;
     double xq = x0q, xv = x0v;

@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(32, AGX_BWM_MINB) backward_mma_kernel(Problem 
   const int g = lane >> 2, q = lane & 3;
   const int b = (int)blockIdx.x * (int)(blockDim.x >> 5) + wrp;
   if (b >= P.B) return;
-  if (S.done[b]) return;
+  if (S.done[b] || S.pending[b]) return;  // pending: the candidate did not change, its sweep is still valid
   double* sm = smem + wrp * MB_SIZE;
   const int T = P.T, T1 = T + 1;
   const bool gl = g < NJ;

@@ -198,6 +198,8 @@ int agx_rnea(agx_handle* h, const double* q, const double* v, const double* a, i
  * In:  x0 [B][nx], xs_ws [B][T+1][nx], us_ws [B][T][nu].
  * Out: out_xs [B][T+1][nx], out_us [B][T][nu], out_K [B][T][nu][nx], out_k [B][T][nu] (may be NULL),
  *      out_cost [B], out_iters [B] (int32), out_status [B] (int32), out_stop [B] (may be NULL).
+ * A problem whose alpha = 1 trial is rejected takes its alpha = 1/2 trial in the next round of launches (deferred line
+ * search), so max_iter + 1 rounds are queued; per problem the iterates are those of the sequential search.
  * Stream-ordered and asynchronous for max_iter <= 32 or opts->fixed_iters; with a larger budget the call
  * synchronises `stream` every 16 iterations to stop as soon as every problem has finished. */
 int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double* us_ws,
