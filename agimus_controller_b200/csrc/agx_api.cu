@@ -82,7 +82,7 @@ int env_cta(const char* name, int dflt, int max_threads) {
   return (n >= 8 && n <= max_threads && n % 8 == 0) ? n : dflt;
 }
 const int NODE_CTA = env_cta("AGX_NODE_CTA", 64, 64);   // calc_diff_kernel is bounded to 64 threads
-const int SEQ_CTA = env_cta("AGX_SEQ_CTA", 32, 128);
+const int SEQ_CTA = env_cta("AGX_SEQ_CTA", 32, 64);    // 8 octet boards of the forward kernels = 27 KB of the 48 KB default
 // backward sweep: "mma" = one warp per problem on the FP64 tensor cores (default), "octet" = 8 lanes per problem
 const bool BW_MMA = !(std::getenv("AGX_BW") && std::string(std::getenv("AGX_BW")) == "octet");
 const int COST_CTA = 64;  // thread-per-node cost kernel: 2 warps, 33 KB of staging shared memory
