@@ -456,11 +456,11 @@ def test_sqp_line_search_failure_and_nan_are_per_problem(orc, m7):
     us = w["us_ws"].copy()
     us[1] = np.nan
     opts = _abi.default_sqp_opts()
-    o = orc.solve_sqp(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], us, 20, opts)
-    e = emu.solve_sqp(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], us, 20, opts)
+    o = orc.solve_sqp(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], us, 12, opts)
+    e = emu.solve_sqp(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], us, 12, opts)
     np.testing.assert_array_equal(e["status"], o["status"])
     assert e["status"][1] != _abi.AGX_STATUS_CONVERGED and e["status"][0] == _abi.AGX_STATUS_CONVERGED
-    alone = emu.solve_sqp(m7, w["refs"][:1], w["dts"], w["x0"][:1], w["xs_ws"][:1], w["us_ws"][:1], 20, opts)
+    alone = emu.solve_sqp(m7, w["refs"][:1], w["dts"], w["x0"][:1], w["xs_ws"][:1], w["us_ws"][:1], 12, opts)
     np.testing.assert_array_equal(e["xs"][0], alone["xs"][0])
 
 
@@ -469,29 +469,29 @@ def test_eager_exit_gives_the_same_results_with_fewer_launches(orc, m7):
     of the budget are not queued."""
     B, T = 2, 8
     w = _workload(orc, m7, B, T)
-    ref = emu.solve(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 30, _abi.default_fddp_opts())
+    ref = emu.solve(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 24, _abi.default_fddp_opts())
     opts = _abi.default_fddp_opts()
     opts.eager_exit = 1
-    e = emu.solve(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 30, opts)
+    e = emu.solve(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 24, opts)
     for k in ("xs", "us", "K", "cost", "iters", "status"):
         np.testing.assert_array_equal(e[k], ref[k])
-    assert int(ref["iters"].max()) < 30 and e["launches"] < ref["launches"]
+    assert int(ref["iters"].max()) < 24 and e["launches"] < ref["launches"]
     assert e["launches"] <= 5 * (int(ref["iters"].max()) + 1) + 3
     so = _abi.default_sqp_opts()
-    sref = emu.solve_sqp(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 30, so)
+    sref = emu.solve_sqp(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 12, so)
     so.eager_exit = 1
-    se = emu.solve_sqp(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 30, so)
+    se = emu.solve_sqp(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 12, so)
     for k in ("xs", "us", "K", "iters", "status"):
         np.testing.assert_array_equal(se[k], sref[k])
     assert se["launches"] < sref["launches"]
 
 
-@pytest.mark.parametrize("iters", [1, 6])
+@pytest.mark.parametrize("iters", [1, 4])
 def test_deferred_line_search_follows_the_sequential_search(orc, m7, iters):
     """Half of this batch rejects its alpha = 1 trial at some iteration (a few problems need alpha < 1/2 too).  The
     kernels defer the alpha = 1/2 trial to the next round's forward pass and run one round past the budget; per problem
     the result must be SolverFDDP's sequential search: same iterates after every budget, same iteration counts."""
-    B, T = 16, 12
+    B, T = 12, 12
     w = goal_reaching_batch(B, T=T, rnea=lambda q, v, a: orc.rnea(m7, q, v, a), q_spread=0.8, target_p=(0.3, -0.4, 0.7))
     opts = _abi.default_fddp_opts(fixed_iters=True)
     o = orc.solve(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], iters, opts)
@@ -505,7 +505,7 @@ def test_deferred_line_search_follows_the_sequential_search(orc, m7, iters):
     one = _abi.default_fddp_opts(fixed_iters=True)
     one.n_alphas = 1
     o1 = orc.solve(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], iters, one)
-    assert (np.abs(o1["xs"] - o["xs"]).max(axis=(1, 2)) > 1e-9).sum() >= 5
+    assert (np.abs(o1["xs"] - o["xs"]).max(axis=(1, 2)) > 1e-9).sum() >= 3
     e1 = emu.solve(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], iters, one)
     assert rel(e1["xs"], o1["xs"]) < 1e-8
     two = _abi.default_fddp_opts(fixed_iters=True)
