@@ -499,8 +499,9 @@ def test_deferred_line_search_follows_the_sequential_search(orc, m7, iters):
     np.testing.assert_array_equal(e["iters"], o["iters"])
     np.testing.assert_array_equal(e["status"], o["status"])
     assert (e["iters"] == iters).all()
-    for k in ("xs", "us", "cost", "K"):
+    for k in ("xs", "us", "cost"):
         assert rel(e[k], o[k]) < 1e-8, k
+    assert rel(e["K"], o["K"]) < 1e-5  # the gains amplify rounding through the ill-conditioned Quu
     # the search really runs: without it (one step length only) the oracle ends elsewhere for several problems
     one = _abi.default_fddp_opts(fixed_iters=True)
     one.n_alphas = 1
