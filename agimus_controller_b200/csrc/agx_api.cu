@@ -190,6 +190,21 @@ bool all_done_sync(agx_handle* h, stream_t st) {
   return true;
 }
 
+// eager_exit, SQP line search: value of a device counter (synchronises)
+int read_counter_sync(agx_handle* h, const int32_t* d_counter, stream_t st) {
+#if AGX_GPU
+  if (!h->h_done) {
+    if (cudaMallocHost((void**)&h->h_done, sizeof(int32_t) * 64) != cudaSuccess) { h->h_done = nullptr; cudaGetLastError(); return 1; }
+  }
+  if (cudaMemcpyAsync(h->h_done, d_counter, sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess) return 1;
+  if (cudaStreamSynchronize(st) != cudaSuccess) return 1;
+  return h->h_done[0];
+#else
+  (void)h; (void)st;
+  return *d_counter;
+#endif
+}
+
 int fail(agx_handle* h, int code, const std::string& msg) {
   if (h) h->err = msg;
   return code;
@@ -723,6 +738,9 @@ int agx_solve_sqp(agx_handle* h, const double* x0, const double* xs_ws, const do
       AGX_LAUNCH_COL(h, sqp_try_kernel, try_ctas, NODE_CTA, sizeof(double) * OCT_BOARD * opc_n, st, P, W,
                  h->S, (const int32_t*)(pend + n));
       AGX_LAUNCH(h, sqp_accept_kernel, (h->B + 127) / 128, 128, 0, st, P, W, h->S, Q, pend + n);
+      // latency mode: stop queueing step lengths once nobody is searching any more
+      if (opts->eager_exit && h->B <= 64 && !h->timing && n + 1 < Q.n_alphas && read_counter_sync(h, pend + n + 1, st) == 0)
+        break;
     }
     phase_end(h, st);
     if (opts->eager_exit && h->B <= 64 && !h->timing && it + 1 < max_iter) {

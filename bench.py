@@ -150,7 +150,7 @@ def run_reference(args):
     return 0
 
 
-def mpc_latency(prob, dev, ticks):
+def mpc_latency(prob, dev, ticks, solver="fddp"):
     """p50 / p99 of one MPC tick's solve (reference: MPCDebugData.duration_ocp_solve_ns, mpc.py:52-64): reference
     update, warm start, solve, read-back of the control the node publishes (us[0], K[0])."""
     import torch
@@ -167,6 +167,8 @@ def mpc_latency(prob, dev, ticks):
     rows_d = torch.as_tensor(rows, device=dev)
     opts = _abi.default_fddp_opts()
     opts.eager_exit = 1   # latency mode: the completion flag is read back after every iteration (include/agx.h)
+    sqp_opts = _abi.default_sqp_opts()
+    sqp_opts.eager_exit = 1
     out = p1.alloc_outputs()
     x = torch.as_tensor(np.concatenate([q[0], v[0]])[None], device=dev)
     xs = torch.cat([torch.as_tensor(q[: T + 1]), torch.as_tensor(v[: T + 1])], dim=1)[None].to(dev).contiguous()
@@ -176,7 +178,10 @@ def mpc_latency(prob, dev, ticks):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         p1.set_refs_window(rows_d, k)                                 # horizon window of the device-resident stream
-        p1.solve(x, xs, us, N_ITERS, opts, out=out)
+        if solver == "fddp":
+            p1.solve(x, xs, us, N_ITERS, opts, out=out)
+        else:
+            p1.solve_sqp(x, xs, us, N_ITERS, sqp_opts, out=out)
         u0 = out["us"][0, 0].cpu()
         K0 = out["K"][0, 0].cpu()                                    # what Control(feedback_gain, feedforward) carries
         ts.append(time.perf_counter() - t0)
@@ -349,6 +354,8 @@ def run_ours(args):
     lat = None
     if rank == 0 and not args.no_latency:
         lat = mpc_latency(prob, dev, args.latency_ticks)
+        lat_sqp = mpc_latency(prob, dev, args.latency_ticks, solver="csqp")
+        lat["csqp_mode"] = {k: lat_sqp[k] for k in ("p50_ms", "p99_ms", "mean_iters", "final_tracking_error_rad")}
 
     # the reference's own solver mode on the same workload (secondary figure, rank 0, N = 1): SQP = SolverCSQP without
     # active constraints, same budget of 10 iterations, per-problem KKT stop at the reference's tolerance 1e-3
