@@ -247,6 +247,13 @@ __global__ void node_cost_kernel(Problem P, const double* __restrict__ xs, const
     const bool terminal = t == P.T;
     const double* x = xs + ((buf * P.B + b) * T1 + t) * NX;
     const double* u = terminal ? nullptr : us + ((buf * P.B + b) * P.T + t) * NJ;
+    {
+      // the reference record (496 B) is read late, in the gradient loop, where its first-touch latency was 20 % of
+      // this kernel's stall samples: ask for its lines now
+      const double* rp = P.refs + (size_t)n * REF_SIZE;
+      AGX_PREFETCH(rp); AGX_PREFETCH(rp + 16); AGX_PREFETCH(rp + 32); AGX_PREFETCH(rp + 48); AGX_PREFETCH(rp + REF_SIZE - 1);
+      if (u) { AGX_PREFETCH(u); AGX_PREFETCH(u + NJ - 1); }
+    }
     const double c = thread_node_cost<DERIV, COL>(model_of(P, b), P.refs + (size_t)n * REF_SIZE, x, u, terminal,
                                                   terminal ? 1.0 : P.dts[t],
                                                   DERIV ? stage + lane * (CREC_SIZE + 1) : nullptr);
