@@ -151,9 +151,9 @@ struct agx_handle {
   double* d_dts = nullptr;
   double* d_x0 = nullptr;
   double* d_K_internal = nullptr;
-  int32_t* d_hidx = nullptr;
+  int32_t* d_hidx = nullptr;  // horizon indexes of the reference stream: cumulative step factors dts[i] / dts[0]
   int32_t* h_done = nullptr;  // pinned host copy of the completion flags (eager_exit)
-  int32_t* d_live = nullptr;  // device counter of unfinished problems  // horizon indexes: cumulative step factors dts[i] / dts[0]
+  int32_t* d_live = nullptr;  // [0]: unfinished problems; [1..12]: problems entering each step length (SQP line search)
   agx::Work W{};
   agx::SolverState S{};
   void* state_block = nullptr;
