@@ -917,6 +917,18 @@ __global__ void accept_linesearch_kernel(Problem P, Work W, SolverState S, FddpO
     double ctry = 0.0, dvp = 0.0;
     bool ok = true;
     for (int t = 0; t <= T; ++t) {
+      if (t < T) {
+        // the next node's operands (state, gap, Vxx fs, gain row, control, reference record) are asked for now: this
+        // loop is one dependent chain per node and it has no other way to hide their latency
+        const int tn = t + 1;
+        AGX_PREFETCH(xs + tn * NX + jj); AGX_PREFETCH(xs + tn * NX + NJ + jj);
+        if (!feasible) { AGX_PREFETCH(fsb + tn * NX + jj); AGX_PREFETCH(gvb + tn * NX + jj); }
+        AGX_PREFETCH(refs + (size_t)tn * REF_SIZE + 8 * j);
+        if (tn < T) {
+          AGX_PREFETCH(Kb + ((size_t)tn * NJ + jj) * NX); AGX_PREFETCH(Kb + ((size_t)tn * NJ + jj) * NX + NX - 1);
+          AGX_PREFETCH(us + tn * NJ + jj); AGX_PREFETCH(kb + tn * NJ + jj);
+        }
+      }
       double tq = xq, tv = xv;
       if (contract && live) {
         tq += fsb[t * NX + j] * (steplength - 1.0);
