@@ -621,8 +621,23 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
     launch_backward(h, P, W, O, st);
     phase_end(h, st);
     phase_begin(h, 2, st);
-    AGX_LAUNCH(h, rollout_try_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * FW_BOARD * opc_s, st, P, W,
-               h->S);
+    {
+      // two warps per group of four problems pay off while the SMs are not full (measured crossover between 1024 and
+      // 2048 problems: 256 problems 0.167 -> 0.145 ms per launch, 4096 problems 0.224 -> 0.370 ms).  The two kernels
+      // agree to rounding, not bitwise, and a slab must give the same bits alone as inside a larger batch (sharding
+      // invariance), so the choice cannot depend on the batch size alone: the two-warp kernel serves the latency mode
+      // (eager_exit, at most 64 problems).  AGX_ROLLOUT=1w / 2w forces one of them
+      static const int forced = [] {
+        const char* e = std::getenv("AGX_ROLLOUT");
+        return !e ? 0 : (std::strcmp(e, "2w") == 0 ? 2 : (std::strcmp(e, "1w") == 0 ? 1 : 0));
+      }();
+      const bool two_warp = forced ? forced == 2 : (opts->eager_exit && h->B <= 64);
+      if (two_warp)
+        AGX_LAUNCH(h, rollout_try2_kernel, (h->B + 3) / 4, 64, sizeof(double) * FW2_BOARD * 4, st, P, W, h->S);
+      else
+        AGX_LAUNCH(h, rollout_try_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * FW_BOARD * opc_s, st, P, W,
+                   h->S);
+    }
     phase_end(h, st);
     phase_begin(h, 3, st);
     AGX_LAUNCH_NODE_COST(h, cost_ctas, COST_CTA, COST_SMEM, st, P, (const double*)W.xs, (const double*)W.us,

@@ -151,16 +151,8 @@ AGX_DEV void scan_se3_prefix(LaneDyn& d, int j, unsigned omask) {
 }
 
 // ---------------------------------------------------------------- body quantities (after the velocity scan)
-// with_B: also the Sym block of the B matrix (derivatives only)
-AGX_DEV void body_terms(LaneDyn& d, int j, const double* __restrict__ model, const double* grav_acc, bool with_B) {
-  // velocity of this body, dV/dq column, bias acceleration term g = c * qd
-#pragma unroll
-  for (int k = 0; k < 6; ++k) d.v[k] = d.vp[k] + d.s[k];
-  crm6(d.vp, d.J, d.c);
-#pragma unroll
-  for (int k = 0; k < 6; ++k) d.g[k] = d.c[k] * d.qd;
-  (void)grav_acc;
-  // world-frame inertia about the origin
+// world-frame inertia of this lane's body about the origin: Y = (m, m c, Ibar) and the start of the composite scan
+AGX_DEV void body_inertia(LaneDyn& d, int j, const double* __restrict__ model) {
   double mass = 0, com[3] = {0, 0, 0}, I6[6] = {0, 0, 0, 0, 0, 0};
   if (j < NJ) {
     mass = model[MF_MASS * 8 + j];
@@ -199,6 +191,18 @@ AGX_DEV void body_terms(LaneDyn& d, int j, const double* __restrict__ model, con
   d.Y[9] = Iw[5] + mass * (cc - cw[2] * cw[2]);
 #pragma unroll
   for (int k = 0; k < 10; ++k) d.Z[k] = d.Y[k];
+}
+
+// with_B: also the Sym block of the B matrix (derivatives only)
+AGX_DEV void body_terms(LaneDyn& d, int j, const double* __restrict__ model, const double* grav_acc, bool with_B) {
+  // velocity of this body, dV/dq column, bias acceleration term g = c * qd
+#pragma unroll
+  for (int k = 0; k < 6; ++k) d.v[k] = d.vp[k] + d.s[k];
+  crm6(d.vp, d.J, d.c);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) d.g[k] = d.c[k] * d.qd;
+  (void)grav_acc;
+  body_inertia(d, j, model);
   // momentum h = Y v
   inertia_apply(d.Y, d.v, d.Z + 10);
   if (with_B) {

@@ -832,6 +832,156 @@ __global__ void rollout_try_kernel(Problem P, Work W, SolverState S) {
   }
 }
 
+// The same forward pass with TWO warps on every group of four problems.  A node's forward dynamics is one long
+// dependent chain; its two halves — the mass matrix with its factorisation, and the bias forces — only share the
+// kinematics.  Warp 0 (role M) runs kinematics, composite inertias, mass matrix, Cholesky; warp 1 (role B) runs the
+// feedback control, kinematics, velocities, bias forces.  They meet twice per node through shared memory: B hands over
+// the control and the bias torques, M solves, integrates and hands back the next state.  Same arithmetic per quantity
+// as rollout_try_kernel.  CTA = 64 threads = 4 problems; shared memory per problem: FW_BOARD doubles (boards, dx, gain
+// blocks) + 48 (exchange: next state [2][8], control [8], bias [8], spare).
+constexpr int FW2_BOARD = FW_BOARD + 48;
+__global__ void __launch_bounds__(64) rollout_try2_kernel(Problem P, Work W, SolverState S) {
+  AGX_SMEM(smem);
+  const int j = (int)(threadIdx.x & 7u);
+  const int oct = (int)((threadIdx.x >> 3) & 3u);
+  const int role = (int)(threadIdx.x >> 5);  // 0: mass matrix and solve, 1: control and bias forces
+  const int b = (int)blockIdx.x * 4 + oct;
+  const unsigned omask = 0xffffffffu;        // whole-warp collectives: the four octets of a warp run one stream
+  const bool valid = b < P.B && !S.done[b < P.B ? b : 0];
+  {
+    // nothing to do for the whole CTA: leave (decided by every thread from the same four flags: no barrier needed)
+    bool any = false;
+    for (int k = 0; k < 4; ++k) {
+      const int bk = (int)blockIdx.x * 4 + k;
+      any = any || (bk < P.B && !S.done[bk]);
+    }
+    if (!any) return;
+  }
+  const int bb = valid ? b : 0;               // idle octets walk along on problem 0's data and write nothing
+  double* sb = smem + oct * FW2_BOARD;
+  double* sc = sb + BRD_B;
+  double* sdx = sc + BRD_C;   // [14]
+  double* sK = sdx + 16;      // [2][7][14]
+  double* sx = sK + 2 * 98;   // exchange: [0..15] next state (q 0..7, v 8..15), [16..23] control, [24..31] bias torque
+  const int T = P.T, T1 = T + 1;
+  const bool live = j < NJ;
+  const int jj = live ? j : 0;
+  const double* model = model_of(P, bb);
+  const size_t buf = buf_of(S.cur, bb, false), obuf = buf ^ 1;
+  const double* xs = W.xs + (buf * P.B + bb) * (size_t)T1 * NX;
+  const double* us = W.us + (buf * P.B + bb) * (size_t)T * NJ;
+  double* xt = W.xs + (obuf * P.B + bb) * (size_t)T1 * NX;
+  double* ut = W.us + (obuf * P.B + bb) * (size_t)T * NJ;
+  const double* gvb = W.gv + (size_t)bb * T1 * NX;
+  const double* fsb = W.fs + (size_t)bb * T1 * NX;
+  const double* Kb = W.K + (size_t)bb * T * NJ * NX;
+  const double* kb = W.k + (size_t)bb * T * NJ;
+  const bool feasible = S.is_feasible[bb] != 0;
+  const double alpha = S.pending[bb] ? 0.5 : 1.0;
+  const bool contract = !feasible && alpha != 1.0;
+  double xq = live ? W.x0[(size_t)bb * NX + jj] : 0.0, xv = live ? W.x0[(size_t)bb * NX + NJ + jj] : 0.0;
+  bool ok = true;
+  if (role == 1) {
+    // ---------------------------------------------------------------- role B: control, kinematics, bias forces
+    struct NodeIn { double us, kff, xsq, xsv, gq, gv, fq, fv; };
+    auto fetch = [&](int t, NodeIn& n) {
+      const bool run = t < T;
+      n.us = (live && run) ? us[t * NJ + jj] : 0.0;
+      n.kff = (live && run) ? kb[t * NJ + jj] : 0.0;
+      n.xsq = live ? xs[t * NX + jj] : 0.0;
+      n.xsv = live ? xs[t * NX + NJ + jj] : 0.0;
+      const bool gaps = live && !feasible;
+      n.gq = gaps ? gvb[t * NX + jj] : 0.0;
+      n.gv = gaps ? gvb[t * NX + NJ + jj] : 0.0;
+      n.fq = (live && contract) ? fsb[t * NX + jj] : 0.0;
+      n.fv = (live && contract) ? fsb[t * NX + NJ + jj] : 0.0;
+      if (run) {
+        double* dst = sK + (t & 1) * 98;
+        const double* srck = Kb + (size_t)t * NJ * NX;
+        for (int c = j; c < 49; c += 8) AGX_CP_ASYNC16(dst + 2 * c, srck + 2 * c);
+      }
+      AGX_CP_ASYNC_COMMIT();
+    };
+    double dvp = 0.0;
+    NodeIn cur;
+    fetch(0, cur);
+    const double zero6[6] = {0, 0, 0, 0, 0, 0};
+    const double agrav[6] = {-model[MT_GRAV + 0], -model[MT_GRAV + 1], -model[MT_GRAV + 2], 0, 0, 0};
+    for (int t = 0; t <= T; ++t) {
+      NodeIn nxt;
+      AGX_CP_ASYNC_WAIT_ALL();
+      if (t < T) fetch(t + 1, nxt);
+      if (contract) { xq += cur.fq * (alpha - 1.0); xv += cur.fv * (alpha - 1.0); }
+      const double dxq = live ? xq - cur.xsq : 0.0, dxv = live ? xv - cur.xsv : 0.0;
+      if (live && valid) { xt[t * NX + j] = xq; xt[t * NX + NJ + j] = xv; }
+      dvp += cur.gq * dxq + cur.gv * dxv;
+      if (t == T) break;
+      if (live) { sdx[j] = dxq; sdx[NJ + j] = dxv; }
+      __syncwarp();
+      double s = 0.0;
+#pragma unroll
+      for (int m = 0; m < NX; ++m) s += sK[(t & 1) * 98 + jj * NX + m] * sdx[m];
+      LaneDyn d;
+      d.q = xq; d.qd = xv;
+      d.u = live ? cur.us - cur.kff * alpha - s : 0.0;
+      if (live && valid) ut[t * NJ + j] = d.u;
+      node_kinematics(d, j, omask, model);
+      scan_prefix_excl<6>(d.s, d.vp, zero6, j, omask);
+      body_terms(d, j, model, nullptr, false);
+      scan_prefix_excl<6>(d.g, d.a0p, agrav, j, omask);
+      body_force(d);
+      scan_suffix_incl<6>(d.Z + 22, j, omask);
+      sx[16 + j] = d.u;
+      sx[24 + j] = dot6(d.J, d.Z + 22);
+      __syncthreads();   // (1) control and bias torques are on the board
+      __syncthreads();   // (2) role M has written the next state
+      xq = live ? sx[j] : 0.0;
+      xv = live ? sx[8 + j] : 0.0;
+      cur = nxt;
+    }
+    const double dv = feasible ? 0.0 : octet_sum(dvp, omask);
+    if (j == 0 && valid) S.dv[b] = dv;
+  } else {
+    // ---------------------------------------------------------------- role M: mass matrix, factorisation, solve
+    for (int t = 0; t < T; ++t) {
+      if (contract && live) { xq += fsb[t * NX + jj] * (alpha - 1.0); xv += fsb[t * NX + NJ + jj] * (alpha - 1.0); }
+      const double dt = P.dts[t];
+      LaneDyn d;
+      d.q = xq; d.qd = xv; d.u = 0.0;
+      node_kinematics(d, j, omask, model);
+      body_inertia(d, j, model);
+      scan_suffix_incl<10>(d.Z, j, omask);
+      inertia_apply(d.Z, d.J, d.dFda);
+      double* o = sb + j * 18;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { o[k] = d.J[k]; o[6 + k] = d.dFda[k]; }
+      __syncwarp();
+      mass_column(d, j, model, sb);
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) sc[i * 8 + j] = d.Mc[i];
+      __syncwarp();
+      double L[28], rinv[NJ];
+      const bool okn = chol7_registers(sc, L, rinv);
+      ok = ok && okn;
+      __syncthreads();   // (1) wait for the control and the bias torques
+      double rhs[NJ];
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) rhs[i] = sx[16 + i] - sx[24 + i];
+      chol_solve7(L, rinv, rhs);
+      double qdd = 0.0;
+#pragma unroll
+      for (int i = 0; i < NJ; ++i)
+        if (i == j) qdd = rhs[i];
+      xq = d.q + (d.qd * dt + qdd * (dt * dt));
+      xv = d.qd + qdd * dt;
+      sx[j] = xq;
+      sx[8 + j] = xv;
+      __syncthreads();   // (2) the next state is on the board
+    }
+    if (j == 0 && valid) S.roll_ok[b] = ok ? 1 : 0;
+  }
+}
+
 // Acceptance test of the alpha = 1 trial (its costs come from node_cost_kernel) and, only if it is rejected,
 // the remaining step lengths alpha = 2^-ia, ia >= 1, with the costs evaluated in line.
 //

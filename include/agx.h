@@ -97,7 +97,9 @@ typedef struct agx_model {
  * eager_exit != 0 (and not fixed_iters): after every iteration the per-problem completion flags are read back and
  * the call returns as soon as every problem has finished — one small device-to-host copy and a stream
  * synchronisation per iteration instead of queueing the whole budget.  Meant for the latency-bound single-problem MPC
- * tick (B <= 64; ignored for larger batches), where the host waits for the result anyway.
+ * tick (B <= 64; ignored for larger batches), where the host waits for the result anyway.  In this mode the FDDP
+ * forward pass runs on a kernel that puts two warps on each problem group; its results agree with the throughput
+ * kernels' to rounding (1e-15), not bitwise.
  */
 typedef struct agx_fddp_opts {
   double reg_min, reg_max, reg_incfactor, reg_decfactor;

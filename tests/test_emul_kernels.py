@@ -279,6 +279,37 @@ print("octet ok")
     assert r.returncode == 0 and "octet ok" in r.stdout, r.stderr[-2000:]
 
 
+def test_two_warp_rollout_matches(orc, m7):
+    """The latency mode (eager_exit, at most 64 problems) runs the two-warp forward pass (rollout_try2_kernel);
+    AGX_ROLLOUT=2w forces it for every solve at library load, so it runs in a subprocess: it must reproduce the oracle's
+    iterates, line searches included."""
+    import os
+    import subprocess
+    import sys
+
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from agimus_controller_b200 import _abi, panda_table
+from agimus_controller_b200.workloads import goal_reaching_batch
+from emul import emu
+from oracle import orc
+m = panda_table().to_struct()
+w = goal_reaching_batch(6, T=10, rnea=lambda q, v, a: orc.rnea(m, q, v, a), q_spread=0.8, target_p=(0.3, -0.4, 0.7))
+for fixed, iters in ((True, 3), (False, 30)):
+    opts = _abi.default_fddp_opts(fixed_iters=fixed)
+    o = orc.solve(m, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], iters, opts)
+    e = emu.solve(m, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], iters, opts)
+    assert (e["iters"] == o["iters"]).all() and (e["status"] == o["status"]).all()
+    for k in ("xs", "us", "cost"):
+        assert np.abs(e[k] - o[k]).max() / np.abs(o[k]).max() < 1e-8, k
+print("two-warp ok")
+''' % (str(ROOT), str(ROOT / "tests"))
+    env = dict(os.environ, AGX_ROLLOUT="2w")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and "two-warp ok" in r.stdout, r.stderr[-2000:]
+
+
 def test_converged_fddp_on_the_shipped_kernels_lands_on_the_golden_solution(orc, golden):
     """KAT-8 on the product kernels (emulated): zero warm start, run to convergence -> the reference's golden
     states / controls within 3e-3 / 0.15, same iteration count and iterates as the oracle."""

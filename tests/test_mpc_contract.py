@@ -107,8 +107,10 @@ def test_batched_overload_matches_single_problem():
     o1.set_reference_weighted_trajectory(horizon)
     for b in (0, 5):
         o1.solve(x0[b], list(xs[b]), list(us[b]))
-        np.testing.assert_array_equal(np.stack(o1.ocp_results.states), rb["xs"][b].cpu().numpy())
-        np.testing.assert_array_equal(np.stack(o1.ocp_results.ricatti_gains), rb["K"][b].cpu().numpy())
+        # the single-problem form runs in latency mode (eager_exit: two-warp forward pass), which agrees with the
+        # throughput kernels to rounding, not bitwise
+        np.testing.assert_allclose(np.stack(o1.ocp_results.states), rb["xs"][b].cpu().numpy(), rtol=1e-11, atol=1e-12)
+        np.testing.assert_allclose(np.stack(o1.ocp_results.ricatti_gains), rb["K"][b].cpu().numpy(), rtol=1e-8, atol=1e-9)
 
 
 def test_batched_closed_loop_with_device_warm_starts(orc):
