@@ -19,7 +19,6 @@ mc = panda_table().with_capsules(PANDA_CAPSULES, PANDA_COLLISION_PAIRS, alpha=0.
 rc = w["refs"].copy(); rc[..., 60:62] = 10.0
 oc = emu.solve(mc, rc, w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 2, _abi.default_fddp_opts())
 emu.calc_diff(mc, rc, w["dts"], oc["xs"], oc["us"]); emu.cost_terms(mc, rc, w["dts"], oc["xs"], oc["us"])
-emu.solve_sqp(mc, rc, w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 1)
 # a hostile start makes the line search (deferred and in line) run
 wh = goal_reaching_batch(4, T=T, rnea=lambda q, v, a: orc.rnea(m, q, v, a), q_spread=0.8, target_p=(0.3, -0.4, 0.7))
 emu.solve(m, wh["refs"], wh["dts"], wh["x0"], wh["xs_ws"], wh["us_ws"], 3, _abi.default_fddp_opts(fixed_iters=True))
