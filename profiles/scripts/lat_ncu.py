@@ -15,6 +15,7 @@ x = torch.as_tensor(np.concatenate([q[0], v[0]])[None], device=dev)
 xs = torch.cat([torch.as_tensor(q[: T + 1]), torch.as_tensor(v[: T + 1])], dim=1)[None].to(dev).contiguous()
 us = torch.as_tensor(u[:T][None], device=dev).contiguous()
 opts = _abi.default_fddp_opts()
+opts.eager_exit = 1  # latency mode
 for k in range(6):
     p1.set_refs_window(rows_d, k)
     p1.solve(x, xs, us, 10, opts, out=out)
