@@ -165,6 +165,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.agx_rnea.restype = C.c_int
     lib.agx_solve.argtypes = [H, _P, _P, _P, C.c_int, C.POINTER(AgxFddpOpts)] + [_P] * 9
     lib.agx_solve.restype = C.c_int
+    lib.agx_set_capsule.argtypes = [H, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, _P]
+    lib.agx_set_capsule.restype = C.c_int
     lib.agx_solve_sqp.argtypes = [H, _P, _P, _P, C.c_int, C.POINTER(AgxSqpOpts)] + [_P] * 9
     lib.agx_solve_sqp.restype = C.c_int
     lib.agx_sqp_opts_default.argtypes = [C.POINTER(AgxSqpOpts)]
@@ -190,5 +192,5 @@ EXPORTED_SYMBOLS = (
     "agx_ref_size", "agx_fddp_opts_default", "agx_create", "agx_destroy", "agx_last_error", "agx_set_refs",
     "agx_calc", "agx_calc_diff", "agx_rollout", "agx_integrate", "agx_rnea", "agx_solve", "agx_launch_count",
     "agx_set_timing", "agx_get_timing", "agx_probe_fp64", "agx_riccati", "agx_cost_terms", "agx_shift_warmstart", "agx_set_refs_window",
-    "agx_solve_sqp", "agx_sqp_opts_default",
+    "agx_solve_sqp", "agx_sqp_opts_default", "agx_set_capsule",
 )

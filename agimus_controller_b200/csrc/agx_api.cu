@@ -146,6 +146,7 @@ bool flatten_model(const agx_model& m, double* out, std::string& why) {
 struct agx_handle {
   int B = 0, T = 0, device = 0, n_models = 0;
   bool col = false;  // some model carries collision pairs: the COL kernel instantiations run
+  int n_capsules = 0;  // capsules of the models (the smallest count over the models)
   double* d_model = nullptr;
   double* d_refs = nullptr;
   double* d_dts = nullptr;
@@ -308,6 +309,7 @@ int agx_create(const agx_model* models_host, int n_models, const double* dts_hos
       return fail(h, AGX_EUNSUPPORTED, why);
     }
     if (models_host[i].n_pairs > 0) h->col = true;
+    h->n_capsules = i == 0 ? models_host[i].n_capsules : std::min(h->n_capsules, (int)models_host[i].n_capsules);
   }
 #if AGX_GPU
   if (cudaSetDevice(device) != cudaSuccess) {
@@ -366,6 +368,16 @@ int agx_set_refs(agx_handle* h, const double* refs, void* stream) {
   if (!copy_d2d(h->d_refs, refs, sizeof(double) * (size_t)h->B * (h->T + 1) * REF_SIZE, (stream_t)stream))
     return fail(h, AGX_ECUDA, "agx_set_refs: copy failed");
   return AGX_OK;
+}
+
+int agx_set_capsule(agx_handle* h, int capsule, const double* a0, const double* a1, double radius, void* stream) {
+  if (!h || !a0 || !a1) return AGX_EINVAL;
+  if (capsule < 0 || capsule >= h->n_capsules) return fail(h, AGX_EINVAL, "agx_set_capsule: no such capsule");
+  if (!(radius >= 0.0)) return fail(h, AGX_EINVAL, "agx_set_capsule: negative radius");
+  DeviceGuard g(h->device);
+  AGX_LAUNCH(h, set_capsule_kernel, (h->n_models + 127) / 128, 128, 0, (stream_t)stream, h->d_model, h->n_models, capsule,
+             a0[0], a0[1], a0[2], a1[0], a1[1], a1[2], radius);
+  return check_launch(h, "agx_set_capsule");
 }
 
 int agx_set_refs_window(agx_handle* h, const double* stream_refs, int n_streams, int n_points, const int32_t* start,

@@ -1281,6 +1281,15 @@ __global__ void rnea_kernel(const double* __restrict__ model, const double* __re
   if (live) out_tau[(size_t)ent * NJ + j] = dot6(d.J, d.Z + 22);
 }
 
+// update_geometry_placement: new end points / radius of one collision capsule in every model table
+__global__ void set_capsule_kernel(double* __restrict__ model, int n_models, int capsule, double a0x, double a0y,
+                                   double a0z, double a1x, double a1y, double a1z, double radius) {
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (i >= n_models) return;
+  double* c = model + (size_t)i * MODEL_SIZE + MT_CAP + 8 * capsule;
+  c[0] = a0x; c[1] = a0y; c[2] = a0z; c[3] = a1x; c[4] = a1y; c[5] = a1z; c[6] = radius;
+}
+
 // number of problems still running (early-exit check of long iteration budgets)
 __global__ void count_live_kernel(int B, const int32_t* __restrict__ done, int32_t* __restrict__ out) {
   const int b = (int)(blockIdx.x * blockDim.x + threadIdx.x);

@@ -258,6 +258,23 @@ class OCPBatchedFDDP(OCPBase):
             self._debug_data.nb_qp_iter = 0
         self._ocp_results = ocp_results
 
+    def update_geometry_placement(self, geometry_name: str, placement) -> None:
+        """Updates placement of the obstacles (``OCPBaseCroco.update_geometry_placement``, ``ocp_base_croco.py:110-131``;
+        called by the controller for every obstacle pose it receives, ``agimus_controller.py:406``).  ``placement`` is
+        the pose of the capsule in the frame of its parent (the world for an obstacle): the capsule keeps its length
+        and radius, its axis is the placement's z axis, its centre the placement's translation."""
+        names = list(self._table.capsules)
+        if geometry_name not in names:
+            raise RuntimeError(f"Unknown geometry name '{geometry_name}' in collision model!")
+        _, a0, a1, radius = self._table.capsules[geometry_name]
+        half = 0.5 * float(np.linalg.norm(np.asarray(a1) - np.asarray(a0)))
+        R = np.asarray(placement.rotation, dtype=np.float64)
+        p = np.asarray(placement.translation, dtype=np.float64)
+        n0, n1 = p - half * R[:, 2], p + half * R[:, 2]
+        self._problem.set_capsule(names.index(geometry_name), n0, n1, radius)
+        par = self._table.capsules[geometry_name][0]
+        self._table.capsules[geometry_name] = (par, n0, n1, radius)
+
     def integrate(self, state, control):
         if isinstance(state, torch.Tensor):
             return self._problem.integrate(state, control, self.dt)

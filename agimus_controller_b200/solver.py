@@ -120,6 +120,13 @@ class BatchedShootingProblem:
         self._check(lib().agx_set_refs(self._h, _ptr(r), self._stream()))
         self._refs_set = True
 
+    def set_capsule(self, capsule: int, a0, a1, radius: float) -> None:
+        """New end points (parent-joint frame, or world frame for an obstacle) and radius of one collision capsule, for
+        every model of the batch (``OCPBaseCroco.update_geometry_placement``, ``ocp_base_croco.py:110-131``)."""
+        a0 = (C.c_double * 3)(*[float(v) for v in a0])
+        a1 = (C.c_double * 3)(*[float(v) for v in a1])
+        self._check(lib().agx_set_capsule(self._h, int(capsule), a0, a1, float(radius), self._stream()))
+
     def set_refs_window(self, stream_refs: torch.Tensor, start) -> None:
         """Select the horizon window out of a device-resident reference stream ``[n_points, ref_size]`` (shared) or
         ``[B, n_points, ref_size]``; ``start`` is an int (all problems) or an int32 device tensor ``[B]``."""

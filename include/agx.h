@@ -148,6 +148,12 @@ const char* agx_last_error(const agx_handle* h);
  * refs: device [B][T+1][ref_size]; copied into the handle (stream ordered). */
 int agx_set_refs(agx_handle* h, const double* refs, void* stream);
 
+/* OCPBaseCroco.update_geometry_placement (ocp_base_croco.py:110-131; the controller calls it for every obstacle pose it
+ * receives, agimus_controller_ros/agimus_controller_ros/agimus_controller.py:406): new end points (in the frame of the
+ * capsule's parent joint, or of the world for an obstacle) and radius of collision capsule `capsule` of every model of
+ * the handle.  a0, a1: HOST pointers to 3 doubles. */
+int agx_set_capsule(agx_handle* h, int capsule, const double* a0, const double* a1, double radius, void* stream);
+
 /* Device-side reference stream: instead of rebuilding the [B][T+1][ref_size] table on the host every tick, keep the
  * whole weighted reference trajectory on the device — stream_refs [n_streams][n_points][ref_size], n_streams = 1
  * (shared by the batch) or B — and select the horizon window: node t of problem b reads point

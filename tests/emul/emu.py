@@ -55,6 +55,11 @@ class Handle:
         if rc != 0:
             raise RuntimeError(f"agx error {rc}: {lib().agx_last_error(self.h).decode()}")
 
+    def set_capsule(self, capsule, a0, a1, radius):
+        a0 = (C.c_double * 3)(*a0)
+        a1 = (C.c_double * 3)(*a1)
+        self.check(lib().agx_set_capsule(self.h, int(capsule), a0, a1, float(radius), None))
+
     def set_refs(self, refs):
         self.refs = _c(refs)
         self.check(lib().agx_set_refs(self.h, _p(self.refs), None))
@@ -75,6 +80,17 @@ def calc(models, refs, dts, xs, us):
     xs, us = _c(xs), _c(us)
     B, T1, nx = xs.shape
     h = _handle(models, refs, dts, B, T1 - 1)
+    cost, xnext = np.zeros((B, T1)), np.zeros((B, T1, nx))
+    h.check(lib().agx_calc(h.h, _p(xs), _p(us), _p(cost), _p(xnext), None))
+    return cost, xnext
+
+
+def calc_with_moved_capsule(models, refs, dts, xs, us, capsule, a0, a1, radius):
+    """`calc` after `agx_set_capsule` on a fresh handle."""
+    xs, us = _c(xs), _c(us)
+    B, T1, nx = xs.shape
+    h = _handle(models, refs, dts, B, T1 - 1)
+    h.set_capsule(capsule, a0, a1, radius)
     cost, xnext = np.zeros((B, T1)), np.zeros((B, T1, nx))
     h.check(lib().agx_calc(h.h, _p(xs), _p(us), _p(cost), _p(xnext), None))
     return cost, xnext

@@ -546,3 +546,22 @@ def test_deferred_line_search_follows_the_sequential_search(orc, m7, iters):
     e2 = emu.solve(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], iters, two)
     np.testing.assert_array_equal(e2["iters"], o2["iters"])
     assert rel(e2["xs"], o2["xs"]) < 1e-8
+
+
+def test_moving_an_obstacle_capsule(orc, col_case):
+    """update_geometry_placement (ocp_base_croco.py:110-131): new end points of a capsule in the device tables give the
+    costs of a model built with the capsule there; an unknown capsule is refused."""
+    import copy
+    from agimus_controller_b200.robot_model import PANDA_CAPSULES, PANDA_COLLISION_PAIRS
+
+    c = col_case
+    a0, a1, radius = (0.30, -0.25, 0.35), (0.42, 0.15, 0.28), 0.04
+    caps = dict(PANDA_CAPSULES)
+    caps["obstacle_capsule"] = (None, a0, a1, radius)
+    moved = panda_table().with_capsules(caps, PANDA_COLLISION_PAIRS, alpha=0.02).to_struct()
+    expect, _ = orc.calc(moved, c["refs"], c["dts"], c["xs"], c["us"])
+    before, _ = orc.calc(c["m"], c["refs"], c["dts"], c["xs"], c["us"])
+    got, _ = emu.calc_with_moved_capsule(c["m"], c["refs"], c["dts"], c["xs"], c["us"], 2, a0, a1, radius)
+    assert rel(got, expect) < 1e-12 and rel(before, expect) > 1e-4
+    with pytest.raises(RuntimeError, match="no such capsule"):
+        emu.calc_with_moved_capsule(c["m"], c["refs"], c["dts"], c["xs"], c["us"], 3, a0, a1, radius)

@@ -241,3 +241,53 @@ def test_check_results(golden):
         np.testing.assert_array_almost_equal(term, ocp.ocp_results.feed_forward_terms[it],
                                              err_msg="Feed forward term are not equal")
     assert ocp.debug_data.problem_solved and ocp.debug_data.nb_iter == 33 and ocp.debug_data.kkt_norm <= 1e-3
+
+
+def test_collision_ocp_and_update_geometry_placement(orc):
+    """The collision-avoidance cost stack (ResidualDistanceCollision + QuadExp, tests/golden/ocp_collision_avoidance.yaml)
+    through the OCP class, and `update_geometry_placement` (ocp_base_croco.py:110-131; the controller calls it for every
+    obstacle pose, agimus_controller.py:406): moving the obstacle changes the device tables exactly as rebuilding the
+    model with the obstacle there would."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import yaml
+
+    from agimus_controller_b200 import _abi
+    from agimus_controller_b200.ocp_batched import (OCPBatchedFDDP, build_reference_rows, flatten_cost_stack,
+                                                    resolve_collision_pairs)
+    from agimus_controller_b200.robot_model import PANDA_CAPSULES
+
+    T, nv = 12, 7
+    yml = pathlib.Path(__file__).parent / "golden" / "ocp_collision_avoidance.yaml"
+    params = OCPParamsBaseCroco(dt=0.01, solver_iters=4, dt_factor_n_seq=DTFactorsNSeq([1], [T]), horizon_size=T)
+    table = panda_table().with_capsules(PANDA_CAPSULES, [])
+    ocp = OCPBatchedFDDP(table, params, str(yml), batch_size=1)
+    horizon = [_wpoint(i, PANDA_Q_NOMINAL) for i in range(T + 1)]
+    for pt in horizon:
+        pt.weights.w_collision_avoidance = 25.0
+    ocp.set_reference_weighted_trajectory(horizon)
+    x0 = np.concatenate([PANDA_Q_NOMINAL + 0.1, np.zeros(nv)])
+    u_grav = ocp.problem.rnea(x0[:nv], np.zeros(nv), np.zeros(nv))[0].cpu().numpy()
+    with pytest.raises(RuntimeError, match="Unknown geometry name 'no_such_obstacle'"):
+        ocp.update_geometry_placement("no_such_obstacle", SE3(np.eye(3), np.zeros(3)))
+    # the obstacle moves next to the hand: capsule axis = the placement's z axis, same length and radius
+    Rz = np.array([[1.0, 0.0, 0.0], [0.0, 0.0, -1.0], [0.0, 1.0, 0.0]])     # z axis -> world y
+    centre = np.array([0.40, 0.0, 0.45])
+    ocp.update_geometry_placement("obstacle_capsule", SE3(Rz, centre))
+    ocp.solve(x0, [x0] * (T + 1), [u_grav] * T)
+    res = ocp.ocp_results
+    # oracle on a model rebuilt with the obstacle at its new place
+    data = yaml.safe_load(yml.read_text())
+    run, term = flatten_cost_stack(data["running_model"], False), flatten_cost_stack(data["terminal_model"], True)
+    caps = dict(PANDA_CAPSULES)
+    half = 0.2
+    caps["obstacle_capsule"] = (None, centre - half * Rz[:, 2], centre + half * Rz[:, 2], 0.05)
+    moved = resolve_collision_pairs(panda_table().with_capsules(caps, []), run, term)
+    rows = build_reference_rows(moved, run, term, horizon)
+    o = orc.solve(moved.to_struct(), rows[None], np.asarray(params.timesteps), x0[None], np.repeat(x0[None, None], T + 1, 1),
+                  np.repeat(u_grav[None, None], T, 1), 4, _abi.default_fddp_opts())
+    assert np.abs(np.stack(res.states) - o["xs"][0]).max() / np.abs(o["xs"]).max() < 1e-6
+    assert np.abs(np.stack(res.feed_forward_terms) - o["us"][0]).max() / np.abs(o["us"]).max() < 1e-6
+    # and the obstacle matters: the distance read-out of the per-cost view is small enough for the cost to act
+    terms = ocp.problem.cost_terms(np.stack(res.states)[None], np.stack(res.feed_forward_terms)[None])
+    assert float(terms["collision_distance"][0, :, 0].min()) < 0.3 and float(terms["collision"][0, :, 0].max()) > 1e-6
