@@ -707,14 +707,15 @@ int agx_solve_sqp(agx_handle* h, const double* x0, const double* xs_ws, const do
   Q.n_alphas = opts->n_alphas;
   agx_fddp_opts od;
   agx_fddp_opts_default(&od);
-  // the sweeps run with a fixed diagonal: a failed factorisation ends the problem (status REGMAX), no retry
+  Q.reg_max = od.reg_max; Q.reg_factor = od.reg_incfactor; Q.th_stepdec = od.th_stepdec; Q.th_stepinc = od.th_stepinc;
+  // a failed factorisation raises the problem's regularisation inside the sweep and retries, up to reg_max
   FddpOpts O;
-  O.reg_min = Q.reg; O.reg_max = Q.reg; O.reg_init = Q.reg; O.reg_incfactor = od.reg_incfactor;
+  O.reg_min = Q.reg; O.reg_max = Q.reg_max; O.reg_init = Q.reg; O.reg_incfactor = od.reg_incfactor;
   O.reg_decfactor = od.reg_decfactor; O.th_grad = od.th_grad; O.th_stepdec = od.th_stepdec; O.th_stepinc = od.th_stepinc;
   O.th_acceptstep = od.th_acceptstep; O.th_acceptnegstep = od.th_acceptnegstep; O.th_stop = od.th_stop;
   O.fixed_iters = 0; O.n_alphas = Q.n_alphas; O.max_iter = max_iter; O.defer = 0;
   FddpOpts Of = O;
-  Of.reg_min = Of.reg_max = Of.reg_init = Q.sigma + Q.reg;
+  Of.reg_min = Of.reg_max = 0.0;  // the last sweep (sigma + the problem's regularisation) is not retried
   const size_t nB = (size_t)h->B, T = (size_t)h->T, T1 = T + 1;
   if (!out_K && !h->d_K_internal) {
     if (!dev_alloc((void**)&h->d_K_internal, sizeof(double) * nB * T * NJ * NX))

@@ -14,6 +14,10 @@ namespace agx {
 struct SqpOpts {
   double sigma, reg, mu, tol;
   int n_alphas;
+  // SolverDDP's regularisation schedule, inherited by the mim_solvers solvers: floor `reg`, x reg_factor after a failed
+  // factorisation or a step length <= th_stepinc (which includes a failed line search), / reg_factor after a step
+  // length > th_stepdec; reaching reg_max ends the problem
+  double reg_max, reg_factor, th_stepdec, th_stepinc;
 };
 
 AGX_DEV double octet_max(double x, unsigned omask) {
@@ -237,20 +241,28 @@ __global__ void sqp_accept_kernel(Problem P, Work W, SolverState S, SqpOpts Q, i
   double c = 0.0, g = 0.0;
   for (int t = 0; t < T1; ++t) { c += r[t * NX]; g += r[t * NX + 1]; }
   const double mt = c + Q.mu * g;
+  const int n_now = S.roll_ok[b];
+  bool finished = false;  // the line search of this iteration is over (step taken, or every step length refused)
   if (mt < S.dg[b]) {
     S.cur[b] ^= 1;
-    S.pending[b] = 0;
     S.iters[b] += 1;
+    finished = true;
+  } else if (n_now + 1 >= Q.n_alphas) {
+    finished = true;
   } else {
-    const int n = S.roll_ok[b] + 1;
-    S.roll_ok[b] = n;
-    if (n >= Q.n_alphas) {
-      S.pending[b] = 0;
-      S.status[b] = 4;
-      S.done[b] = 1;
-    } else {
-      atomicAdd(pend + 1, 1);
+    S.roll_ok[b] = n_now + 1;
+    atomicAdd(pend + 1, 1);
+  }
+  if (finished) {
+    S.pending[b] = 0;
+    const double steplength = ldexp(1.0, -n_now);
+    double reg = S.xreg[b];
+    if (steplength > Q.th_stepdec) reg = fmax(reg / Q.reg_factor, Q.reg);
+    if (steplength <= Q.th_stepinc) {
+      reg = fmin(reg * Q.reg_factor, Q.reg_max);
+      if (reg == Q.reg_max) { S.status[b] = 2; S.done[b] = 1; }
     }
+    S.xreg[b] = reg;
   }
 }
 
@@ -258,7 +270,7 @@ __global__ void sqp_accept_kernel(Problem P, Work W, SolverState S, SqpOpts Q, i
 __global__ void sqp_final_prepare_kernel(int B, SolverState S, SqpOpts Q) {
   const int b = (int)(blockIdx.x * blockDim.x + threadIdx.x);
   if (b >= B) return;
-  S.xreg[b] = Q.sigma + Q.reg;
+  S.xreg[b] = Q.sigma + S.xreg[b];
   S.is_feasible[b] = 0;
   if (S.status[b] != 3) S.done[b] = 0;
 }

@@ -51,7 +51,7 @@ extern "C" {
 #define AGX_STATUS_MAXITER 1   /* iteration budget used */
 #define AGX_STATUS_REGMAX 2    /* regularisation hit reg_max */
 #define AGX_STATUS_NAN 3       /* non-finite value met */
-#define AGX_STATUS_LINESEARCH 4 /* SQP mode: no step length decreased the merit function */
+#define AGX_STATUS_LINESEARCH 4 /* reserved (a refused line search raises the regularisation and the solve goes on) */
 
 /*
  * Kinematic-tree table: what factory/robot_model.py:88-351 (RobotModels.robot_model, .armature)
@@ -221,7 +221,9 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
  * LINEAR rollout du = -k - K dx, dx' = Fx dx + Fu du + fs'; KKT = max(|Lx + Fx^T l' - l|_inf, |Lu + Fu^T l'|_inf,
  * |fs|_inf) with the QP multipliers l; stop when KKT <= termination_tolerance (the iterate is returned as is);
  * otherwise the first step length 2^-n with merit(xs + a dx, us + a du) < merit(xs, us),
- * merit = cost + mu * |gaps|_1.  The gains returned are those of the solver's last backward pass: a sweep at the
+ * merit = cost + mu * |gaps|_1.  The regularisation follows SolverDDP's schedule, which the mim_solvers solvers
+ * inherit: x10 after a failed factorisation or a step length <= 0.01 (a refused line search included), /10 after a
+ * step length > 0.5, floor `reg`, AGX_STATUS_REGMAX at 1e9.  The gains returned are those of the solver's last backward pass: a sweep at the
  * final iterate with sigma + reg on Quu, Qxx, Vxx_T.  (With no constraint the ADMM/proximal inner loop sits at its
  * fixed point, so it is not iterated.)  Replaying the reference's golden test this way (zero warm start,
  * tests/test_ocp_croco_base.py:140-158) stops at the same criterion 6e-5 from the golden states and reproduces the

@@ -1452,30 +1452,50 @@ struct Sqp : Fddp {
     int status = AGX_STATUS_MAXITER, iters = 0;
     stop = 0;
     bool have_diff = false;
+    // the regularisation follows SolverDDP's schedule, which the mim_solvers solvers inherit: floor o.reg, x10 after a
+    // failed factorisation or a step length <= th_stepinc (0.01, which includes a failed line search), /10 after a step
+    // length > th_stepdec (0.5); reaching reg_max = 1e9 ends the problem
+    const double reg_min = o.reg, reg_max = 1e9, reg_factor = 10.0, th_stepdec = 0.5, th_stepinc = 0.01;
+    double reg = o.reg;
     for (int it = 0; it < max_iter; ++it) {
       if (!calc_diff()) { status = AGX_STATUS_NAN; break; }
       have_diff = true;
-      if (!direction(o.reg)) { status = AGX_STATUS_REGMAX; break; }
+      bool dir_ok = direction(reg);
+      while (!dir_ok) {
+        reg = std::fmin(reg * reg_factor, reg_max);
+        if (reg == reg_max) break;
+        dir_ok = direction(reg);
+      }
+      if (!dir_ok) { status = AGX_STATUS_REGMAX; break; }
       stop = kkt;
+      if (!(kkt == kkt)) { status = AGX_STATUS_NAN; break; }
       if (kkt <= o.termination_tolerance) { status = AGX_STATUS_CONVERGED; break; }
       merit = cost + o.mu * gap_l1;
       bool accepted = false;
+      double steplength = 1.0;
       for (int n = 0; n < o.n_alphas; ++n) {
         double mt;
-        if (!try_step(std::ldexp(1.0, -n), o.mu, &mt)) continue;
+        steplength = std::ldexp(1.0, -n);
+        if (!try_step(steplength, o.mu, &mt)) continue;
         if (mt < merit) { accepted = true; break; }
       }
-      if (!accepted) { status = AGX_STATUS_LINESEARCH; break; }
-      xs.swap(xs_try); us.swap(us_try);
-      have_diff = false;
-      ++iters;
+      if (accepted) {
+        xs.swap(xs_try); us.swap(us_try);
+        have_diff = false;
+        ++iters;
+      }
+      if (steplength > th_stepdec) reg = std::fmax(reg / reg_factor, reg_min);
+      if (steplength <= th_stepinc) {
+        reg = std::fmin(reg * reg_factor, reg_max);
+        if (reg == reg_max) { status = AGX_STATUS_REGMAX; break; }
+      }
     }
     // the gains the solver holds: its last backward pass carries sigma + reg on Quu, Qxx, Vxx_T
     if (status != AGX_STATUS_NAN) {
       if (!have_diff && !calc_diff()) status = AGX_STATUS_NAN;
       else {
-        xreg = ureg = o.sigma + o.reg;
-        if (!backward_pass() && status != AGX_STATUS_LINESEARCH) status = AGX_STATUS_REGMAX;
+        xreg = ureg = o.sigma + reg;
+        if (!backward_pass() && status != AGX_STATUS_REGMAX) status = AGX_STATUS_REGMAX;
       }
     }
     *iters_out = iters;
