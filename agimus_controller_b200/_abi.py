@@ -24,6 +24,7 @@ AGX_STATUS_CONVERGED = 0
 AGX_STATUS_MAXITER = 1
 AGX_STATUS_REGMAX = 2
 AGX_STATUS_NAN = 3
+AGX_STATUS_TIMEOUT = 5
 
 _D = C.c_double
 _I = C.c_int32
@@ -78,6 +79,7 @@ class AgxFddpOpts(C.Structure):
         ("n_alphas", _I),
         ("eager_exit", _I),
         ("reserved", _I),
+        ("max_solve_time", _D),
     ]
 
 
@@ -91,6 +93,7 @@ class AgxSqpOpts(C.Structure):
         ("termination_tolerance", _D),
         ("n_alphas", _I),
         ("eager_exit", _I),
+        ("max_solve_time", _D),
     ]
 
 
@@ -98,7 +101,7 @@ def default_sqp_opts(termination_tolerance: float = 1e-3) -> AgxSqpOpts:
     """``mim_solvers.SolverCSQP`` as the reference configures it (ocp_base_croco.py:64-75, ocp_param_base.py:53-61):
     proximal sigma 1e-6, regularisation floor 1e-9, merit weight 10, KKT tolerance 1e-3, step lengths 2^-n, n < 10."""
     return AgxSqpOpts(sigma=1e-6, reg=1e-9, mu=10.0, termination_tolerance=termination_tolerance, n_alphas=10,
-                      eager_exit=0)
+                      eager_exit=0, max_solve_time=0.0)
 
 
 def ref_size(nv: int) -> int:
@@ -124,6 +127,7 @@ def default_fddp_opts(fixed_iters: bool = False) -> AgxFddpOpts:
         n_alphas=10,
         eager_exit=0,
         reserved=0,
+        max_solve_time=0.0,
     )
 
 

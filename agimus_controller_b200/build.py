@@ -9,7 +9,7 @@ HERE = pathlib.Path(__file__).resolve().parent
 SRC = HERE / "csrc"
 LIB = HERE / "libagx.so"
 SOURCES = ["agx_api.cu"]
-HEADERS = ["agx_kernels.cuh", "agx_riccati_mma.cuh", "agx_sqp.cuh", "agx_node.inl", "agx_dynamics.inl", "agx_octet_base.h"]
+HEADERS = ["agx_kernels.cuh", "agx_tree.cuh", "agx_riccati_mma.cuh", "agx_sqp.cuh", "agx_node.inl", "agx_dynamics.inl", "agx_octet_base.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC", "-diag-suppress", "550",

@@ -141,10 +141,129 @@ bool flatten_model(const agx_model& m, double* out, std::string& why) {
   return true;
 }
 
+
+// ---- general-tree path (agx_tree.cuh) ------------------------------------------------------------------
+// sizes the tree kernels are instantiated for
+#define AGX_TREE_NVS(X) X(6) X(7) X(9)
+bool tree_nv_supported(int nv) {
+  switch (nv) {
+#define AGX_X(N) case N: return true;
+    AGX_TREE_NVS(AGX_X)
+#undef AGX_X
+    default: return false;
+  }
+}
+struct TreeSizes { int rec, crec, board, bw; };
+TreeSizes tree_sizes(int nv) {
+  switch (nv) {
+#define AGX_X(N) case N: return TreeSizes{tree::TL<N>::REC, tree::TL<N>::CREC, tree::TL<N>::BOARD, tree::BWL<N>::SIZE};
+    AGX_TREE_NVS(AGX_X)
+#undef AGX_X
+    default: return TreeSizes{0, 0, 0, 0};
+  }
+}
+#define AGX_TREE_LAUNCH(h, KERNEL, grid, block, smem, stream, ...)                                  \
+  do {                                                                                              \
+    switch ((h)->nv) {                                                                              \
+      AGX_TREE_CASES(h, KERNEL, grid, block, smem, stream, __VA_ARGS__)                             \
+      default: break;                                                                               \
+    }                                                                                               \
+  } while (0)
+#define AGX_TREE_CASE(N, h, KERNEL, grid, block, smem, stream, ...) \
+  case N: AGX_LAUNCH(h, tree::KERNEL<N>, grid, block, smem, stream, __VA_ARGS__); break;
+#define AGX_TREE_CASES(h, KERNEL, grid, block, smem, stream, ...)        \
+  AGX_TREE_CASE(6, h, KERNEL, grid, block, smem, stream, __VA_ARGS__)    \
+  AGX_TREE_CASE(7, h, KERNEL, grid, block, smem, stream, __VA_ARGS__)    \
+  AGX_TREE_CASE(9, h, KERNEL, grid, block, smem, stream, __VA_ARGS__)
+
+// is this the shape the tuned chain kernels cover (7 revolute-z joints in series)?
+bool is_chain7(const agx_model& m) {
+  if (m.nv != NJ) return false;
+  for (int i = 0; i < NJ; ++i) {
+    if (m.parent[i] != i - 1) return false;
+    if (m.jtype[i] != AGX_JOINT_REVOLUTE || m.axis[i][0] != 0.0 || m.axis[i][1] != 0.0 || m.axis[i][2] != 1.0) return false;
+  }
+  return true;
+}
+
+// agx_model -> device table of the general-tree kernels (agx_tree.cuh layout)
+bool flatten_tree_model(const agx_model& m, double* out, std::string& why) {
+  using namespace tree;
+  const int nv = m.nv;
+  if (nv < 1 || nv > AGX_MAX_NV || !tree_nv_supported(nv)) {
+    why = "the general-tree kernels are instantiated for nv = 6, 7, 9 (AGX_TREE_NVS in agx_api.cu)";
+    return false;
+  }
+  for (int i = 0; i < nv; ++i) {
+    if (m.parent[i] < -1 || m.parent[i] >= i) { why = "parent[i] must be -1 or a joint before i"; return false; }
+    if (m.jtype[i] != AGX_JOINT_REVOLUTE && m.jtype[i] != AGX_JOINT_PRISMATIC) { why = "unknown joint type"; return false; }
+    const double n2 = m.axis[i][0] * m.axis[i][0] + m.axis[i][1] * m.axis[i][1] + m.axis[i][2] * m.axis[i][2];
+    if (!(std::fabs(n2 - 1.0) < 1e-9)) { why = "joint axes must be unit vectors"; return false; }
+  }
+  if (m.frame_parent < 0 || m.frame_parent >= nv) { why = "frame_parent out of range"; return false; }
+  for (int k = 0; k < TMODEL_SIZE; ++k) out[k] = 0.0;
+  unsigned anc[AGX_MAX_NV], sub[AGX_MAX_NV];
+  for (int i = 0; i < nv; ++i) {
+    anc[i] = (1u << i) | (m.parent[i] >= 0 ? anc[m.parent[i]] : 0u);
+    sub[i] = 0u;
+  }
+  for (int i = 0; i < nv; ++i)
+    for (int a = 0; a < nv; ++a)
+      if ((anc[i] >> a) & 1u) sub[a] |= 1u << i;
+  for (int j = 0; j < GW; ++j) {
+    out[(TF_RP + 0) * GW + j] = out[(TF_RP + 4) * GW + j] = out[(TF_RP + 8) * GW + j] = 1.0;
+    out[(TF_AXIS + 2) * GW + j] = 1.0;
+    out[TF_PARENT * GW + j] = -1.0;
+  }
+  for (int j = 0; j < nv; ++j) {
+    for (int k = 0; k < 9; ++k) out[(TF_RP + k) * GW + j] = m.placement_R[j][k];
+    for (int k = 0; k < 3; ++k) out[(TF_PP + k) * GW + j] = m.placement_p[j][k];
+    out[TF_MASS * GW + j] = m.mass[j];
+    for (int k = 0; k < 3; ++k) out[(TF_COM + k) * GW + j] = m.com[j][k];
+    for (int k = 0; k < 6; ++k) out[(TF_INERTIA + k) * GW + j] = m.inertia[j][k];
+    out[TF_ARM * GW + j] = m.armature[j];
+    for (int k = 0; k < 3; ++k) out[(TF_AXIS + k) * GW + j] = m.axis[j][k];
+    out[TF_JTYPE * GW + j] = (double)m.jtype[j];
+    out[TF_PARENT * GW + j] = (double)m.parent[j];
+    out[TF_SUB * GW + j] = (double)sub[j];
+    out[TF_ANC * GW + j] = (double)anc[j];
+  }
+  for (int k = 0; k < 3; ++k) out[TT_GRAV + k] = m.gravity[k];
+  for (int k = 0; k < 9; ++k) out[TT_FR + k] = m.frame_R[k];
+  for (int k = 0; k < 3; ++k) out[TT_FP + k] = m.frame_p[k];
+  out[TT_FP + 3] = (double)m.frame_parent;
+  if (m.n_capsules < 0 || m.n_capsules > AGX_MAX_CAPSULES || m.n_pairs < 0 || m.n_pairs > AGX_MAX_COLLISION_PAIRS) {
+    why = "capsule / collision pair count out of range";
+    return false;
+  }
+  for (int c = 0; c < MAX_CAPS; ++c) out[TT_CAP + 8 * c + 7] = -1.0;
+  for (int c = 0; c < m.n_capsules; ++c) {
+    if (m.cap_parent[c] < -1 || m.cap_parent[c] >= nv) { why = "capsule parent joint out of range"; return false; }
+    for (int k = 0; k < 3; ++k) { out[TT_CAP + 8 * c + k] = m.cap_a0[c][k]; out[TT_CAP + 8 * c + 3 + k] = m.cap_a1[c][k]; }
+    out[TT_CAP + 8 * c + 6] = m.cap_radius[c];
+    out[TT_CAP + 8 * c + 7] = (double)m.cap_parent[c];
+  }
+  out[TT_COL] = (double)m.n_pairs;
+  out[TT_COL + 1] = m.n_pairs > 0 ? m.col_alpha : 1.0;
+  if (m.n_pairs > 0 && !(m.col_alpha > 0.0)) { why = "col_alpha must be positive"; return false; }
+  for (int k = 0; k < m.n_pairs; ++k) {
+    if (m.pair_a[k] < 0 || m.pair_a[k] >= m.n_capsules || m.pair_b[k] < 0 || m.pair_b[k] >= m.n_capsules) {
+      why = "collision pair refers to a capsule that does not exist";
+      return false;
+    }
+    out[TT_COL + 2 + 2 * k] = (double)m.pair_a[k];
+    out[TT_COL + 3 + 2 * k] = (double)m.pair_b[k];
+  }
+  return true;
+}
+
 }  // namespace
 
 struct agx_handle {
   int B = 0, T = 0, device = 0, n_models = 0;
+  int nv = NJ, nx = NX, ref_size = REF_SIZE, rec_size = REC_SIZE, crec_size = CREC_SIZE, model_size = MODEL_SIZE;
+  bool tree = false;  // general-tree kernels (agx_tree.cuh) instead of the 7-joint chain kernels
+  int tree_board = 0, tree_bw = 0;  // shared-memory doubles per group / per sweep warp of the tree kernels
   bool col = false;  // some model carries collision pairs: the COL kernel instantiations run
   int n_capsules = 0;  // capsules of the models (the smallest count over the models)
   double* d_model = nullptr;
@@ -256,6 +375,131 @@ void launch_backward(agx_handle* h, const agx::Problem& P, const agx::Work& W, c
   }
 }
 
+
+// ---- entry points of the general-tree path ---------------------------------------------------------------
+const int TREE_NODE_CTA = 64;  // 4 groups of 16 lanes
+const int TREE_SEQ_CTA = 32;   // 2 groups
+
+int tree_calc(agx_handle* h, const double* xs, const double* us, double* out_cost, double* out_xnext, stream_t st) {
+  const long long ents = (long long)h->B * (h->T + 1);
+  const int gpc = TREE_NODE_CTA / tree::GW;
+  AGX_TREE_LAUNCH(h, tree_calc_kernel, (ents + gpc - 1) / gpc, TREE_NODE_CTA, sizeof(double) * h->tree_board * gpc, st,
+                  problem_of(h), xs, us, out_cost, out_xnext);
+  return check_launch(h, "agx_calc");
+}
+
+void tree_launch_calc_diff(agx_handle* h, const agx::Problem& P, const double* xs, const double* us, const int32_t* cur,
+                           const int32_t* recalc, const int32_t* done, stream_t st) {
+  const long long ents = (long long)h->B * (h->T + 1);
+  const int gpc = TREE_NODE_CTA / tree::GW;
+  AGX_TREE_LAUNCH(h, tree_calc_diff_kernel, (ents + gpc - 1) / gpc, TREE_NODE_CTA, sizeof(double) * h->tree_board * gpc,
+                  st, P, xs, us, cur, recalc, done, h->W.rec, h->W.crec);
+}
+
+int tree_calc_diff(agx_handle* h, const double* xs, const double* us, double* out_cost, double* out_xnext, double* Fx,
+                   double* Fu, double* Lx, double* Lu, double* Lxx, double* Lxu, double* Luu, stream_t st) {
+  tree_launch_calc_diff(h, problem_of(h), xs, us, nullptr, nullptr, nullptr, st);
+  const long long rows = (long long)h->B * (h->T + 1) * h->nx;
+  AGX_TREE_LAUNCH(h, tree_expand_kernel, (rows + 127) / 128, 128, 0, st, problem_of(h), (const double*)h->W.rec,
+                  (const double*)h->W.crec, out_cost, out_xnext, Fx, Fu, Lx, Lu, Lxx, Lxu, Luu);
+  return check_launch(h, "agx_calc_diff");
+}
+
+int tree_cost_terms(agx_handle* h, const double* xs, const double* us, double* out_terms, stream_t st) {
+  const long long ents = (long long)h->B * (h->T + 1);
+  const int gpc = TREE_NODE_CTA / tree::GW;
+  AGX_TREE_LAUNCH(h, tree_cost_terms_kernel, (ents + gpc - 1) / gpc, TREE_NODE_CTA, sizeof(double) * h->tree_board * gpc,
+                  st, problem_of(h), xs, us, out_terms);
+  return check_launch(h, "agx_cost_terms");
+}
+
+int tree_shift(agx_handle* h, const double* xs, const double* us, double* out_xs, double* out_us, stream_t st) {
+  const long long ents = (long long)h->B * (h->T + 1);
+  const int gpc = TREE_NODE_CTA / tree::GW;
+  AGX_TREE_LAUNCH(h, tree_shift_kernel, (ents + gpc - 1) / gpc, TREE_NODE_CTA, sizeof(double) * h->tree_board * gpc, st,
+                  problem_of(h), xs, us, out_xs, out_us);
+  return check_launch(h, "agx_shift_warmstart");
+}
+
+int tree_rollout(agx_handle* h, const double* x0, const double* us, double* out_xs, stream_t st) {
+  const int gpc = TREE_SEQ_CTA / tree::GW;
+  AGX_TREE_LAUNCH(h, tree_rollout_kernel, (h->B + gpc - 1) / gpc, TREE_SEQ_CTA, sizeof(double) * h->tree_board * gpc, st,
+                  problem_of(h), x0, us, out_xs);
+  return check_launch(h, "agx_rollout");
+}
+
+int tree_integrate(agx_handle* h, const double* x, const double* u, double dt, int n, double* out, int per_row, stream_t st) {
+  const int gpc = TREE_NODE_CTA / tree::GW;
+  AGX_TREE_LAUNCH(h, tree_integrate_kernel, (n + gpc - 1) / gpc, TREE_NODE_CTA, sizeof(double) * h->tree_board * gpc, st,
+                  (const double*)h->d_model, per_row, x, u, dt, n, out);
+  return check_launch(h, "agx_integrate");
+}
+
+int tree_rnea(agx_handle* h, const double* q, const double* v, const double* a, int n, double* out, int per_row, stream_t st) {
+  const int gpc = TREE_NODE_CTA / tree::GW;
+  AGX_TREE_LAUNCH(h, tree_rnea_kernel, (n + gpc - 1) / gpc, TREE_NODE_CTA, 0, st, (const double*)h->d_model, per_row, q, v,
+                  a, n, out);
+  return check_launch(h, "agx_rnea");
+}
+
+void tree_launch_backward(agx_handle* h, const agx::Problem& P, const agx::Work& W, const agx::FddpOpts& O, stream_t st) {
+  AGX_TREE_LAUNCH(h, tree_backward_kernel, h->B, 32, sizeof(double) * h->tree_bw, st, P, W, h->S, O);
+}
+
+// FDDP on the general-tree kernels: 3 launches per iteration (calc_diff, Riccati sweep, forward pass with its line
+// search), all decisions on the device.
+int tree_solve(agx_handle* h, const double* x0, const double* xs_ws, const double* us_ws, int max_iter,
+               const agx_fddp_opts* opts, const FddpOpts& O, double* out_xs, double* out_us, double* out_K, double* out_k,
+               double* out_cost, int32_t* out_iters, int32_t* out_status, double* out_stop, stream_t st) {
+  const size_t nB = (size_t)h->B, T = (size_t)h->T, T1 = T + 1;
+  const int nx = h->nx, nv = h->nv;
+  if (!out_K && !h->d_K_internal) {
+    if (!dev_alloc((void**)&h->d_K_internal, sizeof(double) * nB * T * nv * nx))
+      return fail(h, AGX_ENOMEM, "allocation of the internal gain buffer failed");
+  }
+  Work W = h->W;
+  W.K = out_K ? out_K : h->d_K_internal;
+  W.x0 = h->d_x0;
+  if (!copy_d2d(h->d_x0, x0, sizeof(double) * nB * nx, st)) return fail(h, AGX_ECUDA, "agx_solve: x0 copy failed");
+  const Problem P = problem_of(h);
+  const long long n_init = (long long)(nB * T1 * nx);
+  AGX_LAUNCH(h, init_kernel_n, (n_init + 255) / 256, 256, 0, st, P, nx, nv, W, h->S, O, xs_ws, us_ws);
+  const int gpc = TREE_SEQ_CTA / tree::GW;
+  for (int it = 0; it < max_iter; ++it) {
+    phase_begin(h, 0, st);
+    tree_launch_calc_diff(h, P, W.xs, W.us, h->S.cur, h->S.recalc, h->S.done, st);
+    phase_end(h, st);
+    phase_begin(h, 1, st);
+    tree_launch_backward(h, P, W, O, st);
+    phase_end(h, st);
+    phase_begin(h, 4, st);
+    AGX_TREE_LAUNCH(h, tree_forward_kernel, (h->B + gpc - 1) / gpc, TREE_SEQ_CTA, sizeof(double) * h->tree_board * gpc, st,
+                    P, W, h->S, O);
+    phase_end(h, st);
+    if (it + 1 >= max_iter) break;
+    if (opts->eager_exit && h->B <= 64 && !h->timing) {
+      if (all_done_sync(h, st)) break;
+    } else if (!opts->fixed_iters && max_iter > 32 && (it % 16) == 15) {
+      int32_t live = 1;
+#if AGX_GPU
+      cudaMemsetAsync(h->d_live, 0, sizeof(int32_t), st);
+      AGX_LAUNCH(h, count_live_kernel, (h->B + 255) / 256, 256, 0, st, h->B, (const int32_t*)h->S.done, h->d_live);
+      cudaMemcpyAsync(&live, h->d_live, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+      cudaStreamSynchronize(st);
+#else
+      *h->d_live = 0;
+      AGX_LAUNCH(h, count_live_kernel, (h->B + 255) / 256, 256, 0, st, h->B, (const int32_t*)h->S.done, h->d_live);
+      live = *h->d_live;
+#endif
+      if (live == 0) break;
+    }
+  }
+  const long long n_fin = (long long)(nB * T * nv * nx);
+  AGX_LAUNCH(h, finalize_kernel_n, (n_fin + 255) / 256, 256, 0, st, P, nx, nv, W, h->S, out_xs, out_us, out_K, out_k,
+             out_cost, out_iters, out_status, out_stop);
+  return check_launch(h, "agx_solve");
+}
+
 }  // namespace
 
 extern "C" {
@@ -268,6 +512,7 @@ void agx_fddp_opts_default(agx_fddp_opts* o) {
   o->th_acceptnegstep = 2.0; o->th_stop = 1e-9;
   o->reg_init = nan("");
   o->fixed_iters = 0; o->n_alphas = 10; o->eager_exit = 0; o->reserved = 0;
+  o->max_solve_time = 0.0;
 }
 
 const char* agx_last_error(const agx_handle* h) { return h ? h->err.c_str() : "null handle"; }
@@ -300,11 +545,33 @@ int agx_create(const agx_model* models_host, int n_models, const double* dts_hos
   if (!h) return AGX_ENOMEM;
   *out = h;  // returned even on failure so the caller can read agx_last_error, then agx_destroy
   h->B = B; h->T = T; h->device = device; h->n_models = n_models;
-  double* tab = (double*)std::malloc(sizeof(double) * MODEL_SIZE * (size_t)n_models);
+  // The 7-joint serial revolute-z chain runs on its tuned kernels; every other tree (and the chain too when AGX_TREE=1
+  // asks for it: that is how the two paths are cross-checked) runs on the general-tree kernels.
+  {
+    const char* e = std::getenv("AGX_TREE");
+    bool chain = !(e && std::strcmp(e, "1") == 0);
+    for (int i = 0; i < n_models; ++i) {
+      if (models_host[i].nv != models_host[0].nv) return fail(h, AGX_EINVAL, "the models of a batch must share nv");
+      chain = chain && is_chain7(models_host[i]);
+    }
+    h->tree = !chain;
+  }
+  if (h->tree) {
+    const int nv = models_host[0].nv;
+    if (nv < 1 || nv > AGX_MAX_NV || !tree_nv_supported(nv))
+      return fail(h, AGX_EUNSUPPORTED, "the general-tree kernels are instantiated for nv = 6, 7, 9 (AGX_TREE_NVS in agx_api.cu)");
+    const TreeSizes z = tree_sizes(nv);
+    h->nv = nv; h->nx = 2 * nv; h->ref_size = 6 * nv + 20; h->rec_size = z.rec; h->crec_size = z.crec;
+    h->model_size = tree::TMODEL_SIZE; h->tree_board = z.board; h->tree_bw = z.bw;
+  }
+  const int MSZ = h->model_size;
+  double* tab = (double*)std::malloc(sizeof(double) * MSZ * (size_t)n_models);
   if (!tab) return fail(h, AGX_ENOMEM, "host allocation failed");
   for (int i = 0; i < n_models; ++i) {
     std::string why;
-    if (!flatten_model(models_host[i], tab + (size_t)i * MODEL_SIZE, why)) {
+    const bool okm = h->tree ? flatten_tree_model(models_host[i], tab + (size_t)i * MSZ, why)
+                             : flatten_model(models_host[i], tab + (size_t)i * MSZ, why);
+    if (!okm) {
       std::free(tab);
       return fail(h, AGX_EUNSUPPORTED, why);
     }
@@ -312,29 +579,36 @@ int agx_create(const agx_model* models_host, int n_models, const double* dts_hos
     h->n_capsules = i == 0 ? models_host[i].n_capsules : std::min(h->n_capsules, (int)models_host[i].n_capsules);
   }
 #if AGX_GPU
-  if (cudaSetDevice(device) != cudaSuccess) {
-    std::free(tab);
-    return fail(h, AGX_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(cudaGetLastError()));
+  // the caller's current device is restored on return (PyTorch's current device follows the runtime's)
+  DeviceGuard g(device);
+  {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != device) {
+      std::free(tab);
+      return fail(h, AGX_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(cudaGetLastError()));
+    }
   }
 #endif
   const size_t T1 = (size_t)T + 1, nB = (size_t)B;
+  const size_t nx_ = (size_t)h->nx, nv_ = (size_t)h->nv;
   bool ok = true;
-  ok = ok && dev_alloc((void**)&h->d_model, sizeof(double) * MODEL_SIZE * n_models);
-  ok = ok && dev_alloc((void**)&h->d_refs, sizeof(double) * nB * T1 * REF_SIZE);
+  ok = ok && dev_alloc((void**)&h->d_model, sizeof(double) * MSZ * n_models);
+  ok = ok && dev_alloc((void**)&h->d_refs, sizeof(double) * nB * T1 * h->ref_size);
   ok = ok && dev_alloc((void**)&h->d_dts, sizeof(double) * T);
-  ok = ok && dev_alloc((void**)&h->d_x0, sizeof(double) * nB * NX);
-  ok = ok && dev_alloc((void**)&h->W.xs, sizeof(double) * 2 * nB * T1 * NX);
-  ok = ok && dev_alloc((void**)&h->W.us, sizeof(double) * 2 * nB * T * NJ);
-  ok = ok && dev_alloc((void**)&h->W.rec, sizeof(double) * nB * T1 * REC_SIZE);
-  ok = ok && dev_alloc((void**)&h->W.crec, sizeof(double) * nB * T1 * CREC_SIZE);
-  ok = ok && dev_alloc((void**)&h->W.fs, sizeof(double) * nB * T1 * NX);
-  ok = ok && dev_alloc((void**)&h->W.gv, sizeof(double) * nB * T1 * NX);
-  ok = ok && dev_alloc((void**)&h->W.k, sizeof(double) * nB * T * NJ);
+  ok = ok && dev_alloc((void**)&h->d_x0, sizeof(double) * nB * nx_);
+  ok = ok && dev_alloc((void**)&h->W.xs, sizeof(double) * 2 * nB * T1 * nx_);
+  ok = ok && dev_alloc((void**)&h->W.us, sizeof(double) * 2 * nB * T * nv_);
+  ok = ok && dev_alloc((void**)&h->W.rec, sizeof(double) * nB * T1 * h->rec_size);
+  ok = ok && dev_alloc((void**)&h->W.crec, sizeof(double) * nB * T1 * h->crec_size);
+  ok = ok && dev_alloc((void**)&h->W.fs, sizeof(double) * nB * T1 * nx_);
+  ok = ok && dev_alloc((void**)&h->W.gv, sizeof(double) * nB * T1 * nx_);
+  ok = ok && dev_alloc((void**)&h->W.k, sizeof(double) * nB * T * nv_);
   // solver state: 6 double arrays + 10 int arrays in one block
-  const size_t state_bytes = nB * (6 * sizeof(double) + 10 * sizeof(int32_t)) + 64;
+  const size_t state_bytes = sizeof(double) + nB * (6 * sizeof(double) + 10 * sizeof(int32_t)) + 64;
   ok = ok && dev_alloc(&h->state_block, state_bytes);
   if (!ok) { std::free(tab); return fail(h, AGX_ENOMEM, "device allocation failed"); }
-  double* dp = (double*)h->state_block;
+  h->S.t0 = (long long*)h->state_block;  // device time stamp of the start of the current solve (max_solve_time)
+  double* dp = (double*)h->state_block + 1;
   h->S.xreg = dp; h->S.cost = dp + nB; h->S.dg = dp + 2 * nB; h->S.dq = dp + 3 * nB; h->S.stop = dp + 4 * nB;
   h->S.dv = dp + 5 * nB;
   int32_t* ip = (int32_t*)(dp + 6 * nB);
@@ -352,7 +626,7 @@ int agx_create(const agx_model* models_host, int n_models, const double* dts_hos
     }
     ok = copy_h2d(h->d_hidx, hidx, sizeof(int32_t) * (T + 1), 0);
   }
-  ok = ok && copy_h2d(h->d_model, tab, sizeof(double) * MODEL_SIZE * n_models, 0) && copy_h2d(h->d_dts, dts_host, sizeof(double) * T, 0);
+  ok = ok && copy_h2d(h->d_model, tab, sizeof(double) * MSZ * n_models, 0) && copy_h2d(h->d_dts, dts_host, sizeof(double) * T, 0);
 #if AGX_GPU
   ok = ok && cudaStreamSynchronize(0) == cudaSuccess;
 #endif
@@ -365,7 +639,7 @@ int agx_create(const agx_model* models_host, int n_models, const double* dts_hos
 int agx_set_refs(agx_handle* h, const double* refs, void* stream) {
   if (!h || !refs) return AGX_EINVAL;
   DeviceGuard g(h->device);
-  if (!copy_d2d(h->d_refs, refs, sizeof(double) * (size_t)h->B * (h->T + 1) * REF_SIZE, (stream_t)stream))
+  if (!copy_d2d(h->d_refs, refs, sizeof(double) * (size_t)h->B * (h->T + 1) * h->ref_size, (stream_t)stream))
     return fail(h, AGX_ECUDA, "agx_set_refs: copy failed");
   return AGX_OK;
 }
@@ -375,6 +649,10 @@ int agx_set_capsule(agx_handle* h, int capsule, const double* a0, const double* 
   if (capsule < 0 || capsule >= h->n_capsules) return fail(h, AGX_EINVAL, "agx_set_capsule: no such capsule");
   if (!(radius >= 0.0)) return fail(h, AGX_EINVAL, "agx_set_capsule: negative radius");
   DeviceGuard g(h->device);
+  if (h->tree)
+    AGX_LAUNCH(h, tree::tree_set_capsule_kernel, (h->n_models + 127) / 128, 128, 0, (stream_t)stream, h->d_model,
+               h->n_models, capsule, a0[0], a0[1], a0[2], a1[0], a1[1], a1[2], radius);
+  else
   AGX_LAUNCH(h, set_capsule_kernel, (h->n_models + 127) / 128, 128, 0, (stream_t)stream, h->d_model, h->n_models, capsule,
              a0[0], a0[1], a0[2], a1[0], a1[1], a1[2], radius);
   return check_launch(h, "agx_set_capsule");
@@ -384,7 +662,11 @@ int agx_set_refs_window(agx_handle* h, const double* stream_refs, int n_streams,
                         int start0, void* stream) {
   if (!h || !stream_refs || n_points <= 0 || (n_streams != 1 && n_streams != h->B)) return AGX_EINVAL;
   DeviceGuard g(h->device);
-  const long long n = (long long)h->B * (h->T + 1) * REF_SIZE;
+  const long long n = (long long)h->B * (h->T + 1) * h->ref_size;
+  if (h->tree)
+    AGX_LAUNCH(h, gather_refs_kernel_n, (n + 255) / 256, 256, 0, (stream_t)stream, h->B, h->T + 1, h->ref_size, stream_refs,
+               n_streams, n_points, start, start0, (const int32_t*)h->d_hidx, h->d_refs);
+  else
   AGX_LAUNCH(h, gather_refs_kernel, (n + 255) / 256, 256, 0, (stream_t)stream, h->B, h->T + 1, stream_refs, n_streams,
              n_points, start, start0, (const int32_t*)h->d_hidx, h->d_refs);
   return check_launch(h, "agx_set_refs_window");
@@ -393,6 +675,7 @@ int agx_set_refs_window(agx_handle* h, const double* stream_refs, int n_streams,
 int agx_calc(agx_handle* h, const double* xs, const double* us, double* out_cost, double* out_xnext, void* stream) {
   if (!h || !xs || !us) return AGX_EINVAL;
   DeviceGuard g(h->device);
+  if (h->tree) return tree_calc(h, xs, us, out_cost, out_xnext, (stream_t)stream);
   const long long ents = (long long)h->B * (h->T + 1);
   const int opc = NODE_CTA / 8;
   AGX_LAUNCH_COL(h, calc_kernel, (ents + opc - 1) / opc, NODE_CTA, sizeof(double) * OCT_BOARD * opc, (stream_t)stream,
@@ -404,6 +687,7 @@ int agx_calc_diff(agx_handle* h, const double* xs, const double* us, double* out
                   double* Fu, double* Lx, double* Lu, double* Lxx, double* Lxu, double* Luu, void* stream) {
   if (!h || !xs || !us) return AGX_EINVAL;
   DeviceGuard g(h->device);
+  if (h->tree) return tree_calc_diff(h, xs, us, out_cost, out_xnext, Fx, Fu, Lx, Lu, Lxx, Lxu, Luu, (stream_t)stream);
   const long long ents = (long long)h->B * (h->T + 1);
   const int opc = NODE_CTA / 8;
   AGX_LAUNCH_COL(h, calc_diff_kernel, (ents + opc - 1) / opc, NODE_CTA, sizeof(double) * OCT_BOARD * opc, (stream_t)stream,
@@ -418,6 +702,7 @@ int agx_calc_diff(agx_handle* h, const double* xs, const double* us, double* out
 int agx_cost_terms(agx_handle* h, const double* xs, const double* us, double* out_terms, void* stream) {
   if (!h || !xs || !us || !out_terms) return AGX_EINVAL;
   DeviceGuard g(h->device);
+  if (h->tree) return tree_cost_terms(h, xs, us, out_terms, (stream_t)stream);
   const long long ents = (long long)h->B * (h->T + 1);
   AGX_LAUNCH_COL(h, cost_terms_kernel, (ents + 127) / 128, 128, 0, (stream_t)stream, problem_of(h), xs, us, out_terms);
   return check_launch(h, "agx_cost_terms");
@@ -426,6 +711,7 @@ int agx_cost_terms(agx_handle* h, const double* xs, const double* us, double* ou
 int agx_shift_warmstart(agx_handle* h, const double* xs, const double* us, double* out_xs, double* out_us, void* stream) {
   if (!h || !xs || !us || !out_xs || !out_us || xs == out_xs || us == out_us) return AGX_EINVAL;
   DeviceGuard g(h->device);
+  if (h->tree) return tree_shift(h, xs, us, out_xs, out_us, (stream_t)stream);
   const long long ents = (long long)h->B * (h->T + 1);
   const int opc = NODE_CTA / 8;
   AGX_LAUNCH(h, shift_kernel, (ents + opc - 1) / opc, NODE_CTA, sizeof(double) * OCT_BOARD * opc, (stream_t)stream,
@@ -436,6 +722,7 @@ int agx_shift_warmstart(agx_handle* h, const double* xs, const double* us, doubl
 int agx_rollout(agx_handle* h, const double* x0, const double* us, double* out_xs, void* stream) {
   if (!h || !x0 || !us || !out_xs) return AGX_EINVAL;
   DeviceGuard g(h->device);
+  if (h->tree) return tree_rollout(h, x0, us, out_xs, (stream_t)stream);
   const int opc = SEQ_CTA / 8;
   AGX_LAUNCH(h, rollout_kernel, (h->B + opc - 1) / opc, SEQ_CTA, sizeof(double) * OCT_BOARD * opc, (stream_t)stream,
              problem_of(h), x0, us, out_xs);
@@ -445,20 +732,29 @@ int agx_rollout(agx_handle* h, const double* x0, const double* us, double* out_x
 int agx_integrate(agx_handle* h, const double* x, const double* u, double dt, int n, double* out_xnext, void* stream) {
   if (!h || !x || !u || !out_xnext || n < 0) return AGX_EINVAL;
   if (n == 0) return AGX_OK;
+  // per-problem models (n_models = B): row i uses model i, so n must be the batch size
+  if (h->n_models > 1 && n != h->B)
+    return fail(h, AGX_EUNSUPPORTED, "agx_integrate: a handle with one model per problem integrates exactly B rows");
+  const int per_row = h->n_models > 1 ? 1 : 0;
   DeviceGuard g(h->device);
+  if (h->tree) return tree_integrate(h, x, u, dt, n, out_xnext, per_row, (stream_t)stream);
   const int opc = NODE_CTA / 8;
   AGX_LAUNCH(h, integrate_kernel, (n + opc - 1) / opc, NODE_CTA, sizeof(double) * OCT_BOARD * opc, (stream_t)stream,
-             (const double*)h->d_model, x, u, dt, n, out_xnext);
+             (const double*)h->d_model, per_row, x, u, dt, n, out_xnext);
   return check_launch(h, "agx_integrate");
 }
 
 int agx_rnea(agx_handle* h, const double* q, const double* v, const double* a, int n, double* out_tau, void* stream) {
   if (!h || !q || !v || !a || !out_tau || n < 0) return AGX_EINVAL;
   if (n == 0) return AGX_OK;
+  if (h->n_models > 1 && n != h->B)
+    return fail(h, AGX_EUNSUPPORTED, "agx_rnea: a handle with one model per problem evaluates exactly B rows");
+  const int per_row = h->n_models > 1 ? 1 : 0;
   DeviceGuard g(h->device);
+  if (h->tree) return tree_rnea(h, q, v, a, n, out_tau, per_row, (stream_t)stream);
   const int opc = NODE_CTA / 8;
   AGX_LAUNCH(h, rnea_kernel, (n + opc - 1) / opc, NODE_CTA, sizeof(double) * OCT_BOARD * opc, (stream_t)stream,
-             (const double*)h->d_model, q, v, a, n, out_tau);
+             (const double*)h->d_model, per_row, q, v, a, n, out_tau);
   return check_launch(h, "agx_rnea");
 }
 
@@ -474,13 +770,24 @@ int agx_riccati(agx_handle* h, const double* x0, const double* xs, const double*
   O.th_grad = od.th_grad; O.th_stepdec = od.th_stepdec; O.th_stepinc = od.th_stepinc; O.th_acceptstep = od.th_acceptstep;
   O.th_acceptnegstep = od.th_acceptnegstep; O.th_stop = od.th_stop; O.reg_init = reg; O.fixed_iters = 1; O.n_alphas = 1;
   O.max_iter = 1; O.defer = 0;
+  O.max_solve_ns = 0;
   const size_t nB = (size_t)h->B, T = (size_t)h->T, T1 = T + 1;
   Work W = h->W;
   W.K = out_K;
   W.x0 = h->d_x0;
-  if (!copy_d2d(h->d_x0, x0, sizeof(double) * nB * NX, st)) return fail(h, AGX_ECUDA, "agx_riccati: x0 copy failed");
+  if (!copy_d2d(h->d_x0, x0, sizeof(double) * nB * h->nx, st)) return fail(h, AGX_ECUDA, "agx_riccati: x0 copy failed");
   const Problem P = problem_of(h);
-  const long long n_init = (long long)(nB * T1 * NX);
+  const long long n_init = (long long)(nB * T1 * h->nx);
+  if (h->tree) {
+    AGX_LAUNCH(h, init_kernel_n, (n_init + 255) / 256, 256, 0, st, P, h->nx, h->nv, W, h->S, O, xs, us);
+    tree_launch_calc_diff(h, P, W.xs, W.us, h->S.cur, h->S.recalc, h->S.done, st);
+    tree_launch_backward(h, P, W, O, st);
+    bool okt = true;
+    if (out_k) okt = okt && copy_d2d(out_k, W.k, sizeof(double) * nB * T * h->nv, st);
+    if (out_status) okt = okt && copy_d2d(out_status, h->S.status, sizeof(int32_t) * nB, st);
+    if (!okt) return fail(h, AGX_ECUDA, "agx_riccati: output copy failed");
+    return check_launch(h, "agx_riccati");
+  }
   AGX_LAUNCH(h, init_kernel, (n_init + 255) / 256, 256, 0, st, P, W, h->S, O, xs, us);
   const long long ents = (long long)(nB * T1);
   const int opc_n = NODE_CTA / 8, opc_s = SEQ_CTA / 8;
@@ -593,6 +900,13 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
   O.th_stepinc = opts->th_stepinc; O.th_acceptstep = opts->th_acceptstep; O.th_acceptnegstep = opts->th_acceptnegstep;
   O.th_stop = opts->th_stop; O.reg_init = opts->reg_init; O.fixed_iters = opts->fixed_iters; O.n_alphas = opts->n_alphas;
   O.max_iter = max_iter;
+  // max_solve_time (ocp_base_croco.py:70-71, :166-171): a device-side deadline, see agx_fddp_opts
+  O.max_solve_ns = opts->max_solve_time > 0.0 ? (long long)(opts->max_solve_time * 1e9) : 0;
+  if (h->tree) {
+    O.defer = 0;
+    return tree_solve(h, x0, xs_ws, us_ws, max_iter, opts, O, out_xs, out_us, out_K, out_k, out_cost, out_iters,
+                      out_status, out_stop, st);
+  }
   // deferred line search (accept_linesearch_kernel): on unless AGX_LS=inline asks for the in-line search only
   static const bool ls_inline = [] { const char* e = std::getenv("AGX_LS"); return e && std::strcmp(e, "inline") == 0; }();
   O.defer = (!ls_inline && O.n_alphas > 1) ? 1 : 0;
@@ -688,6 +1002,7 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
 void agx_sqp_opts_default(agx_sqp_opts* o) {
   if (!o) return;
   o->sigma = 1e-6; o->reg = 1e-9; o->mu = 10.0; o->termination_tolerance = 1e-3; o->n_alphas = 10; o->eager_exit = 0;
+  o->max_solve_time = 0.0;
 }
 
 int agx_solve_sqp(agx_handle* h, const double* x0, const double* xs_ws, const double* us_ws, int max_iter,
@@ -702,18 +1017,21 @@ int agx_solve_sqp(agx_handle* h, const double* x0, const double* xs_ws, const do
   if (opts->n_alphas < 1 || opts->n_alphas > 10) return fail(h, AGX_EINVAL, "n_alphas must be in 1..10");
   if (!(opts->sigma >= 0.0) || !(opts->reg >= 0.0) || !(opts->mu >= 0.0))
     return fail(h, AGX_EINVAL, "sigma, reg and mu must be non-negative");
+  if (h->tree)
+    return fail(h, AGX_EUNSUPPORTED, "the SQP mode runs on the 7-joint chain kernels only (general trees: use agx_solve)");
   SqpOpts Q;
   Q.sigma = opts->sigma; Q.reg = opts->reg; Q.mu = opts->mu; Q.tol = opts->termination_tolerance;
   Q.n_alphas = opts->n_alphas;
   agx_fddp_opts od;
   agx_fddp_opts_default(&od);
   Q.reg_max = od.reg_max; Q.reg_factor = od.reg_incfactor; Q.th_stepdec = od.th_stepdec; Q.th_stepinc = od.th_stepinc;
+  Q.max_solve_ns = opts->max_solve_time > 0.0 ? (long long)(opts->max_solve_time * 1e9) : 0;
   // a failed factorisation raises the problem's regularisation inside the sweep and retries, up to reg_max
   FddpOpts O;
   O.reg_min = Q.reg; O.reg_max = Q.reg_max; O.reg_init = Q.reg; O.reg_incfactor = od.reg_incfactor;
   O.reg_decfactor = od.reg_decfactor; O.th_grad = od.th_grad; O.th_stepdec = od.th_stepdec; O.th_stepinc = od.th_stepinc;
   O.th_acceptstep = od.th_acceptstep; O.th_acceptnegstep = od.th_acceptnegstep; O.th_stop = od.th_stop;
-  O.fixed_iters = 0; O.n_alphas = Q.n_alphas; O.max_iter = max_iter; O.defer = 0;
+  O.fixed_iters = 0; O.n_alphas = Q.n_alphas; O.max_iter = max_iter; O.defer = 0; O.max_solve_ns = 0;
   FddpOpts Of = O;
   Of.reg_min = Of.reg_max = 0.0;  // the last sweep (sigma + the problem's regularisation) is not retried
   const size_t nB = (size_t)h->B, T = (size_t)h->T, T1 = T + 1;

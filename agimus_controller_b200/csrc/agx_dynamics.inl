@@ -152,15 +152,8 @@ AGX_DEV void scan_se3_prefix(LaneDyn& d, int j, unsigned omask) {
 
 // ---------------------------------------------------------------- body quantities (after the velocity scan)
 // world-frame inertia of this lane's body about the origin: Y = (m, m c, Ibar) and the start of the composite scan
-AGX_DEV void body_inertia(LaneDyn& d, int j, const double* __restrict__ model) {
-  double mass = 0, com[3] = {0, 0, 0}, I6[6] = {0, 0, 0, 0, 0, 0};
-  if (j < NJ) {
-    mass = model[MF_MASS * 8 + j];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) com[k] = model[(MF_COM + k) * 8 + j];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) I6[k] = model[(MF_INERTIA + k) * 8 + j];
-  }
+template <class LD>
+AGX_DEV void body_inertia_from(LD& d, double mass, const double* com, const double* I6) {
   double cw[3];
   mv3(d.R, com, cw);
 #pragma unroll
@@ -192,18 +185,31 @@ AGX_DEV void body_inertia(LaneDyn& d, int j, const double* __restrict__ model) {
 #pragma unroll
   for (int k = 0; k < 10; ++k) d.Z[k] = d.Y[k];
 }
+AGX_DEV void body_inertia(LaneDyn& d, int j, const double* __restrict__ model) {
+  double mass = 0, com[3] = {0, 0, 0}, I6[6] = {0, 0, 0, 0, 0, 0};
+  if (j < NJ) {
+    mass = model[MF_MASS * 8 + j];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) com[k] = model[(MF_COM + k) * 8 + j];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) I6[k] = model[(MF_INERTIA + k) * 8 + j];
+  }
+  body_inertia_from(d, mass, com, I6);
+}
 
 // with_B: also the Sym block of the B matrix (derivatives only)
-AGX_DEV void body_terms(LaneDyn& d, int j, const double* __restrict__ model, const double* grav_acc, bool with_B) {
-  // velocity of this body, dV/dq column, bias acceleration term g = c * qd
+// first half: velocity of this body, dV/dq column, bias acceleration term g = c * qd
+template <class LD>
+AGX_DEV void body_motion(LD& d) {
 #pragma unroll
   for (int k = 0; k < 6; ++k) d.v[k] = d.vp[k] + d.s[k];
   crm6(d.vp, d.J, d.c);
 #pragma unroll
   for (int k = 0; k < 6; ++k) d.g[k] = d.c[k] * d.qd;
-  (void)grav_acc;
-  body_inertia(d, j, model);
-  // momentum h = Y v
+}
+// second half (after the body inertia d.Y is known): momentum h = Y v and, with_B, the Sym block
+template <class LD>
+AGX_DEV void body_momentum(LD& d, bool with_B) {
   inertia_apply(d.Y, d.v, d.Z + 10);
   if (with_B) {
     // Sym = P + P^T - (mc vl^T + vl mc^T) + 2 (vl . mc) I,  P = [w]x Ibar
@@ -228,8 +234,15 @@ AGX_DEV void body_terms(LaneDyn& d, int j, const double* __restrict__ model, con
     for (int k = 16; k < 22; ++k) d.Z[k] = 0;
   }
 }
+AGX_DEV void body_terms(LaneDyn& d, int j, const double* __restrict__ model, const double* grav_acc, bool with_B) {
+  (void)grav_acc;
+  body_motion(d);
+  body_inertia(d, j, model);
+  body_momentum(d, with_B);
+}
 // bias force with qdd = 0: f0 = Y a0 + v x* h   (after the acceleration scan filled a0p)
-AGX_DEV void body_force(LaneDyn& d) {
+template <class LD>
+AGX_DEV void body_force(LD& d) {
   double a0[6], Ya[6], vh[6];
 #pragma unroll
   for (int k = 0; k < 6; ++k) a0[k] = d.a0p[k] + d.g[k];
@@ -239,8 +252,8 @@ AGX_DEV void body_force(LaneDyn& d) {
   for (int k = 0; k < 6; ++k) d.Z[22 + k] = Ya[k] + vh[k];
 }
 // column quantities: nle, dFda, BS; stored on board B as [J(6) dFda(6) BS(3) b(1)] stride 18
-template <bool DERIV>
-AGX_DEV void column_terms(LaneDyn& d, int j, double* sbb) {
+template <bool DERIV, class LD>
+AGX_DEV void column_terms(LD& d, int j, double* sbb) {
   d.b = dot6(d.J, d.Z + 22);
   inertia_apply(d.Z, d.J, d.dFda);
   double* o = sbb + j * 18;
@@ -331,7 +344,8 @@ AGX_DEV void chol_solve7(const double* L, const double* rinv, double* r) {
 
 // ---------------------------------------------------------------- second pass (with qdd) and derivative columns
 // after the qdd prefix scan: d.g holds (parent) delta acceleration from qdd
-AGX_DEV void deriv_columns(LaneDyn& d, int j, const double* dap /*prefix of J qdd*/, const double* dfc /*suffix of Y da*/,
+template <class LD>
+AGX_DEV void deriv_columns(LD& d, int j, const double* dap /*prefix of J qdd*/, const double* dfc /*suffix of Y da*/,
                            double* dFdq, double* dFdv) {
   // parent acceleration incl. qdd, dA/dq column
   double ap[6], A[6], t1[6], t2[6];
@@ -473,11 +487,9 @@ AGX_DEV void log6_and_jac(const double* R, const double* p, double* r, double* J
 }
 
 // frame placement residual: given joint-6 world placement (R6, p6) -> r (6) and, if Jl, Jlog6 blocks and oMf
-AGX_DEV void frame_residual(const double* R6, const double* p6, const double* __restrict__ model,
-                            const double* __restrict__ Rref, const double* __restrict__ pref, double* Rf, double* pf,
-                            double* r, double* Jl) {
-  const double* FR = model + MT_FR;
-  const double* FP = model + MT_FP;
+AGX_DEV void frame_residual_at(const double* R6, const double* p6, const double* __restrict__ FR,
+                               const double* __restrict__ FP, const double* __restrict__ Rref,
+                               const double* __restrict__ pref, double* Rf, double* pf, double* r, double* Jl) {
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
 #pragma unroll
@@ -493,6 +505,11 @@ AGX_DEV void frame_residual(const double* R6, const double* p6, const double* __
   for (int k = 0; k < 3; ++k) dp[k] = pf[k] - pref[k];
   mtv3(Rref, dp, pr);
   log6_and_jac(Rr, pr, r, Jl);
+}
+AGX_DEV void frame_residual(const double* R6, const double* p6, const double* __restrict__ model,
+                            const double* __restrict__ Rref, const double* __restrict__ pref, double* Rf, double* pf,
+                            double* r, double* Jl) {
+  frame_residual_at(R6, p6, model + MT_FR, model + MT_FP, Rref, pref, Rf, pf, r, Jl);
 }
 
 // ---------------------------------------------------------------------------------------------

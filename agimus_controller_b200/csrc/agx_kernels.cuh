@@ -40,6 +40,7 @@ struct FddpOpts {
   int fixed_iters, n_alphas;
   int max_iter;  // iteration budget of every problem (a problem whose search was deferred finishes a round later)
   int defer;     // a rejected alpha = 1 trial tries alpha = 1/2 in the next round's forward pass (see accept_linesearch_kernel)
+  long long max_solve_ns;  // max_solve_time in ns (0: none), measured on the device clock from SolverState::t0
 };
 
 // workspace of a solve (device pointers owned by the handle)
@@ -725,6 +726,8 @@ AGX_DEV void finish_iteration(const SolverState& S, const FddpOpts& O, int b, bo
   S.iters[b] += 1;
   if (!done && !O.fixed_iters && was_feasible && S.stop[b] < O.th_stop) { status = 0; done = 1; }
   if (!done && S.iters[b] >= O.max_iter) done = 1;  // budget used (status stays MAXITER)
+  // max_solve_time (ocp_base_croco.py:70-71): checked at the end of an iteration, as the reference's solver does
+  if (!done && O.max_solve_ns > 0 && agx_now_ns() - *S.t0 > O.max_solve_ns) { status = 5; done = 1; }
   if (done) { S.status[b] = status; S.done[b] = 1; }
 }
 
@@ -1232,11 +1235,12 @@ __global__ void shift_kernel(Problem P, const double* __restrict__ xs, const dou
 }
 
 // IntegratedActionModelEuler.calc -> xnext for n independent (x, u) pairs (costs skipped)
-__global__ void integrate_kernel(const double* __restrict__ model, const double* __restrict__ x,
+__global__ void integrate_kernel(const double* __restrict__ models, int per_row, const double* __restrict__ x,
                                  const double* __restrict__ u, double dt, int n, double* __restrict__ out) {
   AGX_SMEM(smem);
   AGX_OCTET_SETUP();
   if (ent >= n) return;
+  const double* model = models + (per_row ? (size_t)ent * MODEL_SIZE : 0);
   double* sb = smem + oct_in_cta * OCT_BOARD;
   double* sc = sb + BRD_B;
   LaneDyn d;
@@ -1251,12 +1255,13 @@ __global__ void integrate_kernel(const double* __restrict__ model, const double*
 }
 
 // pin.rnea(q, v, a) for n independent triples: tau = nle(q, v) + M(q) a (no armature)
-__global__ void rnea_kernel(const double* __restrict__ model, const double* __restrict__ q,
+__global__ void rnea_kernel(const double* __restrict__ models, int per_row, const double* __restrict__ q,
                             const double* __restrict__ v, const double* __restrict__ a, int n,
                             double* __restrict__ out_tau) {
   AGX_SMEM(smem);
   AGX_OCTET_SETUP();
   if (ent >= n) return;
+  const double* model = models + (per_row ? (size_t)ent * MODEL_SIZE : 0);
   double* sb = smem + oct_in_cta * OCT_BOARD;
   double* sc = sb + BRD_B;
   const bool live = j < NJ;
@@ -1304,6 +1309,7 @@ __global__ void init_kernel(Problem P, Work W, SolverState S, FddpOpts O, const 
   const long long nxs = (long long)P.B * T1 * NX, nus = (long long)P.B * P.T * NJ;
   if (gid < nxs) W.xs[gid] = xs_ws[gid];
   if (gid < nus) W.us[gid] = us_ws[gid];
+  if (gid == 0) *S.t0 = agx_now_ns();
   if (gid < P.B) {
     const int b = (int)gid;
     S.xreg[b] = (O.reg_init == O.reg_init) ? O.reg_init : O.reg_min;
@@ -1338,5 +1344,63 @@ __global__ void finalize_kernel(Problem P, Work W, SolverState S, double* out_xs
   }
 }
 
+// ---- the same three kernels with run-time sizes (general-tree path, agx_tree.cuh)
+__global__ void gather_refs_kernel_n(int B, int T1, int ref_size, const double* __restrict__ stream, int n_streams,
+                                     int n_points, const int32_t* __restrict__ start, int start0,
+                                     const int32_t* __restrict__ hidx, double* __restrict__ refs) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = gid / ref_size;
+  const int k = (int)(gid % ref_size);
+  if (n >= (long long)B * T1) return;
+  const int b = (int)(n / T1), t = (int)(n % T1);
+  int p = (start ? start[b] : start0) + hidx[t];
+  if (p >= n_points) p = n_points - 1;
+  if (p < 0) p = 0;
+  refs[gid] = stream[((size_t)(n_streams > 1 ? b : 0) * n_points + p) * ref_size + k];
+}
+
+__global__ void init_kernel_n(Problem P, int nx, int nv, Work W, SolverState S, FddpOpts O,
+                              const double* __restrict__ xs_ws, const double* __restrict__ us_ws) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int T1 = P.T + 1;
+  const long long nxs = (long long)P.B * T1 * nx, nus = (long long)P.B * P.T * nv;
+  if (gid < nxs) W.xs[gid] = xs_ws[gid];
+  if (gid < nus) W.us[gid] = us_ws[gid];
+  if (gid == 0) *S.t0 = agx_now_ns();
+  if (gid < P.B) {
+    const int b = (int)gid;
+    S.xreg[b] = (O.reg_init == O.reg_init) ? O.reg_init : O.reg_min;
+    S.cost[b] = 0.0; S.dg[b] = 0.0; S.dq[b] = 0.0; S.stop[b] = 0.0;
+    S.is_feasible[b] = 0; S.was_feasible[b] = 0; S.recalc[b] = 1; S.done[b] = 0;
+    S.status[b] = 1; S.iters[b] = 0; S.cur[b] = 0;
+    S.dv[b] = 0.0; S.recalc_cost[b] = 1; S.pending[b] = 0; S.roll_ok[b] = 0;
+  }
+}
+
+__global__ void finalize_kernel_n(Problem P, int nx, int nv, Work W, SolverState S, double* out_xs, double* out_us,
+                                  double* out_K, double* out_k, double* out_cost, int32_t* out_iters,
+                                  int32_t* out_status, double* out_stop) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int T1 = P.T + 1;
+  const long long per_xs = (long long)T1 * nx, per_us = (long long)P.T * nv, per_K = (long long)P.T * nv * nx;
+  if (gid < P.B * per_xs) {
+    const int b = (int)(gid / per_xs);
+    out_xs[gid] = W.xs[(size_t)(S.cur[b] & 1) * P.B * per_xs + gid];
+  }
+  if (gid < P.B * per_us) {
+    const int b = (int)(gid / per_us);
+    out_us[gid] = W.us[(size_t)(S.cur[b] & 1) * P.B * per_us + gid];
+    if (out_k) out_k[gid] = W.k[gid];
+  }
+  if (out_K && out_K != W.K && gid < P.B * per_K) out_K[gid] = W.K[gid];
+  if (gid < P.B) {
+    out_cost[gid] = S.cost[gid];
+    out_iters[gid] = S.iters[gid];
+    out_status[gid] = S.status[gid];
+    if (out_stop) out_stop[gid] = S.stop[gid];
+  }
+}
+
 }  // namespace agx
+#include "agx_tree.cuh"
 #endif  // AGX_KERNELS_CUH_

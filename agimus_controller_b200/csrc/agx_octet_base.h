@@ -56,6 +56,20 @@
 #define AGX_DMMA(d0, d1, a, b, c0, c1) agx_emul_dmma((d0), (d1), (a), (b), (c0), (c1))
 #endif
 
+// device wall clock in nanoseconds (%globaltimer); the emulator build reads the host's steady clock
+#if AGX_GPU
+__device__ __forceinline__ long long agx_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return (long long)t;
+}
+#else
+#include <chrono>
+inline long long agx_now_ns() {
+  return (long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+#endif
+
 namespace agx {
 
 constexpr int NJ = 7;            // joints handled by one octet
@@ -123,6 +137,7 @@ struct SolverState {
   int32_t* recalc_cost;  // the cost part of the node records must be recomputed for the candidate
   int32_t* pending;   // the alpha = 1 trial was rejected: the line search continues with smaller steps
   int32_t* roll_ok;   // the alpha = 1 rollout met no NaN / failed factorisation
+  long long* t0;      // [1] device time stamp (ns) of the start of the solve (max_solve_time)
 };
 
 // ---- 3-vector helpers (per-lane, register resident)

@@ -18,6 +18,7 @@ struct SqpOpts {
   // factorisation or a step length <= th_stepinc (which includes a failed line search), / reg_factor after a step
   // length > th_stepdec; reaching reg_max ends the problem
   double reg_max, reg_factor, th_stepdec, th_stepinc;
+  long long max_solve_ns;  // as FddpOpts::max_solve_ns
 };
 
 AGX_DEV double octet_max(double x, unsigned omask) {
@@ -245,7 +246,6 @@ __global__ void sqp_accept_kernel(Problem P, Work W, SolverState S, SqpOpts Q, i
   bool finished = false;  // the line search of this iteration is over (step taken, or every step length refused)
   if (mt < S.dg[b]) {
     S.cur[b] ^= 1;
-    S.iters[b] += 1;
     finished = true;
   } else if (n_now + 1 >= Q.n_alphas) {
     finished = true;
@@ -255,6 +255,7 @@ __global__ void sqp_accept_kernel(Problem P, Work W, SolverState S, SqpOpts Q, i
   }
   if (finished) {
     S.pending[b] = 0;
+    S.iters[b] += 1;  // the solver counts every pass of its loop, whether the step was taken or every length refused
     const double steplength = ldexp(1.0, -n_now);
     double reg = S.xreg[b];
     if (steplength > Q.th_stepdec) reg = fmax(reg / Q.reg_factor, Q.reg);
@@ -263,6 +264,7 @@ __global__ void sqp_accept_kernel(Problem P, Work W, SolverState S, SqpOpts Q, i
       if (reg == Q.reg_max) { S.status[b] = 2; S.done[b] = 1; }
     }
     S.xreg[b] = reg;
+    if (!S.done[b] && Q.max_solve_ns > 0 && agx_now_ns() - *S.t0 > Q.max_solve_ns) { S.status[b] = 5; S.done[b] = 1; }
   }
 }
 

@@ -104,25 +104,31 @@ PICK_AND_PLACE_Q_INIT = np.array([-0.3619834760502907, -1.3575006398318104, 0.96
 
 def pick_and_place_collision_batch(B, T=100, dt=0.01, rnea=None, seed=4, alpha=1e-4, w_col=(10.0, 10.0), w_q=3.0,
                                    w_v=0.12, w_u=8e-4, armature=0.1, move_duration=1.0, q_spread=0.05,
-                                   capsules=None, pairs=None):
+                                   capsules=None, pairs=None, lock_fingers=True, finger_opening=0.02):
     """Config 4: joint-space quintic move ``q_init -> q_nominal`` over ``move_duration`` (generic_trajectory.py with
     the weights of panda_pick_and_place/config/trajectory_weigths_params.yaml:4-9) with ``ResidualDistanceCollision`` +
     ``ActivationModelQuadExp(alpha)`` costs on the link7/link3 and link7/obstacle capsule pairs
-    (config/agimus_controller_params.yaml:16-20, tests/resources/environment.xacro:23-24).  Fingers locked (nv = 7:
-    the kernels cover the 7-joint arm); capsule geometry is the synthetic table of robot_model.PANDA_CAPSULES.
-    Initial states are ``q_init`` plus a per-problem offset."""
-    table = panda_table(lock_fingers=True, armature=armature).with_capsules(
+    (config/agimus_controller_params.yaml:16-20, tests/resources/environment.xacro:23-24).  ``lock_fingers=False`` is
+    BASELINE config 4 as stated — nv = 9, the two prismatic finger joints branching off the hand
+    (factory/robot_model.py:231-259 locks them only when asked to): the fingers start closed (``q_init`` of
+    panda_pick_and_place/main.py:81-91 ends in 0, 0) and are asked to open to ``finger_opening`` along the move.  Capsule
+    geometry is the synthetic table of robot_model.PANDA_CAPSULES.  Initial states are ``q_init`` plus a per-problem
+    offset on the arm joints."""
+    table = panda_table(lock_fingers=lock_fingers, armature=armature).with_capsules(
         PANDA_CAPSULES if capsules is None else capsules, PANDA_COLLISION_PAIRS if pairs is None else pairs, alpha)
     nv = table.nv
     rng = np.random.default_rng(seed)
-    off = rng.uniform(-q_spread, q_spread, size=(B, nv))
+    off = np.zeros((B, nv))
+    off[:, :7] = rng.uniform(-q_spread, q_spread, size=(B, 7))
+    q_init = np.concatenate([PICK_AND_PLACE_Q_INIT, np.zeros(nv - 7)])
+    q_goal = np.concatenate([PANDA_Q_NOMINAL, np.full(nv - 7, finger_opening)])
     tt = dt * np.arange(T + 1)
     s = np.clip(tt / move_duration, 0.0, 1.0)
     p = 10 * s**3 - 15 * s**4 + 6 * s**5
     dp = np.where(s < 1.0, (30 * s**2 - 60 * s**3 + 30 * s**4) / move_duration, 0.0)
     ddp = np.where(s < 1.0, (60 * s - 180 * s**2 + 120 * s**3) / move_duration**2, 0.0)
-    dq = (PANDA_Q_NOMINAL - PICK_AND_PLACE_Q_INIT)[None, None, :]
-    q = PICK_AND_PLACE_Q_INIT[None, None, :] + off[:, None, :] * (1.0 - p)[None, :, None] + dq * p[None, :, None]
+    dq = (q_goal - q_init)[None, None, :]
+    q = q_init[None, None, :] + off[:, None, :] * (1.0 - p)[None, :, None] + dq * p[None, :, None]
     v = (dq - off[:, None, :]) * dp[None, :, None]
     a = (dq - off[:, None, :]) * ddp[None, :, None]
     u = (np.asarray(rnea(q.reshape(-1, nv), v.reshape(-1, nv), a.reshape(-1, nv))).reshape(B, T + 1, nv)

@@ -52,6 +52,7 @@ extern "C" {
 #define AGX_STATUS_REGMAX 2    /* regularisation hit reg_max */
 #define AGX_STATUS_NAN 3       /* non-finite value met */
 #define AGX_STATUS_LINESEARCH 4 /* reserved (a refused line search raises the regularisation and the solve goes on) */
+#define AGX_STATUS_TIMEOUT 5    /* max_solve_time elapsed: the current iterate is returned */
 
 /*
  * Kinematic-tree table: what factory/robot_model.py:88-351 (RobotModels.robot_model, .armature)
@@ -109,6 +110,12 @@ typedef struct agx_fddp_opts {
   int32_t n_alphas; /* step lengths 2^-n, n = 0..n_alphas-1 (<= 10) */
   int32_t eager_exit;
   int32_t reserved;
+  /* max_solve_time of the reference's solver (ocp_base_croco.py:70-71, passed when use_iteration_limits_and_timeout,
+   * :166-171), in seconds; <= 0: none.  The deadline is kept ON THE DEVICE: the solve's first kernel stamps the device
+   * clock, and a problem whose iteration ends later than stamp + max_solve_time stops iterating and returns its current
+   * iterate (status AGX_STATUS_TIMEOUT) -- no host synchronisation, the remaining launches find the problem finished.
+   * The clock starts when the solve starts EXECUTING on the stream, not when it is queued. */
+  double max_solve_time;
 } agx_fddp_opts;
 
 /*
@@ -121,6 +128,7 @@ typedef struct agx_sqp_opts {
   double sigma, reg, mu, termination_tolerance;
   int32_t n_alphas;
   int32_t eager_exit; /* as in agx_fddp_opts */
+  double max_solve_time; /* as in agx_fddp_opts */
 } agx_sqp_opts;
 
 typedef struct agx_handle agx_handle;
@@ -228,7 +236,8 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
  * fixed point, so it is not iterated.)  Replaying the reference's golden test this way (zero warm start,
  * tests/test_ocp_croco_base.py:140-158) stops at the same criterion 6e-5 from the golden states and reproduces the
  * golden gains to 1e-11 at the golden point.
- * Out as agx_solve; out_stop = the KKT norm; out_iters = accepted steps; status AGX_STATUS_CONVERGED = KKT met. */
+ * Out as agx_solve; out_stop = the KKT norm; out_iters = passes of the solver loop whose line search ran (the
+ * solver's iter counter: a pass whose every step length is refused counts too); AGX_STATUS_CONVERGED = KKT met. */
 int agx_solve_sqp(agx_handle* h, const double* x0, const double* xs_ws, const double* us_ws,
                   int max_iter, const agx_sqp_opts* opts, double* out_xs, double* out_us,
                   double* out_K, double* out_k, double* out_cost, int32_t* out_iters,

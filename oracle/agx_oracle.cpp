@@ -1184,7 +1184,7 @@ void agx_fddp_opts_default(agx_fddp_opts* o) {
   o->th_grad = 1e-12; o->th_stepdec = 0.5; o->th_stepinc = 0.01; o->th_acceptstep = 0.1;
   o->th_acceptnegstep = 2.0; o->th_stop = 1e-9;
   o->reg_init = std::numeric_limits<double>::quiet_NaN();
-  o->fixed_iters = 0; o->n_alphas = 10; o->eager_exit = 0; o->reserved = 0;
+  o->fixed_iters = 0; o->n_alphas = 10; o->eager_exit = 0; o->reserved = 0; o->max_solve_time = 0.0;
 }
 
 void orc_rnea(const agx_model* m, const double* q, const double* v, const double* a, int n, double* tau) {
@@ -1482,8 +1482,8 @@ struct Sqp : Fddp {
       if (accepted) {
         xs.swap(xs_try); us.swap(us_try);
         have_diff = false;
-        ++iters;
       }
+      ++iters;  // the solver's iteration counter counts every pass of its loop, step taken or not
       if (steplength > th_stepdec) reg = std::fmax(reg / reg_factor, reg_min);
       if (steplength <= th_stepinc) {
         reg = std::fmin(reg * reg_factor, reg_max);
@@ -1552,7 +1552,7 @@ int orc_riccati_sigma(const agx_model* m, const double* refs, const double* dts,
 }
 
 void agx_sqp_opts_default(agx_sqp_opts* o) {
-  o->sigma = 1e-6; o->reg = 1e-9; o->mu = 10.0; o->termination_tolerance = 1e-3; o->n_alphas = 10; o->eager_exit = 0;
+  o->sigma = 1e-6; o->reg = 1e-9; o->mu = 10.0; o->termination_tolerance = 1e-3; o->n_alphas = 10; o->eager_exit = 0; o->max_solve_time = 0.0;
 }
 
 // SolverCSQP.solve (unconstrained) over B problems; one problem per OpenMP thread

@@ -110,12 +110,6 @@ def test_regularisation_failure_path(orc, m7):
     np.testing.assert_array_equal(e["iters"], o["iters"])
 
 
-def test_unsupported_models_are_refused():
-    t9 = panda_table(lock_fingers=False)
-    with pytest.raises(RuntimeError, match="only nv = 7"):
-        emu.Handle(t9.to_struct(), np.full(3, 0.01), 1, 3)
-
-
 def test_golden_gains_through_the_shipped_kernels(orc, golden):
     """KAT-1 / KAT-3 of SURVEY.md 8(c) on the product kernels (emulated): the reference's golden states follow
     from its golden controls through `integrate`, and its golden Riccati gains are reproduced by the backward
