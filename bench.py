@@ -150,7 +150,7 @@ def run_reference(args):
     return 0
 
 
-def mpc_latency(prob, dev, ticks, solver="fddp"):
+def mpc_latency(prob, dev, ticks, solver="fddp", with_cpu=False):
     """p50 / p99 of one MPC tick's solve (reference: MPCDebugData.duration_ocp_solve_ns, mpc.py:52-64): reference
     update, warm start, solve, read-back of the control the node publishes (us[0], K[0])."""
     import torch
@@ -192,8 +192,24 @@ def mpc_latency(prob, dev, ticks, solver="fddp"):
     del u0, K0
     ts = np.array(ts[20:]) * 1e3
     track = float(np.abs(x[0, :nv].cpu().numpy() - q[ticks]).max())
+    cpu = None
+    if solver == "fddp" and with_cpu:
+        # the same closed loop on the host: CPU restatement, one thread, then node-parallel calc/calcDiff
+        # (ShootingProblem.nthreads, ocp_base_croco.py:62); timed span = horizon window + solve, as on the device
+        from oracle import orc
+
+        m = table.to_struct()
+        x0h, xs0h, us0h = np.concatenate([q[0], v[0]]), np.concatenate([q[: T + 1], v[: T + 1]], 1), u[:T]
+        cpu = {"kind": "port", "what": "CPU restatement of Crocoddyl FDDP (oracle/agx_oracle.cpp), same closed loop, same "
+                                       "ticks; wall time of horizon window + solve per tick"}
+        cores = len(os.sched_getaffinity(0))
+        for name, nt in (("threads_1", 1), ("node_parallel", min(8, cores))):
+            ns, it_c, xf = orc.mpc_latency(m, rows, np.full(T, dt), x0h, xs0h, us0h, ticks, N_ITERS, None, nt)
+            cpu[name] = {"threads": nt, "p50_ms": float(np.percentile(ns[20:], 50)) * 1e-6,
+                         "p99_ms": float(np.percentile(ns[20:], 99)) * 1e-6, "mean_iters": float(it_c[20:].mean()),
+                         "final_tracking_error_rad": float(np.abs(xf[:nv] - q[ticks]).max())}
     return {"p50_ms": float(np.percentile(ts, 50)), "p99_ms": float(np.percentile(ts, 99)), "ticks": int(len(ts)),
-            "mean_iters": float(np.mean(iters[20:])), "final_tracking_error_rad": track,
+            "mean_iters": float(np.mean(iters[20:])), "final_tracking_error_rad": track, "cpu_baseline": cpu,
             "workload": "cfg1: B=1, T=20, dt=0.01, sine in configuration space (0.2 rad, 4 s), closed loop with shift "
                         "warm start, <=10 FDDP iterations per tick (eager_exit: no launches queued past convergence); host wall clock of set_refs_window + solve + D2H of us[0], K[0]"}
 
@@ -353,7 +369,7 @@ def run_ours(args):
     # with the shift warm start, <= 10 FDDP iterations per tick (early exit allowed), rank 0 only
     lat = None
     if rank == 0 and not args.no_latency:
-        lat = mpc_latency(prob, dev, args.latency_ticks)
+        lat = mpc_latency(prob, dev, args.latency_ticks, with_cpu=not args.no_cpu)
         lat_sqp = mpc_latency(prob, dev, args.latency_ticks, solver="csqp")
         lat["csqp_mode"] = {k: lat_sqp[k] for k in ("p50_ms", "p99_ms", "mean_iters", "final_tracking_error_rad")}
 
@@ -500,7 +516,7 @@ def main():
     ap.add_argument("--sample", type=int, default=None, help="problems per step of the reference arm")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-latency", action="store_true", help="skip the B=1 latency leg")
-    ap.add_argument("--latency-ticks", type=int, default=300, help="MPC ticks of the B=1 latency leg")
+    ap.add_argument("--latency-ticks", type=int, default=1000, help="MPC ticks of the B=1 latency leg")
     ap.add_argument("--no-probe", action="store_true", help="skip the FP64 peak probe (profiler runs)")
     ap.add_argument("--no-sqp", action="store_true", help="skip the SQP-mode leg")
     args = ap.parse_args()

@@ -30,6 +30,7 @@
 // collision residuals.
 //
 // Build: see oracle/Makefile (g++ -O3 -march=x86-64-v3 -fopenmp -ffp-contract=off).
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -893,13 +894,27 @@ struct Fddp {
     Vxx.assign((T + 1) * nx * nx, 0); Vx.assign((T + 1) * nx, 0);
   }
   // problem.calc + calcDiff at (xs, us), then the gaps (SolverAbstract::computeDynamicFeasibility)
+  int node_threads = 1;  // > 1: problem.calc / calcDiff run over the nodes in parallel (ShootingProblem.nthreads,
+                         // ocp_base_croco.py:62) -- the B = 1 latency baseline; the batched baseline keeps 1
   bool calc_diff() {
     double c = 0;
-    for (int t = 0; t <= T; ++t) {
-      const bool term = (t == T);
-      if (!node_calc_diff(*m, refs + t * rs, term ? 0.0 : dts[t], term, &xs[t * nx], term ? nullptr : &us[t * nv], nd[t]))
-        return false;
-      c += nd[t].cost;
+    if (node_threads > 1) {
+      int bad = 0;
+#pragma omp parallel for num_threads(node_threads) schedule(static) reduction(+ : bad)
+      for (int t = 0; t <= T; ++t) {
+        const bool term = (t == T);
+        if (!node_calc_diff(*m, refs + t * rs, term ? 0.0 : dts[t], term, &xs[t * nx], term ? nullptr : &us[t * nv], nd[t]))
+          bad += 1;
+      }
+      if (bad) return false;
+      for (int t = 0; t <= T; ++t) c += nd[t].cost;
+    } else {
+      for (int t = 0; t <= T; ++t) {
+        const bool term = (t == T);
+        if (!node_calc_diff(*m, refs + t * rs, term ? 0.0 : dts[t], term, &xs[t * nx], term ? nullptr : &us[t * nv], nd[t]))
+          return false;
+        c += nd[t].cost;
+      }
     }
     cost = c;
     if (!is_feasible) {
@@ -1359,6 +1374,48 @@ int orc_solve(const agx_model* models, int n_models, const double* refs, const d
       if (out_stop) out_stop[b] = s.stop;
     }
   }
+  return 0;
+}
+
+// Closed-loop single-problem MPC on the CPU (the B = 1 latency baseline of bench.py; BASELINE config 1): per tick the
+// horizon window of the reference stream (uniform steps: point k + t for node t; past the end the last point repeats),
+// FDDP from the shifted previous solution with early exit, then the plant = the OCP's integrator.  Mirrors MPC.run
+// (mpc.py:32-66) with WarmStartShiftPreviousSolution; out_ns[k] = wall time of tick k's window copy + solve
+// (mpc.py:52-64 stamps the same span as duration_ocp_solve_ns).  node_threads = ShootingProblem.nthreads.
+int orc_mpc_latency(const agx_model* m, const double* stream_refs, int n_points, const double* dts, int T,
+                    const double* x_init, const double* xs_init, const double* us_init, int ticks, int max_iter,
+                    const agx_fddp_opts* opts, int node_threads, long long* out_ns, int32_t* out_iters,
+                    double* out_x_final) {
+  const int nv = m->nv, nx = 2 * nv, rs = agx_ref_size(nv);
+  std::vector<double> refs((size_t)(T + 1) * rs), x(x_init, x_init + nx), xs(xs_init, xs_init + (size_t)(T + 1) * nx),
+      us(us_init, us_init + (size_t)T * nv), xs2(xs.size()), us2(us.size());
+  Fddp s;
+  s.init(m, refs.data(), dts, T);
+  s.node_threads = node_threads > 1 ? node_threads : 1;
+  for (int k = 0; k < ticks; ++k) {
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int t = 0; t <= T; ++t) {
+      int pnt = k + t;
+      if (pnt >= n_points) pnt = n_points - 1;
+      std::memcpy(&refs[(size_t)t * rs], stream_refs + (size_t)pnt * rs, sizeof(double) * rs);
+    }
+    int iters = 0;
+    s.solve(x.data(), xs.data(), us.data(), max_iter, *opts, &iters);
+    const auto t1 = std::chrono::steady_clock::now();
+    out_ns[k] = (long long)std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count();
+    out_iters[k] = iters;
+    // plant step with the first control, then the shifted warm start (uniform steps)
+    double xn[MAXX], c;
+    if (!node_calc(*m, refs.data(), dts[0], false, x.data(), s.us.data(), xn, &c)) return -1;
+    for (int i = 0; i < nx; ++i) x[i] = xn[i];
+    for (int t = 0; t < T; ++t) std::memcpy(&xs2[(size_t)t * nx], &s.xs[(size_t)(t + 1) * nx], sizeof(double) * nx);
+    std::memcpy(&xs2[(size_t)T * nx], &s.xs[(size_t)T * nx], sizeof(double) * nx);
+    for (int t = 0; t < T; ++t)
+      std::memcpy(&us2[(size_t)t * nv], &s.us[(size_t)(t + 1 < T ? t + 1 : t) * nv], sizeof(double) * nv);
+    xs = xs2; us = us2;
+    for (int i = 0; i < nx; ++i) xs[i] = x[i];
+  }
+  for (int i = 0; i < nx; ++i) out_x_final[i] = x[i];
   return 0;
 }
 

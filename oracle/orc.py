@@ -177,6 +177,25 @@ def solve(models, refs, dts, x0, xs_ws, us_ws, max_iter, opts=None, nthreads=0):
     return out
 
 
+def mpc_latency(m, stream_refs, dts, x0, xs0, us0, ticks, max_iter, opts=None, node_threads=1):
+    """Closed-loop single-problem MPC on the CPU (``orc_mpc_latency``): per-tick solve times in ns, iterations, final x."""
+    stream_refs, dts, x0, xs0, us0 = _c(stream_refs), _c(dts), _c(x0), _c(xs0), _c(us0)
+    T = len(dts)
+    if opts is None:
+        opts = _abi.default_fddp_opts()
+    ns = np.zeros(ticks, dtype=np.int64)
+    iters = np.zeros(ticks, dtype=np.int32)
+    xf = np.zeros(2 * m.nv)
+    f = lib().orc_mpc_latency
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, _P, C.c_int, _P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                  C.c_void_p, _P]
+    rc = f(C.addressof(m), _p(stream_refs), stream_refs.shape[0], _p(dts), T, _p(x0), _p(xs0), _p(us0), int(ticks),
+           int(max_iter), C.addressof(opts), int(node_threads), ns.ctypes.data, iters.ctypes.data, _p(xf))
+    assert rc == 0
+    return ns, iters, xf
+
+
 def solve_sqp(models, refs, dts, x0, xs_ws, us_ws, max_iter, opts=None, nthreads=0):
     """mim_solvers.SolverCSQP (unconstrained) restated: see ``Sqp`` in agx_oracle.cpp."""
     mp, nm, nv = _models(models)

@@ -32,6 +32,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     helper = BatchedShootingProblem(panda_table(), np.full(2, 0.01), 1, device=dev)
     rn = lambda q, v, a: helper.rnea(q, v, a).cpu().numpy()  # noqa: E731
+    helper9 = BatchedShootingProblem(panda_table(lock_fingers=False), np.full(2, 0.01), 1, device=dev)
+    rn9 = lambda q, v, a: helper9.rnea(q, v, a).cpu().numpy()  # noqa: E731
     steps, warm = int(os.environ.get("AGX_STEPS", "10")), 3
     which = os.environ.get("AGX_CONFIGS", "3,4,5").split(",")
     per_gpu5 = int(os.environ.get("AGX_CFG5_PER_GPU", "8192"))
@@ -40,6 +42,9 @@ def main():
               lambda B: cartesian_sine_batch(B, T=50, rnea=rn)),
         "4": ("cfg4: 4096 pick-and-place OCPs with two capsule-pair collision costs (fingers locked), T=100, 3 FDDP "
               "iterations", 4096, 3, lambda B: pick_and_place_collision_batch(B, T=100, rnea=rn)),
+        "4f": ("cfg4 as BASELINE.json states it: 4096 pick-and-place OCPs, nv=9 WITH the finger joints (general-tree "
+               "kernels), two capsule-pair collision costs, T=100, 3 FDDP iterations", 4096, 3,
+               lambda B: pick_and_place_collision_batch(B, T=100, rnea=rn9, lock_fingers=False)),
         "5": (f"cfg5: {per_gpu5 * world} goal-reaching OCPs with per-problem inertial tables, T=50, 10 FDDP iterations",
               per_gpu5 * world, 10, lambda B: model_sensibility_batch(B, T=50, rnea=rn)),
     }
@@ -57,6 +62,12 @@ def main():
         for _ in range(warm):
             prob.solve(x0, xs, us, iters, opts, out=out)
         torch.cuda.synchronize()
+        phases = None
+        if os.environ.get("AGX_PHASES"):
+            prob.set_timing(True)
+            prob.solve(x0, xs, us, iters, opts, out=out)
+            phases = {k: v for k, v in prob.get_timing().items() if v["launches"]}
+            prob.set_timing(False)
         if world > 1:
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -72,7 +83,8 @@ def main():
         if rank == 0:
             print(json.dumps({"config": name, "n_gpus": world, "B_total": B, "iters": iters, "steps": steps,
                               "ms_per_step": float(ms) / steps, "solves_per_s": B * steps / (float(ms) * 1e-3),
-                              "finite": finite, "mean_cost_rank0": float(out["cost"].mean())}), flush=True)
+                              "finite": finite, "mean_cost_rank0": float(out["cost"].mean()), "phases": phases}),
+                  flush=True)
         del prob
     if world > 1:
         dist.destroy_process_group()
