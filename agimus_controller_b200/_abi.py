@@ -10,9 +10,12 @@ AGX_MAX_NV = 16
 AGX_MAX_CAPSULES = 4
 AGX_MAX_COLLISION_PAIRS = 2
 AGX_N_COST_TERMS = 13
+AGX_N_COSTS = 5
 AGX_STATUS_LINESEARCH = 4
 AGX_JOINT_REVOLUTE = 0
 AGX_JOINT_PRISMATIC = 1
+AGX_POSE_PLACEMENT = 0
+AGX_POSE_TRANSLATION_WORLD = 1
 
 AGX_OK = 0
 AGX_EINVAL = -1
@@ -57,6 +60,8 @@ class AgxModel(C.Structure):
         ("n_pairs", _I),
         ("pair_a", _I * AGX_MAX_COLLISION_PAIRS),
         ("pair_b", _I * AGX_MAX_COLLISION_PAIRS),
+        ("pose_mode", _I),
+        ("reserved_", _I),
     ]
 
 
@@ -177,6 +182,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.agx_sqp_opts_default.restype = None
     lib.agx_cost_terms.argtypes = [H, _P, _P, _P, _P]
     lib.agx_cost_terms.restype = C.c_int
+    lib.agx_cost_derivatives.argtypes = [H, _P, _P, _P, _P, _P]
+    lib.agx_cost_derivatives.restype = C.c_int
     lib.agx_shift_warmstart.argtypes = [H, _P, _P, _P, _P, _P]
     lib.agx_shift_warmstart.restype = C.c_int
     lib.agx_riccati.argtypes = [H, _P, _P, _P, C.c_double, _P, _P, _P, _P]
@@ -196,5 +203,5 @@ EXPORTED_SYMBOLS = (
     "agx_ref_size", "agx_fddp_opts_default", "agx_create", "agx_destroy", "agx_last_error", "agx_set_refs",
     "agx_calc", "agx_calc_diff", "agx_rollout", "agx_integrate", "agx_rnea", "agx_solve", "agx_launch_count",
     "agx_set_timing", "agx_get_timing", "agx_probe_fp64", "agx_riccati", "agx_cost_terms", "agx_shift_warmstart", "agx_set_refs_window",
-    "agx_solve_sqp", "agx_sqp_opts_default", "agx_set_capsule",
+    "agx_solve_sqp", "agx_sqp_opts_default", "agx_set_capsule", "agx_cost_derivatives",
 )

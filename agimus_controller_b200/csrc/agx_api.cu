@@ -138,6 +138,8 @@ bool flatten_model(const agx_model& m, double* out, std::string& why) {
     out[MT_COL + 2 + 2 * k] = (double)m.pair_a[k];
     out[MT_COL + 3 + 2 * k] = (double)m.pair_b[k];
   }
+  if (m.pose_mode != AGX_POSE_PLACEMENT && m.pose_mode != AGX_POSE_TRANSLATION_WORLD) { why = "unknown pose_mode"; return false; }
+  out[MT_COL + 6] = (double)m.pose_mode;
   return true;
 }
 
@@ -254,6 +256,8 @@ bool flatten_tree_model(const agx_model& m, double* out, std::string& why) {
     out[TT_COL + 2 + 2 * k] = (double)m.pair_a[k];
     out[TT_COL + 3 + 2 * k] = (double)m.pair_b[k];
   }
+  if (m.pose_mode != AGX_POSE_PLACEMENT && m.pose_mode != AGX_POSE_TRANSLATION_WORLD) { why = "unknown pose_mode"; return false; }
+  out[TT_COL + 6] = (double)m.pose_mode;
   return true;
 }
 
@@ -271,6 +275,7 @@ struct agx_handle {
   double* d_dts = nullptr;
   double* d_x0 = nullptr;
   double* d_K_internal = nullptr;
+  double* d_refs_scratch = nullptr;  // masked copy of the references (agx_cost_derivatives), allocated on first use
   int32_t* d_hidx = nullptr;  // horizon indexes of the reference stream: cumulative step factors dts[i] / dts[0]
   int32_t* h_done = nullptr;  // pinned host copy of the completion flags (eager_exit)
   int32_t* d_live = nullptr;  // [0]: unfinished problems; [1..12]: problems entering each step length (SQP line search)
@@ -522,7 +527,7 @@ int agx_destroy(agx_handle* h) {
   if (!h) return AGX_OK;
   {
     DeviceGuard g(h->device);
-    dev_free(h->d_model); dev_free(h->d_refs); dev_free(h->d_dts); dev_free(h->d_x0); dev_free(h->d_K_internal); dev_free(h->d_hidx); dev_free(h->d_live);
+    dev_free(h->d_model); dev_free(h->d_refs); dev_free(h->d_dts); dev_free(h->d_x0); dev_free(h->d_K_internal); dev_free(h->d_hidx); dev_free(h->d_live); dev_free(h->d_refs_scratch);
 #if AGX_GPU
     if (h->h_done) cudaFreeHost(h->h_done);
 #endif
@@ -706,6 +711,39 @@ int agx_cost_terms(agx_handle* h, const double* xs, const double* us, double* ou
   const long long ents = (long long)h->B * (h->T + 1);
   AGX_LAUNCH_COL(h, cost_terms_kernel, (ents + 127) / 128, 128, 0, (stream_t)stream, problem_of(h), xs, us, out_terms);
   return check_launch(h, "agx_cost_terms");
+}
+
+int agx_cost_derivatives(agx_handle* h, const double* xs, const double* us, double* out_Lx, double* out_Lu, void* stream) {
+  if (!h || !xs || !us || (!out_Lx && !out_Lu)) return AGX_EINVAL;
+  DeviceGuard g(h->device);
+  stream_t st = (stream_t)stream;
+  const long long ents = (long long)h->B * (h->T + 1);
+  if (!h->d_refs_scratch && !dev_alloc((void**)&h->d_refs_scratch, sizeof(double) * ents * h->ref_size))
+    return fail(h, AGX_ENOMEM, "agx_cost_derivatives: allocation of the scratch reference table failed");
+  Problem P = problem_of(h);
+  P.refs = h->d_refs_scratch;
+  int off_lq = CK_LQ, off_lv = CK_LV, off_lu = CK_LU;
+  if (h->tree) {
+    const int ntri = h->nv * (h->nv + 1) / 2;
+    off_lq = ntri + 2 * h->nv; off_lv = ntri + 3 * h->nv; off_lu = ntri + 4 * h->nv;
+  }
+  for (int slot = 0; slot < AGX_N_COSTS; ++slot) {
+    const long long nref = ents * h->ref_size;
+    AGX_LAUNCH(h, mask_refs_kernel, (nref + 255) / 256, 256, 0, st, ents, h->nv, h->ref_size, slot,
+               (const double*)h->d_refs, h->d_refs_scratch);
+    if (h->tree) {
+      tree_launch_calc_diff(h, P, xs, us, nullptr, nullptr, nullptr, st);
+    } else {
+      const int opc = NODE_CTA / 8;
+      AGX_LAUNCH_COL(h, calc_diff_kernel, (ents + opc - 1) / opc, NODE_CTA, sizeof(double) * OCT_BOARD * opc, st, P, xs, us,
+                     (const int32_t*)nullptr, (const int32_t*)nullptr, (const int32_t*)nullptr, 1,
+                     (const int32_t*)nullptr, h->W.rec, h->W.crec);
+    }
+    const long long nout = ents * h->nv;
+    AGX_LAUNCH(h, extract_gradients_kernel, (nout + 255) / 256, 256, 0, st, ents, h->T + 1, h->nv, h->crec_size, off_lq,
+               off_lv, off_lu, (const double*)h->d_dts, slot, AGX_N_COSTS, (const double*)h->W.crec, out_Lx, out_Lu);
+  }
+  return check_launch(h, "agx_cost_derivatives");
 }
 
 int agx_shift_warmstart(agx_handle* h, const double* xs, const double* us, double* out_xs, double* out_us, void* stream) {

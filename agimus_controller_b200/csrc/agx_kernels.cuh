@@ -1344,6 +1344,37 @@ __global__ void finalize_kernel(Problem P, Work W, SolverState S, double* out_xs
   }
 }
 
+// ---- per-cost derivatives (agx_cost_derivatives): the references with every weight but one cost's zeroed, and the
+// gradient part of the cost records unscaled into [n][AGX_N_COSTS][nx] / [n][AGX_N_COSTS][nv]
+__global__ void mask_refs_kernel(long long n_nodes, int nv, int ref_size, int slot, const double* __restrict__ refs,
+                                 double* __restrict__ out) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n_nodes * ref_size) return;
+  const int k = (int)(gid % ref_size), nx = 2 * nv, o = 2 * nx + 2 * nv;
+  double v = refs[gid];
+  const bool is_wx = k >= nx && k < 2 * nx, is_wu = k >= 2 * nx + nv && k < o, is_wp = k >= o + 12 && k < o + 18;
+  const bool is_c0 = k == o + 18, is_c1 = k == o + 19;
+  if ((is_wx && slot != 0) || (is_wu && slot != 1) || (is_wp && slot != 2) || (is_c0 && slot != 3) || (is_c1 && slot != 4))
+    v = 0.0;
+  out[gid] = v;
+}
+__global__ void extract_gradients_kernel(long long n_nodes, int T1, int nv, int crec_size, int off_lq, int off_lv,
+                                         int off_lu, const double* __restrict__ dts, int slot, int n_slots,
+                                         const double* __restrict__ crec, double* __restrict__ out_Lx,
+                                         double* __restrict__ out_Lu) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n_nodes * nv) return;
+  const long long n = gid / nv;
+  const int i = (int)(gid % nv), t = (int)(n % T1);
+  const double inv = t == T1 - 1 ? 1.0 : 1.0 / dts[t];
+  const double* C = crec + (size_t)n * crec_size;
+  if (out_Lx) {
+    out_Lx[((size_t)n * n_slots + slot) * 2 * nv + i] = C[off_lq + i] * inv;
+    out_Lx[((size_t)n * n_slots + slot) * 2 * nv + nv + i] = C[off_lv + i] * inv;
+  }
+  if (out_Lu) out_Lu[((size_t)n * n_slots + slot) * nv + i] = t == T1 - 1 ? 0.0 : C[off_lu + i] * inv;
+}
+
 // ---- the same three kernels with run-time sizes (general-tree path, agx_tree.cuh)
 __global__ void gather_refs_kernel_n(int B, int T1, int ref_size, const double* __restrict__ stream, int n_streams,
                                      int n_points, const int32_t* __restrict__ start, int start0,

@@ -132,6 +132,11 @@ AGX_DEV double node_costs(const LaneDyn& d, int j, unsigned omask, const double*
   const double* wp = pref + 3;
   double Rf[9], pf[3], r6[6], Jl[18];
   frame_residual(R6, p6, model, Rref, pref, Rf, pf, r6, DERIV ? Jl : nullptr);
+  const bool tworld = model[MT_COL + 6] != 0.0;  // ResidualModelFrameTranslation: linear part p_f - pref in the world
+  if (tworld) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) r6[k] = pf[k] - pref[k];
+  }
   double cpose = 0.0;
 #pragma unroll
   for (int k = 0; k < 6; ++k) cpose += 0.5 * wp[k] * r6[k] * r6[k];
@@ -208,6 +213,10 @@ AGX_DEV double node_costs(const LaneDyn& d, int j, unsigned omask, const double*
       rqc[i] = A[3 * i] * cl[0] + A[3 * i + 1] * cl[1] + A[3 * i + 2] * cl[2] + Bm[3 * i] * ca[0] +
                Bm[3 * i + 1] * ca[1] + Bm[3 * i + 2] * ca[2];
       rqc[3 + i] = A[3 * i] * ca[0] + A[3 * i + 1] * ca[1] + A[3 * i + 2] * ca[2];
+    }
+    if (tworld) {  // d(p_f)/dq_j = world velocity of the frame origin under joint j
+#pragma unroll
+      for (int k = 0; k < 3; ++k) rqc[k] = t[k];
     }
 #pragma unroll
     for (int k = 0; k < 6; ++k) srq[j * 6 + k] = rqc[k];
@@ -325,6 +334,11 @@ AGX_DEV double thread_node_cost(const double* __restrict__ model, const double* 
   const double* wp = pref + 3;
   double Rf[9], pf[3], r6[6], Jl[18];
   frame_residual(Rf0, pf0, model, Rref, pref, Rf, pf, r6, DERIV ? Jl : nullptr);
+  const bool tworld = model[MT_COL + 6] != 0.0;  // ResidualModelFrameTranslation: linear part p_f - pref in the world
+  if (tworld) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) r6[k] = pf[k] - pref[k];
+  }
   double cost = 0.0;
 #pragma unroll
   for (int k = 0; k < 6; ++k) cost += 0.5 * wp[k] * r6[k] * r6[k];
@@ -429,6 +443,10 @@ AGX_DEV double thread_node_cost(const double* __restrict__ model, const double* 
         Jw[i][k] = A[3 * k] * cl[0] + A[3 * k + 1] * cl[1] + A[3 * k + 2] * cl[2] + Bm[3 * k] * ca[0] +
                    Bm[3 * k + 1] * ca[1] + Bm[3 * k + 2] * ca[2];
         Jw[i][3 + k] = A[3 * k] * ca[0] + A[3 * k + 1] * ca[1] + A[3 * k + 2] * ca[2];
+      }
+      if (tworld) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) Jw[i][k] = t[k];
       }
 #pragma unroll
       for (int k = 0; k < 6; ++k) lq += Jw[i][k] * wr6[k];

@@ -30,58 +30,131 @@ from .problem import pack_refs
 from .robot_model import RobotTable
 from .solver import BatchedShootingProblem
 
-_SUPPORTED_RESIDUALS = ("ResidualModelState", "ResidualModelControl", "ResidualModelFramePlacement",
-                        "ResidualDistanceCollision")
+# YAML residual classes (ocp_croco_generic.py:153-550) -> (slot of the reference record, kind)
+_RESIDUALS = {
+    "ResidualModelState": ("state", "state"),
+    "ResidualModelControl": ("control", "control"),
+    "ResidualModelFramePlacement": ("pose", "placement"),
+    "ResidualModelFramePlacementStatic": ("pose", "placement"),
+    "ResidualModelFrameTranslation": ("pose", "translation"),
+    "ResidualModelFrameTranslationStatic": ("pose", "translation"),
+    "ResidualModelFrameRotation": ("pose", "rotation"),
+    "ResidualModelFrameRotationStatic": ("pose", "rotation"),
+    "ResidualModelVisualServoing": ("pose", "visual_servoing"),
+    "ResidualDistanceCollision": ("collision", "collision"),
+    "ResidualDistanceCollision2": ("collision", "collision"),  # same residual, evaluated on the state's shared geometry
+}
+# not on the device path: their Hessians need the Lxu / Lqv blocks the compact cost record does not carry
+_REFUSED = {
+    "ResidualModelControlGrav": "its Gauss-Newton Hessian couples q and u (Lxu != 0)",
+    "ResidualModelFrameVelocity": "its residual depends on q and v (Lqv != 0)",
+    "ResidualModelFrameVelocityStatic": "its residual depends on q and v (Lqv != 0)",
+}
+_NR = {"state": None, "control": None, "placement": 6, "translation": 3, "rotation": 3, "visual_servoing": 6}
 
 
-def flatten_cost_stack(model_def: dict, terminal: bool) -> dict:
-    """``{slot: CostModelSum weight}`` for the three residual slots the kernels implement.
+def _static_weights(act: T.Optional[dict], nr: int) -> np.ndarray:
+    """Activation weights as ``ActivationModelWeightedQuad.build`` resolves them (ocp_croco_generic.py:106-114):
+    no activation / ``weights: null`` -> ones, a scalar -> that scalar, a list -> itself."""
+    w = None if act is None else act.get("weights")
+    if w is None:
+        return np.ones(nr)
+    try:
+        return float(w) * np.ones(nr)
+    except (ValueError, TypeError):
+        w = np.asarray(w, dtype=np.float64)
+        assert w.size == nr, f"activation weights have {w.size} entries, the residual {nr}"
+        return w
 
-    ``model_def`` is the ``running_model`` / ``terminal_model`` subtree of the OCP definition YAML
-    (``ocp_goal_reaching.yaml:1-63``).  Anything the device path does not cover raises instead of being dropped.
-    """
+
+def flatten_cost_stack(model_def: dict, terminal: bool, nv: int = 7) -> dict:
+    """One cost stack (``running_model`` / ``terminal_model`` subtree of the OCP definition YAML,
+    ``ocp_goal_reaching.yaml:1-63``) flattened into descriptors of the reference record's slots:
+
+    ``{"state": d | None, "control": d | None, "pose": [d, ...], "collisions": [d, ...], "weights": {slot: w}, "names":
+    {slot: name}}`` with ``d = dict(name, kind, weight (CostModelSum weight, 0 when inactive), update, ref (the YAML's
+    static reference or None), w (the YAML's static activation weights), publish, frame, ...)``.
+
+    ``update: false`` keeps the YAML's reference and weights for every tick, ``update: true`` takes them from the
+    trajectory point (``DifferentialActionModelFreeFwdDynamics.update``, ``ocp_croco_generic.py:712-724``).  Anything
+    the device path does not cover raises instead of being dropped."""
     if model_def.get("class") != "IntegratedActionModelEuler":
         raise NotImplementedError(f"integrator {model_def.get('class')} is not supported on the device path")
     diff = model_def["differential"]
     if diff.get("class") != "DifferentialActionModelFreeFwdDynamics":
         raise NotImplementedError(f"differential model {diff.get('class')} is not supported on the device path")
     if diff.get("constraints"):
-        raise NotImplementedError("constraints need the CSQP solver mode (SURVEY.md 8f N1): not on the FDDP device path")
-    slots = {"state": 0.0, "control": 0.0, "pose": 0.0}
-    names = {}
-    collisions = []
+        raise NotImplementedError("constraints need CSQP's ADMM loop for inequality constraints: not on the device path")
+    out = {"state": None, "control": None, "pose": [], "collisions": []}
     for item in diff.get("costs", []):
         cost = item["cost"]
         if cost.get("class") != "CostModelResidual":
             raise NotImplementedError(f"cost class {cost.get('class')}")
         act = cost.get("activation")
-        rcls = cost["residual"].get("class")
-        if rcls not in _SUPPORTED_RESIDUALS:
+        res = cost["residual"]
+        rcls = res.get("class")
+        if rcls in _REFUSED:
+            raise NotImplementedError(f"residual {rcls} is not supported on the device path: {_REFUSED[rcls]}")
+        if rcls not in _RESIDUALS:
             raise NotImplementedError(f"residual {rcls} is not supported on the device path")
-        if rcls == "ResidualDistanceCollision":
+        slot, kind = _RESIDUALS[rcls]
+        weight = float(item.get("weight", 1.0)) if item.get("active", True) else 0.0
+        d = dict(name=item["name"], kind=kind, weight=weight, update=bool(item.get("update", False)),
+                 publish=bool(item.get("publish_residual", False)))
+        if slot == "collision":
             # colmpc distance residual under the squared-exponential activation
-            # (ocp_croco_generic.py:119-147, :499-535; ocp_traj_tracking_collision_avoidance.yaml:36-46)
+            # (ocp_croco_generic.py:119-147, :499-550; ocp_traj_tracking_collision_avoidance.yaml:36-46)
             acls = (act or {}).get("class")
             quad_exp = acls == "ActivationModelQuadExp" or (acls == "ActivationModelExp" and int(act.get("exponent", 1)) == 2)
             if not quad_exp:
                 raise NotImplementedError(f"activation {acls} on a collision residual is not supported on the device path")
-            res = cost["residual"]
             pair = tuple(res["collision_pair"]) if "collision_pair" in res else int(res.get("collision_pair_id", 0))
-            collisions.append(dict(name=item["name"], pair=pair, alpha=float(act.get("alpha", 1.0)),
-                                   weight=float(item.get("weight", 1.0)) if item.get("active", True) else 0.0,
-                                   update=bool(item.get("update", False))))
+            d.update(pair=pair, alpha=float(act.get("alpha", 1.0)))
+            out["collisions"].append(d)
             continue
         if act is not None and act.get("class") != "ActivationModelWeightedQuad":
             raise NotImplementedError(f"activation {act.get('class')} is not supported on the device path")
-        slot = {"ResidualModelState": "state", "ResidualModelControl": "control",
-                "ResidualModelFramePlacement": "pose"}[rcls]
         if slot == "control" and terminal:
             continue  # the terminal node has no control
-        if names.get(slot):
-            raise NotImplementedError(f"two costs on the {slot} residual")
-        names[slot] = item["name"]
-        slots[slot] = float(item.get("weight", 1.0)) if item.get("active", True) else 0.0
-    return {"weights": slots, "names": names, "collisions": collisions}
+        if slot in ("state", "control"):
+            if out[slot] is not None:
+                raise NotImplementedError(f"two costs on the {slot} residual")
+            nr = 2 * nv if slot == "state" else nv
+            ref = res.get("xref" if slot == "state" else "uref")
+            d.update(ref=None if ref is None else np.asarray(ref, dtype=np.float64), w=_static_weights(act, nr))
+            out[slot] = d
+            continue
+        # task-frame costs share the pose slot
+        static_frame = rcls.endswith("Static")
+        d.update(static_frame=static_frame, frame=res.get("frame_id") if static_frame else res.get("id"),
+                 ref=None if res.get("pref") is None else np.asarray(res["pref"], dtype=np.float64),
+                 w=_static_weights(act, _NR[kind]))
+        if kind == "visual_servoing":
+            d.update(frame=res["robot_frame"], static_frame=True, input_key=res["robot_frame"] + "_vs",
+                     transforms_key=(res["world_frame"], res["object_frame"]))
+        if any(o["kind"] == kind for o in out["pose"]):
+            raise NotImplementedError(f"two {kind} costs on the task frame")
+        out["pose"].append(d)
+    kinds = {d["kind"] for d in out["pose"]}
+    if len(kinds) > 1 and kinds != {"translation", "rotation"}:
+        raise NotImplementedError(f"task-frame costs {sorted(kinds)} cannot share the pose record")
+    # summary kept for callers that only need the CostModelSum weights / names per slot
+    out["weights"] = {"state": out["state"]["weight"] if out["state"] else 0.0,
+                      "control": out["control"]["weight"] if out["control"] else 0.0,
+                      "pose": max([d["weight"] for d in out["pose"]], default=0.0)}
+    out["names"] = {k: out[k]["name"] for k in ("state", "control") if out[k]}
+    if out["pose"]:
+        out["names"]["pose"] = out["pose"][0]["name"]
+    return out
+
+
+def pose_mode_of(running: dict, terminal: dict) -> int:
+    """``agx_model.pose_mode`` the two stacks ask for: world-frame translation when a FrameTranslation cost is there."""
+    kinds = [{d["kind"] for d in st["pose"]} for st in (running, terminal)]
+    tr = ["translation" in k for k in kinds]
+    if any(tr) and any(("placement" in k or "visual_servoing" in k) for k in kinds):
+        raise NotImplementedError("FrameTranslation and FramePlacement costs in one OCP: the pose record has one form")
+    return _abi.AGX_POSE_TRANSLATION_WORLD if any(tr) else _abi.AGX_POSE_PLACEMENT
 
 
 def resolve_collision_pairs(table: RobotTable, running: dict, terminal: dict) -> RobotTable:
@@ -113,60 +186,126 @@ def resolve_collision_pairs(table: RobotTable, running: dict, terminal: dict) ->
     return table.with_capsules({n: c for n, c in table.capsules.items()}, pairs, alphas.pop())
 
 
-def build_reference_rows(table: RobotTable, running: dict, terminal: dict, horizon: list) -> np.ndarray:
-    """``[T+1, ref_size]`` reference records of one horizon: what ``DifferentialActionModelFreeFwdDynamics.update``
-    (``ocp_croco_generic.py:712-724``) writes into the Crocoddyl residuals / activations of every node, with the
+def _pose_of(pt, key):
+    poses = pt.end_effector_poses
+    return poses[key] if key is not None else next(iter(poses.values()))
+
+
+def node_references(table: RobotTable, stack: dict, wp, transforms: T.Optional[dict] = None) -> dict:
+    """What ``DifferentialActionModelFreeFwdDynamics.update`` (``ocp_croco_generic.py:712-724``) leaves in the
+    residuals / activations of ONE node: ``{cost name: (reference, activation weights)}`` plus the packed slots
+    ``xref, wx, uref, wu, Rref, pref, wpose, wcol`` (CostModelSum weights folded in)."""
+    nv = table.nv
+    pt, wt = wp.point, wp.weights
+    out = {"by_name": {}}
+    xref, wx = np.zeros(2 * nv), np.zeros(2 * nv)
+    d = stack["state"]
+    if d is not None:
+        if d["update"]:
+            ref, w = np.asarray(pt.robot_state, dtype=np.float64), np.asarray(wt.w_robot_state, dtype=np.float64)
+        else:
+            ref = d["ref"] if d["ref"] is not None else np.zeros(2 * nv)  # ResidualModelState(state): xref = state.zero()
+            w = d["w"]
+        out["by_name"][d["name"]] = (ref, w)
+        xref, wx = ref, d["weight"] * w
+    uref, wu = np.zeros(nv), np.zeros(nv)
+    d = stack["control"]
+    if d is not None:
+        if d["update"]:
+            ref, w = np.asarray(pt.robot_effort, dtype=np.float64), np.asarray(wt.w_robot_effort, dtype=np.float64)
+        else:
+            ref, w = (d["ref"] if d["ref"] is not None else np.zeros(nv)), d["w"]
+        out["by_name"][d["name"]] = (ref, w)
+        uref, wu = ref, d["weight"] * w
+    Rref, pref, wpose = np.eye(3), np.zeros(3), np.zeros(6)
+    for d in stack["pose"]:
+        kind = d["kind"]
+        sl = {"placement": slice(0, 6), "visual_servoing": slice(0, 6), "translation": slice(0, 3),
+              "rotation": slice(3, 6)}[kind]
+        if d["update"]:
+            poses = pt.end_effector_poses
+            assert len(poses) == 1, (
+                f"{kind} residual requires exactly one end-effector pose, current is {poses}.")
+            key = d.get("input_key") if kind == "visual_servoing" else (d["frame"] if d["static_frame"] else None)
+            if key is not None:
+                assert key in poses, f"end_effector_poses should contain the key {key}"
+            ee_name = key if key is not None else next(iter(poses))
+            frame_name = d["frame"] if d["static_frame"] else ee_name
+            if frame_name != table.frame_name:
+                raise NotImplementedError(f"the device tables were built for frame '{table.frame_name}', got '{frame_name}'")
+            pose = poses[ee_name]
+            R, p = np.asarray(pose.rotation, dtype=np.float64), np.asarray(pose.translation, dtype=np.float64)
+            w6 = np.asarray(wt.w_end_effector_poses[ee_name], dtype=np.float64)
+            if kind == "visual_servoing":
+                # reference = wMo_vision * oMf_target when the transform is known (ocp_croco_generic.py:455-475)
+                wMo = (transforms or {}).get(d["transforms_key"])
+                assert not np.any(w6 != 0) or wMo is not None, (
+                    f"Weights are not all zeros and no transform for {d['transforms_key']}")
+                if wMo is not None:
+                    Rw, pw = np.asarray(wMo.rotation, dtype=np.float64), np.asarray(wMo.translation, dtype=np.float64)
+                    R, p = Rw @ R, pw + Rw @ p
+            w = w6[sl] if kind in ("translation", "rotation") else w6
+        else:
+            if d["frame"] is not None and isinstance(d["frame"], str) and d["frame"] != table.frame_name:
+                raise NotImplementedError(f"the device tables were built for frame '{table.frame_name}', got '{d['frame']}'")
+            if d["ref"] is None:
+                R, p = np.eye(3), np.zeros(3)
+            else:
+                from .robot_model import xyzquat_to_se3
+
+                R, p = xyzquat_to_se3(d["ref"]) if len(d["ref"]) >= 7 else (np.eye(3), np.asarray(d["ref"][:3]))
+            w = d["w"]
+        if kind in ("placement", "visual_servoing"):
+            Rref, pref = R, p
+            out["by_name"][d["name"]] = ((R, p), w)
+        elif kind == "translation":
+            pref = p
+            out["by_name"][d["name"]] = (p, w)
+        else:
+            Rref = R
+            out["by_name"][d["name"]] = (R, w)
+        wpose[sl] = d["weight"] * w
+    wcol = np.zeros(_abi.AGX_MAX_COLLISION_PAIRS)
+    for col in stack.get("collisions", []):
+        # the collision activation has no weight vector: update() sets the scalar CostModelSum weight
+        # (ocp_croco_generic.py:714-719)
+        wcol[col["slot"]] += float(wt.w_collision_avoidance) if col["update"] else col["weight"]
+    out.update(xref=xref, wx=wx, uref=uref, wu=wu, Rref=Rref, pref=pref, wpose=wpose, wcol=wcol)
+    return out
+
+
+def build_reference_rows(table: RobotTable, running: dict, terminal: dict, horizon: list,
+                         transforms: T.Optional[dict] = None) -> np.ndarray:
+    """``[T+1, ref_size]`` reference records of one horizon: what ``set_reference_weighted_trajectory``
+    (``ocp_croco_generic.py:855-892``) writes into the Crocoddyl residuals / activations of every node, with the
     CostModelSum weight folded into the activation weights.  The last point feeds the terminal model."""
     T1 = len(horizon)
     nv = table.nv
     rows = np.zeros((T1, _abi.ref_size(nv)))
     for t, wp in enumerate(horizon):
-        stack = terminal if t == T1 - 1 else running
-        w = stack["weights"]
-        pt, wt = wp.point, wp.weights
-        xref, wx = np.zeros(2 * nv), np.zeros(2 * nv)
-        if w["state"] != 0.0:
-            xref = np.asarray(pt.robot_state, dtype=np.float64)
-            wx = w["state"] * np.asarray(wt.w_robot_state, dtype=np.float64)
-        uref, wu = np.zeros(nv), np.zeros(nv)
-        if w["control"] != 0.0:
-            uref = np.asarray(pt.robot_effort, dtype=np.float64)
-            wu = w["control"] * np.asarray(wt.w_robot_effort, dtype=np.float64)
-        Rref, pref, wpose = np.eye(3), np.zeros(3), np.zeros(6)
-        if w["pose"] != 0.0:
-            assert len(pt.end_effector_poses) == 1, (
-                "ResidualModelFramePlacement requires exactly one end-effector pose, current is "
-                f"{pt.end_effector_poses}.")
-            ee_name, ee_pose = next(iter(pt.end_effector_poses.items()))
-            if ee_name != table.frame_name:
-                raise NotImplementedError(
-                    f"the device tables were built for frame '{table.frame_name}', got '{ee_name}'")
-            Rref = np.asarray(ee_pose.rotation, dtype=np.float64)
-            pref = np.asarray(ee_pose.translation, dtype=np.float64)
-            wpose = w["pose"] * np.asarray(wt.w_end_effector_poses[ee_name], dtype=np.float64)
-        wcol = np.zeros(_abi.AGX_MAX_COLLISION_PAIRS)
-        for col in stack.get("collisions", []):
-            # the collision activation has no weight vector: update() sets the scalar CostModelSum weight
-            # (ocp_croco_generic.py:714-719)
-            wcol[col["slot"]] += float(wt.w_collision_avoidance) if col["update"] else col["weight"]
-        rows[t] = pack_refs(nv, 0, 1, xref, wx, uref, wu, Rref, pref, wpose, wcol=wcol)[0, 0]
-        if t == T1 - 1:
-            rows[t, 5 * nv: 6 * nv] = 0.0  # the terminal node has no control cost
-        else:
-            rows[t, 5 * nv: 6 * nv] = wu   # pack_refs treats its last node as terminal
+        last = t == T1 - 1
+        r = node_references(table, terminal if last else running, wp, transforms)
+        rows[t] = pack_refs(nv, 0, 1, r["xref"], r["wx"], r["uref"], r["wu"], r["Rref"], r["pref"], r["wpose"],
+                            wcol=r["wcol"])[0, 0]
+        rows[t, 5 * nv: 6 * nv] = 0.0 if last else r["wu"]  # pack_refs treats its last node as terminal
     return rows
 
 
 class OCPBatchedFDDP(OCPBase):
-    def __init__(self, robot_table: RobotTable, params: OCPParamsBaseCroco,
+    def __init__(self, robot_table, params: OCPParamsBaseCroco,
                  yaml_file: T.Union[str, dict, T.IO], batch_size: int = 1, device=None,
-                 fddp_opts: T.Optional[_abi.AgxFddpOpts] = None, solver: str = "fddp") -> None:
-        """``solver = "fddp"`` (the solver BASELINE.json's north_star names) or ``"csqp"``: the solver the reference
-        instantiates (``mim_solvers.SolverCSQP``, ``ocp_base_croco.py:64-75``) in its unconstrained form, configured
-        from ``params.termination_tolerance`` as the reference does."""
+                 fddp_opts: T.Optional[_abi.AgxFddpOpts] = None, solver: str = "fddp", frame: T.Optional[str] = None) -> None:
+        """``robot_table``: a ``RobotTable``, or the reference's ``RobotModels`` (anything with ``robot_model`` /
+        ``collision_model`` / ``armature``: flattened with ``RobotTable.from_robot_models``; ``frame`` then names the task
+        frame).  ``solver = "fddp"`` (the solver BASELINE.json's north_star names) or ``"csqp"``: the solver the
+        reference instantiates (``mim_solvers.SolverCSQP``, ``ocp_base_croco.py:64-75``) in its unconstrained form,
+        configured from ``params.termination_tolerance`` as the reference does."""
         if solver not in ("fddp", "csqp"):
             raise ValueError(f"solver must be 'fddp' or 'csqp', got {solver!r}")
         self._solver = solver
+        if getattr(params, "use_filter_line_search", False):
+            raise NotImplementedError("use_filter_line_search: the device solvers use the merit / expected-improvement "
+                                      "line searches only")
         if isinstance(yaml_file, dict):
             data = yaml_file
         elif hasattr(yaml_file, "read"):
@@ -174,9 +313,20 @@ class OCPBatchedFDDP(OCPBase):
         else:
             with open(yaml_file, "r") as f:
                 data = yaml.safe_load(f)
-        self._running = flatten_cost_stack(data["running_model"], terminal=False)
-        self._terminal = flatten_cost_stack(data["terminal_model"], terminal=True)
+        if not isinstance(robot_table, RobotTable):
+            robot_table = RobotTable.from_robot_models(robot_table, frame)
+        elif frame is not None:
+            robot_table = robot_table.with_frame(frame)
+        nv = robot_table.nv
+        self._running = flatten_cost_stack(data["running_model"], terminal=False, nv=nv)
+        self._terminal = flatten_cost_stack(data["terminal_model"], terminal=True, nv=nv)
         robot_table = resolve_collision_pairs(robot_table, self._running, self._terminal)
+        robot_table = robot_table.with_pose_mode(pose_mode_of(self._running, self._terminal))
+        if not robot_table.frame_name:
+            # the frame a static task-frame cost names, else any frame: a stack without pose costs never reads it
+            named = [d["frame"] for st in (self._running, self._terminal) for d in st["pose"]
+                     if isinstance(d.get("frame"), str)]
+            robot_table = robot_table.with_frame(named[0] if named else next(iter(robot_table.frames)))
         self._table = robot_table
         self._ocp_params = params
         self._B = int(batch_size)
@@ -192,6 +342,12 @@ class OCPBatchedFDDP(OCPBase):
         self._results_batched: T.Optional[dict] = None
         self._debug_data = OCPDebugData()
         self._out = self._problem.alloc_outputs()
+        # transforms requested by the OCP and provided externally (BuildData.transforms, ocp_croco_generic.py:84-88)
+        self._transforms: dict = {d["transforms_key"]: None for st in (self._running, self._terminal)
+                                  for d in st["pose"] if d["kind"] == "visual_servoing"}
+        self._node0_refs: dict = {}
+        self._last_refs: T.Optional[np.ndarray] = None
+        self.init_debug_data_attributes()
 
     # ------------------------------------------------------------------ OCPBase properties
     @property
@@ -211,20 +367,81 @@ class OCPBatchedFDDP(OCPBase):
         """The device-side shooting problem (``calc`` / ``calc_diff`` / ``rollout``), as ``OCPBaseCroco.problem``."""
         return self._problem
 
+    @property
+    def input_transforms(self) -> dict:
+        """``OCPCrocoGeneric.input_transforms`` (``ocp_croco_generic.py:894-897``): ``{(parent, child): SE3 | None}``."""
+        return self._transforms
+
+    # ------------------------------------------------------------------ debug data (ocp_croco_generic.py:814-853)
+    def init_debug_data_attributes(self) -> None:
+        for d in self._running_costs():
+            if d["update"] and d["kind"] != "collision":
+                self._debug_data.references.append((d["name"], None))
+            if d["publish"]:
+                self._debug_data.residuals.append((d["name"], None))
+
+    def _running_costs(self) -> list:
+        r = self._running
+        return [d for d in (r["control"], r["state"]) if d is not None] + list(r["pose"]) + list(r["collisions"])
+
+    def _fill_references_and_residuals(self, out: dict) -> None:
+        """References of the first running node and residual predictions of the running nodes, as
+        ``OCPCrocoGeneric.fill_debug_data`` reads them off the Crocoddyl data (``ocp_croco_generic.py:827-853``)."""
+        from .robot_model import se3_to_xyzquat
+
+        dd = self._debug_data
+        for i, (name, _) in enumerate(dd.references):
+            ref = self._node0_refs.get(name, (None, None))[0]
+            if isinstance(ref, tuple):  # an SE3 reference is published as XYZQUAT
+                ref = se3_to_xyzquat(*ref)
+            dd.references[i] = (name, None if ref is None else np.array(ref, copy=True))
+        if not dd.residuals or self._last_refs is None:
+            return
+        T_ = self.n_controls
+        xs, us = out["xs"][:1], out["us"][:1]
+        terms = self._problem.cost_terms(out["xs"], out["us"])
+        xs_h, us_h = xs[0].cpu().numpy(), us[0].cpu().numpy()
+        r6 = terms["r_pose"][0].cpu().numpy()
+        dist = terms["collision_distance"][0].cpu().numpy()
+        nx, nv = self._problem.nx, self._problem.nv
+        refs = self._last_refs
+        by_name = {d["name"]: d for d in self._running_costs()}
+        for i, (name, _) in enumerate(dd.residuals):
+            d = by_name[name]
+            if d["kind"] == "state":
+                r = xs_h[:T_] - refs[:T_, :nx]
+            elif d["kind"] == "control":
+                r = us_h[:T_] - refs[:T_, 2 * nx: 2 * nx + nv]
+            elif d["kind"] in ("placement", "visual_servoing"):
+                r = r6[:T_]
+            elif d["kind"] == "translation":
+                r = r6[:T_, :3]
+            elif d["kind"] == "rotation":
+                r = r6[:T_, 3:]
+            else:
+                r = dist[:T_, d["slot"]: d["slot"] + 1]
+            dd.residuals[i] = (name, np.array(r, copy=True))
+
     # ------------------------------------------------------------------ references
     def reference_table(self, reference_weighted_trajectory: list) -> np.ndarray:
         """``[T+1, ref_size]`` rows from a list of WeightedTrajectoryPoint (one MPC horizon)."""
         assert len(reference_weighted_trajectory) == self.n_controls + 1
-        return build_reference_rows(self._table, self._running, self._terminal, reference_weighted_trajectory)
+        return build_reference_rows(self._table, self._running, self._terminal, reference_weighted_trajectory,
+                                    self._transforms)
 
     def set_reference_weighted_trajectory(self, reference_weighted_trajectory: list) -> None:
         """One horizon for every problem of the batch (list of points) or one horizon per problem (list of lists)."""
         if reference_weighted_trajectory and isinstance(reference_weighted_trajectory[0], (list, tuple)):
             assert len(reference_weighted_trajectory) == self._B
             refs = np.stack([self.reference_table(h) for h in reference_weighted_trajectory])
+            first = reference_weighted_trajectory[0]
         else:
             rows = self.reference_table(reference_weighted_trajectory)
             refs = np.broadcast_to(rows, (self._B,) + rows.shape)
+            first = reference_weighted_trajectory
+        if self._ocp_params.use_debug_data and (self._debug_data.references or self._debug_data.residuals):
+            self._node0_refs = node_references(self._table, self._running, first[0], self._transforms)["by_name"]
+            self._last_refs = np.array(refs[0], copy=True)
         self._problem.set_refs(np.ascontiguousarray(refs))
 
     def set_reference_table(self, refs) -> None:
@@ -234,6 +451,12 @@ class OCPBatchedFDDP(OCPBase):
     # ------------------------------------------------------------------ solve
     def solve(self, x0, x_warmstart, u_warmstart, use_iteration_limits_and_timeout: bool = True) -> None:
         max_iters = self._ocp_params.solver_iters if use_iteration_limits_and_timeout else 1000
+        # max_solve_time: passed on only when the user set it, and lifted for the unlimited first solve
+        # (ocp_base_croco.py:160-171); the deadline runs on the device clock (include/agx.h)
+        mst = getattr(self._ocp_params, "max_solve_time", None)
+        timeout = float(mst) if (mst is not None and use_iteration_limits_and_timeout and np.isfinite(mst)) else 0.0
+        self._opts.max_solve_time = timeout
+        self._sqp_opts.max_solve_time = timeout
         batched = isinstance(x0, torch.Tensor) and x0.dim() == 2
         run = ((lambda *a: self._problem.solve_sqp(*a, self._sqp_opts, out=self._out)) if self._solver == "csqp"
                else (lambda *a: self._problem.solve(*a, self._opts, out=self._out)))
@@ -255,7 +478,8 @@ class OCPBatchedFDDP(OCPBase):
             self._debug_data.result = ocp_results
             self._debug_data.kkt_norm = float(out["stop"][0])
             self._debug_data.nb_iter = int(out["iters"][0])
-            self._debug_data.nb_qp_iter = 0
+            self._debug_data.nb_qp_iter = 0  # no constraint is active: the QP is solved by one Riccati sweep
+            self._fill_references_and_residuals(out)
         self._ocp_results = ocp_results
 
     def update_geometry_placement(self, geometry_name: str, placement) -> None:
@@ -263,23 +487,25 @@ class OCPBatchedFDDP(OCPBase):
         called by the controller for every obstacle pose it receives, ``agimus_controller.py:406``).  ``placement`` is
         the pose of the capsule in the frame of its parent (the world for an obstacle): the capsule keeps its length
         and radius, its axis is the placement's z axis, its centre the placement's translation."""
-        names = list(self._table.capsules)
-        if geometry_name not in names:
+        if geometry_name not in self._table.capsules:
             raise RuntimeError(f"Unknown geometry name '{geometry_name}' in collision model!")
+        names = self._table.device_capsules()
         _, a0, a1, radius = self._table.capsules[geometry_name]
         half = 0.5 * float(np.linalg.norm(np.asarray(a1) - np.asarray(a0)))
         R = np.asarray(placement.rotation, dtype=np.float64)
         p = np.asarray(placement.translation, dtype=np.float64)
         n0, n1 = p - half * R[:, 2], p + half * R[:, 2]
-        self._problem.set_capsule(names.index(geometry_name), n0, n1, radius)
+        if geometry_name in names:  # geometries no collision pair uses are not on the device
+            self._problem.set_capsule(names.index(geometry_name), n0, n1, radius)
         par = self._table.capsules[geometry_name][0]
         self._table.capsules[geometry_name] = (par, n0, n1, radius)
 
     def integrate(self, state, control):
         if isinstance(state, torch.Tensor):
-            return self._problem.integrate(state, control, self.dt)
+            return self._problem.integrate(state, control, self._ocp_params.timesteps[0])
+        # runningModels[0].calc: the first running node's step (ocp_base_croco.py:184-189)
         return self._problem.integrate(np.asarray(state, dtype=np.float64), np.asarray(control, dtype=np.float64),
-                                       self.dt)[0].cpu().numpy()
+                                       self._ocp_params.timesteps[0])[0].cpu().numpy()
 
     # ------------------------------------------------------------------ results
     @property

@@ -39,6 +39,59 @@ def _sym(i6: T.Sequence[float]) -> np.ndarray:
     return np.array([[xx, xy, xz], [xy, yy, yz], [xz, yz, zz]], dtype=np.float64)
 
 
+def quat_to_matrix(q: T.Sequence[float]) -> np.ndarray:
+    """Unit quaternion ``(x, y, z, w)`` (Pinocchio / ROS order) -> rotation matrix."""
+    x, y, z, w = (float(v) for v in q)
+    n = np.sqrt(x * x + y * y + z * z + w * w)
+    x, y, z, w = x / n, y / n, z / n, w / n
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def matrix_to_quat(R: np.ndarray) -> np.ndarray:
+    """Rotation matrix -> unit quaternion ``(x, y, z, w)`` with ``w >= 0``."""
+    R = np.asarray(R, dtype=np.float64)
+    tr = R[0, 0] + R[1, 1] + R[2, 2]
+    if tr > 0:
+        s_ = 2.0 * np.sqrt(1.0 + tr)
+        q = np.array([(R[2, 1] - R[1, 2]) / s_, (R[0, 2] - R[2, 0]) / s_, (R[1, 0] - R[0, 1]) / s_, 0.25 * s_])
+    else:
+        i = int(np.argmax([R[0, 0], R[1, 1], R[2, 2]]))
+        j, k = (i + 1) % 3, (i + 2) % 3
+        s_ = 2.0 * np.sqrt(1.0 + R[i, i] - R[j, j] - R[k, k])
+        q = np.zeros(4)
+        q[i] = 0.25 * s_
+        q[j] = (R[j, i] + R[i, j]) / s_
+        q[k] = (R[k, i] + R[i, k]) / s_
+        q[3] = (R[k, j] - R[j, k]) / s_
+    return q if q[3] >= 0 else -q
+
+
+def xyzquat_to_se3(v: T.Sequence[float]) -> tuple[np.ndarray, np.ndarray]:
+    """``pinocchio.XYZQUATToSE3``: ``[x y z qx qy qz qw]`` -> ``(R, p)``."""
+    v = np.asarray(v, dtype=np.float64)
+    return quat_to_matrix(v[3:7]), v[:3].copy()
+
+
+def se3_to_xyzquat(R: np.ndarray, p: np.ndarray) -> np.ndarray:
+    """``pinocchio.SE3ToXYZQUAT``."""
+    return np.concatenate([np.asarray(p, dtype=np.float64), matrix_to_quat(R)])
+
+
+# Pinocchio joint short names -> (joint type, axis in the joint frame); *Unaligned joints carry their own axis
+_PIN_JOINTS = {
+    "JointModelRX": (0, (1.0, 0.0, 0.0)), "JointModelRY": (0, (0.0, 1.0, 0.0)), "JointModelRZ": (0, (0.0, 0.0, 1.0)),
+    "JointModelPX": (1, (1.0, 0.0, 0.0)), "JointModelPY": (1, (0.0, 1.0, 0.0)), "JointModelPZ": (1, (0.0, 0.0, 1.0)),
+    "JointModelRevoluteUnaligned": (0, None), "JointModelPrismaticUnaligned": (1, None),
+}
+
+
+def _rp(se3) -> tuple[np.ndarray, np.ndarray]:
+    """(rotation, translation) of a pinocchio.SE3-like object."""
+    return np.asarray(se3.rotation, dtype=np.float64), np.asarray(se3.translation, dtype=np.float64).reshape(3)
+
+
 @dataclasses.dataclass
 class Link:
     """One URDF link + the joint that attaches it to ``parent`` (``None`` = world)."""
@@ -76,6 +129,9 @@ class RobotTable:
     capsules: dict = dataclasses.field(default_factory=dict)
     collision_pairs: list = dataclasses.field(default_factory=list)  # [(capsule name, capsule name)], at most two
     collision_alpha: float = 1e-4  # ActivationModelQuadExp alpha (ocp_traj_tracking_collision_avoidance.yaml:44)
+    # form of the task-frame residual: 0 = log6 placement (ResidualModelFramePlacement / FrameRotation),
+    # 1 = world-frame translation for the linear part (ResidualModelFrameTranslation); include/agx.h
+    pose_mode: int = 0
 
     @property
     def nv(self) -> int:
@@ -92,6 +148,10 @@ class RobotTable:
     def with_frame(self, frame_name: str) -> "RobotTable":
         assert frame_name in self.frames, f"Frame '{frame_name}' does not exist!"
         return dataclasses.replace(self, frame_name=frame_name)
+
+    def with_pose_mode(self, pose_mode: int) -> "RobotTable":
+        assert pose_mode in (_abi.AGX_POSE_PLACEMENT, _abi.AGX_POSE_TRANSLATION_WORLD)
+        return dataclasses.replace(self, pose_mode=int(pose_mode))
 
     def with_armature(self, armature) -> "RobotTable":
         a = np.broadcast_to(np.asarray(armature, dtype=np.float64), (self.nv,)).copy()
@@ -110,7 +170,7 @@ class RobotTable:
             else:
                 pi = int(parent)
             caps[name] = (pi, np.asarray(a0, dtype=np.float64), np.asarray(a1, dtype=np.float64), float(radius))
-        assert len(caps) <= _abi.AGX_MAX_CAPSULES and len(pairs) <= _abi.AGX_MAX_COLLISION_PAIRS
+        assert len(pairs) <= _abi.AGX_MAX_COLLISION_PAIRS
         for a, b in pairs:
             assert a in caps and b in caps, f"Geometry object '{a if a not in caps else b}' not found."
         return dataclasses.replace(self, capsules=caps, collision_pairs=list(pairs), collision_alpha=float(alpha))
@@ -184,7 +244,7 @@ class RobotTable:
             m.frame_p[k] = float(fp[k])
         for k in range(9):
             m.frame_R[k] = float(np.asarray(fR).reshape(9)[k])
-        names = list(self.capsules)
+        names = self.device_capsules()
         m.n_capsules = len(names)
         for c, name in enumerate(names):
             pi, a0, a1, radius = self.capsules[name]
@@ -198,7 +258,105 @@ class RobotTable:
             m.pair_a[k] = names.index(a)
             m.pair_b[k] = names.index(b)
         m.col_alpha = float(self.collision_alpha)
+        m.pose_mode = int(self.pose_mode)
         return m
+
+    # ------------------------------------------------------------------ from a Pinocchio model
+    @staticmethod
+    def from_pinocchio_like(model, collision_model=None, armature=None, frame: T.Optional[str] = None,
+                            alpha: float = 1e-4) -> "RobotTable":
+        """Flatten a (reduced) Pinocchio model into the device table — what the solve path needs of
+        ``RobotModels.robot_model`` / ``.collision_model`` / ``.armature``
+        (``agimus_controller/agimus_controller/factory/robot_model.py:88-351``).
+
+        Duck-typed: only attribute access, so the object may be a real ``pinocchio.Model`` or anything with the same
+        fields: ``njoints``, ``names``, ``parents``, ``jointPlacements[i].rotation/.translation``,
+        ``inertias[i].mass/.lever/.inertia``, ``joints[i].shortname()`` (+ ``.axis`` for the *Unaligned joints),
+        ``gravity.linear``, ``frames[k].name/.parentJoint/.placement``; for the collision model
+        ``geometryObjects[k].name/.parentJoint/.placement/.geometry`` (capsule: ``radius`` + ``halfLength`` along the
+        local z axis, as ``coal.Capsule``; sphere: ``radius`` only) and ``collisionPairs[k].first/.second``.
+        Joints with nq != nv (free-flyer, spherical, continuous) are refused: the state is a vector space on the device.
+        """
+        nj = int(model.njoints)
+        nv = nj - 1
+        if nv < 1 or nv > _abi.AGX_MAX_NV:
+            raise NotImplementedError(f"{nv} joints: the device tables hold 1..{_abi.AGX_MAX_NV}")
+        names, parent = [], np.full(nv, -1, dtype=np.int32)
+        jtype, axis = np.zeros(nv, dtype=np.int32), np.zeros((nv, 3))
+        pl_R, pl_p = np.zeros((nv, 3, 3)), np.zeros((nv, 3))
+        mass, com, inertia = np.zeros(nv), np.zeros((nv, 3)), np.zeros((nv, 3, 3))
+        for i in range(1, nj):
+            j = i - 1
+            names.append(str(model.names[i]))
+            parent[j] = int(model.parents[i]) - 1
+            jm = model.joints[i]
+            short = jm.shortname() if callable(getattr(jm, "shortname", None)) else str(jm.shortname)
+            if short not in _PIN_JOINTS:
+                raise NotImplementedError(f"joint '{names[-1]}' is a {short}: only 1-DoF revolute / prismatic joints "
+                                          "(nq = nv) are supported on the device path")
+            jt, ax = _PIN_JOINTS[short]
+            jtype[j] = jt
+            axis[j] = np.asarray(jm.axis if ax is None else ax, dtype=np.float64).reshape(3)
+            axis[j] /= np.linalg.norm(axis[j])
+            pl_R[j], pl_p[j] = _rp(model.jointPlacements[i])
+            Y = model.inertias[i]
+            mass[j] = float(Y.mass)
+            com[j] = np.asarray(Y.lever, dtype=np.float64).reshape(3)
+            inertia[j] = np.asarray(Y.inertia, dtype=np.float64).reshape(3, 3)
+        frames = {}
+        for f in model.frames:
+            pj = int(getattr(f, "parentJoint", getattr(f, "parent", 0)))
+            if pj >= 1:
+                R, p_ = _rp(f.placement)
+                frames[str(f.name)] = (pj - 1, R, p_)
+        g = getattr(getattr(model, "gravity", None), "linear", (0.0, 0.0, -9.81))
+        arm = np.zeros(nv) if armature is None else np.broadcast_to(np.asarray(armature, dtype=np.float64), (nv,)).copy()
+        t = RobotTable(joint_names=names, parent=parent, jtype=jtype, axis=axis, placement_R=pl_R, placement_p=pl_p,
+                       mass=mass, com=com, inertia=inertia, armature=arm,
+                       gravity=np.asarray(g, dtype=np.float64).reshape(3), frames=frames)
+        if frame is not None:
+            t = t.with_frame(frame)
+        if collision_model is not None:
+            caps, gnames = {}, []
+            for go in collision_model.geometryObjects:
+                geo = go.geometry
+                gnames.append(str(go.name))
+                if not hasattr(geo, "radius"):
+                    continue  # boxes / meshes: no distance residual on the device path
+                half = float(getattr(geo, "halfLength", 0.0))  # a sphere is a capsule of zero length
+                R, p_ = _rp(go.placement)
+                pj = int(go.parentJoint)
+                caps[str(go.name)] = (pj - 1 if pj >= 1 else -1, p_ - half * R[:, 2], p_ + half * R[:, 2], float(geo.radius))
+            pairs = []
+            for cp in getattr(collision_model, "collisionPairs", []):
+                a, b = gnames[int(cp.first)], gnames[int(cp.second)]
+                if a in caps and b in caps:
+                    pairs.append((a, b))
+            t = dataclasses.replace(t, capsules=caps, collision_pairs=pairs[: _abi.AGX_MAX_COLLISION_PAIRS] if
+                                    len(caps) <= _abi.AGX_MAX_CAPSULES else [], collision_alpha=float(alpha))
+        return t
+
+    @staticmethod
+    def from_robot_models(robot_models, frame: T.Optional[str] = None) -> "RobotTable":
+        """``RobotModels`` (factory/robot_model.py:88) -> device table: its reduced ``robot_model``, its
+        ``collision_model`` (capsules / spheres) and its ``armature``."""
+        return RobotTable.from_pinocchio_like(robot_models.robot_model, getattr(robot_models, "collision_model", None),
+                                              getattr(robot_models, "armature", None), frame)
+
+    def device_capsules(self) -> list:
+        """Names of the capsules that go to the device, in table order: all of them while they fit, otherwise the ones
+        the collision pairs use (a full robot carries dozens: the fer model of the reference's tests has 142 pairs)."""
+        if len(self.capsules) <= _abi.AGX_MAX_CAPSULES:
+            return list(self.capsules)
+        used = []
+        for a, b in self.collision_pairs:
+            for n in (a, b):
+                if n not in used:
+                    used.append(n)
+        if len(used) > _abi.AGX_MAX_CAPSULES:
+            raise NotImplementedError(f"{len(used)} capsules in collision pairs: the device table holds "
+                                      f"{_abi.AGX_MAX_CAPSULES}")
+        return used
 
     @staticmethod
     def from_links(
@@ -207,8 +365,11 @@ class RobotTable:
         frames: T.Optional[dict[str, tuple[str, T.Sequence[float], T.Sequence[float]]]] = None,
         armature: T.Union[float, T.Sequence[float]] = 0.0,
         gravity: T.Sequence[float] = (0.0, 0.0, -9.81),
+        geometries: T.Sequence[tuple] = (),
     ) -> "RobotTable":
-        """Reduce a link list: fixed and locked joints (at q = 0) are folded into the moving ancestor."""
+        """Reduce a link list: fixed and locked joints (at q = 0) are folded into the moving ancestor.
+        ``geometries``: collision primitives ``(name, link, xyz, rpy, radius, length)`` — a capsule along the local z axis
+        (length 0: a sphere) attached to ``link``; they end up in ``capsules`` expressed in the moving ancestor's frame."""
         locked = set(locked_joints)
         by_name = {l.name: l for l in links}
         moving: list[Link] = [
@@ -283,7 +444,15 @@ class RobotTable:
             Rf = rpy_to_matrix(*rpy)
             fr[name] = (bi, R @ Rf, p + R @ np.asarray(xyz, dtype=np.float64))
         arm = np.broadcast_to(np.asarray(armature, dtype=np.float64), (nv,)).copy()
+        caps = {}
+        for gname, glink, gxyz, grpy, gradius, glength in geometries:
+            bi, R, p = resolve(glink)
+            Rg = R @ rpy_to_matrix(*grpy)
+            pg = p + R @ np.asarray(gxyz, dtype=np.float64)
+            half = 0.5 * float(glength)
+            caps[gname] = (bi, pg - half * Rg[:, 2], pg + half * Rg[:, 2], float(gradius))
         return RobotTable(
+            capsules=caps,
             joint_names=[l.joint_name for l in moving],
             parent=parent,
             jtype=jtype,

@@ -197,6 +197,19 @@ class BatchedShootingProblem:
         return dict(state_reg=out[..., 0], control_reg=out[..., 1], goal_tracking=out[..., 2], r_pose=out[..., 3:9],
                     collision=out[..., 9:11], collision_distance=out[..., 11:13])
 
+    COST_NAMES = ("state_reg", "control_reg", "goal_tracking", "collision_0", "collision_1")
+
+    def cost_derivatives(self, xs, us) -> dict:
+        """Per-cost gradients ``w * Lx``, ``w * Lu`` of every node, unscaled by the time step — what the debugger reads
+        off ``runningDatas[i].differential.costs.costs[name]`` (``mpc_debugger_node.py:303-323``):
+        ``{"Lx": [B, T+1, 5, nx], "Lu": [B, T+1, 5, nu]}``, costs in the order of ``COST_NAMES``."""
+        xs = self._t(xs, (self.B, self.T + 1, self.nx))
+        us = self._t(us, (self.B, self.T, self.nv))
+        Lx = self._empty(self.B, self.T + 1, _abi.AGX_N_COSTS, self.nx)
+        Lu = self._empty(self.B, self.T + 1, _abi.AGX_N_COSTS, self.nv)
+        self._check(lib().agx_cost_derivatives(self._h, _ptr(xs), _ptr(us), _ptr(Lx), _ptr(Lu), self._stream()))
+        return dict(Lx=Lx, Lu=Lu)
+
     def shift_warmstart(self, xs, us):
         """Previous solution shifted by the first time step (``WarmStartShiftPreviousSolution.shift``)."""
         xs = self._t(xs, (self.B, self.T + 1, self.nx))

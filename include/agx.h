@@ -90,7 +90,18 @@ typedef struct agx_model {
   int32_t n_pairs;
   int32_t pair_a[AGX_MAX_COLLISION_PAIRS];
   int32_t pair_b[AGX_MAX_COLLISION_PAIRS];
+  /* Form of the task-frame residual (the "pose" slot of the reference record):
+   *   AGX_POSE_PLACEMENT (0): r = log6(Mref^-1 oMf) -- ResidualModelFramePlacement[Static]
+   *                           (ocp_croco_generic.py:197-249).  With zero weights on its linear part this is also
+   *                           ResidualModelFrameRotation[Static] (:306-357): r_ang = log3(Rref^T oRf), same Jacobian rows;
+   *   AGX_POSE_TRANSLATION_WORLD (1): linear part r = p_f - pref in the WORLD frame, Rq = oRf fJf[:3] --
+   *                           ResidualModelFrameTranslation[Static] (:252-303); the angular part stays log3(Rref^T oRf), so
+   *                           a FrameTranslation cost and a FrameRotation cost on the same frame share the record. */
+  int32_t pose_mode;
+  int32_t reserved_;
 } agx_model;
+#define AGX_POSE_PLACEMENT 0
+#define AGX_POSE_TRANSLATION_WORLD 1
 
 /*
  * FDDP parameters (Crocoddyl SolverFDDP defaults are what agx_fddp_opts_default fills).
@@ -191,6 +202,14 @@ int agx_calc_diff(agx_handle* h, const double* xs, const double* us, double* out
  * collision cost of pair 0 / 1, signed distance of pair 0 / 1 (plots/plots_utils.py:160-208)]. */
 #define AGX_N_COST_TERMS 13
 int agx_cost_terms(agx_handle* h, const double* xs, const double* us, double* out_terms, void* stream);
+
+/* Per-cost gradients (what mpc_debugger_node.py:303-323 reads: w * d.Lx, w * d.Lu of every named cost of
+ * runningDatas[i].differential.costs, i.e. UNSCALED by the time step): out_Lx [B][T+1][AGX_N_COSTS][nx],
+ * out_Lu [B][T+1][AGX_N_COSTS][nu] (either may be NULL), costs in the order [state_reg, control_reg, task frame
+ * (goal_tracking), collision pair 0, collision pair 1], CostModelSum weights included (they are folded into the
+ * reference record).  Computed by problem.calcDiff with the other costs' weights zeroed, one pass per cost. */
+#define AGX_N_COSTS 5
+int agx_cost_derivatives(agx_handle* h, const double* xs, const double* us, double* out_Lx, double* out_Lu, void* stream);
 
 /* WarmStartShiftPreviousSolution.shift (warm_start_shift_previous_solution.py:85-104) for the whole batch:
  * nodes whose time step equals dts[0] take the next node's state and control (the last control is repeated),

@@ -597,6 +597,9 @@ void pose_residual(const agx_model& m, const Kin& kin, const NodeRef& ref, doubl
   double d[3] = {oMf.p[0] - ref.pref[0], oMf.p[1] - ref.pref[1], oMf.p[2] - ref.pref[2]};
   mtv3(ref.Rref, d, rMf.p);
   log6(rMf, r);
+  // ResidualModelFrameTranslation (ocp_croco_generic.py:252-303): r = p_f - pref in the world, Rq = oRf fJf[:3]
+  const bool tworld = m.pose_mode == AGX_POSE_TRANSLATION_WORLD;
+  if (tworld) for (int k = 0; k < 3; ++k) r[k] = d[k];
   if (Rq) {
     const int nv = m.nv;
     double Jl[36], fJ[6 * MAXV];
@@ -607,6 +610,13 @@ void pose_residual(const agx_model& m, const Kin& kin, const NodeRef& ref, doubl
         double s = 0;
         for (int k = 0; k < 6; ++k) s += Jl[6 * i + k] * fJ[k * nv + j];
         Rq[i * nv + j] = s;
+      }
+    if (tworld)
+      for (int j = 0; j < nv; ++j) {
+        const double l[3] = {fJ[0 * nv + j], fJ[1 * nv + j], fJ[2 * nv + j]};
+        double w[3];
+        mv3(oMf.R, l, w);
+        for (int i = 0; i < 3; ++i) Rq[i * nv + j] = w[i];
       }
   }
 }

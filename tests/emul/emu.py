@@ -196,6 +196,15 @@ def cost_terms(models, refs, dts, xs, us):
     return out
 
 
+def cost_derivatives(models, refs, dts, xs, us):
+    xs, us = _c(xs), _c(us)
+    B, T1, nx = xs.shape
+    h = _handle(models, refs, dts, B, T1 - 1)
+    Lx, Lu = np.zeros((B, T1, _abi.AGX_N_COSTS, nx)), np.zeros((B, T1, _abi.AGX_N_COSTS, nx // 2))
+    h.check(lib().agx_cost_derivatives(h.h, _p(xs), _p(us), _p(Lx), _p(Lu), None))
+    return Lx, Lu
+
+
 def shift_warmstart(models, refs, dts, xs, us):
     xs, us = _c(xs), _c(us)
     B, T1, nx = xs.shape

@@ -37,7 +37,7 @@ def test_library_builds_and_exports_every_symbol():
 def test_struct_sizes_match_the_header():
     # agx_model: 2 + 16 + 16 ints, then doubles (8-byte aligned)
     n_d = 16 * 3 + 16 * 9 + 16 * 3 + 16 + 16 * 3 + 16 * 6 + 16 + 3 + 9 + 3 + 4 * 3 + 4 * 3 + 4 + 1
-    assert ctypes.sizeof(_abi.AgxModel) == 34 * 4 + n_d * 8 + 10 * 4
+    assert ctypes.sizeof(_abi.AgxModel) == 34 * 4 + n_d * 8 + 12 * 4
     assert ctypes.sizeof(_abi.AgxFddpOpts) == 11 * 8 + 4 * 4 + 8
     assert ctypes.sizeof(_abi.AgxSqpOpts) == 4 * 8 + 2 * 4 + 8
 

@@ -559,3 +559,63 @@ def test_moving_an_obstacle_capsule(orc, col_case):
     assert rel(got, expect) < 1e-12 and rel(before, expect) > 1e-4
     with pytest.raises(RuntimeError, match="no such capsule"):
         emu.calc_with_moved_capsule(c["m"], c["refs"], c["dts"], c["xs"], c["us"], 3, a0, a1, radius)
+
+
+def test_frame_translation_mode_matches_oracle(orc):
+    """pose_mode = 1 (ResidualModelFrameTranslation: world-frame p_f - pref for the linear part, log3 for the angular
+    part) through both cost paths of the chain kernels: the octet one (agx_calc_diff) and the thread-per-node one (the
+    solve's node_cost_kernel)."""
+    t = panda_table().with_pose_mode(_abi.AGX_POSE_TRANSLATION_WORLD)
+    m = t.to_struct()
+    B, T = 3, 6
+    w = _workload(orc, m, B, T, w_pose=50.0)
+    rng = np.random.default_rng(3)
+    xs = w["xs_ws"] + rng.uniform(-0.2, 0.2, w["xs_ws"].shape)
+    us = w["us_ws"] + rng.uniform(-2, 2, w["us_ws"].shape)
+    o = orc.calc_diff(m, w["refs"], w["dts"], xs, us)
+    e = emu.calc_diff(m, w["refs"], w["dts"], xs, us)
+    for k in ("cost", "Lx", "Lxx"):
+        assert rel(e[k], o[k]) < 1e-9, k
+    # not the placement residual
+    o0 = orc.calc_diff(panda_table().to_struct(), w["refs"], w["dts"], xs, us)
+    assert rel(o["cost"], o0["cost"]) > 1e-3
+    opts = _abi.default_fddp_opts(fixed_iters=True)
+    so = orc.solve(m, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 3, opts)
+    se = emu.solve(m, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 3, opts)
+    for k in ("xs", "us", "cost"):
+        assert rel(se[k], so[k]) < 1e-6, k
+    te = emu.cost_terms(m, w["refs"], w["dts"], xs, us)
+    R, p = t.frame_placement(xs[1, 2, :7])
+    assert np.abs(te[1, 2, 3:6] - (p - w["refs"][1, 2, 51:54])).max() < 1e-12
+
+
+def test_per_cost_derivatives(orc):
+    """agx_cost_derivatives: the per-cost gradients the debugger reads (mpc_debugger_node.py:303-323) — each named
+    cost's unscaled Lx / Lu; they sum to the node's total gradient, and each equals the oracle's calcDiff on a
+    reference table that keeps only that cost's weights."""
+    from agimus_controller_b200.workloads import pick_and_place_collision_batch
+
+    m0 = panda_table().to_struct()
+    w = pick_and_place_collision_batch(2, T=4, rnea=lambda q, v, a: orc.rnea(m0, q, v, a), alpha=1e-3, w_col=(20.0, 20.0))
+    m = w["table"].to_struct()
+    refs = w["refs"].copy()
+    refs[..., 42:51] = np.diag([1.0, -1.0, -1.0]).reshape(9)
+    refs[..., 51:54] = [0.5, 0.2, 0.5]
+    refs[..., 54:60] = 10.0
+    rng = np.random.default_rng(9)
+    xs = w["xs_ws"] + rng.uniform(-0.05, 0.05, w["xs_ws"].shape)
+    us = w["us_ws"] + rng.uniform(-1, 1, w["us_ws"].shape)
+    Lx, Lu = emu.cost_derivatives(m, refs, w["dts"], xs, us)
+    s = np.concatenate([w["dts"], [1.0]])[None, :, None]
+    o = orc.calc_diff(m, refs, w["dts"], xs, us)
+    assert rel(Lx.sum(2) * s, o["Lx"]) < 1e-9
+    assert rel(Lu[:, :-1].sum(2) * s[:, :-1], o["Lu"][:, :-1]) < 1e-9
+    keep = {0: slice(14, 28), 1: slice(35, 42), 2: slice(54, 60), 3: slice(60, 61), 4: slice(61, 62)}
+    for slot, sl in keep.items():
+        r1 = refs.copy()
+        for other, so in keep.items():
+            if other != slot:
+                r1[..., so] = 0.0
+        o1 = orc.calc_diff(m, r1, w["dts"], xs, us)
+        assert rel(Lx[:, :, slot] * s, o1["Lx"]) < 1e-9, slot
+        assert np.abs(Lx[:, :, slot]).max() > 0.0 or slot == 1, slot

@@ -194,3 +194,18 @@ def test_unsupported_tree_sizes_are_refused():
     t5 = RobotTable.from_links(links, (), {"tool": ("l4", (0, 0, 0.1), (0, 0, 0))}).with_frame("tool")
     with pytest.raises(RuntimeError, match="instantiated for nv"):
         emu.Handle(t5.to_struct(), np.full(3, 0.01), 1, 3)
+
+
+def test_panda9_frame_translation_mode(orc, t9):
+    """pose_mode = 1 (ResidualModelFrameTranslation) on the tree kernels."""
+    rng = np.random.default_rng(8)
+    t = t9.with_pose_mode(_abi.AGX_POSE_TRANSLATION_WORLD)
+    w = _goal9(t, 2, 4, rng, orc, w_pose=30.0)
+    xs = w["xs_ws"] + rng.uniform(-0.1, 0.1, w["xs_ws"].shape)
+    us = w["us_ws"] + rng.uniform(-1, 1, w["us_ws"].shape)
+    o = orc.calc_diff(w["m"], w["refs"], w["dts"], xs, us)
+    e = emu.calc_diff(w["m"], w["refs"], w["dts"], xs, us)
+    for k in ("cost", "Lx", "Lxx"):
+        assert rel(e[k], o[k]) < 1e-9, k
+    o0 = orc.calc_diff(t9.to_struct(), w["refs"], w["dts"], xs, us)
+    assert rel(o["cost"], o0["cost"]) > 1e-3

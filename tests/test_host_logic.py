@@ -158,3 +158,265 @@ def test_collision_flattening_errors():
     with pytest.raises(NotImplementedError, match="different activation alphas"):
         resolve_collision_pairs(panda_table().with_capsules(PANDA_CAPSULES, []),
                                 flatten_cost_stack(bad["running_model"], terminal=False), term)
+
+
+# ------------------------------------------------------------------ round 2: update flags, Frame* residuals, adapters
+def _stack_yaml(running_costs, terminal_costs=None):
+    mk = lambda costs: {"class": "IntegratedActionModelEuler",  # noqa: E731
+                        "differential": {"class": "DifferentialActionModelFreeFwdDynamics", "costs": costs}}
+    return {"running_model": mk(running_costs), "terminal_model": mk(terminal_costs or [])}
+
+
+def _cost(name, residual, update=True, weight=1.0, weights=None, publish=False):
+    act = {"class": "ActivationModelWeightedQuad"}
+    if weights is not None:
+        act["weights"] = weights
+    return {"name": name, "update": update, "weight": weight, "publish_residual": publish,
+            "cost": {"class": "CostModelResidual", "activation": act, "residual": residual}}
+
+
+def _point2(nv=7, pose=None, frame="panda_hand_tcp"):
+    from agimus_controller_b200.ocp_interface import SE3, TrajectoryPoint, TrajectoryPointWeights, WeightedTrajectoryPoint
+
+    pose = pose or SE3(np.diag([1.0, -1.0, -1.0]), np.array([0.5, 0.2, 0.5]))
+    return WeightedTrajectoryPoint(
+        point=TrajectoryPoint(robot_configuration=np.arange(nv) * 0.1, robot_velocity=np.ones(nv), robot_acceleration=np.zeros(nv),
+                              robot_effort=np.full(nv, 2.0), end_effector_poses={frame: pose}),
+        weights=TrajectoryPointWeights(w_robot_configuration=np.full(nv, 3.0), w_robot_velocity=np.full(nv, 4.0),
+                                       w_robot_acceleration=np.zeros(nv), w_robot_effort=np.full(nv, 5.0),
+                                       w_end_effector_poses={frame: np.arange(1.0, 7.0)}))
+
+
+def test_update_false_keeps_the_yaml_reference_and_weights():
+    """DifferentialActionModelFreeFwdDynamics.update (ocp_croco_generic.py:712-724) only touches costs with
+    `update: true`; the others keep the reference and activation weights the YAML built them with (:97-114, :153-219)."""
+    from agimus_controller_b200.ocp_batched import build_reference_rows, flatten_cost_stack
+
+    nv = 7
+    xref = list(np.linspace(-1, 1, 2 * nv))
+    data = _stack_yaml([
+        _cost("state_reg", {"class": "ResidualModelState", "xref": xref}, update=False, weight=2.0, weights=0.5),
+        _cost("control_reg", {"class": "ResidualModelControl"}, update=False, weights=list(np.arange(1.0, 8.0))),
+        _cost("goal", {"class": "ResidualModelFramePlacement", "id": "panda_hand_tcp",
+                       "pref": [0.1, 0.2, 0.3, 0.0, 0.0, 0.0, 1.0]}, update=False, weight=3.0),
+    ], [_cost("state_reg", {"class": "ResidualModelState"}, update=True)])
+    table = panda_table()
+    run = flatten_cost_stack(data["running_model"], False, nv)
+    term = flatten_cost_stack(data["terminal_model"], True, nv)
+    rows = build_reference_rows(table, run, term, [_point2(), _point2()])
+    r0 = rows[0]
+    np.testing.assert_allclose(r0[:14], xref)                      # the YAML's xref, not the point's state
+    np.testing.assert_allclose(r0[14:28], 2.0 * 0.5)               # CostModelSum weight x scalar activation weight
+    np.testing.assert_allclose(r0[28:35], 0.0)                     # ResidualModelControl(state): uref = 0
+    np.testing.assert_allclose(r0[35:42], np.arange(1.0, 8.0))
+    np.testing.assert_allclose(r0[42:51], np.eye(3).reshape(9))    # pref: identity quaternion
+    np.testing.assert_allclose(r0[51:54], [0.1, 0.2, 0.3])
+    np.testing.assert_allclose(r0[54:60], 3.0)                     # no weights in the YAML: ones
+    # the terminal stack updates: the point's state and weights
+    np.testing.assert_allclose(rows[1][:7], np.arange(7) * 0.1)
+    np.testing.assert_allclose(rows[1][14:21], 3.0)
+
+
+def test_frame_translation_rotation_and_static_variants():
+    from agimus_controller_b200.ocp_batched import build_reference_rows, flatten_cost_stack, pose_mode_of
+
+    data = _stack_yaml([
+        _cost("tr", {"class": "ResidualModelFrameTranslationStatic", "frame_id": "panda_hand_tcp"}, weight=2.0),
+        _cost("rot", {"class": "ResidualModelFrameRotation", "id": 0}, weight=10.0),
+    ], [_cost("pl", {"class": "ResidualModelFrameRotationStatic", "frame_id": "panda_hand_tcp"})])
+    run = flatten_cost_stack(data["running_model"], False)
+    term = flatten_cost_stack(data["terminal_model"], True)
+    assert pose_mode_of(run, term) == _abi.AGX_POSE_TRANSLATION_WORLD
+    rows = build_reference_rows(panda_table(), run, term, [_point2(), _point2()])
+    np.testing.assert_allclose(rows[0][54:57], 2.0 * np.array([1.0, 2.0, 3.0]))   # w_end_effector_poses[:3]
+    np.testing.assert_allclose(rows[0][57:60], 10.0 * np.array([4.0, 5.0, 6.0]))  # w_end_effector_poses[3:]
+    np.testing.assert_allclose(rows[0][51:54], [0.5, 0.2, 0.5])
+    np.testing.assert_allclose(rows[1][54:57], 0.0)                               # rotation only on the terminal node
+    np.testing.assert_allclose(rows[1][57:60], [4.0, 5.0, 6.0])
+    # a placement cost cannot share the record with a translation cost
+    bad = _stack_yaml([_cost("tr", {"class": "ResidualModelFrameTranslation", "id": 0})],
+                      [_cost("pl", {"class": "ResidualModelFramePlacement", "id": 0})])
+    with pytest.raises(NotImplementedError, match="one form"):
+        pose_mode_of(flatten_cost_stack(bad["running_model"], False), flatten_cost_stack(bad["terminal_model"], True))
+    # a static frame that is not the table's
+    other = _stack_yaml([_cost("tr", {"class": "ResidualModelFramePlacementStatic", "frame_id": "panda_link5"})])
+    with pytest.raises((NotImplementedError, AssertionError)):
+        build_reference_rows(panda_table(), flatten_cost_stack(other["running_model"], False),
+                             flatten_cost_stack(other["terminal_model"], True), [_point2(), _point2()])
+
+
+@pytest.mark.parametrize("cls", ["ResidualModelControlGrav", "ResidualModelFrameVelocity", "ResidualModelFrameVelocityStatic"])
+def test_residuals_outside_the_record_structure_are_refused(cls):
+    from agimus_controller_b200.ocp_batched import flatten_cost_stack
+
+    data = _stack_yaml([_cost("c", {"class": cls, "id": 0})])
+    with pytest.raises(NotImplementedError, match="not supported on the device path"):
+        flatten_cost_stack(data["running_model"], False)
+
+
+def test_visual_servoing_reference_is_the_transform_times_the_target():
+    """ResidualModelVisualServoing (ocp_croco_generic.py:434-491): reference = wMo_vision * oMf_target, input key
+    `<robot_frame>_vs`, transform requested through input_transforms."""
+    from agimus_controller_b200.ocp_batched import flatten_cost_stack, node_references
+    from agimus_controller_b200.ocp_interface import SE3
+
+    data = _stack_yaml([_cost("vs", {"class": "ResidualModelVisualServoing", "world_frame": "universe",
+                                     "object_frame": "box", "robot_frame": "panda_hand_tcp"})])
+    run = flatten_cost_stack(data["running_model"], False)
+    d = run["pose"][0]
+    assert d["input_key"] == "panda_hand_tcp_vs" and d["transforms_key"] == ("universe", "box")
+    target = SE3(np.diag([1.0, -1.0, -1.0]), np.array([0.1, 0.0, 0.2]))
+    pt = _point2(pose=target, frame="panda_hand_tcp_vs")
+    wMo = SE3(np.array([[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]]), np.array([1.0, 2.0, 3.0]))
+    r = node_references(panda_table(), run, pt, {("universe", "box"): wMo})
+    np.testing.assert_allclose(r["Rref"], wMo.rotation @ target.rotation)
+    np.testing.assert_allclose(r["pref"], wMo.translation + wMo.rotation @ target.translation)
+    with pytest.raises(AssertionError, match="no transform"):
+        node_references(panda_table(), run, pt, {("universe", "box"): None})
+
+
+class _FakeSE3:
+    def __init__(self, R, p):
+        self.rotation, self.translation = np.asarray(R, dtype=float), np.asarray(p, dtype=float)
+
+
+class _FakePinModel:
+    """Attribute-for-attribute stand-in of a reduced pinocchio.Model built from the Panda link table."""
+
+    def __init__(self, t):
+        class J:
+            def __init__(self, short, axis):
+                self._s, self.axis = short, axis
+
+            def shortname(self):
+                return self._s
+
+        class Y:
+            pass
+
+        class F:
+            pass
+
+        nv = t.nv
+        self.njoints = nv + 1
+        self.names = ["universe"] + list(t.joint_names)
+        self.parents = [0] + [int(p) + 1 for p in t.parent]
+        self.jointPlacements = [_FakeSE3(np.eye(3), np.zeros(3))] + [_FakeSE3(t.placement_R[i], t.placement_p[i]) for i in range(nv)]
+        self.joints = [J("JointModelRZ", None)]
+        for i in range(nv):
+            ax = tuple(t.axis[i])
+            if t.jtype[i] == 0:
+                self.joints.append(J("JointModelRZ", None) if ax == (0.0, 0.0, 1.0) else J("JointModelRevoluteUnaligned", np.array(ax)))
+            else:
+                self.joints.append(J("JointModelPY", None) if ax == (0.0, 1.0, 0.0) else J("JointModelPrismaticUnaligned", np.array(ax)))
+        self.inertias = [None]
+        for i in range(nv):
+            y = Y()
+            y.mass, y.lever, y.inertia = t.mass[i], t.com[i], t.inertia[i]
+            self.inertias.append(y)
+        self.frames = []
+        for name, (par, R, p) in t.frames.items():
+            f = F()
+            f.name, f.parentJoint, f.placement = name, par + 1, _FakeSE3(R, p)
+            self.frames.append(f)
+
+        class G:
+            linear = np.array([0.0, 0.0, -9.81])
+
+        self.gravity = G()
+
+
+def test_table_from_a_pinocchio_like_model():
+    """RobotTable.from_pinocchio_like: the adapter from RobotModels.robot_model / .collision_model / .armature
+    (factory/robot_model.py:88-351) to the device table, on a duck-typed model — 9-DoF Panda with its prismatic
+    finger joints (one aligned, one unaligned) and a collision model with capsules, a sphere and a box."""
+    from agimus_controller_b200.robot_model import RobotTable
+
+    t9 = panda_table(lock_fingers=False, armature=0.1)
+    pm = _FakePinModel(t9)
+
+    class Geo:
+        pass
+
+    def geom(name, parent_joint, R, p, **shape):
+        g = Geo()
+        g.name, g.parentJoint, g.placement = name, parent_joint, _FakeSE3(R, p)
+        g.geometry = Geo()
+        for k, v in shape.items():
+            setattr(g.geometry, k, v)
+        return g
+
+    class Pair:
+        def __init__(self, a, b):
+            self.first, self.second = a, b
+
+    class CM:
+        geometryObjects = [geom("link3_capsule_0", 3, np.eye(3), [0.0, 0.0, -0.07], radius=0.07, halfLength=0.05),
+                           geom("hand_box_0", 7, np.eye(3), [0, 0, 0.1], halfSide=np.ones(3)),
+                           geom("link7_capsule_0", 7, np.eye(3), [0.0, 0.0, 0.13], radius=0.06, halfLength=0.07),
+                           geom("obstacle_0", 0, np.eye(3), [0.35, 0.0, 0.30], radius=0.05)]
+        collisionPairs = [Pair(2, 0), Pair(2, 3), Pair(1, 3)]
+
+    class RM:
+        robot_model, collision_model, armature = pm, CM(), np.full(9, 0.1)
+
+    t = RobotTable.from_robot_models(RM(), frame="panda_hand_tcp")
+    for f in ("parent", "jtype", "axis", "placement_R", "placement_p", "mass", "com", "inertia", "armature", "gravity"):
+        np.testing.assert_allclose(np.asarray(getattr(t, f), dtype=float), np.asarray(getattr(t9, f), dtype=float), atol=0)
+    assert t.joint_names == t9.joint_names and t.frame_name == "panda_hand_tcp"
+    assert set(t.capsules) == {"link3_capsule_0", "link7_capsule_0", "obstacle_0"}   # the box is skipped
+    par, a0, a1, r = t.capsules["link3_capsule_0"]
+    assert par == 2 and r == 0.07
+    np.testing.assert_allclose(a0, [0, 0, -0.12])
+    np.testing.assert_allclose(a1, [0, 0, -0.02])
+    par, a0, a1, r = t.capsules["obstacle_0"]                                        # a sphere: zero-length capsule
+    assert par == -1 and np.array_equal(a0, a1)
+    assert t.collision_pairs == [("link7_capsule_0", "link3_capsule_0"), ("link7_capsule_0", "obstacle_0")]
+    m = t.to_struct()
+    assert m.nv == 9 and m.n_capsules == 3 and m.n_pairs == 2
+    # joints the device state cannot carry are refused
+    pm.joints[3] = type(pm.joints[3])("JointModelSpherical", None)
+    with pytest.raises(NotImplementedError, match="JointModelSpherical"):
+        RobotTable.from_pinocchio_like(pm)
+
+
+def test_urdf_reader_reproduces_the_panda_table():
+    """agimus_controller_b200.urdf.load_urdf: links / joints / inertial origins / locked joints / collision cylinders
+    -> capsules named <link>_capsule_<i> (factory/robot_model.py:231-302) on a URDF written from the Panda link table."""
+    from agimus_controller_b200.robot_model import PANDA_FRAMES, panda_links
+    from agimus_controller_b200.urdf import load_urdf
+
+    out = ['<robot name="panda">', '<link name="world"/>']
+    for l in panda_links():
+        out.append(f'<link name="{l.name}">')
+        if l.mass > 0:
+            i = l.inertia
+            out.append(f'<inertial><origin xyz="{l.com[0]} {l.com[1]} {l.com[2]}" rpy="0 0 0"/><mass value="{l.mass}"/>'
+                       f'<inertia ixx="{i[0]}" ixy="{i[1]}" ixz="{i[2]}" iyy="{i[3]}" iyz="{i[4]}" izz="{i[5]}"/></inertial>')
+        if l.name == "panda_link3":
+            out.append('<collision><origin xyz="0 0 -0.07" rpy="0 0 0"/><geometry><cylinder radius="0.07" length="0.1"/></geometry></collision>')
+            out.append('<collision><origin xyz="0 0 0" rpy="0 0 0"/><geometry><sphere radius="0.07"/></geometry></collision>')
+        if l.name == "panda_hand":
+            out.append('<collision><origin xyz="0 0 0.02" rpy="0 1.57079632679 0"/><geometry><cylinder radius="0.04" length="0.2"/></geometry></collision>')
+        out.append('</link>')
+        out.append(f'<joint name="{l.joint_name}" type="{l.joint_type}"><parent link="{l.parent or "world"}"/><child link="{l.name}"/>'
+                   f'<origin xyz="{l.xyz[0]} {l.xyz[1]} {l.xyz[2]}" rpy="{l.rpy[0]} {l.rpy[1]} {l.rpy[2]}"/>'
+                   f'<axis xyz="{l.axis[0]} {l.axis[1]} {l.axis[2]}"/></joint>')
+    for n, (pl, xyz, rpy) in PANDA_FRAMES.items():
+        out.append(f'<link name="{n}"/><joint name="{n}_joint" type="fixed"><parent link="{pl}"/><child link="{n}"/>'
+                   f'<origin xyz="{xyz[0]} {xyz[1]} {xyz[2]}" rpy="{rpy[0]} {rpy[1]} {rpy[2]}"/></joint>')
+    out.append('</robot>')
+    xml = "\n".join(out)
+    arm = [f"panda_joint{i}" for i in range(1, 8)]
+    for moving, ref in ((arm, panda_table(lock_fingers=True)), (None, panda_table(lock_fingers=False))):
+        t = load_urdf(xml, moving, frame="panda_hand_tcp", armature=0.1,
+                      collision_pairs=[("panda_hand_capsule_0", "panda_link3_capsule_0")])
+        for f in ("parent", "jtype", "axis", "placement_R", "placement_p", "mass", "com", "inertia"):
+            np.testing.assert_allclose(np.asarray(getattr(t, f), float), np.asarray(getattr(ref, f), float), atol=1e-15)
+        np.testing.assert_allclose(t.frames["panda_hand_tcp"][2], ref.frames["panda_hand_tcp"][2], atol=1e-15)
+        assert set(t.capsules) == {"panda_link3_capsule_0", "panda_link3_1", "panda_hand_capsule_0"}
+        par, a0, a1, r = t.capsules["panda_hand_capsule_0"]     # hand is welded to joint 7: expressed in its frame
+        assert par == 6 and r == 0.04 and abs(np.linalg.norm(a1 - a0) - 0.2) < 1e-12
+        assert t.to_struct().n_pairs == 1
+    with pytest.raises(ValueError, match="not in the model"):
+        load_urdf(xml, ["no_such_joint"])

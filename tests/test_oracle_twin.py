@@ -203,3 +203,51 @@ def test_fddp_converges_and_is_stationary(orc):
     for b in range(2):
         _, p = orc.frame_placement(m, res["xs"][b, -1, :7])
         assert np.linalg.norm(p - np.array([0.5, 0.2, 0.5])) < 0.05
+
+
+def test_frame_translation_and_rotation_residuals(orc):
+    """ResidualModelFrameTranslation / FrameRotation (ocp_croco_generic.py:252-357) through the pose slot:
+    pose_mode = 1 makes the linear part p_f - pref in the world (Rq = oRf fJf[:3]); with zero linear weights the
+    placement record is the rotation residual log3(Rref^T oRf).  Checked against the twin's complex-step kinematics and
+    scipy's matrix logarithm."""
+    import scipy.linalg
+
+    from agimus_controller_b200.problem import pack_refs
+
+    t = panda_table().with_pose_mode(_abi.AGX_POSE_TRANSLATION_WORLD)
+    m = t.to_struct()
+    nv = t.nv
+    rng = np.random.default_rng(7)
+    q = PANDA_Q_NOMINAL + rng.uniform(-0.5, 0.5, nv)
+    x = np.concatenate([q, np.zeros(nv)])[None, None]
+    pref = np.array([0.4, 0.1, 0.6])
+    th = 0.3
+    Rref = np.diag([1.0, -1.0, -1.0]) @ np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]])
+    w_lin = np.array([3.0, 5.0, 7.0])
+    # translation only
+    refs = pack_refs(nv, 0, 1, np.zeros(2 * nv), np.zeros(2 * nv), np.zeros(nv), np.zeros(nv), Rref, pref,
+                     np.concatenate([w_lin, np.zeros(3)]))
+    o = orc.calc_diff(m, refs, np.zeros(0), x, np.zeros((1, 0, nv)))
+    pos = lambda z: tw.frame_placement(t, z)[:3, 3]  # noqa: E731
+    J = tw.complex_step_jac(pos, q)
+    r = pos(q) - pref
+    assert abs(o["cost"][0, 0] - 0.5 * np.sum(w_lin * r * r)) < 1e-13
+    np.testing.assert_allclose(o["Lx"][0, 0, :nv], J.T @ (w_lin * r), atol=1e-12)
+    np.testing.assert_allclose(o["Lxx"][0, 0, :nv, :nv], J.T @ np.diag(w_lin) @ J, atol=1e-12)
+    # rotation only (placement record, zero linear weights): r = log3(Rref^T R_f)
+    w_ang = np.array([2.0, 4.0, 6.0])
+    refs = pack_refs(nv, 0, 1, np.zeros(2 * nv), np.zeros(2 * nv), np.zeros(nv), np.zeros(nv), Rref, pref,
+                     np.concatenate([np.zeros(3), w_ang]))
+    o = orc.calc_diff(m, refs, np.zeros(0), x, np.zeros((1, 0, nv)))
+
+    def rot_res(z):
+        R = tw.frame_placement(t, z)[:3, :3]
+        L = np.real(scipy.linalg.logm(Rref.T @ R))
+        return np.array([L[2, 1], L[0, 2], L[1, 0]])
+
+    ra = rot_res(q)
+    assert abs(o["cost"][0, 0] - 0.5 * np.sum(w_ang * ra * ra)) < 1e-12
+    h = 1e-6
+    Ja = np.stack([(rot_res(q + h * e) - rot_res(q - h * e)) / (2 * h) for e in np.eye(nv)], axis=1)
+    np.testing.assert_allclose(o["Lx"][0, 0, :nv], Ja.T @ (w_ang * ra), atol=1e-7)
+    np.testing.assert_allclose(o["Lxx"][0, 0, :nv, :nv], Ja.T @ np.diag(w_ang) @ Ja, atol=1e-6)
