@@ -83,7 +83,7 @@ class AgxFddpOpts(C.Structure):
         ("fixed_iters", _I),
         ("n_alphas", _I),
         ("eager_exit", _I),
-        ("reserved", _I),
+        ("accept_rule", _I),
         ("max_solve_time", _D),
     ]
 
@@ -131,7 +131,7 @@ def default_fddp_opts(fixed_iters: bool = False) -> AgxFddpOpts:
         fixed_iters=1 if fixed_iters else 0,
         n_alphas=10,
         eager_exit=0,
-        reserved=0,
+        accept_rule=0,
         max_solve_time=0.0,
     )
 

@@ -516,7 +516,7 @@ void agx_fddp_opts_default(agx_fddp_opts* o) {
   o->th_grad = 1e-12; o->th_stepdec = 0.5; o->th_stepinc = 0.01; o->th_acceptstep = 0.1;
   o->th_acceptnegstep = 2.0; o->th_stop = 1e-9;
   o->reg_init = nan("");
-  o->fixed_iters = 0; o->n_alphas = 10; o->eager_exit = 0; o->reserved = 0;
+  o->fixed_iters = 0; o->n_alphas = 10; o->eager_exit = 0; o->accept_rule = AGX_ACCEPT_CROCODDYL2;
   o->max_solve_time = 0.0;
 }
 
@@ -807,7 +807,7 @@ int agx_riccati(agx_handle* h, const double* x0, const double* xs, const double*
   O.reg_min = reg; O.reg_max = reg; O.reg_incfactor = od.reg_incfactor; O.reg_decfactor = od.reg_decfactor;
   O.th_grad = od.th_grad; O.th_stepdec = od.th_stepdec; O.th_stepinc = od.th_stepinc; O.th_acceptstep = od.th_acceptstep;
   O.th_acceptnegstep = od.th_acceptnegstep; O.th_stop = od.th_stop; O.reg_init = reg; O.fixed_iters = 1; O.n_alphas = 1;
-  O.max_iter = 1; O.defer = 0;
+  O.max_iter = 1; O.defer = 0; O.accept_rule = 0;
   O.max_solve_ns = 0;
   const size_t nB = (size_t)h->B, T = (size_t)h->T, T1 = T + 1;
   Work W = h->W;
@@ -938,6 +938,7 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
   O.th_stepinc = opts->th_stepinc; O.th_acceptstep = opts->th_acceptstep; O.th_acceptnegstep = opts->th_acceptnegstep;
   O.th_stop = opts->th_stop; O.reg_init = opts->reg_init; O.fixed_iters = opts->fixed_iters; O.n_alphas = opts->n_alphas;
   O.max_iter = max_iter;
+  O.accept_rule = opts->accept_rule;
   // max_solve_time (ocp_base_croco.py:70-71, :166-171): a device-side deadline, see agx_fddp_opts
   O.max_solve_ns = opts->max_solve_time > 0.0 ? (long long)(opts->max_solve_time * 1e9) : 0;
   if (h->tree) {
@@ -947,9 +948,12 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
   }
   // deferred line search (accept_linesearch_kernel): on unless AGX_LS=inline asks for the in-line search only
   static const bool ls_inline = [] { const char* e = std::getenv("AGX_LS"); return e && std::strcmp(e, "inline") == 0; }();
-  O.defer = (!ls_inline && O.n_alphas > 1) ? 1 : 0;
-  // a problem that deferred once is one round behind: one more round lets it use its whole budget
-  const int rounds = max_iter + ((O.defer && max_iter > 0) ? 1 : 0);
+  // depth of the deferral: how many rejected step lengths of a problem (over the whole solve) move into later rounds
+  // instead of being searched in line while the batch waits (AGX_DEFER_DEPTH, default 2)
+  static const int defer_depth = [] { const char* e = std::getenv("AGX_DEFER_DEPTH"); const int d = e ? std::atoi(e) : 2; return d < 0 ? 0 : (d > 8 ? 8 : d); }();
+  O.defer = (!ls_inline && O.n_alphas > 1) ? defer_depth : 0;
+  // a problem that deferred d times is d rounds behind: O.defer more rounds let every problem use its whole budget
+  const int rounds = max_iter + (max_iter > 0 ? O.defer : 0);
   const size_t nB = (size_t)h->B, T = (size_t)h->T, T1 = T + 1;
   if (!out_K && !h->d_K_internal) {
     if (!dev_alloc((void**)&h->d_K_internal, sizeof(double) * nB * T * NJ * NX))
@@ -1069,7 +1073,7 @@ int agx_solve_sqp(agx_handle* h, const double* x0, const double* xs_ws, const do
   O.reg_min = Q.reg; O.reg_max = Q.reg_max; O.reg_init = Q.reg; O.reg_incfactor = od.reg_incfactor;
   O.reg_decfactor = od.reg_decfactor; O.th_grad = od.th_grad; O.th_stepdec = od.th_stepdec; O.th_stepinc = od.th_stepinc;
   O.th_acceptstep = od.th_acceptstep; O.th_acceptnegstep = od.th_acceptnegstep; O.th_stop = od.th_stop;
-  O.fixed_iters = 0; O.n_alphas = Q.n_alphas; O.max_iter = max_iter; O.defer = 0; O.max_solve_ns = 0;
+  O.fixed_iters = 0; O.n_alphas = Q.n_alphas; O.max_iter = max_iter; O.defer = 0; O.max_solve_ns = 0; O.accept_rule = 0;
   FddpOpts Of = O;
   Of.reg_min = Of.reg_max = 0.0;  // the last sweep (sigma + the problem's regularisation) is not retried
   const size_t nB = (size_t)h->B, T = (size_t)h->T, T1 = T + 1;

@@ -39,8 +39,9 @@ struct FddpOpts {
   double reg_init;
   int fixed_iters, n_alphas;
   int max_iter;  // iteration budget of every problem (a problem whose search was deferred finishes a round later)
-  int defer;     // a rejected alpha = 1 trial tries alpha = 1/2 in the next round's forward pass (see accept_linesearch_kernel)
+  int defer;     // rounds a problem may fall behind by deferring rejected step lengths into the next round's forward pass (0: in-line search only; see accept_linesearch_kernel)
   long long max_solve_ns;  // max_solve_time in ns (0: none), measured on the device clock from SolverState::t0
+  int accept_rule;         // agx_fddp_opts::accept_rule
 };
 
 // workspace of a solve (device pointers owned by the handle)
@@ -732,9 +733,11 @@ AGX_DEV void finish_iteration(const SolverState& S, const FddpOpts& O, int b, bo
 }
 
 // dV / dVexp test of SolverFDDP::solve
-AGX_DEV bool accept_step(const FddpOpts& O, double dV, double d1, double dVexp) {
-  if (dVexp >= 0.0) return d1 < O.th_grad || dV > O.th_acceptstep * dVexp;
-  return dV > O.th_acceptnegstep * dVexp;
+// (accept_rule: 0 = Crocoddyl >= 2.0 — |d1| and no negative-expectation step from a feasible candidate; 1 = 1.x)
+AGX_DEV bool accept_step(const FddpOpts& O, double dV, double d1, double dVexp, bool feasible) {
+  const bool legacy = O.accept_rule != 0;
+  if (dVexp >= 0.0) return (legacy ? d1 : fabs(d1)) < O.th_grad || dV > O.th_acceptstep * dVexp;
+  return (legacy || !feasible) && dV > O.th_acceptnegstep * dVexp;
 }
 
 __global__ void rollout_try_kernel(Problem P, Work W, SolverState S) {
@@ -765,7 +768,7 @@ __global__ void rollout_try_kernel(Problem P, Work W, SolverState S) {
   const double* kb = W.k + (size_t)b * T * NJ;
   const bool feasible = S.is_feasible[b] != 0;
   // a problem whose alpha = 1 trial was rejected in the previous round tries alpha = 1/2 here (deferred line search)
-  const double alpha = S.pending[b] ? 0.5 : 1.0;
+  const double alpha = ldexp(1.0, -S.pending[b]);  // pending = n: the search stands at step length 2^-n
   const double* fsb = W.fs + (size_t)b * T1 * NX;
   // per-node inputs are fetched one node ahead (scalars into registers, gain rows into L1)
   struct NodeIn { double us, kff, dt, xsq, xsv, gq, gv, fq, fv; };
@@ -880,7 +883,7 @@ __global__ void __launch_bounds__(64) rollout_try2_kernel(Problem P, Work W, Sol
   const double* Kb = W.K + (size_t)bb * T * NJ * NX;
   const double* kb = W.k + (size_t)bb * T * NJ;
   const bool feasible = S.is_feasible[bb] != 0;
-  const double alpha = S.pending[bb] ? 0.5 : 1.0;
+  const double alpha = ldexp(1.0, -S.pending[bb]);
   const bool contract = !feasible && alpha != 1.0;
   double xq = live ? W.x0[(size_t)bb * NX + jj] : 0.0, xv = live ? W.x0[(size_t)bb * NX + NJ + jj] : 0.0;
   bool ok = true;
@@ -994,6 +997,8 @@ __global__ void __launch_bounds__(64) rollout_try2_kernel(Problem P, Work W, Sol
 // round's rollout_try / node_cost launches together with everybody else's alpha = 1 trial.  The sequence of operations
 // of the problem is SolverFDDP's; only the round in which its alpha = 1/2 trial runs moves.  A problem defers once
 // (round - iterations < 1), so one extra round after the budget lets every problem finish its max_iter iterations.
+// Generalised: `pending` holds the index n of the step length 2^-n the search stands at, and a problem may defer
+// O.defer times over a solve (it is then O.defer rounds behind); the host queues max_iter + O.defer rounds.
 template <bool COL>
 __global__ void accept_linesearch_kernel(Problem P, Work W, SolverState S, FddpOpts O, int round) {
   AGX_SMEM(smem);
@@ -1001,8 +1006,8 @@ __global__ void accept_linesearch_kernel(Problem P, Work W, SolverState S, FddpO
   const int b = (int)ent;
   if (b >= P.B) return;
   if (S.done[b]) return;
-  const bool was_pending = S.pending[b] != 0;
-  const double a1 = was_pending ? 0.5 : 1.0;  // the step length the fast path evaluated this round
+  const int pend = S.pending[b];
+  const double a1 = ldexp(1.0, -pend);  // the step length the fast path evaluated this round
   {
     const double* crec0 = W.crec + (size_t)b * (P.T + 1) * CREC_SIZE;
     double part = 0.0;
@@ -1015,10 +1020,11 @@ __global__ void accept_linesearch_kernel(Problem P, Work W, SolverState S, FddpO
       const double dv = S.dv[b];
       const double d1 = S.dg[b] + dv, d2 = S.dq[b] - 2.0 * dv;
       stop1 = fabs(d1 + 0.5 * d2);
-      acc1 = accept_step(O, S.cost[b] - cost1, d1, a1 * (d1 + 0.5 * a1 * d2));
+      acc1 = accept_step(O, S.cost[b] - cost1, d1, a1 * (d1 + 0.5 * a1 * d2), S.is_feasible[b] != 0);
     }
-    const bool last_alpha = O.n_alphas <= (was_pending ? 2 : 1);
-    const bool defer = !acc1 && !last_alpha && !was_pending && O.defer && round - S.iters[b] < 1;
+    const bool last_alpha = O.n_alphas <= pend + 1;
+    // a problem may run up to O.defer rounds behind the batch (one round per deferred step length)
+    const bool defer = !acc1 && !last_alpha && O.defer > 0 && round - S.iters[b] < O.defer;
     AGX_OSYNC();  // every lane has read the state before lane 0 updates it
     if (acc1 || last_alpha) {
       if (j == 0) {
@@ -1031,7 +1037,7 @@ __global__ void accept_linesearch_kernel(Problem P, Work W, SolverState S, FddpO
     if (defer) {
       if (j == 0) {
         S.stop[b] = stop1;
-        S.pending[b] = 1;
+        S.pending[b] = pend + 1;
         S.recalc[b] = 0;       // same candidate: its dynamics records stay valid ...
         S.recalc_cost[b] = 0;  // ... and its cost records are not needed before the search ends
       }
@@ -1063,7 +1069,7 @@ __global__ void accept_linesearch_kernel(Problem P, Work W, SolverState S, FddpO
 
   double steplength = 1.0, cost_try = 0.0, stop = S.stop[b];
   bool accepted = false;
-  for (int ia = was_pending ? 2 : 1; ia < O.n_alphas; ++ia) {
+  for (int ia = pend + 1; ia < O.n_alphas; ++ia) {
     steplength = ldexp(1.0, -ia);
     const bool contract = !feasible;
     double xq = x0q, xv = x0v;
@@ -1122,7 +1128,7 @@ __global__ void accept_linesearch_kernel(Problem P, Work W, SolverState S, FddpO
     const double d1 = dg + dv, d2 = dq - 2.0 * dv;
     stop = fabs(d1 + 0.5 * d2);
     const double dVexp = steplength * (d1 + 0.5 * steplength * d2);
-    accepted = accept_step(O, dV, d1, dVexp);
+    accepted = accept_step(O, dV, d1, dVexp, feasible);
     if (accepted) break;
   }
   if (j == 0) {

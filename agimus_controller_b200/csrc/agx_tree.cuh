@@ -1108,7 +1108,7 @@ __global__ void tree_forward_kernel(Problem P, Work W, SolverState S, FddpOpts O
     const double d1 = dg + dv, d2 = dq - 2.0 * dv;
     stop = fabs(d1 + 0.5 * d2);
     const double dVexp = steplength * (d1 + 0.5 * steplength * d2);
-    accepted = accept_step(O, dV, d1, dVexp);
+    accepted = accept_step(O, dV, d1, dVexp, feasible);
     if (accepted) break;
   }
   if (j == 0) {

@@ -266,9 +266,10 @@ def run_ours(args):
     s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
 
     class Slot:
-        def __init__(self):
+        def __init__(self, full_K=False):
             self.d_in = [torch.empty_like(t, device=dev) for t in h_in]
             self.out = prob.alloc_outputs()
+            self.K_full = torch.empty(self.out["K"].shape, dtype=torch.float64).pin_memory() if full_K else None
             self.res = dict(xs=torch.empty(self.out["xs"].shape, dtype=torch.float64).pin_memory(),
                             us=torch.empty(self.out["us"].shape, dtype=torch.float64).pin_memory(),
                             K0=torch.empty((B,) + tuple(self.out["K"].shape[2:]), dtype=torch.float64).pin_memory(),
@@ -306,7 +307,10 @@ def run_ours(args):
             s_out.wait_event(sl.ev_solved)
             sl.res["xs"].copy_(sl.out["xs"], non_blocking=True)
             sl.res["us"].copy_(sl.out["us"], non_blocking=True)
-            sl.res["K0"].copy_(sl.out["K"][:, 0], non_blocking=True)
+            if sl.K_full is not None:
+                sl.K_full.copy_(sl.out["K"], non_blocking=True)   # every gain matrix, as OCPResults.ricatti_gains
+            else:
+                sl.res["K0"].copy_(sl.out["K"][:, 0], non_blocking=True)
             sl.res["cost"].copy_(sl.out["cost"], non_blocking=True)
             sl.res["iters"].copy_(sl.out["iters"], non_blocking=True)
             sl.res["status"].copy_(sl.out["status"], non_blocking=True)
@@ -326,7 +330,9 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(step, steps, finish=None):
+    per_rank = {}
+
+    def timed(step, steps, finish=None, tag=None):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
@@ -338,7 +344,13 @@ def run_ours(args):
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
+            allms = torch.empty(world, dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(allms, ms)
+            if tag:
+                per_rank[tag] = [float(v) / steps for v in allms.cpu()]
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        elif tag:
+            per_rank[tag] = [float(ms.item()) / steps]
         return float(ms.item())
 
     fp64_peak = probe_fp64_tflops(local, 0.5) if (rank == 0 and not args.no_probe) else None
@@ -352,7 +364,7 @@ def run_ours(args):
         sampler.start()
     prob.set_timing(True)
     l0 = prob.launch_count
-    ms_total = timed(step_resident, args.steps)
+    ms_total = timed(step_resident, args.steps, tag="resident")
     launches = prob.launch_count - l0
     phases = prob.get_timing()
     prob.set_timing(False)
@@ -361,9 +373,52 @@ def run_ours(args):
     for _ in range(max(min(args.warmup, 2), 1)):
         step_e2e()
     drain_e2e()
-    ms_e2e = timed(step_e2e, args.steps, finish=drain_e2e)
+    ms_e2e = timed(step_e2e, args.steps, finish=drain_e2e, tag="e2e")
     # the results that came back are the solver's: same costs as the resident run
     assert torch.equal(slots[0].res["cost"], out["cost"].cpu()), "e2e results differ from the resident run"
+    # the same end-to-end step returning EVERY gain matrix (OCPResults.ricatti_gains holds all T of them,
+    # ocp_base_croco.py:173-177): + 157 MB of D2H per step
+    e2e_full = None
+    if not args.no_full_k:
+        slots[:] = [Slot(full_K=True), Slot(full_K=True)]
+        e2e_state["i"] = 0
+        for _ in range(2):
+            step_e2e()
+        drain_e2e()
+        n_fk = max(3, min(args.steps, 10))
+        ms_fk = timed(step_e2e, n_fk, finish=drain_e2e)
+        d2h_fk = d2h_bytes - slots[0].res["K0"].numel() * 8 + slots[0].K_full.numel() * 8
+        assert torch.equal(slots[0].K_full, slots[0].out["K"].cpu())
+        e2e_full = {"value": world * B * n_fk / (ms_fk * 1e-3), "unit": "solves/s", "ms_per_step": ms_fk / n_fk,
+                    "d2h_bytes_per_step": d2h_fk, "steps": n_fk,
+                    "returned": "xs, us, K (all T gain matrices), cost, iters, status"}
+        slots[:] = []
+        torch.cuda.empty_cache()
+
+    # strong scaling (driver-visible beside the weak-scaling headline): a FIXED total batch split over the ranks in
+    # contiguous slabs, inputs resident, same 10 fixed iterations; max over ranks
+    strong = None
+    if not args.no_strong:
+        from agimus_controller_b200.sharding import shard_range
+
+        strong = {"what": "cfg-2 problems, total batch fixed, contiguous slabs per rank, inputs resident, 10 fixed "
+                          "FDDP iterations; ms = max over ranks", "cases": []}
+        for B_total in (4096, 16384):
+            ws, _ = build_workload(B_total, 0, lambda q, v, a: prob.rnea(q, v, a).cpu().numpy()) if B_total != B or world > 1 or seed != 0 else (w, m)
+            sl_ = shard_range(B_total, world, rank)
+            nb = sl_.stop - sl_.start
+            ps = BatchedShootingProblem(panda_table(), np.full(T_NODES, DT), nb, device=dev)
+            ps.set_refs(torch.as_tensor(ws["refs"][sl_], device=dev))
+            sx0, sxs, sus = (torch.as_tensor(ws[k][sl_], device=dev) for k in ("x0", "xs_ws", "us_ws"))
+            so = ps.alloc_outputs()
+            for _ in range(2):
+                ps.solve(sx0, sxs, sus, N_ITERS, opts, out=so)
+            n_s = max(3, min(args.steps, 10))
+            ms_s = timed(lambda: ps.solve(sx0, sxs, sus, N_ITERS, opts, out=so), n_s)
+            strong["cases"].append({"B_total": B_total, "B_per_gpu": nb, "ms_per_step": ms_s / n_s,
+                                    "solves_per_s": B_total * n_s / (ms_s * 1e-3)})
+            del ps, so, sx0, sxs, sus
+            torch.cuda.empty_cache()
 
     # single-MPC latency (BASELINE config 1): B = 1, T = 20, dt = 0.01, sine wave in configuration space, closed loop
     # with the shift warm start, <= 10 FDDP iterations per tick (early exit allowed), rank 0 only
@@ -499,7 +554,8 @@ def run_ours(args):
                 "pipelining": "copies of step i+1 (H2D) and i-1 (D2H) overlap the solve of step i on separate streams; "
                               "the host waits for step i-1's results before issuing step i+1"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-        "latency_b1": lat, "sqp_mode": sqp,
+        "latency_b1": lat, "sqp_mode": sqp, "e2e_full_K": e2e_full, "strong_scaling": strong,
+        "ms_per_step_per_rank": per_rank,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -519,6 +575,8 @@ def main():
     ap.add_argument("--latency-ticks", type=int, default=1000, help="MPC ticks of the B=1 latency leg")
     ap.add_argument("--no-probe", action="store_true", help="skip the FP64 peak probe (profiler runs)")
     ap.add_argument("--no-sqp", action="store_true", help="skip the SQP-mode leg")
+    ap.add_argument("--no-full-k", action="store_true", help="skip the end-to-end leg that returns every gain matrix")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

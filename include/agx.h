@@ -52,6 +52,8 @@ extern "C" {
 #define AGX_STATUS_REGMAX 2    /* regularisation hit reg_max */
 #define AGX_STATUS_NAN 3       /* non-finite value met */
 #define AGX_STATUS_LINESEARCH 4 /* reserved (a refused line search raises the regularisation and the solve goes on) */
+#define AGX_ACCEPT_CROCODDYL2 0
+#define AGX_ACCEPT_CROCODDYL1 1
 #define AGX_STATUS_TIMEOUT 5    /* max_solve_time elapsed: the current iterate is returned */
 
 /*
@@ -120,7 +122,15 @@ typedef struct agx_fddp_opts {
   int32_t fixed_iters;
   int32_t n_alphas; /* step lengths 2^-n, n = 0..n_alphas-1 (<= 10) */
   int32_t eager_exit;
-  int32_t reserved;
+  /* Acceptance test of a trial step (SolverFDDP::solve).  Crocoddyl's releases differ in two details and its source is
+   * not in the reference tree, so both forms are provided:
+   *   AGX_ACCEPT_CROCODDYL2 (0, default; Crocoddyl >= 2.0, what the reference's flake pins):
+   *       dVexp >= 0: |d1| < th_grad or dV > th_acceptstep dVexp;   dVexp < 0: NOT feasible and dV > th_acceptnegstep dVexp
+   *   AGX_ACCEPT_CROCODDYL1 (1; Crocoddyl 1.x): d1 < th_grad without the absolute value, no feasibility guard.
+   * They differ only for d1 < 0 (gap terms dominating) or for dVexp < 0 on a feasible candidate -- which exact
+   * arithmetic excludes (feasible: d1 + d2/2 = Qu.k/2 >= 0); tests/test_gpu_parity.py checks that the benchmark batch
+   * gives the same iterates under both. */
+  int32_t accept_rule;
   /* max_solve_time of the reference's solver (ocp_base_croco.py:70-71, passed when use_iteration_limits_and_timeout,
    * :166-171), in seconds; <= 0: none.  The deadline is kept ON THE DEVICE: the solve's first kernel stamps the device
    * clock, and a problem whose iteration ends later than stamp + max_solve_time stops iterating and returns its current
@@ -233,8 +243,9 @@ int agx_rnea(agx_handle* h, const double* q, const double* v, const double* a, i
  * In:  x0 [B][nx], xs_ws [B][T+1][nx], us_ws [B][T][nu].
  * Out: out_xs [B][T+1][nx], out_us [B][T][nu], out_K [B][T][nu][nx], out_k [B][T][nu] (may be NULL),
  *      out_cost [B], out_iters [B] (int32), out_status [B] (int32), out_stop [B] (may be NULL).
- * A problem whose alpha = 1 trial is rejected takes its alpha = 1/2 trial in the next round of launches (deferred line
- * search), so max_iter + 1 rounds are queued; per problem the iterates are those of the sequential search.
+ * A problem whose trial step is rejected takes its next step length in the next round of launches (deferred line
+ * search, up to twice per solve; deeper searches run in line), so max_iter + 2 rounds are queued; per problem the
+ * iterates are those of the sequential search.
  * Stream-ordered and asynchronous for max_iter <= 32 or opts->fixed_iters; with a larger budget the call
  * synchronises `stream` every 16 iterations to stop as soon as every problem has finished. */
 int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double* us_ws,

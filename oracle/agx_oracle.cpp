@@ -1165,10 +1165,12 @@ struct Fddp {
         expected_improvement();
         dVexp = steplength * (d1 + 0.5 * steplength * d2);
         bool accept = false;
+        // SolverFDDP::solve's acceptance test; the two forms are those of Crocoddyl >= 2.0 (default) and 1.x (agx.h)
+        const bool legacy = o.accept_rule == AGX_ACCEPT_CROCODDYL1;
         if (dVexp >= 0) {
-          if (d1 < o.th_grad || dV > o.th_acceptstep * dVexp) accept = true;
+          if ((legacy ? d1 : std::fabs(d1)) < o.th_grad || dV > o.th_acceptstep * dVexp) accept = true;
         } else {
-          if (dV > o.th_acceptnegstep * dVexp) accept = true;
+          if ((legacy || !is_feasible) && dV > o.th_acceptnegstep * dVexp) accept = true;
         }
         if (accept) {
           was_feasible = is_feasible;
@@ -1209,7 +1211,7 @@ void agx_fddp_opts_default(agx_fddp_opts* o) {
   o->th_grad = 1e-12; o->th_stepdec = 0.5; o->th_stepinc = 0.01; o->th_acceptstep = 0.1;
   o->th_acceptnegstep = 2.0; o->th_stop = 1e-9;
   o->reg_init = std::numeric_limits<double>::quiet_NaN();
-  o->fixed_iters = 0; o->n_alphas = 10; o->eager_exit = 0; o->reserved = 0; o->max_solve_time = 0.0;
+  o->fixed_iters = 0; o->n_alphas = 10; o->eager_exit = 0; o->accept_rule = AGX_ACCEPT_CROCODDYL2; o->max_solve_time = 0.0;
 }
 
 void orc_rnea(const agx_model* m, const double* q, const double* v, const double* a, int n, double* tau) {
