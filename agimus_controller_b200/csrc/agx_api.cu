@@ -373,7 +373,14 @@ struct DeviceGuard { explicit DeviceGuard(int) {} };
 void launch_backward(agx_handle* h, const agx::Problem& P, const agx::Work& W, const agx::FddpOpts& O, stream_t st) {
   if (BW_MMA) {
     const int wpc = 1;  // one warp per CTA (matches the kernel's __launch_bounds__)
-    AGX_LAUNCH(h, backward_mma_kernel, (h->B + wpc - 1) / wpc, 32 * wpc, sizeof(double) * MB_SIZE * wpc, st, P, W, h->S, O);
+    // AGX_BW_SMEM_KB (tuning): dynamic shared memory per CTA, to cap the resident CTAs per SM below the register limit
+    static const size_t smem_bytes = [] {
+      const char* e = std::getenv("AGX_BW_SMEM_KB");
+      const size_t need = sizeof(double) * MB_SIZE;
+      const size_t want = e ? (size_t)std::atoi(e) * 1024 : 0;
+      return want > need && want <= 48 * 1024 ? want : need;
+    }();
+    AGX_LAUNCH(h, backward_mma_kernel, (h->B + wpc - 1) / wpc, 32 * wpc, smem_bytes * wpc, st, P, W, h->S, O);
   } else {
     const int opc_s = SEQ_CTA / 8;
     AGX_LAUNCH(h, backward_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * BW_SIZE * opc_s, st, P, W, h->S, O);

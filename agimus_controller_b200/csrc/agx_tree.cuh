@@ -757,42 +757,66 @@ __global__ void tree_expand_kernel(Problem P, const double* __restrict__ rec, co
   }
 }
 
-// ---------------------------------------------------------------- Riccati sweep: one WARP per problem, matrices in
-// shared memory.  Same algebra as the chain kernels (agx_kernels.cuh): Fx = [I 0; 0 0] + S G, Fu = S N with
-// G = [dt aq, I + dt av] (NV x 2NV), S = [dt I; I], N = dt Minv:
+// ---------------------------------------------------------------- Riccati sweep: one WARP per problem on the FP64
+// tensor cores (mma.sync m8n8k4, SASS DMMA), any nv.  Same algebra as the chain kernels (agx_kernels.cuh):
+// Fx = [I 0; 0 0] + S G, Fu = S N with G = [dt aq, I + dt av] (NV x 2NV), S = [dt I; I], N = dt Minv:
 //   Z = S^T V', Vs = Z S, W = Vs G + [Zq 0], Qxx = Lxx + [V'qq 0; 0 0] + G^T W + [Zq^T G; 0], Qux = N^T W,
-//   Quu = Luu + N^T Vs N, Qx = Lx + [v'q; 0] + G^T S^T v', Qu = Lu + N^T S^T v'.
+//   Quu = Luu + N^T Vs N, Qx = Lx + [v'q; 0] + G^T S^T v', Qu = Lu + N^T S^T v', Vxx = Qxx - Qux^T K.
+// The state keeps its natural order [q; v]; every matrix lives on a zero-padded shared-memory board (NV -> KP = 4-
+// multiple in the contraction dimension, RP = 8-multiple in rows; 2NV -> NP = 8-multiple) and every product is a loop
+// of 8 x 8 x 4 tile products whose operands are read from the boards: lane T (g = T / 4, q = T % 4) holds
+// a = A[g][4 kc + q], b = B[4 kc + q][g] and the accumulator pair C[g][2q], C[g][2q + 1].  nv = 9: 132 tile products
+// per node.  The Quu Cholesky runs redundantly in registers; lanes 0..2NV each solve one column of [Qux | Qu].
 template <int NV>
 struct BWL {
-  static constexpr int N = 2 * NV, N1 = N + 1, M1 = NV + 1;
-  static constexpr int V = 0;                 // [N][N1]   V' (value Hessian of the next node)
-  static constexpr int Q = V + N * N1;        // [N][N1]   Qxx, then the unsymmetrised Vxx
-  static constexpr int G = Q + N * N1;        // [NV][N1]
-  static constexpr int Z = G + NV * N1;       // [NV][N1]
-  static constexpr int W = Z + NV * N1;       // [NV][N1]
-  static constexpr int U = W + NV * N1;       // [NV][N1]  Qux
-  static constexpr int K = U + NV * N1;       // [NV][N1]  gains
-  static constexpr int NN = K + NV * N1;      // [NV][M1]  N
-  static constexpr int VS = NN + NV * M1;     // [NV][M1]
-  static constexpr int VN = VS + NV * M1;     // [NV][M1]
-  static constexpr int QUU = VN + NV * M1;    // [NV][M1]
-  static constexpr int VX = QUU + NV * M1;    // [N]
-  static constexpr int QX = VX + N;           // [N]
-  static constexpr int FS = QX + N;           // [N]
-  static constexpr int GV = FS + N;           // [N]
-  static constexpr int SV = GV + N;           // [NV]
-  static constexpr int QU = SV + NV;          // [NV]
-  static constexpr int KF = QU + NV;          // [NV]  feed-forward k
-  static constexpr int SIZE = (KF + NV + 1) & ~1;
+  static constexpr int N = 2 * NV;
+  static constexpr int KP = (NV + 3) & ~3;     // contraction length (multiple of 4)
+  static constexpr int RP = (NV + 7) & ~7;     // rows of the NV-row boards (multiple of 8)
+  static constexpr int NP = (N + 7) & ~7;      // padded state dimension
+  static constexpr int KC = KP / 4, RT = RP / 8, NT = NP / 8;
+  static constexpr int LDN = NP + 4, LDR = RP + 4;   // row strides (doubles)
+  static constexpr int V = 0;                  // [NP][LDN]  V' (value Hessian of the next node)
+  static constexpr int G = V + NP * LDN;       // [KP][LDN]
+  static constexpr int NN = G + KP * LDN;      // [KP][LDR]  N
+  static constexpr int Z = NN + KP * LDR;      // [RP][LDN]  Z, later [Qux]
+  static constexpr int VS = Z + RP * LDN;      // [RP][LDR]  Vs, later Quu
+  static constexpr int W = VS + RP * LDR;      // [RP][LDN]  W, later K
+  static constexpr int VN = W + RP * LDN;      // [RP][LDR]
+  static constexpr int VX = VN + RP * LDR;     // [NP]
+  static constexpr int QX = VX + NP;           // [NP]
+  static constexpr int FS = QX + NP;           // [NP]
+  static constexpr int SV = FS + NP;           // [RP]
+  static constexpr int QU = SV + RP;           // [RP]
+  static constexpr int KF = QU + RP;           // [RP]  feed-forward k
+  static constexpr int ZERO_END = (KF + RP + 1) & ~1;   // boards up to here are zero-padded work space
+  static constexpr int CB = ZERO_END;          // [CREC]  cost record of the current node
+  static constexpr int ST = CB + TL<NV>::CREC; // staged records of the NEXT node: dynamics, cost, gap row
+  static constexpr int ST_REC = ST, ST_CREC = ST + TL<NV>::REC, ST_FS = ST_CREC + TL<NV>::CREC;
+  static constexpr int SIZE = (ST_FS + N + 1) & ~1;
 };
+
+// asynchronous copy of node t's records (and gap row) into the stage buffer: 16-byte chunks over the 32 lanes
+template <int NV>
+AGX_DEV void tree_stage_node(double* sm, const double* __restrict__ rec, const double* __restrict__ crec,
+                             const double* __restrict__ fs, bool gaps, int lane) {
+  using B_ = BWL<NV>;
+  constexpr int NREC = TL<NV>::REC / 2, NCREC = TL<NV>::CREC / 2, NFS = NV;  // 2 NV doubles = NV chunks
+  for (int c = lane; c < NREC + NCREC + NFS; c += 32) {
+    if (c < NREC) AGX_CP_ASYNC16(sm + B_::ST_REC + 2 * c, rec + 2 * c);
+    else if (c < NREC + NCREC) AGX_CP_ASYNC16(sm + B_::ST_CREC + 2 * (c - NREC), crec + 2 * (c - NREC));
+    else if (gaps) AGX_CP_ASYNC16(sm + B_::ST_FS + 2 * (c - NREC - NCREC), fs + 2 * (c - NREC - NCREC));
+  }
+  AGX_CP_ASYNC_COMMIT();
+}
 
 template <int NV>
 __global__ void __launch_bounds__(32) tree_backward_kernel(Problem P, Work W, SolverState S, FddpOpts O) {
   using Lt = TL<NV>;
   using B_ = BWL<NV>;
-  constexpr int N = 2 * NV, N1 = N + 1, M1 = NV + 1;
+  constexpr int N = 2 * NV, KC = B_::KC, RT = B_::RT, NT = B_::NT, LDN = B_::LDN, LDR = B_::LDR, NP = B_::NP, RP = B_::RP;
   AGX_SMEM(sm);
   const int lane = (int)(threadIdx.x & 31u);
+  const int g = lane >> 2, q = lane & 3;
   const int b = (int)blockIdx.x;
   if (b >= P.B) return;
   if (S.done[b] || S.pending[b]) return;
@@ -820,7 +844,29 @@ __global__ void __launch_bounds__(32) tree_backward_kernel(Problem P, Work W, So
     fsb[c] = W.x0[(size_t)b * N + c] - xs[c];
     for (int t = 0; t < T; ++t) fsb[(t + 1) * N + c] = rec0[(size_t)t * Lt::REC + rk * GW + jj] - xs[(t + 1) * N + c];
   }
+  // the pads of every board stay zero for the whole sweep: only valid entries are ever rewritten
+  for (int idx = lane; idx < B_::ZERO_END; idx += 32) sm[idx] = 0.0;
   __syncwarp();
+
+  // tile products: acc += A(rows r0.., k) B(k, cols c0..); *_t: the A operand is stored transposed ([k][row])
+  auto mma_nn = [&](double* acc, const double* A, int lda, int r0, const double* Bm, int ldb, int c0) {
+#pragma unroll
+    for (int kc = 0; kc < KC; ++kc) {
+      const double a = A[(r0 + g) * lda + 4 * kc + q], bb = Bm[(4 * kc + q) * ldb + c0 + g];
+      AGX_DMMA(acc[0], acc[1], a, bb, acc[0], acc[1]);
+    }
+  };
+  auto mma_tn = [&](double* acc, const double* A, int lda, int r0, const double* Bm, int ldb, int c0, double sgn, int row_lim) {
+#pragma unroll
+    for (int kc = 0; kc < KC; ++kc) {
+      const double a = (r0 + g < row_lim) ? sgn * A[(4 * kc + q) * lda + r0 + g] : 0.0, bb = Bm[(4 * kc + q) * ldb + c0 + g];
+      AGX_DMMA(acc[0], acc[1], a, bb, acc[0], acc[1]);
+    }
+  };
+  auto store_tile = [&](double* C, int ldc, int r0, int c0, const double* acc) {
+    C[(r0 + g) * ldc + c0 + 2 * q] = acc[0];
+    C[(r0 + g) * ldc + c0 + 2 * q + 1] = acc[1];
+  };
 
   bool failed = !(cost == cost);
   double dg = 0.0, dq = 0.0;
@@ -828,6 +874,9 @@ __global__ void __launch_bounds__(32) tree_backward_kernel(Problem P, Work W, So
     bool ok = !failed;
     double dgp = 0.0, dqp = 0.0;
     if (ok) {
+      // the first running node's records start flowing into shared memory while the terminal node is handled
+      tree_stage_node<NV>(sm, rec0 + (size_t)(T - 1) * Lt::REC, crec0 + (size_t)(T - 1) * Lt::CREC,
+                          fsb + (size_t)(T - 1) * N, !feasible, lane);
       // ---- terminal node: Vxx = Lxx (+ xreg), Vx = Lx (+ Vxx fs)
       const double* C = crec0 + (size_t)T * Lt::CREC;
       for (int idx = lane; idx < N * N; idx += 32) {
@@ -836,7 +885,7 @@ __global__ void __launch_bounds__(32) tree_backward_kernel(Problem P, Work W, So
         if (r < NV && c < NV) v = C[Lt::CK_LQQ + (r >= c ? tidx(NV, r, c) : tidx(NV, c, r))];
         else if (r == c) v = C[Lt::CK_LVV + r - NV];
         if (r == c) v += xreg;
-        sm[B_::V + r * N1 + c] = v;
+        sm[B_::V + r * LDN + c] = v;
       }
       if (lane < N) {
         sm[B_::VX + lane] = lane < NV ? C[Lt::CK_LQ + lane] : C[Lt::CK_LV + lane - NV];
@@ -844,118 +893,140 @@ __global__ void __launch_bounds__(32) tree_backward_kernel(Problem P, Work W, So
       }
       __syncwarp();
       if (!feasible) {
-        double g = 0.0, f = 0.0;
         if (lane < N) {
-          f = sm[B_::FS + lane];
-          for (int c = 0; c < N; ++c) g += sm[B_::V + lane * N1 + c] * sm[B_::FS + c];
-          const double vx = sm[B_::VX + lane] + g;
+          double gg = 0.0;
+          const double f = sm[B_::FS + lane];
+          for (int c = 0; c < N; ++c) gg += sm[B_::V + lane * LDN + c] * sm[B_::FS + c];
+          const double vx = sm[B_::VX + lane] + gg;
           sm[B_::VX + lane] = vx;
-          gvb[T * N + lane] = g;
+          gvb[T * N + lane] = gg;
           dgp -= vx * f;
-          dqp += g * f;
+          dqp += gg * f;
         }
         __syncwarp();
       }
     }
     for (int t = T - 1; ok && t >= 0; --t) {
       const double h = P.dts[t];
-      const double* R = rec0 + (size_t)t * Lt::REC;
-      const double* C = crec0 + (size_t)t * Lt::CREC;
-      // node operands
+      // node t's records were staged during the previous node; they are unpacked onto the boards, then the next
+      // node's records start flowing in behind the arithmetic
+      AGX_CP_ASYNC_WAIT_ALL();
+      __syncwarp();
+      const double* R = sm + B_::ST_REC;
+      const double* C = sm + B_::CB;
+      for (int idx = lane; idx < Lt::CREC; idx += 32) sm[B_::CB + idx] = sm[B_::ST_CREC + idx];
+      // node operands: G = [dt aq, I + dt av], N = dt Minv; Z = S^T V', sv = S^T v'
       for (int idx = lane; idx < NV * N; idx += 32) {
         const int i = idx / N, c = idx % N;
-        sm[B_::G + i * N1 + c] = c < NV ? R[(Lt::RK_AQ + i) * GW + c] : R[(Lt::RK_AV + i) * GW + (c - NV)] + ((c - NV == i) ? 1.0 : 0.0);
+        sm[B_::G + i * LDN + c] = c < NV ? R[(Lt::RK_AQ + i) * GW + c] : R[(Lt::RK_AV + i) * GW + (c - NV)] + ((c - NV == i) ? 1.0 : 0.0);
+        sm[B_::Z + i * LDN + c] = h * sm[B_::V + i * LDN + c] + sm[B_::V + (NV + i) * LDN + c];
       }
       for (int idx = lane; idx < NV * NV; idx += 32) {
         const int i = idx / NV, c = idx % NV;
-        sm[B_::NN + i * M1 + c] = R[(Lt::RK_MI + i) * GW + c];
+        sm[B_::NN + i * LDR + c] = R[(Lt::RK_MI + i) * GW + c];
       }
-      if (lane < N) sm[B_::FS + lane] = feasible ? 0.0 : fsb[t * N + lane];
-      // Z = S^T V', sv = S^T v'
-      for (int idx = lane; idx < NV * N; idx += 32) {
-        const int i = idx / N, c = idx % N;
-        sm[B_::Z + i * N1 + c] = h * sm[B_::V + i * N1 + c] + sm[B_::V + (NV + i) * N1 + c];
-      }
+      if (lane < N) sm[B_::FS + lane] = feasible ? 0.0 : sm[B_::ST_FS + lane];
       if (lane < NV) sm[B_::SV + lane] = h * sm[B_::VX + lane] + sm[B_::VX + NV + lane];
       __syncwarp();
+      if (t > 0)
+        tree_stage_node<NV>(sm, rec0 + (size_t)(t - 1) * Lt::REC, crec0 + (size_t)(t - 1) * Lt::CREC,
+                            fsb + (size_t)(t - 1) * N, !feasible, lane);
       for (int idx = lane; idx < NV * NV; idx += 32) {
         const int i = idx / NV, m = idx % NV;
-        sm[B_::VS + i * M1 + m] = h * sm[B_::Z + i * N1 + m] + sm[B_::Z + i * N1 + NV + m];
+        sm[B_::VS + i * LDR + m] = h * sm[B_::Z + i * LDN + m] + sm[B_::Z + i * LDN + NV + m];
       }
       __syncwarp();
       // W = Vs G + [Zq 0], VN = Vs N
-      for (int idx = lane; idx < NV * N; idx += 32) {
-        const int i = idx / N, c = idx % N;
-        double a = c < NV ? sm[B_::Z + i * N1 + c] : 0.0;
 #pragma unroll
-        for (int m = 0; m < NV; ++m) a += sm[B_::VS + i * M1 + m] * sm[B_::G + m * N1 + c];
-        sm[B_::W + i * N1 + c] = a;
-      }
-      for (int idx = lane; idx < NV * NV; idx += 32) {
-        const int i = idx / NV, c = idx % NV;
-        double a = 0.0;
+      for (int rt = 0; rt < RT; ++rt) {
 #pragma unroll
-        for (int m = 0; m < NV; ++m) a += sm[B_::VS + i * M1 + m] * sm[B_::NN + m * M1 + c];
-        sm[B_::VN + i * M1 + c] = a;
+        for (int ct = 0; ct < NT; ++ct) {
+          double acc[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int c = 8 * ct + 2 * q + e;
+            acc[e] = c < NV ? sm[B_::Z + (8 * rt + g) * LDN + c] : 0.0;
+          }
+          mma_nn(acc, sm + B_::VS, LDR, 8 * rt, sm + B_::G, LDN, 8 * ct);
+          store_tile(sm + B_::W, LDN, 8 * rt, 8 * ct, acc);
+        }
+#pragma unroll
+        for (int ct = 0; ct < RT; ++ct) {
+          double acc[2] = {0.0, 0.0};
+          mma_nn(acc, sm + B_::VS, LDR, 8 * rt, sm + B_::NN, LDR, 8 * ct);
+          store_tile(sm + B_::VN, LDR, 8 * rt, 8 * ct, acc);
+        }
       }
       __syncwarp();
-      // Qxx, Qx
-      for (int idx = lane; idx < N * N; idx += 32) {
-        const int r = idx / N, c = idx % N;
-        double a = 0.0;
-        if (r < NV && c < NV) a = C[Lt::CK_LQQ + (r >= c ? tidx(NV, r, c) : tidx(NV, c, r))] + sm[B_::V + r * N1 + c];
-        else if (r == c) a = C[Lt::CK_LVV + r - NV];
+      // Qxx = Lxx + [V'qq 0; 0 0] + G^T W + [Zq^T G; 0] (kept in registers), Qx
+      double Qt[NT][NT][2];
 #pragma unroll
-        for (int i = 0; i < NV; ++i) a += sm[B_::G + i * N1 + r] * sm[B_::W + i * N1 + c];
-        if (r < NV) {
+      for (int rt = 0; rt < NT; ++rt)
 #pragma unroll
-          for (int i = 0; i < NV; ++i) a += sm[B_::Z + i * N1 + r] * sm[B_::G + i * N1 + c];
+        for (int ct = 0; ct < NT; ++ct) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int r = 8 * rt + g, c = 8 * ct + 2 * q + e;
+            double a = 0.0;
+            if (r < NV && c < NV) a = C[Lt::CK_LQQ + (r >= c ? tidx(NV, r, c) : tidx(NV, c, r))] + sm[B_::V + r * LDN + c];
+            else if (r == c && r < N) a = C[Lt::CK_LVV + r - NV];
+            Qt[rt][ct][e] = a;
+          }
+          mma_tn(Qt[rt][ct], sm + B_::G, LDN, 8 * rt, sm + B_::W, LDN, 8 * ct, 1.0, N);
+          if (8 * rt < NV) mma_tn(Qt[rt][ct], sm + B_::Z, LDN, 8 * rt, sm + B_::G, LDN, 8 * ct, 1.0, NV);
         }
-        sm[B_::Q + r * N1 + c] = a;
-      }
       if (lane < N) {
         const int r = lane;
         double a = r < NV ? C[Lt::CK_LQ + r] + sm[B_::VX + r] : C[Lt::CK_LV + r - NV];
 #pragma unroll
-        for (int i = 0; i < NV; ++i) a += sm[B_::G + i * N1 + r] * sm[B_::SV + i];
+        for (int i = 0; i < NV; ++i) a += sm[B_::G + i * LDN + r] * sm[B_::SV + i];
         sm[B_::QX + r] = a;
-      }
-      // Qux = N^T W, Qu, Quu = Luu + N^T VN (+ ureg)
-      for (int idx = lane; idx < NV * N; idx += 32) {
-        const int i = idx / N, c = idx % N;
-        double a = 0.0;
-#pragma unroll
-        for (int m = 0; m < NV; ++m) a += sm[B_::NN + m * M1 + i] * sm[B_::W + m * N1 + c];
-        sm[B_::U + i * N1 + c] = a;
       }
       if (lane < NV) {
         double a = C[Lt::CK_LU + lane];
 #pragma unroll
-        for (int m = 0; m < NV; ++m) a += sm[B_::NN + m * M1 + lane] * sm[B_::SV + m];
+        for (int m = 0; m < NV; ++m) a += sm[B_::NN + m * LDR + lane] * sm[B_::SV + m];
         sm[B_::QU + lane] = a;
       }
-      for (int idx = lane; idx < NV * NV; idx += 32) {
-        const int i = idx / NV, c = idx % NV;
-        double a = (i == c) ? C[Lt::CK_LUU + i] + xreg : 0.0;
+      __syncwarp();  // every lane is done reading Z and Vs: Qux and Quu take their boards
+      // Qux = N^T W -> Z board, Quu = Luu + N^T VN (+ ureg) -> Vs board
 #pragma unroll
-        for (int m = 0; m < NV; ++m) a += sm[B_::NN + m * M1 + i] * sm[B_::VN + m * M1 + c];
-        sm[B_::QUU + i * M1 + c] = a;
+      for (int rt = 0; rt < RT; ++rt) {
+#pragma unroll
+        for (int ct = 0; ct < NT; ++ct) {
+          double acc[2] = {0.0, 0.0};
+          mma_tn(acc, sm + B_::NN, LDR, 8 * rt, sm + B_::W, LDN, 8 * ct, 1.0, NV);
+          store_tile(sm + B_::Z, LDN, 8 * rt, 8 * ct, acc);
+        }
+#pragma unroll
+        for (int ct = 0; ct < RT; ++ct) {
+          double acc[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int i = 8 * rt + g, c = 8 * ct + 2 * q + e;
+            acc[e] = (i == c && i < NV) ? C[Lt::CK_LUU + i] + xreg : 0.0;
+          }
+          mma_tn(acc, sm + B_::NN, LDR, 8 * rt, sm + B_::VN, LDR, 8 * ct, 1.0, NV);
+          store_tile(sm + B_::VS, LDR, 8 * rt, 8 * ct, acc);
+        }
       }
       __syncwarp();
       // computeGains: every lane factors Quu in registers; lanes 0..N solve one column of [Qux | Qu] each
       {
         double L[Lt::NTRI], rinv[NV];
-        ok = chol_registers<NV>(sm + B_::QUU, M1, L, rinv);
+        ok = chol_registers<NV>(sm + B_::VS, LDR, L, rinv);
         if (!ok) break;
         if (lane <= N) {
           const int c = lane;
           double col[NV];
 #pragma unroll
-          for (int i = 0; i < NV; ++i) col[i] = c < N ? sm[B_::U + i * N1 + c] : sm[B_::QU + i];
+          for (int i = 0; i < NV; ++i) col[i] = c < N ? sm[B_::Z + i * LDN + c] : sm[B_::QU + i];
           chol_solve<NV>(L, rinv, col);
           if (c < N) {
 #pragma unroll
-            for (int i = 0; i < NV; ++i) { sm[B_::K + i * N1 + c] = col[i]; Kb[(t * NV + i) * N + c] = col[i]; }
+            for (int i = 0; i < NV; ++i) { sm[B_::W + i * LDN + c] = col[i]; Kb[(t * NV + i) * N + c] = col[i]; }
+#pragma unroll
+            for (int i = NV; i < RP; ++i) sm[B_::W + i * LDN + c] = 0.0;
           } else {
             double qk = 0.0;
 #pragma unroll
@@ -963,46 +1034,65 @@ __global__ void __launch_bounds__(32) tree_backward_kernel(Problem P, Work W, So
             dgp += qk;   // Qu . k
             dqp -= qk;   // k . Quu k = k . Qu
           }
+        } else if (lane < NP + 1) {
+          // pad columns of the K board (it held W): back to zero
+          const int c = lane - 1;
+#pragma unroll
+          for (int i = 0; i < RP; ++i) sm[B_::W + i * LDN + c] = 0.0;
         }
       }
       __syncwarp();
-      // Vxx = Qxx - Qxu K (unsymmetrised, in place), Vx = Qx - K^T Qu
-      for (int idx = lane; idx < N * N; idx += 32) {
-        const int r = idx / N, c = idx % N;
-        double a = sm[B_::Q + r * N1 + c];
+      // Vxx = Qxx - Qux^T K (unsymmetrised, in registers), Vx = Qx - K^T Qu
 #pragma unroll
-        for (int i = 0; i < NV; ++i) a -= sm[B_::U + i * N1 + r] * sm[B_::K + i * N1 + c];
-        sm[B_::Q + r * N1 + c] = a;
-      }
+      for (int rt = 0; rt < NT; ++rt)
+#pragma unroll
+        for (int ct = 0; ct < NT; ++ct) mma_tn(Qt[rt][ct], sm + B_::Z, LDN, 8 * rt, sm + B_::W, LDN, 8 * ct, -1.0, N);
+      double nvx = 0.0;
       if (lane < N) {
-        double a = sm[B_::QX + lane];
+        nvx = sm[B_::QX + lane];
 #pragma unroll
-        for (int i = 0; i < NV; ++i) a -= sm[B_::K + i * N1 + lane] * sm[B_::QU + i];
-        sm[B_::VX + lane] = a;
+        for (int i = 0; i < NV; ++i) nvx -= sm[B_::W + i * LDN + lane] * sm[B_::QU + i];
       }
+      // symmetrise through the V board: unsymmetrised tiles out, (r, c) and (c, r) back in
+#pragma unroll
+      for (int rt = 0; rt < NT; ++rt)
+#pragma unroll
+        for (int ct = 0; ct < NT; ++ct) store_tile(sm + B_::V, LDN, 8 * rt, 8 * ct, Qt[rt][ct]);
       __syncwarp();
-      for (int idx = lane; idx < N * N; idx += 32) {
-        const int r = idx / N, c = idx % N;
-        sm[B_::V + r * N1 + c] = 0.5 * (sm[B_::Q + r * N1 + c] + sm[B_::Q + c * N1 + r]) + ((r == c) ? xreg : 0.0);
-      }
+#pragma unroll
+      for (int rt = 0; rt < NT; ++rt)
+#pragma unroll
+        for (int ct = 0; ct < NT; ++ct)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int r = 8 * rt + g, c = 8 * ct + 2 * q + e;
+            const double tv = sm[B_::V + c * LDN + r];
+            Qt[rt][ct][e] = (r < N && c < N) ? 0.5 * (Qt[rt][ct][e] + tv) + ((r == c) ? xreg : 0.0) : 0.0;
+          }
+      __syncwarp();
+#pragma unroll
+      for (int rt = 0; rt < NT; ++rt)
+#pragma unroll
+        for (int ct = 0; ct < NT; ++ct) store_tile(sm + B_::V, LDN, 8 * rt, 8 * ct, Qt[rt][ct]);
+      if (lane < N) sm[B_::VX + lane] = nvx;
       __syncwarp();
       if (!feasible) {
         if (lane < N) {
-          double g = 0.0;
-          for (int c = 0; c < N; ++c) g += sm[B_::V + lane * N1 + c] * sm[B_::FS + c];
+          double gg = 0.0;
+          for (int c = 0; c < N; ++c) gg += sm[B_::V + lane * LDN + c] * sm[B_::FS + c];
           const double f = sm[B_::FS + lane];
-          const double vx = sm[B_::VX + lane] + g;
+          const double vx = sm[B_::VX + lane] + gg;
           sm[B_::VX + lane] = vx;
-          gvb[t * N + lane] = g;
+          gvb[t * N + lane] = gg;
           dgp -= vx * f;
-          dqp += g * f;
+          dqp += gg * f;
         }
       }
       __syncwarp();
     }
     if (ok) {
       double chk = lane < N ? sm[B_::VX + lane] : 0.0;
-      for (int idx = lane; idx < N * N; idx += 32) chk += sm[B_::V + (idx / N) * N1 + (idx % N)];
+      for (int idx = lane; idx < N * N; idx += 32) chk += sm[B_::V + (idx / N) * LDN + (idx % N)];
       chk = warp_sum(chk);
       if (!(chk - chk == 0.0)) ok = false;
     }
@@ -1019,6 +1109,11 @@ __global__ void __launch_bounds__(32) tree_backward_kernel(Problem P, Work W, So
       if (lane == 0) { S.status[b] = 2; S.done[b] = 1; }
       break;
     }
+    // a restarted sweep starts from clean boards (a failed one may have left non-finite numbers in the pads)
+    AGX_CP_ASYNC_WAIT_ALL();
+    __syncwarp();
+    for (int idx = lane; idx < B_::ZERO_END; idx += 32) sm[idx] = 0.0;
+    __syncwarp();
   }
   if (lane == 0) {
     S.xreg[b] = xreg;
