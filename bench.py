@@ -494,7 +494,7 @@ def run_ours(args):
     try:
         import csv
 
-        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r1_ncu_full_final_raw.csv"))))
+        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r2_ncu_full_raw.csv"))))
         hdr, units = rows[0], rows[1]
         kname = {"backward": "backward_mma_kernel", "node_cost": "node_cost_kernel"}.get(top, (top or "") + "_kernel")
         for row in rows[2:]:
@@ -514,7 +514,7 @@ def run_ours(args):
             "bound": "fp64", "achieved": per[top]["tflops"], "peak": fp64_peak,
             "unit": "TFLOP/s", "frac": per[top]["tflops"] / fp64_peak if fp64_peak else None, "traffic": traffic,
             "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from "
-                            "profiles/r1_ncu_full_final_raw.csv; algorithmic bytes per launch: "
+                            "profiles/r2_ncu_full_raw.csv; algorithmic bytes per launch: "
                             f"{bytes_alg[top]:.0f}",
             "peak_source": "in-run DFMA probe (agx_probe_fp64); MEASURED_PEAKS.json carries no FP64 figure",
             "hbm": {"achieved": per[top]["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": per[top]["gbs"] / hbm_peak,
