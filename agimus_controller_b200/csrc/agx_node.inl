@@ -98,8 +98,17 @@ AGX_DEV void node_rnea_derivatives(LaneDyn& d, int j, unsigned omask, const doub
   scan_prefix_excl<6>(jq, dap, zero6, j, omask);
 #pragma unroll
   for (int k = 0; k < 6; ++k) da[k] = dap[k] + jq[k];
-  inertia_apply(d.Y, da, dfc);
-  scan_suffix_incl<6>(dfc, j, omask);
+  // sum_{l >= j} Y_l da_l = Yc_j da_j + sum_{m > j} (Yc_m J_m) qdd_m: the own inertia Y is not needed any more
+  double fq[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) fq[k] = d.dFda[k] * d.qdd;
+  scan_suffix_incl<6>(fq, j, omask);
+  inertia_apply(d.Z, da, dfc);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const double up = __shfl_down_sync(omask, fq[k], 1, 8);
+    dfc[k] += (j + 1 < 8) ? up : 0.0;
+  }
   double dFdq[6], dFdv[6];
   deriv_columns(d, j, dap, dfc, dFdq, dFdv);
   deriv_fill(d, j, dFdq, dFdv, sb);

@@ -323,7 +323,10 @@ AGX_DEV bool forward_dynamics(TLane<NV>& d, int j, unsigned gm, const double* __
   scan_anc_excl<6, RD>(d.g, d.a0p, agrav, d.par, j, gm);
   body_force(d);
   if (DERIV) {
-    subtree_sum<28, NV>(d.Z, d.sub, gm);
+    // in three pieces: the accumulators of one 28-wide sum would double the live composites
+    subtree_sum<10, NV>(d.Z, d.sub, gm);
+    subtree_sum<12, NV>(d.Z + 10, d.sub, gm);
+    subtree_sum<6, NV>(d.Z + 22, d.sub, gm);
   } else {
     subtree_sum<10, NV>(d.Z, d.sub, gm);
     subtree_sum<6, NV>(d.Z + 22, d.sub, gm);
@@ -359,7 +362,31 @@ AGX_DEV bool forward_dynamics(TLane<NV>& d, int j, unsigned gm, const double* __
 #pragma unroll
   for (int i = 0; i < NV; ++i)
     if (i == j) d.qdd = rhs[i];
+  if (DERIV) {
+    // park the factor on the board so that its registers are free during the derivative phase (column k by lane k)
+    AGX_GSYNC();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      if (k == j) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+          if (i >= k) sc[i * CS + k] = L[tidx(NV, i, k)];
+        sc[k * CS + GW] = rinv[k];
+      }
+    }
+  }
   return ok;
+}
+// reload the parked factor (after a group barrier)
+template <int NV>
+AGX_DEV void factor_reload(const double* sc, double* L, double* rinv) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if (i >= k) L[tidx(NV, i, k)] = sc[i * CS + k];
+    rinv[k] = sc[k * CS + GW];
+  }
 }
 
 // dtau/dq, dtau/dv columns (computeRNEADerivatives at the forward-dynamics acceleration)
@@ -403,6 +430,8 @@ AGX_DEV void node_dyn_diff(TLane<NV>& d, int j, unsigned gm, const double* __res
     rec[Lt::RK_VN * GW + j] = ok ? d.qd + d.qdd * dt : nan("");
   }
   rnea_derivatives<NV>(d, j, gm, sb);
+  AGX_GSYNC();
+  factor_reload<NV>(sc, L, rinv);
   double col[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) col[i] = d.tq[i];
