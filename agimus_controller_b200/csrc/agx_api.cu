@@ -512,6 +512,80 @@ int tree_solve(agx_handle* h, const double* x0, const double* xs_ws, const doubl
   return check_launch(h, "agx_solve");
 }
 
+
+// SQP mode on the general-tree kernels (same loop as agx_solve_sqp below)
+int tree_solve_sqp(agx_handle* h, const double* x0, const double* xs_ws, const double* us_ws, int max_iter,
+                   const agx_sqp_opts* opts, const SqpOpts& Q, const FddpOpts& O, const FddpOpts& Of, double* out_xs,
+                   double* out_us, double* out_K, double* out_k, double* out_cost, int32_t* out_iters, int32_t* out_status,
+                   double* out_stop, stream_t st) {
+  const size_t nB = (size_t)h->B, T = (size_t)h->T, T1 = T + 1;
+  const int nx = h->nx, nv = h->nv;
+  if (!out_K && !h->d_K_internal) {
+    if (!dev_alloc((void**)&h->d_K_internal, sizeof(double) * nB * T * nv * nx))
+      return fail(h, AGX_ENOMEM, "allocation of the internal gain buffer failed");
+  }
+  Work W = h->W;
+  W.K = out_K ? out_K : h->d_K_internal;
+  W.x0 = h->d_x0;
+  if (!copy_d2d(h->d_x0, x0, sizeof(double) * nB * nx, st)) return fail(h, AGX_ECUDA, "agx_solve_sqp: x0 copy failed");
+  const Problem P = problem_of(h);
+  const long long n_init = (long long)(nB * T1 * nx);
+  AGX_LAUNCH(h, init_kernel_n, (n_init + 255) / 256, 256, 0, st, P, nx, nv, W, h->S, O, xs_ws, us_ws);
+  const long long ents = (long long)(nB * T1);
+  const int gpc_n = TREE_NODE_CTA / tree::GW, gpc_s = TREE_SEQ_CTA / tree::GW;
+  for (int it = 0; it < max_iter; ++it) {
+    phase_begin(h, 0, st);
+    tree_launch_calc_diff(h, P, W.xs, W.us, h->S.cur, nullptr, h->S.done, st);
+    phase_end(h, st);
+    phase_begin(h, 1, st);
+    tree_launch_backward(h, P, W, O, st);
+    phase_end(h, st);
+    phase_begin(h, 2, st);
+    int32_t* pend = h->d_live + 1;
+#if AGX_GPU
+    cudaMemsetAsync(pend, 0, sizeof(int32_t) * 12, st);
+#else
+    std::memset(pend, 0, sizeof(int32_t) * 12);
+#endif
+    AGX_TREE_LAUNCH(h, tree_sqp_direction_kernel, (h->B + gpc_s - 1) / gpc_s, TREE_SEQ_CTA, 0, st, P, W, h->S, Q, pend);
+    phase_end(h, st);
+    phase_begin(h, 4, st);
+    for (int n = 0; n < Q.n_alphas; ++n) {
+      const long long try_ctas = n < 3 ? (ents + gpc_n - 1) / gpc_n : std::min<long long>((ents + gpc_n - 1) / gpc_n, 148 * 8);
+      AGX_TREE_LAUNCH(h, tree_sqp_try_kernel, try_ctas, TREE_NODE_CTA, sizeof(double) * h->tree_board * gpc_n, st, P, W, h->S,
+                      (const int32_t*)(pend + n));
+      AGX_LAUNCH(h, tree::sqp_accept_kernel_n, (h->B + 127) / 128, 128, 0, st, P, nx, W, h->S, Q, pend + n);
+      if (opts->eager_exit && h->B <= 64 && !h->timing && n + 1 < Q.n_alphas && read_counter_sync(h, pend + n + 1, st) == 0)
+        break;
+    }
+    phase_end(h, st);
+    if (opts->eager_exit && h->B <= 64 && !h->timing && it + 1 < max_iter) {
+      if (all_done_sync(h, st)) break;
+    } else if (max_iter > 32 && (it % 16) == 15 && it + 1 < max_iter) {
+      int32_t live = 1;
+#if AGX_GPU
+      cudaMemsetAsync(h->d_live, 0, sizeof(int32_t), st);
+      AGX_LAUNCH(h, count_live_kernel, (h->B + 255) / 256, 256, 0, st, h->B, (const int32_t*)h->S.done, h->d_live);
+      cudaMemcpyAsync(&live, h->d_live, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+      cudaStreamSynchronize(st);
+#else
+      *h->d_live = 0;
+      AGX_LAUNCH(h, count_live_kernel, (h->B + 255) / 256, 256, 0, st, h->B, (const int32_t*)h->S.done, h->d_live);
+      live = *h->d_live;
+#endif
+      if (live == 0) break;
+    }
+  }
+  // the gains of the solver's last backward pass (sigma + reg on the diagonals), at the final iterate
+  AGX_LAUNCH(h, sqp_final_prepare_kernel, (h->B + 255) / 256, 256, 0, st, h->B, h->S, Q);
+  tree_launch_calc_diff(h, P, W.xs, W.us, h->S.cur, nullptr, h->S.done, st);
+  tree_launch_backward(h, P, W, Of, st);
+  const long long n_fin = (long long)(nB * T * nv * nx);
+  AGX_LAUNCH(h, finalize_kernel_n, (n_fin + 255) / 256, 256, 0, st, P, nx, nv, W, h->S, out_xs, out_us, out_K, out_k,
+             out_cost, out_iters, out_status, out_stop);
+  return check_launch(h, "agx_solve_sqp");
+}
+
 }  // namespace
 
 extern "C" {
@@ -1066,8 +1140,7 @@ int agx_solve_sqp(agx_handle* h, const double* x0, const double* xs_ws, const do
   if (opts->n_alphas < 1 || opts->n_alphas > 10) return fail(h, AGX_EINVAL, "n_alphas must be in 1..10");
   if (!(opts->sigma >= 0.0) || !(opts->reg >= 0.0) || !(opts->mu >= 0.0))
     return fail(h, AGX_EINVAL, "sigma, reg and mu must be non-negative");
-  if (h->tree)
-    return fail(h, AGX_EUNSUPPORTED, "the SQP mode runs on the 7-joint chain kernels only (general trees: use agx_solve)");
+
   SqpOpts Q;
   Q.sigma = opts->sigma; Q.reg = opts->reg; Q.mu = opts->mu; Q.tol = opts->termination_tolerance;
   Q.n_alphas = opts->n_alphas;
@@ -1083,6 +1156,9 @@ int agx_solve_sqp(agx_handle* h, const double* x0, const double* xs_ws, const do
   O.fixed_iters = 0; O.n_alphas = Q.n_alphas; O.max_iter = max_iter; O.defer = 0; O.max_solve_ns = 0; O.accept_rule = 0;
   FddpOpts Of = O;
   Of.reg_min = Of.reg_max = 0.0;  // the last sweep (sigma + the problem's regularisation) is not retried
+  if (h->tree)
+    return tree_solve_sqp(h, x0, xs_ws, us_ws, max_iter, opts, Q, O, Of, out_xs, out_us, out_K, out_k, out_cost, out_iters,
+                          out_status, out_stop, st);
   const size_t nB = (size_t)h->B, T = (size_t)h->T, T1 = T + 1;
   if (!out_K && !h->d_K_internal) {
     if (!dev_alloc((void**)&h->d_K_internal, sizeof(double) * nB * T * NJ * NX))

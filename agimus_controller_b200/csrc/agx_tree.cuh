@@ -1379,6 +1379,217 @@ __global__ void tree_shift_kernel(Problem P, const double* __restrict__ xs, cons
   }
 }
 
+// ---------------------------------------------------------------- SQP mode on general trees (agx_sqp.cuh restated for
+// 16-lane groups): the linear rollout of the QP solution, the QP multipliers and the KKT norm.  Lane j owns row j.
+AGX_DEV double gmax(double x, unsigned gm) {
+  x = fmax(x, __shfl_xor_sync(gm, x, 1, GW));
+  x = fmax(x, __shfl_xor_sync(gm, x, 2, GW));
+  x = fmax(x, __shfl_xor_sync(gm, x, 4, GW));
+  x = fmax(x, __shfl_xor_sync(gm, x, 8, GW));
+  return x;
+}
+
+template <int NV>
+__global__ void tree_sqp_direction_kernel(Problem P, Work W, SolverState S, SqpOpts Q, int32_t* __restrict__ pend) {
+  using Lt = TL<NV>;
+  constexpr int NX = 2 * NV;
+  AGX_TREE_SETUP();
+  const int b = (int)ent;
+  if (b >= P.B) return;
+  if (S.done[b]) return;
+  const int T = P.T, T1 = T + 1;
+  const bool live = j < NV;
+  const int jj = live ? j : 0;
+  const double* fsb = W.fs + (size_t)b * T1 * NX;
+  double* dxb = W.gv + (size_t)b * T1 * NX;
+  const double* Kb = W.K + (size_t)b * T * NV * NX;
+  double* kb = W.k + (size_t)b * T * NV;
+  const double* rec0 = W.rec + (size_t)b * T1 * Lt::REC;
+  const double* crec0 = W.crec + (size_t)b * T1 * Lt::CREC;
+
+  double dq = live ? fsb[jj] : 0.0, dv = live ? fsb[NV + jj] : 0.0;
+  double gl1 = fabs(dq) + fabs(dv), ginf = fmax(fabs(dq), fabs(dv));
+  for (int t = 0; t < T; ++t) {
+    const double* Kr = Kb + ((size_t)t * NV + jj) * NX;
+    const double* R = rec0 + (size_t)t * Lt::REC;
+    if (live) { dxb[t * NX + j] = dq; dxb[t * NX + NV + j] = dv; }
+    double dqm[NV], dvm[NV];
+#pragma unroll
+    for (int m = 0; m < NV; ++m) { dqm[m] = __shfl_sync(gm, dq, m, GW); dvm[m] = __shfl_sync(gm, dv, m, GW); }
+    double s = -kb[t * NV + jj];
+#pragma unroll
+    for (int m = 0; m < NV; ++m) s -= Kr[m] * dqm[m] + Kr[NV + m] * dvm[m];
+    const double du = live ? s : 0.0;
+    if (live) kb[t * NV + j] = du;
+    double acc = 0.0;
+#pragma unroll
+    for (int m = 0; m < NV; ++m) {
+      const double dum = __shfl_sync(gm, du, m, GW);
+      acc += R[(Lt::RK_AQ + jj) * GW + m] * dqm[m] + R[(Lt::RK_AV + jj) * GW + m] * dvm[m] + R[(Lt::RK_MI + jj) * GW + m] * dum;
+    }
+    const double fq = live ? fsb[(t + 1) * NX + jj] : 0.0, fv = live ? fsb[(t + 1) * NX + NV + jj] : 0.0;
+    const double dt = P.dts[t];
+    const double dvn = dv + acc + fv;
+    const double dqn = dq + dt * (dv + acc) + fq;
+    gl1 += fabs(fq) + fabs(fv);
+    ginf = fmax(ginf, fmax(fabs(fq), fabs(fv)));
+    dq = live ? dqn : 0.0;
+    dv = live ? dvn : 0.0;
+  }
+  if (live) { dxb[T * NX + j] = dq; dxb[T * NX + NV + j] = dv; }
+  // multipliers and stationarity
+  double lq, lv, kkt;
+  {
+    const double* C = crec0 + (size_t)T * Lt::CREC;
+    double hq = 0.0;
+#pragma unroll
+    for (int m = 0; m < NV; ++m)
+      hq += C[Lt::CK_LQQ + (jj >= m ? tidx(NV, jj, m) : tidx(NV, m, jj))] * __shfl_sync(gm, dq, m, GW);
+    const double hv = C[Lt::CK_LVV + jj] * dv;
+    lq = C[Lt::CK_LQ + jj] + hq;
+    lv = C[Lt::CK_LV + jj] + hv;
+    kkt = live ? fmax(fabs(hq), fabs(hv)) : 0.0;
+  }
+  for (int t = T - 1; t >= 0; --t) {
+    const double* R = rec0 + (size_t)t * Lt::REC;
+    const double* C = crec0 + (size_t)t * Lt::CREC;
+    const double dt = P.dts[t];
+    const double w = live ? dt * lq + lv : 0.0;
+    double su = C[Lt::CK_LU + jj], aq = 0.0, av = 0.0;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const double wi = __shfl_sync(gm, w, i, GW);
+      su += R[(Lt::RK_MI + i) * GW + jj] * wi;
+      aq += R[(Lt::RK_AQ + i) * GW + jj] * wi;
+      av += R[(Lt::RK_AV + i) * GW + jj] * wi;
+    }
+    const double xq = live ? dxb[t * NX + jj] : 0.0, xv = live ? dxb[t * NX + NV + jj] : 0.0;
+    double hq = 0.0;
+#pragma unroll
+    for (int m = 0; m < NV; ++m)
+      hq += C[Lt::CK_LQQ + (jj >= m ? tidx(NV, jj, m) : tidx(NV, m, jj))] * __shfl_sync(gm, xq, m, GW);
+    const double hv = C[Lt::CK_LVV + jj] * xv;
+    const double nlq = C[Lt::CK_LQ + jj] + hq + lq + aq;
+    const double nlv = C[Lt::CK_LV + jj] + hv + w + av;
+    if (live) kkt = fmax(kkt, fmax(fabs(su), fmax(fabs(hq), fabs(hv))));
+    lq = nlq;
+    lv = nlv;
+  }
+  const double bad = gsum((live && !(lq - lq == 0.0 && lv - lv == 0.0)) ? 1.0 : 0.0, gm);
+  kkt = fmax(gmax(kkt, gm), gmax(ginf, gm));
+  gl1 = gsum(live ? gl1 : 0.0, gm);
+  if (j == 0) {
+    if (bad != 0.0) {
+      S.stop[b] = nan("");
+      S.status[b] = 3;
+      S.done[b] = 1;
+    } else {
+      S.stop[b] = kkt;
+      if (kkt <= Q.tol) {
+        S.status[b] = 0;
+        S.done[b] = 1;
+      } else {
+        S.dg[b] = S.cost[b] + Q.mu * gl1;
+        S.pending[b] = 1;
+        S.roll_ok[b] = 0;
+        atomicAdd(pend, 1);
+      }
+    }
+  }
+}
+
+// SolverCSQP::tryStep for the step length 2^-n the problem is at: one group per (problem, node)
+template <int NV>
+__global__ void tree_sqp_try_kernel(Problem P, Work W, SolverState S, const int32_t* __restrict__ pend) {
+  if (*pend == 0) return;
+  using Lt = TL<NV>;
+  constexpr int NX = 2 * NV;
+  AGX_SMEM(smem);
+  AGX_TREE_SETUP();
+  const int T = P.T, T1 = T + 1;
+  double* brd = smem + grp_in_cta * Lt::BOARD;
+  const long long total = (long long)P.B * T1, stride = (long long)gridDim.x * grps_per_cta;
+  for (long long e = ent; e < total; e += stride) {
+    const int b = (int)(e / T1), t = (int)(e % T1);
+    if (S.done[b] || !S.pending[b]) continue;
+    const double a = ldexp(1.0, -S.roll_ok[b]);
+    const size_t cur = (size_t)(S.cur[b] & 1), oth = cur ^ 1;
+    const bool live = j < NV, terminal = t == T;
+    const int jj = live ? j : 0;
+    const double* xs = W.xs + (cur * P.B + b) * (size_t)T1 * NX;
+    const double* us = W.us + (cur * P.B + b) * (size_t)T * NV;
+    double* xt = W.xs + (oth * P.B + b) * (size_t)T1 * NX;
+    double* ut = W.us + (oth * P.B + b) * (size_t)T * NV;
+    const double* dx = W.gv + (size_t)b * T1 * NX;
+    const double* du = W.k + (size_t)b * T * NV;
+    TLane<NV> d;
+    d.q = live ? xs[t * NX + jj] + a * dx[t * NX + jj] : 0.0;
+    d.qd = live ? xs[t * NX + NV + jj] + a * dx[t * NX + NV + jj] : 0.0;
+    d.u = (live && !terminal) ? us[t * NV + jj] + a * du[t * NV + jj] : 0.0;
+    d.qdd = 0.0;
+    const double q0 = d.q, v0 = d.qd;
+    if (live) {
+      xt[t * NX + j] = d.q;
+      xt[t * NX + NV + j] = d.qd;
+      if (!terminal) ut[t * NV + j] = d.u;
+    }
+    double c, qn, vn;
+    const bool ok = node_calc<NV>(d, j, gm, tmodel_of(P, b), P.refs + (size_t)e * Lt::REF, terminal ? 0.0 : P.dts[t],
+                                  terminal, brd, &c, &qn, &vn);
+    double g = 0.0;
+    if (live && !terminal) {
+      const double nq = xs[(t + 1) * NX + jj] + a * dx[(t + 1) * NX + jj];
+      const double nvv = xs[(t + 1) * NX + NV + jj] + a * dx[(t + 1) * NX + NV + jj];
+      g = fabs(qn - nq) + fabs(vn - nvv);
+    }
+    if (live && t == 0) g += fabs(W.x0[(size_t)b * NX + jj] - q0) + fabs(W.x0[(size_t)b * NX + NV + jj] - v0);
+    g = gsum(g, gm);
+    if (j == 0) {
+      double* out = W.fs + ((size_t)b * T1 + t) * NX;
+      out[0] = ok ? c : nan("");
+      out[1] = g;
+    }
+    AGX_GSYNC();
+  }
+}
+
+// merit_try < merit: take the step; otherwise the next step length (run-time state dimension)
+__global__ void sqp_accept_kernel_n(Problem P, int nx, Work W, SolverState S, SqpOpts Q, int32_t* __restrict__ pend) {
+  if (*pend == 0) return;
+  const int b = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (b >= P.B) return;
+  if (S.done[b] || !S.pending[b]) return;
+  const int T1 = P.T + 1;
+  const double* r = W.fs + (size_t)b * T1 * nx;
+  double c = 0.0, g = 0.0;
+  for (int t = 0; t < T1; ++t) { c += r[t * nx]; g += r[t * nx + 1]; }
+  const double mt = c + Q.mu * g;
+  const int n_now = S.roll_ok[b];
+  bool finished = false;
+  if (mt < S.dg[b]) {
+    S.cur[b] ^= 1;
+    finished = true;
+  } else if (n_now + 1 >= Q.n_alphas) {
+    finished = true;
+  } else {
+    S.roll_ok[b] = n_now + 1;
+    atomicAdd(pend + 1, 1);
+  }
+  if (finished) {
+    S.pending[b] = 0;
+    S.iters[b] += 1;
+    const double steplength = ldexp(1.0, -n_now);
+    double reg = S.xreg[b];
+    if (steplength > Q.th_stepdec) reg = fmax(reg / Q.reg_factor, Q.reg);
+    if (steplength <= Q.th_stepinc) {
+      reg = fmin(reg * Q.reg_factor, Q.reg_max);
+      if (reg == Q.reg_max) { S.status[b] = 2; S.done[b] = 1; }
+    }
+    S.xreg[b] = reg;
+    if (!S.done[b] && Q.max_solve_ns > 0 && agx_now_ns() - *S.t0 > Q.max_solve_ns) { S.status[b] = 5; S.done[b] = 1; }
+  }
+}
+
 __global__ void tree_set_capsule_kernel(double* __restrict__ model, int n_models, int capsule, double a0x, double a0y,
                                         double a0z, double a1x, double a1y, double a1z, double radius) {
   const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);

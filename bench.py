@@ -451,6 +451,57 @@ def run_ours(args):
                "what": "agx_solve_sqp (mim_solvers.SolverCSQP, unconstrained form, termination_tolerance 1e-3) on the "
                        "cfg-2 batch, inputs resident; includes the final sigma sweep for the reported gains"}
 
+    # BASELINE config 4 as stated (secondary figure, rank 0, N = 1): 4096 pick-and-place OCPs, nv = 9 WITH the finger
+    # joints (general-tree kernels), T = 100, two capsule-pair collision costs, 3 fixed FDDP iterations; the CPU
+    # restatement beside it on a bounded sample
+    cfg4 = None
+    if rank == 0 and world == 1 and not args.no_cfg4:
+        from agimus_controller_b200.workloads import pick_and_place_collision_batch
+
+        t9 = panda_table(lock_fingers=False)
+        h9 = BatchedShootingProblem(t9, np.full(2, DT), 1, device=dev)
+        w4 = pick_and_place_collision_batch(B, T=100, rnea=lambda q, v, a: h9.rnea(q, v, a).cpu().numpy(),
+                                            lock_fingers=False)
+        p4 = BatchedShootingProblem(w4["table"], w4["dts"], B, device=dev)
+        p4.set_refs(torch.as_tensor(w4["refs"], device=dev))
+        a4 = [torch.as_tensor(w4[k], device=dev) for k in ("x0", "xs_ws", "us_ws")]
+        o4 = p4.alloc_outputs()
+        for _ in range(2):
+            p4.solve(*a4, 3, opts, out=o4)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n4 = max(3, min(args.steps, 10))
+        e0.record()
+        for _ in range(n4):
+            p4.solve(*a4, 3, opts, out=o4)
+        e1.record()
+        torch.cuda.synchronize()
+        ms4 = e0.elapsed_time(e1) / n4
+        cfg4 = {"workload": "cfg4: 4096 pick-and-place OCPs, nv=9 with the finger joints (branching tree, prismatic "
+                            "joints; general-tree kernels), T=100, two capsule-pair collision costs (QuadExp), 3 fixed "
+                            "FDDP iterations, inputs resident",
+                "value": B / (ms4 * 1e-3), "unit": "solves/s", "ms_per_step": ms4, "steps": n4,
+                "finite": bool(torch.isfinite(o4["xs"]).all())}
+        if not args.no_cpu:
+            from oracle import orc
+
+            cores = len(os.sched_getaffinity(0))
+            n_c = min(B, 32 * cores)
+            m4 = w4["table"].to_struct()
+            run4 = lambda: orc.solve(m4, w4["refs"][:n_c], w4["dts"], w4["x0"][:n_c], w4["xs_ws"][:n_c],  # noqa: E731
+                                     w4["us_ws"][:n_c], 3, opts, nthreads=cores)
+            run4()
+            t0, reps4 = time.perf_counter(), 0
+            while time.perf_counter() - t0 < 5.0 and reps4 < 64:
+                run4()
+                reps4 += 1
+            dt4 = time.perf_counter() - t0
+            cfg4["cpu_baseline"] = {"value": n_c * reps4 / dt4, "unit": "solves/s", "cores": cores, "kind": "port",
+                                    "sample": f"first {n_c} of the 4096 problems x {reps4} passes ({dt4:.1f} s), OpenMP one "
+                                              "problem per thread; CPU restatement of Crocoddyl FDDP, not Crocoddyl itself"}
+        del p4, o4, a4
+        torch.cuda.empty_cache()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -554,7 +605,7 @@ def run_ours(args):
                 "pipelining": "copies of step i+1 (H2D) and i-1 (D2H) overlap the solve of step i on separate streams; "
                               "the host waits for step i-1's results before issuing step i+1"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-        "latency_b1": lat, "sqp_mode": sqp, "e2e_full_K": e2e_full, "strong_scaling": strong,
+        "latency_b1": lat, "sqp_mode": sqp, "e2e_full_K": e2e_full, "strong_scaling": strong, "cfg4_nv9": cfg4,
         "ms_per_step_per_rank": per_rank,
     }
     print(json.dumps(line), flush=True)
@@ -577,6 +628,7 @@ def main():
     ap.add_argument("--no-sqp", action="store_true", help="skip the SQP-mode leg")
     ap.add_argument("--no-full-k", action="store_true", help="skip the end-to-end leg that returns every gain matrix")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg")
+    ap.add_argument("--no-cfg4", action="store_true", help="skip the config-4 (nv = 9, general-tree kernels) leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

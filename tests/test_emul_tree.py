@@ -209,3 +209,19 @@ def test_panda9_frame_translation_mode(orc, t9):
         assert rel(e[k], o[k]) < 1e-9, k
     o0 = orc.calc_diff(t9.to_struct(), w["refs"], w["dts"], xs, us)
     assert rel(o["cost"], o0["cost"]) > 1e-3
+
+
+def test_panda9_sqp_mode_matches_oracle(orc, t9):
+    """The reference's own solver (mim_solvers.SolverCSQP without active constraints, agx_solve_sqp) on the 9-DoF tree:
+    same iterates, KKT norms and decisions as the CPU restatement."""
+    rng = np.random.default_rng(12)
+    w = _goal9(t9, 3, 8, rng, orc)
+    for max_iter in (2, 25):
+        o = orc.solve_sqp(w["m"], w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], max_iter)
+        e = emu.solve_sqp(w["m"], w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], max_iter)
+        np.testing.assert_array_equal(e["iters"], o["iters"])
+        np.testing.assert_array_equal(e["status"], o["status"])
+        for k in ("xs", "us", "cost", "stop"):
+            assert rel(e[k], o[k]) < 1e-6, k
+        assert rel(e["K"], o["K"]) < 1e-5
+    assert (e["status"] == _abi.AGX_STATUS_CONVERGED).any()

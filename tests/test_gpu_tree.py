@@ -206,3 +206,19 @@ def test_panda9_shift_and_reference_window(solver_mod, orc, t9):
     c_ref, _ = orc.calc(w["m"], refs_host, dts, xs_h, w["us_ws"])
     # the stream rows are running-node records: the terminal node keeps its control weights but has no control
     assert rel(c_dev.cpu().numpy(), c_ref) < 1e-12
+
+
+def test_panda9_sqp_mode(solver_mod, orc, t9):
+    """agx_solve_sqp (the solver the reference instantiates, unconstrained form) on the 9-DoF tree."""
+    B, T = 64, 50
+    w = _goal9(t9, B, T, 6, orc)
+    p = _problem(solver_mod, t9, w["dts"], w["refs"], B)
+    for max_iter in (3, 60):
+        o = orc.solve_sqp(w["m"], w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], max_iter)
+        g = {k: v.cpu().numpy() for k, v in p.solve_sqp(w["x0"], w["xs_ws"], w["us_ws"], max_iter).items()}
+        np.testing.assert_array_equal(g["iters"], o["iters"])
+        np.testing.assert_array_equal(g["status"], o["status"])
+        for k in ("xs", "us", "cost", "stop"):
+            assert rel(g[k], o[k]) < TRAJ_RTOL, k
+        assert rel(g["K"], o["K"]) < 1e-5
+    assert (g["status"] == _abi.AGX_STATUS_CONVERGED).mean() > 0.9
