@@ -81,7 +81,8 @@ int env_cta(const char* name, int dflt, int max_threads) {
   const int n = std::atoi(v);
   return (n >= 8 && n <= max_threads && n % 8 == 0) ? n : dflt;
 }
-const int NODE_CTA = env_cta("AGX_NODE_CTA", 64, 64);   // calc_diff_kernel is bounded to 64 threads
+const int NODE_CTA = env_cta("AGX_NODE_CTA", 64, 64);
+const int CD_CTA = env_cta("AGX_CD_CTA", AGX_CD_THREADS, AGX_CD_THREADS);   // calc_diff_kernel's CTA (its launch bound)
 const int SEQ_CTA = env_cta("AGX_SEQ_CTA", 32, 64);    // 8 octet boards of the forward kernels = 27 KB of the 48 KB default
 // backward sweep: "mma" = one warp per problem on the FP64 tensor cores (default), "octet" = 8 lanes per problem
 const bool BW_MMA = !(std::getenv("AGX_BW") && std::string(std::getenv("AGX_BW")) == "octet");
@@ -650,6 +651,12 @@ int agx_create(const agx_model* models_host, int n_models, const double* dts_hos
     h->nv = nv; h->nx = 2 * nv; h->ref_size = 6 * nv + 20; h->rec_size = z.rec; h->crec_size = z.crec;
     h->model_size = tree::TMODEL_SIZE; h->tree_board = z.board; h->tree_bw = z.bw;
   }
+#if AGX_GPU
+  if (sizeof(double) * OCT_BOARD * (CD_CTA / 8) > 48 * 1024) {
+    cudaFuncSetAttribute(calc_diff_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * OCT_BOARD * (CD_CTA / 8)));
+    cudaFuncSetAttribute(calc_diff_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * OCT_BOARD * (CD_CTA / 8)));
+  }
+#endif
   const int MSZ = h->model_size;
   double* tab = (double*)std::malloc(sizeof(double) * MSZ * (size_t)n_models);
   if (!tab) return fail(h, AGX_ENOMEM, "host allocation failed");
@@ -776,7 +783,7 @@ int agx_calc_diff(agx_handle* h, const double* xs, const double* us, double* out
   if (h->tree) return tree_calc_diff(h, xs, us, out_cost, out_xnext, Fx, Fu, Lx, Lu, Lxx, Lxu, Luu, (stream_t)stream);
   const long long ents = (long long)h->B * (h->T + 1);
   const int opc = NODE_CTA / 8;
-  AGX_LAUNCH_COL(h, calc_diff_kernel, (ents + opc - 1) / opc, NODE_CTA, sizeof(double) * OCT_BOARD * opc, (stream_t)stream,
+  AGX_LAUNCH_COL(h, calc_diff_kernel, (ents + (CD_CTA / 8) - 1) / (CD_CTA / 8), CD_CTA, sizeof(double) * OCT_BOARD * (CD_CTA / 8), (stream_t)stream,
              problem_of(h), xs, us, (const int32_t*)nullptr, (const int32_t*)nullptr, (const int32_t*)nullptr, 1,
              (const int32_t*)nullptr, h->W.rec, h->W.crec);
   const long long rows = ents * NX;
@@ -816,7 +823,7 @@ int agx_cost_derivatives(agx_handle* h, const double* xs, const double* us, doub
       tree_launch_calc_diff(h, P, xs, us, nullptr, nullptr, nullptr, st);
     } else {
       const int opc = NODE_CTA / 8;
-      AGX_LAUNCH_COL(h, calc_diff_kernel, (ents + opc - 1) / opc, NODE_CTA, sizeof(double) * OCT_BOARD * opc, st, P, xs, us,
+      AGX_LAUNCH_COL(h, calc_diff_kernel, (ents + (CD_CTA / 8) - 1) / (CD_CTA / 8), CD_CTA, sizeof(double) * OCT_BOARD * (CD_CTA / 8), st, P, xs, us,
                      (const int32_t*)nullptr, (const int32_t*)nullptr, (const int32_t*)nullptr, 1,
                      (const int32_t*)nullptr, h->W.rec, h->W.crec);
     }
@@ -910,7 +917,7 @@ int agx_riccati(agx_handle* h, const double* x0, const double* xs, const double*
   AGX_LAUNCH(h, init_kernel, (n_init + 255) / 256, 256, 0, st, P, W, h->S, O, xs, us);
   const long long ents = (long long)(nB * T1);
   const int opc_n = NODE_CTA / 8, opc_s = SEQ_CTA / 8;
-  AGX_LAUNCH_COL(h, calc_diff_kernel, (ents + opc_n - 1) / opc_n, NODE_CTA, sizeof(double) * OCT_BOARD * opc_n, st, P,
+  AGX_LAUNCH_COL(h, calc_diff_kernel, (ents + (CD_CTA / 8) - 1) / (CD_CTA / 8), CD_CTA, sizeof(double) * OCT_BOARD * (CD_CTA / 8), st, P,
              (const double*)W.xs, (const double*)W.us, (const int32_t*)h->S.cur, (const int32_t*)h->S.recalc,
              (const int32_t*)h->S.recalc_cost, 0, (const int32_t*)h->S.done, W.rec, W.crec);
   launch_backward(h, P, W, O, st);
@@ -1062,7 +1069,7 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
       phase_end(h, st);
     }
     phase_begin(h, 0, st);
-    AGX_LAUNCH_COL(h, calc_diff_kernel, (ents + opc_n - 1) / opc_n, NODE_CTA, sizeof(double) * OCT_BOARD * opc_n, st, P,
+    AGX_LAUNCH_COL(h, calc_diff_kernel, (ents + (CD_CTA / 8) - 1) / (CD_CTA / 8), CD_CTA, sizeof(double) * OCT_BOARD * (CD_CTA / 8), st, P,
                (const double*)W.xs, (const double*)W.us, (const int32_t*)h->S.cur, (const int32_t*)h->S.recalc,
                (const int32_t*)(it == 0 ? nullptr : h->S.recalc_cost), 0, (const int32_t*)h->S.done, W.rec, W.crec);
     phase_end(h, st);
@@ -1181,7 +1188,7 @@ int agx_solve_sqp(agx_handle* h, const double* x0, const double* xs_ws, const do
                (const int32_t*)h->S.cur, 0, (const int32_t*)h->S.done, (const int32_t*)nullptr, W.crec, (double*)nullptr);
     phase_end(h, st);
     phase_begin(h, 0, st);
-    AGX_LAUNCH_COL(h, calc_diff_kernel, (ents + opc_n - 1) / opc_n, NODE_CTA, sizeof(double) * OCT_BOARD * opc_n, st, P,
+    AGX_LAUNCH_COL(h, calc_diff_kernel, (ents + (CD_CTA / 8) - 1) / (CD_CTA / 8), CD_CTA, sizeof(double) * OCT_BOARD * (CD_CTA / 8), st, P,
                (const double*)W.xs, (const double*)W.us, (const int32_t*)h->S.cur, (const int32_t*)nullptr,
                (const int32_t*)nullptr, 0, (const int32_t*)h->S.done, W.rec, W.crec);
     phase_end(h, st);

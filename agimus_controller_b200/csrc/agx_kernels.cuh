@@ -23,6 +23,17 @@
 #include "agx_dynamics.inl"
 #include "agx_node.inl"
 
+#ifndef AGX_CD_THREADS
+#define AGX_CD_THREADS 64
+#endif
+// AGX_CD_SYNC: CTA-wide barriers at the phase boundaries of calc_diff keep the warps of a CTA at the same place in the
+// (long, fully unrolled) instruction stream, so that they share instruction fetches
+#ifdef AGX_CD_SYNC
+#define AGX_CD_PHASE() __syncthreads()
+#else
+#define AGX_CD_PHASE() ((void)0)
+#endif
+
 namespace agx {
 
 struct Problem {
@@ -85,11 +96,14 @@ AGX_DEV void lane_load_state(LaneDyn& d, int j, const double* x, const double* u
 AGX_DEV void node_dyn_diff(LaneDyn& d, int j, unsigned omask, const double* __restrict__ model, double dt, double* sb,
                            double* sc, double* __restrict__ rec) {
   node_kinematics(d, j, omask, model);
+  AGX_CD_PHASE();
   double L[28], rinv[NJ];
   const bool ok = node_forward_dynamics<true>(d, j, omask, model, sb, sc, L, rinv);
+  AGX_CD_PHASE();
   rec[RK_QN * 8 + j] = ok ? d.q + (d.qd * dt + d.qdd * (dt * dt)) : nan("");
   rec[RK_VN * 8 + j] = ok ? d.qd + d.qdd * dt : nan("");
   node_rnea_derivatives(d, j, omask, sb);
+  AGX_CD_PHASE();
   AGX_OSYNC();
   factor_reload(sc, L, rinv);
   double col[NJ];
@@ -144,7 +158,7 @@ AGX_DEV size_t buf_of(const int32_t* cur, int b, bool other) {
 #endif
 // COL: the models carry collision pairs (A10); the plain instantiation is the one every benchmark runs.
 template <bool COL>
-__global__ void __launch_bounds__(64, AGX_CD_MINB)
+__global__ void __launch_bounds__(AGX_CD_THREADS, AGX_CD_MINB)
 calc_diff_kernel(Problem P, const double* __restrict__ xs, const double* __restrict__ us,
                                  const int32_t* __restrict__ cur, const int32_t* __restrict__ recalc,
                                  const int32_t* __restrict__ recalc_cost, int cost_everywhere,
