@@ -14,6 +14,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/agx.h"
 #include "agx_kernels.cuh"
@@ -288,11 +289,12 @@ struct agx_handle {
   // optional per-phase device timing (bench evidence): event pairs around the solve's kernels
   bool timing = false;
   int n_pairs = 0;
+  // event pairs of agx_set_timing: created on first use, at most MAX_TIMING_PAIRS between two reads
+  static constexpr int MAX_TIMING_PAIRS = 4096;
 #if AGX_GPU
-  cudaEvent_t ev[2 * 4096];
-  int ev_made = 0;
+  std::vector<cudaEvent_t> ev;
 #endif
-  int pair_phase[4096];
+  std::vector<int> pair_phase;
 };
 
 namespace {
@@ -341,13 +343,18 @@ int check_launch(agx_handle* h, const char* what) {
 }
 #if AGX_GPU
 inline void phase_begin(agx_handle* h, int phase, cudaStream_t st) {
-  if (!h->timing || h->n_pairs >= 4096) return;
-  while (h->ev_made < 2 * (h->n_pairs + 1)) cudaEventCreate(&h->ev[h->ev_made++]);
+  if (!h->timing || h->n_pairs >= agx_handle::MAX_TIMING_PAIRS) return;
+  while ((int)h->ev.size() < 2 * (h->n_pairs + 1)) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    h->ev.push_back(e);
+  }
+  if ((int)h->pair_phase.size() <= h->n_pairs) h->pair_phase.resize(h->n_pairs + 1);
   h->pair_phase[h->n_pairs] = phase;
   cudaEventRecord(h->ev[2 * h->n_pairs], st);
 }
 inline void phase_end(agx_handle* h, cudaStream_t st) {
-  if (!h->timing || h->n_pairs >= 4096) return;
+  if (!h->timing || h->n_pairs >= agx_handle::MAX_TIMING_PAIRS) return;
   cudaEventRecord(h->ev[2 * h->n_pairs + 1], st);
   ++h->n_pairs;
 }
@@ -616,7 +623,7 @@ int agx_destroy(agx_handle* h) {
     dev_free(h->W.xs); dev_free(h->W.us); dev_free(h->W.rec); dev_free(h->W.crec); dev_free(h->W.fs); dev_free(h->W.gv); dev_free(h->W.k);
     dev_free(h->state_block);
 #if AGX_GPU
-    for (int i = 0; i < h->ev_made; ++i) cudaEventDestroy(h->ev[i]);
+    for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
 #endif
   }
   delete h;

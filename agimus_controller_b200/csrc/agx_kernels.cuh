@@ -1,21 +1,26 @@
-// agx_kernels.cuh — the CUDA kernels of the batched FDDP solve path (fp64, sm_100a, no tensor cores).
+// agx_kernels.cuh — the CUDA kernels of the batched solve path for the 7-joint chain (fp64, sm_100a).
 //
-//   calc_diff_kernel   one octet per (problem, node): problem.calc + calcDiff  -> compact node record
-//   calc_kernel        one octet per (problem, node): problem.calc             -> cost, xnext
-//   backward_kernel    one octet per problem: gaps, Riccati sweep t = T-1..0 with regularisation
-//                      retries, gains K/k, expected-improvement terms  (SolverFDDP::backwardPass,
-//                      computeGains, updateExpectedImprovement)
-//   forward_kernel     one octet per problem: line search over alpha = 2^-n, nonlinear rollout with
-//                      gap contraction, acceptance test, regularisation update, stop criterion
-//                      (SolverFDDP::forwardPass, tryStep, expectedImprovement, solve loop body)
-//   rollout_kernel / integrate_kernel / rnea_kernel / expand_kernel / init_kernel / finalize_kernel
+//   calc_diff_kernel          one octet per (problem, node): problem.calc + calcDiff -> compact dynamics record
+//                             (and the cost record where it is stale)
+//   node_cost_kernel          one THREAD per (problem, node): cost terms and their Gauss-Newton derivatives -> cost record
+//   backward_mma_kernel       one WARP per problem on the FP64 tensor cores (agx_riccati_mma.cuh): gaps, Riccati sweep
+//                             t = T-1..0 with regularisation retries, gains K/k, expected-improvement terms
+//                             (SolverFDDP::backwardPass, computeGains, updateExpectedImprovement);
+//   backward_kernel           the same sweep with DFMA, one octet per problem (cross-check, AGX_BW=octet)
+//   rollout_try_kernel        one octet per problem: nonlinear rollout of the trial step with gap contraction
+//   rollout_try2_kernel       the same with two warps per group of four problems (latency mode)
+//   accept_linesearch_kernel  acceptance test, deferred / in-line line search over alpha = 2^-n, regularisation update,
+//                             stop criterion (SolverFDDP::forwardPass, tryStep, expectedImprovement, solve loop body)
+//   calc / rollout / integrate / rnea / shift / cost_terms / expand / gather_refs / mask_refs / extract_gradients /
+//   init / finalize kernels   the remaining entry points of include/agx.h
+// The SQP mode is in agx_sqp.cuh, the kernels for general kinematic trees in agx_tree.cuh.
 //
 // Reference entry points replaced: solver.solve at
 // agimus_controller/agimus_controller/ocp_base_croco.py:172 and the Crocoddyl objects built at
 // :36-64; algorithm statements in SURVEY.md Appendix B.4/B.5.
 //
 // No host synchronisation happens inside a solve: all per-problem decisions (step acceptance,
-// regularisation, termination) are taken on the device and kept in SolverState.
+// regularisation, termination, the max_solve_time deadline) are taken on the device and kept in SolverState.
 #ifndef AGX_KERNELS_CUH_
 #define AGX_KERNELS_CUH_
 

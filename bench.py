@@ -124,8 +124,8 @@ def run_reference(args):
     # torchrun exports OMP_NUM_THREADS=1: the thread count is passed explicitly so that the reference arm
     # uses every host core it may run on
     cores = len(os.sched_getaffinity(0))
-    n = 64 * cores if args.sample is None else args.sample
-    n = min(n, B_PER_GPU)
+    # the whole batch of the metric per step (same config as our arm); --sample bounds it on slow hosts
+    n = B_PER_GPU if args.sample is None else min(args.sample, B_PER_GPU)
     from agimus_controller_b200 import panda_table
 
     m0 = panda_table().to_struct()
@@ -139,7 +139,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"first {n} of the 4096 problems per step"},
+        "config": {"workload": WORKLOAD, "B_per_gpu": B_PER_GPU, "T": T_NODES, "dt": DT, "fddp_iters": N_ITERS,
+                   "sample": f"{n} of the {B_PER_GPU} problems per step"},
         "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port",
                          "sample": f"{n} problems x {args.steps} steps, OpenMP one problem per thread, "
                                    "CPU restatement of Crocoddyl FDDP (oracle/agx_oracle.cpp)"},
