@@ -215,6 +215,29 @@ def mpc_latency(prob, dev, ticks, solver="fddp", with_cpu=False):
                         "warm start, <=10 FDDP iterations per tick (eager_exit: no launches queued past convergence); host wall clock of set_refs_window + solve + D2H of us[0], K[0]"}
 
 
+def pin_to_gpu_numa_node(local):
+    """CPU affinity of this process := the cores of the NUMA node GPU `local` hangs off (sysfs); None when unknown."""
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"node": node, "cores": len(cpus)}
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -229,7 +252,11 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (the solve path has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = None
     if world > 1:
+        # one rank per GPU: keep the rank (and the pinned host buffers it first-touches) on the NUMA node of its GPU, so
+        # that eight ranks do not pull their end-to-end copies through one socket
+        numa = pin_to_gpu_numa_node(local)
         dist.init_process_group("nccl", device_id=dev)
 
     B = B_PER_GPU
@@ -249,8 +276,18 @@ def run_ours(args):
     stats = torch.empty(B, 3, dtype=torch.float64, device=dev)
     gathered = torch.empty(world * B, 3, dtype=torch.float64, device=dev) if world > 1 else None
 
+    solve_events = []
+
     def step_resident():
-        prob.solve(x0_d, xs_d, us_d, N_ITERS, opts, out=out)
+        if world > 1 and len(solve_events) < 64:
+            # this rank's solve alone (the all_gather below makes every rank's step as long as the slowest slab's)
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record()
+            prob.solve(x0_d, xs_d, us_d, N_ITERS, opts, out=out)
+            eb.record()
+            solve_events.append((ea, eb))
+        else:
+            prob.solve(x0_d, xs_d, us_d, N_ITERS, opts, out=out)
         if world > 1:
             stats[:, 0] = out["cost"]
             stats[:, 1] = out["iters"]
@@ -365,7 +402,14 @@ def run_ours(args):
         sampler.start()
     prob.set_timing(True)
     l0 = prob.launch_count
+    solve_events.clear()
     ms_total = timed(step_resident, args.steps, tag="resident")
+    if world > 1:
+        mine = torch.tensor([float(np.mean([x.elapsed_time(y) for x, y in solve_events])) if solve_events else 0.0],
+                            dtype=torch.float64, device=dev)
+        allm = torch.empty(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allm, mine)
+        per_rank["solve_only"] = [float(v) for v in allm.cpu()]
     launches = prob.launch_count - l0
     phases = prob.get_timing()
     prob.set_timing(False)
@@ -607,7 +651,7 @@ def run_ours(args):
                               "the host waits for step i-1's results before issuing step i+1"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "latency_b1": lat, "sqp_mode": sqp, "e2e_full_K": e2e_full, "strong_scaling": strong, "cfg4_nv9": cfg4,
-        "ms_per_step_per_rank": per_rank,
+        "ms_per_step_per_rank": per_rank, "rank0_numa": numa,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
