@@ -185,6 +185,19 @@ def test_six_joint_arm_with_mixed_axes(orc):
     e = emu.calc_diff(m, refs, dts, xs, us)
     for k in ("cost", "xnext", "Fx", "Fu", "Lx", "Lxx"):
         assert node_rel(e[k], o[k]) < 1e-9, k
+    # and whole solves (FDDP, fixed and converged; the sweep's nv = 6 tile shapes)
+    x0 = xs[:, 0].copy()
+    xs_ws = np.repeat(x0[:, None, :], T + 1, 1)
+    z = np.zeros((B, nv))
+    us_ws = np.repeat(orc.rnea(m, x0[:, :nv], z, z)[:, None, :], T, 1)
+    for fixed, iters in ((True, 3), (False, 30)):
+        opts = _abi.default_fddp_opts(fixed_iters=fixed)
+        so = orc.solve(m, refs, dts, x0, xs_ws, us_ws, iters, opts)
+        se = emu.solve(m, refs, dts, x0, xs_ws, us_ws, iters, opts)
+        np.testing.assert_array_equal(se["iters"], so["iters"])
+        np.testing.assert_array_equal(se["status"], so["status"])
+        for k in ("xs", "us", "cost", "K"):
+            assert rel(se[k], so[k]) < 1e-6, k
 
 
 def test_unsupported_tree_sizes_are_refused():
