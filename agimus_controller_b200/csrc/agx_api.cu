@@ -412,8 +412,21 @@ void tree_launch_calc_diff(agx_handle* h, const agx::Problem& P, const double* x
                            const int32_t* recalc, const int32_t* done, stream_t st) {
   const long long ents = (long long)h->B * (h->T + 1);
   const int gpc = TREE_NODE_CTA / tree::GW;
-  AGX_TREE_LAUNCH(h, tree_calc_diff_kernel, (ents + gpc - 1) / gpc, TREE_NODE_CTA, sizeof(double) * h->tree_board * gpc,
-                  st, P, xs, us, cur, recalc, done, h->W.rec, h->W.crec);
+  // two launches: cost records, then dynamics records (see tree_calc_diff_kernel)
+#define AGX_TREE_CD_COST(N) tree_calc_diff_kernel<N, 1>
+#define AGX_TREE_CD_DYN(N) tree_calc_diff_kernel<N, 2>
+  switch (h->nv) {
+#define AGX_X(N)                                                                                                     \
+    case N:                                                                                                          \
+      AGX_LAUNCH(h, tree::AGX_TREE_CD_COST(N), (ents + gpc - 1) / gpc, TREE_NODE_CTA, sizeof(double) * h->tree_board * gpc, \
+                 st, P, xs, us, cur, recalc, done, h->W.rec, h->W.crec);                                             \
+      AGX_LAUNCH(h, tree::AGX_TREE_CD_DYN(N), (ents + gpc - 1) / gpc, TREE_NODE_CTA, sizeof(double) * h->tree_board * gpc,  \
+                 st, P, xs, us, cur, recalc, done, h->W.rec, h->W.crec);                                             \
+      break;
+    AGX_TREE_NVS(AGX_X)
+#undef AGX_X
+    default: break;
+  }
 }
 
 int tree_calc_diff(agx_handle* h, const double* xs, const double* us, double* out_cost, double* out_xnext, double* Fx,

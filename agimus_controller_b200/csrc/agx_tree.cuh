@@ -132,18 +132,34 @@ AGX_DEV void scan_anc_excl(const double* x, double* out, const double* seed, int
   }
 }
 // x_j <- sum over j and its descendants
-template <int N, int NV>
+template <int N, int NV, bool ROLLED = false>
 AGX_DEV void subtree_sum(double* x, unsigned sub, unsigned gm) {
   double acc[N];
 #pragma unroll
   for (int m = 0; m < N; ++m) acc[m] = 0.0;
+  // a real loop over the source lanes (the source lane of a shuffle may be a run-time value): the unrolled form was
+  // NV x N shuffle / add pairs of straight-line code, and the node kernels are bound by instruction fetch
+  // (ROLLED for the node kernels, which are bound by instruction fetch; unrolled for the sequential kernels, which
+  // are bound by the latency of this very chain)
+  if (ROLLED) {
+#pragma unroll 1
+    for (int k = 0; k < NV; ++k) {
+      const bool in = ((sub >> k) & 1u) != 0u;
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const bool in = ((sub >> k) & 1u) != 0u;
+      for (int m = 0; m < N; ++m) {
+        const double t = __shfl_sync(gm, x[m], k, GW);
+        if (in) acc[m] += t;
+      }
+    }
+  } else {
 #pragma unroll
-    for (int m = 0; m < N; ++m) {
-      const double t = __shfl_sync(gm, x[m], k, GW);
-      if (in) acc[m] += t;
+    for (int k = 0; k < NV; ++k) {
+      const bool in = ((sub >> k) & 1u) != 0u;
+#pragma unroll
+      for (int m = 0; m < N; ++m) {
+        const double t = __shfl_sync(gm, x[m], k, GW);
+        if (in) acc[m] += t;
+      }
     }
   }
 #pragma unroll
@@ -324,9 +340,9 @@ AGX_DEV bool forward_dynamics(TLane<NV>& d, int j, unsigned gm, const double* __
   body_force(d);
   if (DERIV) {
     // in three pieces: the accumulators of one 28-wide sum would double the live composites
-    subtree_sum<10, NV>(d.Z, d.sub, gm);
-    subtree_sum<12, NV>(d.Z + 10, d.sub, gm);
-    subtree_sum<6, NV>(d.Z + 22, d.sub, gm);
+    subtree_sum<10, NV, true>(d.Z, d.sub, gm);
+    subtree_sum<12, NV, true>(d.Z + 10, d.sub, gm);
+    subtree_sum<6, NV, true>(d.Z + 22, d.sub, gm);
   } else {
     subtree_sum<10, NV>(d.Z, d.sub, gm);
     subtree_sum<6, NV>(d.Z + 22, d.sub, gm);
@@ -401,7 +417,7 @@ AGX_DEV void rnea_derivatives(TLane<NV>& d, int j, unsigned gm, const double* sb
 #pragma unroll
   for (int k = 0; k < 6; ++k) da[k] = dap[k] + jq[k];
   inertia_apply(d.Y, da, dfc);
-  subtree_sum<6, NV>(dfc, d.sub, gm);
+  subtree_sum<6, NV, true>(dfc, d.sub, gm);
   double dFdq[6], dFdv[6];
   deriv_columns(d, j, dap, dfc, dFdq, dFdv);  // leaves A_j in d.g
 #pragma unroll
@@ -644,7 +660,10 @@ AGX_DEV const double* tmodel_of(const Problem& P, int b) {
 
 // ================================================================ kernels
 // problem.calc + calcDiff: one group per (problem, node) -> dynamics record + cost record
-template <int NV>
+// PART: 0 = cost record and dynamics record, 1 = cost record only, 2 = dynamics record only.  The solve launches the
+// two halves as separate kernels: one kernel with both is 8 000 straight-line instructions per warp (130 KB of SASS),
+// more than the instruction cache holds, and ran with `no_instruction` as its first stall reason.
+template <int NV, int PART = 0>
 __global__ void __launch_bounds__(64) tree_calc_diff_kernel(Problem P, const double* __restrict__ xs,
                                                            const double* __restrict__ us, const int32_t* __restrict__ cur,
                                                            const int32_t* __restrict__ recalc,
@@ -670,20 +689,23 @@ __global__ void __launch_bounds__(64) tree_calc_diff_kernel(Problem P, const dou
   TLane<NV> d;
   lane_load<NV>(d, j, x, terminal ? nullptr : us + ((buf * P.B + b) * P.T + t) * NV);
   kinematics<NV>(d, j, gm, tm);
-  const double s = terminal ? 1.0 : P.dts[t];
-  double lq, lv, lu, Lqq[NV];
-  const double l = node_costs<true, NV>(d, j, gm, tm, ref, terminal, brd + Lt::SQ, &lq, &lv, &lu, Lqq);
-  if (live) {
+  if (PART != 2) {
+    const double s = terminal ? 1.0 : P.dts[t];
+    double lq, lv, lu, Lqq[NV];
+    const double l = node_costs<true, NV>(d, j, gm, tm, ref, terminal, brd + Lt::SQ, &lq, &lv, &lu, Lqq);
+    if (live) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i)
-      if (i >= j) C[Lt::CK_LQQ + tidx(NV, i, j)] = s * Lqq[i];
-    C[Lt::CK_LVV + j] = s * ref[NX + NV + j];
-    C[Lt::CK_LUU + j] = terminal ? 0.0 : s * ref[2 * NX + NV + j];
-    C[Lt::CK_LQ + j] = s * lq;
-    C[Lt::CK_LV + j] = s * lv;
-    C[Lt::CK_LU + j] = s * lu;
+      for (int i = 0; i < NV; ++i)
+        if (i >= j) C[Lt::CK_LQQ + tidx(NV, i, j)] = s * Lqq[i];
+      C[Lt::CK_LVV + j] = s * ref[NX + NV + j];
+      C[Lt::CK_LUU + j] = terminal ? 0.0 : s * ref[2 * NX + NV + j];
+      C[Lt::CK_LQ + j] = s * lq;
+      C[Lt::CK_LV + j] = s * lv;
+      C[Lt::CK_LU + j] = s * lu;
+    }
+    if (j == 0) C[Lt::CK_COST] = s * l;
   }
-  if (j == 0) C[Lt::CK_COST] = s * l;
+  if (PART == 1) return;
   if (terminal) {
     if (live) {
 #pragma unroll
@@ -1193,6 +1215,17 @@ __global__ void tree_forward_kernel(Problem P, Work W, SolverState S, FddpOpts O
     double ctry = 0.0, dvp = 0.0;
     bool ok = true;
     for (int t = 0; t <= T; ++t) {
+      if (t < T) {
+        // the next node's operands are asked for now: this loop is one dependent chain per node
+        const int tn = t + 1;
+        AGX_PREFETCH(xs + tn * NX + jj); AGX_PREFETCH(xs + tn * NX + NV + jj);
+        if (!feasible) { AGX_PREFETCH(fsb + tn * NX + jj); AGX_PREFETCH(gvb + tn * NX + jj); AGX_PREFETCH(gvb + tn * NX + NV + jj); }
+        AGX_PREFETCH(refs + (size_t)tn * Lt::REF + 8 * j);
+        if (tn < T) {
+          AGX_PREFETCH(Kb + ((size_t)tn * NV + jj) * NX); AGX_PREFETCH(Kb + ((size_t)tn * NV + jj) * NX + NX - 1);
+          AGX_PREFETCH(us + tn * NV + jj); AGX_PREFETCH(kb + tn * NV + jj);
+        }
+      }
       double tq = xq, tv = xv;
       if (contract && live) {
         tq += fsb[t * NX + j] * (steplength - 1.0);

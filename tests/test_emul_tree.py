@@ -93,7 +93,7 @@ def test_panda9_solve_matches_oracle(orc, t9, fixed, iters):
     for k in ("xs", "us", "cost", "K", "k"):
         assert rel(e[k], o[k]) < 1e-6, k
     if fixed:
-        assert e["launches"] == 3 * iters + 2  # init + (calc_diff, sweep, forward) per iteration + finalize
+        assert e["launches"] == 4 * iters + 2  # init + (cost records, dynamics records, sweep, forward) per iteration + finalize
 
 
 def test_panda9_ragged_dts_rollout_shift(orc, t9):
