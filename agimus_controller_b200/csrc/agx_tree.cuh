@@ -686,6 +686,10 @@ __global__ void __launch_bounds__(64) tree_calc_diff_kernel(Problem P, const dou
   double* R = rec + (size_t)ent * Lt::REC;
   double* C = crec + (size_t)ent * Lt::CREC;
   const double* ref = P.refs + (size_t)ent * Lt::REF;
+  if (PART != 2) {
+    // the reference record is read late (weights, targets): ask for its lines now, one line per lane
+    if (j * 16 < Lt::REF) AGX_PREFETCH(ref + j * 16);
+  }
   TLane<NV> d;
   lane_load<NV>(d, j, x, terminal ? nullptr : us + ((buf * P.B + b) * P.T + t) * NV);
   kinematics<NV>(d, j, gm, tm);
