@@ -295,6 +295,20 @@ struct agx_handle {
   std::vector<cudaEvent_t> ev;
 #endif
   std::vector<int> pair_phase;
+#if AGX_GPU
+  // the MPC tick as one graph launch (latency mode, agx_solve): built on first use, rebuilt when the options change
+  struct TickGraph {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaStream_t capture_stream = nullptr;
+    agx::IoTable* d_io = nullptr;   // the caller's pointers of the current tick, read by the graph's first and last kernel
+    int32_t* d_round = nullptr;     // round counter of the loop
+    int nodes_fixed = 0, nodes_round = 0;  // kernels outside / inside the loop (agx_launch_count)
+    int max_iter = -1;
+    agx_fddp_opts opts{};
+    bool failed = false;            // the driver refused the graph once: the stream path serves this handle
+  } tick;
+#endif
 };
 
 namespace {
@@ -637,6 +651,10 @@ int agx_destroy(agx_handle* h) {
     dev_free(h->state_block);
 #if AGX_GPU
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+    if (h->tick.exec) cudaGraphExecDestroy(h->tick.exec);
+    if (h->tick.graph) cudaGraphDestroy(h->tick.graph);
+    if (h->tick.capture_stream) cudaStreamDestroy(h->tick.capture_stream);
+    dev_free(h->tick.d_io); dev_free(h->tick.d_round);
 #endif
   }
   delete h;
@@ -1063,70 +1081,182 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
   // a problem that deferred d times is d rounds behind: O.defer more rounds let every problem use its whole budget
   const int rounds = max_iter + (max_iter > 0 ? O.defer : 0);
   const size_t nB = (size_t)h->B, T = (size_t)h->T, T1 = T + 1;
+  Work W = h->W;
+  const Problem P = problem_of(h);
+  const long long n_init = (long long)(nB * T1 * NX);
+  const long long n_fin = (long long)(nB * T * NJ * NX);
+  const long long ents = (long long)(nB * T1);
+  const int opc_n = NODE_CTA / 8, opc_s = SEQ_CTA / 8;
+  const long long cost_ctas = (ents + COST_CTA - 1) / COST_CTA;
+  (void)opc_n;
+  // two warps per group of four problems pay off while the SMs are not full (measured crossover between 1024 and
+  // 2048 problems: 256 problems 0.167 -> 0.145 ms per launch, 4096 problems 0.224 -> 0.370 ms).  The two kernels
+  // agree to rounding, not bitwise, and a slab must give the same bits alone as inside a larger batch (sharding
+  // invariance), so the choice cannot depend on the batch size alone: the two-warp kernel serves the latency mode
+  // (eager_exit, at most 64 problems).  AGX_ROLLOUT=1w / 2w forces one of them
+  static const int forced = [] {
+    const char* e = std::getenv("AGX_ROLLOUT");
+    return !e ? 0 : (std::strcmp(e, "2w") == 0 ? 2 : (std::strcmp(e, "1w") == 0 ? 1 : 0));
+  }();
+  const bool latency_mode = opts->eager_exit && h->B <= 64;
+  const bool two_warp = forced ? forced == 2 : latency_mode;
+  // first iteration: every cost record is stale; the thread-per-node kernel is the cheap way to fill them
+  // (later iterations only meet stale cost records after a line search, handled in line by calc_diff_kernel)
+  auto enqueue_first_costs = [&](stream_t s) {
+    phase_begin(h, 3, s);
+    AGX_LAUNCH_NODE_COST(h, cost_ctas, COST_CTA, COST_SMEM, s, P, (const double*)W.xs, (const double*)W.us,
+               (const int32_t*)h->S.cur, 0, (const int32_t*)h->S.done, (const int32_t*)nullptr, W.crec, (double*)nullptr);
+    phase_end(h, s);
+  };
+  // one round: problem.calc + calcDiff at the candidate (dynamics records, plus the cost records where they are stale:
+  // after an alpha = 1 acceptance they were already written for the trial by node_cost_kernel), Riccati sweep, trial
+  // rollout, trial costs, acceptance.  `round_dev` = the device-side round counter of the tick graph, else null
+  auto enqueue_round = [&](stream_t s, int it, const int32_t* stale_costs, const int32_t* round_dev) {
+    phase_begin(h, 0, s);
+    AGX_LAUNCH_COL(h, calc_diff_kernel, (ents + (CD_CTA / 8) - 1) / (CD_CTA / 8), CD_CTA, sizeof(double) * OCT_BOARD * (CD_CTA / 8), s, P,
+               (const double*)W.xs, (const double*)W.us, (const int32_t*)h->S.cur, (const int32_t*)h->S.recalc,
+               stale_costs, 0, (const int32_t*)h->S.done, W.rec, W.crec);
+    phase_end(h, s);
+    phase_begin(h, 1, s);
+    launch_backward(h, P, W, O, s);
+    phase_end(h, s);
+    phase_begin(h, 2, s);
+    if (two_warp)
+      AGX_LAUNCH(h, rollout_try2_kernel, (h->B + 3) / 4, 64, sizeof(double) * FW2_BOARD * 4, s, P, W, h->S);
+    else
+      AGX_LAUNCH(h, rollout_try_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * FW_BOARD * opc_s, s, P, W,
+                 h->S);
+    phase_end(h, s);
+    phase_begin(h, 3, s);
+    AGX_LAUNCH_NODE_COST(h, cost_ctas, COST_CTA, COST_SMEM, s, P, (const double*)W.xs, (const double*)W.us,
+               (const int32_t*)h->S.cur, 1, (const int32_t*)h->S.done, (const int32_t*)nullptr, W.crec, (double*)nullptr);
+    phase_end(h, s);
+    phase_begin(h, 4, s);
+    AGX_LAUNCH_COL(h, accept_linesearch_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * FW_BOARD * opc_s, s, P, W,
+               h->S, O, it, round_dev);
+    phase_end(h, s);
+  };
+
+#if AGX_GPU
+  // ---- latency mode: the whole tick is ONE graph launch -------------------------------------------------------------
+  // init -> first costs -> WHILE (some problem unfinished and rounds left) { round } -> finalize, the loop a conditional
+  // graph node whose condition the last kernel of the body sets on the device: no host round trip between iterations,
+  // and the call stays stream-ordered (the stream path below reads the completion flags back after every round).
+  // AGX_TICK_GRAPH=0 keeps the stream path.
+  static const bool tick_graph_on = [] { const char* e = std::getenv("AGX_TICK_GRAPH"); return !(e && e[0] == '0'); }();
+  if (tick_graph_on && latency_mode && !h->timing && !h->tick.failed && max_iter > 0) {
+    auto& G = h->tick;
+    W.K = h->d_K_internal;
+    if (!W.K) {
+      if (!dev_alloc((void**)&h->d_K_internal, sizeof(double) * nB * T * NJ * NX))
+        return fail(h, AGX_ENOMEM, "allocation of the internal gain buffer failed");
+      W.K = h->d_K_internal;
+    }
+    W.x0 = h->d_x0;
+    const bool stale = !G.exec || G.max_iter != max_iter || std::memcmp(&G.opts, opts, sizeof(agx_fddp_opts)) != 0;
+    if (stale) {
+      if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+      if (G.graph) { cudaGraphDestroy(G.graph); G.graph = nullptr; }
+      bool ok = true;
+      if (!G.capture_stream) ok = ok && cudaStreamCreateWithFlags(&G.capture_stream, cudaStreamNonBlocking) == cudaSuccess;
+      if (!G.d_io) ok = ok && dev_alloc((void**)&G.d_io, sizeof(IoTable));
+      if (!G.d_round) ok = ok && dev_alloc((void**)&G.d_round, sizeof(int32_t));
+      const long long before = h->launches;
+      cudaStream_t cs = G.capture_stream;
+      cudaGraphNode_t loop_node = nullptr;
+      cudaGraph_t body = nullptr;
+      ok = ok && cudaGraphCreate(&G.graph, 0) == cudaSuccess;
+      // head of the graph
+      ok = ok && cudaStreamBeginCaptureToGraph(cs, G.graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      if (ok) {
+        AGX_LAUNCH(h, init_io_kernel, (n_init + 255) / 256, 256, 0, cs, P, W, h->S, O, (const IoTable*)G.d_io, h->d_x0, G.d_round);
+        enqueue_first_costs(cs);
+        ok = cudaStreamEndCapture(cs, &G.graph) == cudaSuccess;
+      }
+      // the loop: a WHILE node behind the head's last kernel
+      if (ok) {
+        size_t n_nodes = 0;
+        ok = cudaGraphGetNodes(G.graph, nullptr, &n_nodes) == cudaSuccess && n_nodes > 0;
+        std::vector<cudaGraphNode_t> nodes(n_nodes);
+        ok = ok && cudaGraphGetNodes(G.graph, nodes.data(), &n_nodes) == cudaSuccess;
+        cudaGraphNode_t leaf = nullptr;
+        for (size_t i = 0; ok && i < n_nodes; ++i) {
+          size_t n_dep = 0;
+          if (cudaGraphNodeGetDependentNodes(nodes[i], nullptr, &n_dep) == cudaSuccess && n_dep == 0) leaf = nodes[i];
+        }
+        cudaGraphConditionalHandle cond{};
+        ok = ok && leaf && cudaGraphConditionalHandleCreate(&cond, G.graph, 1, cudaGraphCondAssignDefault) == cudaSuccess;
+        cudaGraphNodeParams np = {};
+        np.type = cudaGraphNodeTypeConditional;
+        np.conditional.handle = cond;
+        np.conditional.type = cudaGraphCondTypeWhile;
+        np.conditional.size = 1;
+        ok = ok && cudaGraphAddNode(&loop_node, G.graph, &leaf, 1, &np) == cudaSuccess;
+        if (ok) body = np.conditional.phGraph_out[0];
+        G.nodes_fixed = (int)(h->launches - before);
+        ok = ok && cudaStreamBeginCaptureToGraph(cs, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+          enqueue_round(cs, 0, (const int32_t*)h->S.recalc_cost, (const int32_t*)G.d_round);
+          AGX_LAUNCH(h, loop_condition_kernel, 1, 64, 0, cs, h->B, (const int32_t*)h->S.done, G.d_round, rounds, cond);
+          ok = cudaStreamEndCapture(cs, &body) == cudaSuccess;
+        }
+        G.nodes_round = (int)(h->launches - before) - G.nodes_fixed;
+      }
+      // tail: the results go to the caller's buffers
+      ok = ok && cudaStreamBeginCaptureToGraph(cs, G.graph, &loop_node, nullptr, 1, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      if (ok) {
+        AGX_LAUNCH(h, finalize_io_kernel, (n_fin + 255) / 256, 256, 0, cs, P, W, h->S, (const IoTable*)G.d_io);
+        ok = cudaStreamEndCapture(cs, &G.graph) == cudaSuccess;
+        ++G.nodes_fixed;
+      }
+      ok = ok && cudaGraphInstantiate(&G.exec, G.graph, 0) == cudaSuccess;
+      h->launches = before;  // capturing is not launching
+      if (!ok) {
+        // a driver without conditional nodes: remember, clear the error, serve this handle on the stream path
+        cudaGetLastError();
+        cudaStreamCaptureStatus cst;
+        if (G.capture_stream && cudaStreamIsCapturing(G.capture_stream, &cst) == cudaSuccess && cst != cudaStreamCaptureStatusNone) {
+          cudaGraph_t junk = nullptr;
+          cudaStreamEndCapture(G.capture_stream, &junk);
+          if (junk && junk != G.graph) cudaGraphDestroy(junk);
+        }
+        cudaGetLastError();
+        if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+        G.failed = true;
+      } else {
+        G.max_iter = max_iter;
+        G.opts = *opts;
+      }
+    }
+    if (G.exec) {
+      IoTable io{x0, xs_ws, us_ws, out_xs, out_us, out_K, out_k, out_cost, out_iters, out_status, out_stop};
+      // pageable source on purpose: the runtime stages such a small copy before it returns, so ticks may be queued back
+      // to back without the next call overwriting a table the previous copy has not read yet
+      if (cudaMemcpyAsync(G.d_io, &io, sizeof(IoTable), cudaMemcpyHostToDevice, st) != cudaSuccess)
+        return fail(h, AGX_ECUDA, "agx_solve: pointer table copy failed");
+      if (cudaGraphLaunch(G.exec, st) != cudaSuccess) return fail(h, AGX_ECUDA, "agx_solve: graph launch failed");
+      // at least one round runs; how many more is decided on the device (agx_launch_count counts the first)
+      h->launches += G.nodes_fixed + G.nodes_round;
+      return check_launch(h, "agx_solve");
+    }
+  }
+#endif
+
   if (!out_K && !h->d_K_internal) {
     if (!dev_alloc((void**)&h->d_K_internal, sizeof(double) * nB * T * NJ * NX))
       return fail(h, AGX_ENOMEM, "allocation of the internal gain buffer failed");
   }
-  Work W = h->W;
   W.K = out_K ? out_K : h->d_K_internal;
   W.x0 = h->d_x0;
   if (!copy_d2d(h->d_x0, x0, sizeof(double) * nB * NX, st)) return fail(h, AGX_ECUDA, "agx_solve: x0 copy failed");
-  const Problem P = problem_of(h);
-  const long long n_init = (long long)(nB * T1 * NX);
   AGX_LAUNCH(h, init_kernel, (n_init + 255) / 256, 256, 0, st, P, W, h->S, O, xs_ws, us_ws);
-  const long long ents = (long long)(nB * T1);
-  const int opc_n = NODE_CTA / 8, opc_s = SEQ_CTA / 8;
-  const long long cost_ctas = (ents + COST_CTA - 1) / COST_CTA;
   for (int it = 0; it < rounds; ++it) {
-    // problem.calc + calcDiff at the candidate: dynamics records, plus the cost records where they are stale
-    // (after an alpha = 1 acceptance they were already written for the trial by node_cost_kernel)
-    if (it == 0) {
-      // first iteration: every cost record is stale; the thread-per-node kernel is the cheap way to fill them
-      // (later iterations only meet stale cost records after a line search, handled in line by calc_diff_kernel)
-      phase_begin(h, 3, st);
-      AGX_LAUNCH_NODE_COST(h, cost_ctas, COST_CTA, COST_SMEM, st, P, (const double*)W.xs, (const double*)W.us,
-                 (const int32_t*)h->S.cur, 0, (const int32_t*)h->S.done, (const int32_t*)nullptr, W.crec, (double*)nullptr);
-      phase_end(h, st);
-    }
-    phase_begin(h, 0, st);
-    AGX_LAUNCH_COL(h, calc_diff_kernel, (ents + (CD_CTA / 8) - 1) / (CD_CTA / 8), CD_CTA, sizeof(double) * OCT_BOARD * (CD_CTA / 8), st, P,
-               (const double*)W.xs, (const double*)W.us, (const int32_t*)h->S.cur, (const int32_t*)h->S.recalc,
-               (const int32_t*)(it == 0 ? nullptr : h->S.recalc_cost), 0, (const int32_t*)h->S.done, W.rec, W.crec);
-    phase_end(h, st);
-    phase_begin(h, 1, st);
-    launch_backward(h, P, W, O, st);
-    phase_end(h, st);
-    phase_begin(h, 2, st);
-    {
-      // two warps per group of four problems pay off while the SMs are not full (measured crossover between 1024 and
-      // 2048 problems: 256 problems 0.167 -> 0.145 ms per launch, 4096 problems 0.224 -> 0.370 ms).  The two kernels
-      // agree to rounding, not bitwise, and a slab must give the same bits alone as inside a larger batch (sharding
-      // invariance), so the choice cannot depend on the batch size alone: the two-warp kernel serves the latency mode
-      // (eager_exit, at most 64 problems).  AGX_ROLLOUT=1w / 2w forces one of them
-      static const int forced = [] {
-        const char* e = std::getenv("AGX_ROLLOUT");
-        return !e ? 0 : (std::strcmp(e, "2w") == 0 ? 2 : (std::strcmp(e, "1w") == 0 ? 1 : 0));
-      }();
-      const bool two_warp = forced ? forced == 2 : (opts->eager_exit && h->B <= 64);
-      if (two_warp)
-        AGX_LAUNCH(h, rollout_try2_kernel, (h->B + 3) / 4, 64, sizeof(double) * FW2_BOARD * 4, st, P, W, h->S);
-      else
-        AGX_LAUNCH(h, rollout_try_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * FW_BOARD * opc_s, st, P, W,
-                   h->S);
-    }
-    phase_end(h, st);
-    phase_begin(h, 3, st);
-    AGX_LAUNCH_NODE_COST(h, cost_ctas, COST_CTA, COST_SMEM, st, P, (const double*)W.xs, (const double*)W.us,
-               (const int32_t*)h->S.cur, 1, (const int32_t*)h->S.done, (const int32_t*)nullptr, W.crec, (double*)nullptr);
-    phase_end(h, st);
-    phase_begin(h, 4, st);
-    AGX_LAUNCH_COL(h, accept_linesearch_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * FW_BOARD * opc_s, st, P, W,
-               h->S, O, it);
-    phase_end(h, st);
+    if (it == 0) enqueue_first_costs(st);
+    enqueue_round(st, it, (const int32_t*)(it == 0 ? nullptr : h->S.recalc_cost), (const int32_t*)nullptr);
     // Long budgets (the controller's first solve runs with max_iter = 1000, agimus_controller.py:376-381): once in a
     // while ask the device whether anything is still running, instead of queueing hundreds of empty launches.  Budgets
     // up to 32 iterations (every MPC tick) never synchronise.
-    if (opts->eager_exit && h->B <= 64 && !h->timing && it + 1 < rounds) {
+    if (latency_mode && !h->timing && it + 1 < rounds) {
       if (all_done_sync(h, st)) break;
     } else if (!opts->fixed_iters && max_iter > 32 && (it % 16) == 15 && it + 1 < rounds) {
       int32_t live = 1;
@@ -1143,7 +1273,6 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
       if (live == 0) break;
     }
   }
-  const long long n_fin = (long long)(nB * T * NJ * NX);
   AGX_LAUNCH(h, finalize_kernel, (n_fin + 255) / 256, 256, 0, st, P, W, h->S, out_xs, out_us, out_K, out_k, out_cost,
              out_iters, out_status, out_stop);
   return check_launch(h, "agx_solve");

@@ -1019,7 +1019,10 @@ __global__ void __launch_bounds__(64) rollout_try2_kernel(Problem P, Work W, Sol
 // Generalised: `pending` holds the index n of the step length 2^-n the search stands at, and a problem may defer
 // O.defer times over a solve (it is then O.defer rounds behind); the host queues max_iter + O.defer rounds.
 template <bool COL>
-__global__ void accept_linesearch_kernel(Problem P, Work W, SolverState S, FddpOpts O, int round) {
+__global__ void accept_linesearch_kernel(Problem P, Work W, SolverState S, FddpOpts O, int round_host,
+                                         const int32_t* __restrict__ round_dev) {
+  // the round index comes from the host loop, or from the device counter of the tick graph (agx_api.cu: TickGraph)
+  const int round = round_dev ? *round_dev : round_host;
   AGX_SMEM(smem);
   AGX_OCTET_SETUP();
   const int b = (int)ent;
@@ -1371,6 +1374,72 @@ __global__ void finalize_kernel(Problem P, Work W, SolverState S, double* out_xs
 
 // ---- per-cost derivatives (agx_cost_derivatives): the references with every weight but one cost's zeroed, and the
 // gradient part of the cost records unscaled into [n][AGX_N_COSTS][nx] / [n][AGX_N_COSTS][nv]
+// ---- the MPC tick as ONE graph launch (agx_api.cu: TickGraph) ------------------------------------------------------
+// The graph's kernel arguments are fixed when it is built, the caller's buffers change from tick to tick: the first and
+// the last kernel of the graph read the caller's pointers from a small table in device memory that agx_solve refreshes
+// with one copy before each launch.
+struct IoTable {
+  const double* x0; const double* xs_ws; const double* us_ws;
+  double* out_xs; double* out_us; double* out_K; double* out_k; double* out_cost;
+  int32_t* out_iters; int32_t* out_status; double* out_stop;
+};
+
+// init_kernel + the x0 copy; the cost records are written by the node_cost launch that follows in the graph, so the
+// first calc_diff of the loop finds recalc_cost = 0
+__global__ void init_io_kernel(Problem P, Work W, SolverState S, FddpOpts O, const IoTable* __restrict__ io,
+                               double* __restrict__ x0_dst, int32_t* __restrict__ round_ctr) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int T1 = P.T + 1;
+  const long long nxs = (long long)P.B * T1 * NX, nus = (long long)P.B * P.T * NJ;
+  if (gid < nxs) W.xs[gid] = io->xs_ws[gid];
+  if (gid < nus) W.us[gid] = io->us_ws[gid];
+  if (gid < (long long)P.B * NX) x0_dst[gid] = io->x0[gid];
+  if (gid == 0) { *S.t0 = agx_now_ns(); *round_ctr = 0; }
+  if (gid < P.B) {
+    const int b = (int)gid;
+    S.xreg[b] = (O.reg_init == O.reg_init) ? O.reg_init : O.reg_min;
+    S.cost[b] = 0.0; S.dg[b] = 0.0; S.dq[b] = 0.0; S.stop[b] = 0.0;
+    S.is_feasible[b] = 0; S.was_feasible[b] = 0; S.recalc[b] = 1; S.done[b] = 0;
+    S.status[b] = 1; S.iters[b] = 0; S.cur[b] = 0;
+    S.dv[b] = 0.0; S.recalc_cost[b] = 0; S.pending[b] = 0; S.roll_ok[b] = 0;
+  }
+}
+
+__global__ void finalize_io_kernel(Problem P, Work W, SolverState S, const IoTable* __restrict__ io) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int T1 = P.T + 1;
+  const long long per_xs = (long long)T1 * NX, per_us = (long long)P.T * NJ, per_K = (long long)P.T * NJ * NX;
+  if (gid < P.B * per_xs) {
+    const int b = (int)(gid / per_xs);
+    io->out_xs[gid] = W.xs[(size_t)(S.cur[b] & 1) * P.B * per_xs + gid];
+  }
+  if (gid < P.B * per_us) {
+    const int b = (int)(gid / per_us);
+    io->out_us[gid] = W.us[(size_t)(S.cur[b] & 1) * P.B * per_us + gid];
+    if (io->out_k) io->out_k[gid] = W.k[gid];
+  }
+  if (io->out_K && gid < P.B * per_K) io->out_K[gid] = W.K[gid];
+  if (gid < P.B) {
+    io->out_cost[gid] = S.cost[gid];
+    io->out_iters[gid] = S.iters[gid];
+    io->out_status[gid] = S.status[gid];
+    if (io->out_stop) io->out_stop[gid] = S.stop[gid];
+  }
+}
+
+#if AGX_GPU
+// last kernel of the loop body: one more round while some problem is unfinished and the budget allows it
+__global__ void loop_condition_kernel(int B, const int32_t* __restrict__ done, int32_t* __restrict__ round_ctr,
+                                      int rounds, cudaGraphConditionalHandle handle) {
+  const int live = __syncthreads_or((int)threadIdx.x < B && !done[threadIdx.x]);
+  if (threadIdx.x == 0) {
+    const int r = *round_ctr + 1;
+    *round_ctr = r;
+    cudaGraphSetConditional(handle, (live && r < rounds) ? 1u : 0u);
+  }
+}
+#endif
+
 __global__ void mask_refs_kernel(long long n_nodes, int nv, int ref_size, int slot, const double* __restrict__ refs,
                                  double* __restrict__ out) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;

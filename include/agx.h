@@ -108,12 +108,19 @@ typedef struct agx_model {
 /*
  * FDDP parameters (Crocoddyl SolverFDDP defaults are what agx_fddp_opts_default fills).
  * fixed_iters != 0: run exactly max_iter iterations, no early exit (benchmark mode).
- * eager_exit != 0 (and not fixed_iters): after every iteration the per-problem completion flags are read back and
- * the call returns as soon as every problem has finished — one small device-to-host copy and a stream
- * synchronisation per iteration instead of queueing the whole budget.  Meant for the latency-bound single-problem MPC
- * tick (B <= 64; ignored for larger batches), where the host waits for the result anyway.  In this mode the FDDP
- * forward pass runs on a kernel that puts two warps on each problem group; its results agree with the throughput
- * kernels' to rounding (1e-15), not bitwise.
+ * eager_exit != 0 (and not fixed_iters): latency mode of the single MPC tick (B <= 64; ignored for larger batches): no
+ * kernel runs past the iteration in which the last problem finishes.
+ *   agx_solve on the 7-joint chain: the whole solve is ONE graph launch -- init, first costs, a conditional WHILE node
+ *   around the FDDP round whose condition the round's last kernel sets on the device, finalize -- so there is no host
+ *   round trip between iterations and the call stays stream-ordered (no synchronisation; ticks may be queued back to
+ *   back).  The caller's pointers reach the graph through a small device table refreshed by one copy per call.
+ *   AGX_TICK_GRAPH=0 in the environment, a timing run (agx_set_timing) or a driver that refuses conditional nodes
+ *   select the stream path below; both give the same bits (tests/test_gpu_tick_graph.py).
+ *   agx_solve on other trees, agx_solve_sqp, and the stream path: after every iteration the per-problem completion
+ *   flags are read back (one small device-to-host copy and a stream synchronisation per iteration) and the call
+ *   returns as soon as every problem has finished.
+ * In this mode the FDDP forward pass of the chain runs on a kernel that puts two warps on each problem group; its
+ * results agree with the throughput kernels' to rounding (1e-15), not bitwise.
  */
 typedef struct agx_fddp_opts {
   double reg_min, reg_max, reg_incfactor, reg_decfactor;
@@ -295,7 +302,9 @@ int agx_get_timing(agx_handle* h, double* out_ms, long long* out_launches);
  * a register-only probe kernel run for about `seconds`; out_ms (may be NULL) = device time of the run. */
 int agx_probe_fp64(int device, double seconds, double* out_tflops, double* out_ms);
 
-/* Number of kernel launches the library issued on this handle since creation (bench evidence). */
+/* Number of kernel launches the library issued on this handle since creation (bench evidence).  A tick-graph solve
+ * (eager_exit, see agx_fddp_opts) counts the kernels outside the loop plus ONE round: how many further rounds ran is
+ * decided on the device and reported per problem in out_iters. */
 long long agx_launch_count(const agx_handle* h);
 
 #ifdef __cplusplus

@@ -1,0 +1,46 @@
+"""Closed-loop MPC ticks in latency mode (eager_exit, at most 64 problems) through the C ABI; the results of every tick go
+to an .npz file.  test_gpu_tick_graph.py runs this once with the tick graph and once with AGX_TICK_GRAPH=0 (the stream
+path) and compares the two files bit for bit."""
+import sys
+
+import numpy as np
+import torch
+
+from agimus_controller_b200 import _abi, panda_table
+from agimus_controller_b200.solver import BatchedShootingProblem
+from agimus_controller_b200.workloads import goal_reaching_batch
+
+
+def run(B, ticks, queue_without_sync):
+    table = panda_table()
+    helper = BatchedShootingProblem(table, np.full(2, 0.01), 1)
+    rn = lambda q, v, a: helper.rnea(q, v, a).cpu().numpy()  # noqa: E731
+    w = goal_reaching_batch(B, T=20, rnea=rn, seed=5)
+    p = BatchedShootingProblem(table, w["dts"], B)
+    p.set_refs(w["refs"])
+    opts = _abi.default_fddp_opts()
+    opts.eager_exit = 1
+    x = torch.as_tensor(w["x0"], device="cuda")
+    xs = torch.as_tensor(w["xs_ws"], device="cuda")
+    us = torch.as_tensor(w["us_ws"], device="cuda")
+    res = {}
+    outs = [p.alloc_outputs() for _ in range(ticks)] if queue_without_sync else None
+    for k in range(ticks):
+        out = p.solve(x, xs, us, 10, opts, out=outs[k] if outs else None)
+        if not queue_without_sync:
+            for name in ("xs", "us", "K", "cost", "iters", "status"):
+                res[f"{name}_{k}"] = out[name].cpu().numpy()
+        xs, us = p.shift_warmstart(out["xs"], out["us"])
+        x = xs[:, 0].contiguous()
+    if queue_without_sync:
+        torch.cuda.synchronize()
+        for k in range(ticks):
+            for name in ("xs", "us", "K", "cost", "iters", "status"):
+                res[f"{name}_{k}"] = outs[k][name].cpu().numpy()
+    res["launches"] = np.array([p.launch_count])
+    return res
+
+
+if __name__ == "__main__":
+    out_path, B, ticks, queue = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+    np.savez(out_path, **run(B, ticks, bool(queue)))

@@ -1,0 +1,50 @@
+"""Latency mode as one graph launch (agx_api.cu: TickGraph, a conditional WHILE node around the FDDP round) against
+the stream path that reads the completion flags back after every round: same bits, tick after tick, closed loop."""
+import os
+import pathlib
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+CASE = ROOT / "tests" / "gpu_tick_case.py"
+
+
+def _run(tmp_path, tag, B, ticks, queue, graph):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    out = tmp_path / f"{tag}.npz"
+    env = dict(os.environ, PYTHONPATH=str(ROOT), AGX_TICK_GRAPH="1" if graph else "0")
+    subprocess.run([sys.executable, str(CASE), str(out), str(B), str(ticks), str(int(queue))], check=True, env=env,
+                   cwd=str(ROOT), timeout=600)
+    return dict(np.load(out))
+
+
+@pytest.mark.parametrize("B", [1, 8, 64])
+def test_tick_graph_gives_the_bits_of_the_stream_path(tmp_path, B):
+    ticks = 12
+    g = _run(tmp_path, "graph", B, ticks, False, True)
+    s = _run(tmp_path, "stream", B, ticks, False, False)
+    for k in range(ticks):
+        for name in ("iters", "status", "xs", "us", "K", "cost"):
+            np.testing.assert_array_equal(g[f"{name}_{k}"], s[f"{name}_{k}"], err_msg=f"{name} tick {k}")
+    # the ticks did real work, with different iteration counts over the loop (the WHILE node ran 1..n rounds)
+    iters = np.stack([g[f"iters_{k}"] for k in range(ticks)])
+    assert iters.max() > 1 and iters.min() >= 1
+    assert np.isfinite(g[f"xs_{ticks - 1}"]).all()
+
+
+def test_ticks_queued_back_to_back_without_a_synchronisation(tmp_path):
+    """The graph path never blocks the host: ticks queued on the stream one after the other (each into its own output
+    buffers, each reading the previous one's shifted solution) give the results of the tick-by-tick loop."""
+    ticks = 6
+    q = _run(tmp_path, "queued", 4, ticks, True, True)
+    s = _run(tmp_path, "stream", 4, ticks, False, False)
+    for k in range(ticks):
+        for name in ("iters", "status", "xs", "us", "K", "cost"):
+            np.testing.assert_array_equal(q[f"{name}_{k}"], s[f"{name}_{k}"], err_msg=f"{name} tick {k}")
