@@ -9,11 +9,13 @@ N > 1 (torchrun, one rank per GPU): every rank solves its own slab of 4096 probl
 data-path collective; one NCCL all_gather of cost/iters/status per step).
 
 Printed JSON (rank 0, one line):
-  value        solves/s with inputs resident in HBM (device-timed with CUDA events, max over ranks)
+  value        solves/s with inputs resident in HBM (device-timed with CUDA events, max over ranks); three batches
+               are in flight (step i on handle/stream i % 3: independent batches run in the idle last waves of each
+               other's sequential kernels); `serial` = one batch at a time
   e2e          same metric through the public API with HOST buffers: pinned H2D of x0 / warm start /
                references and D2H of xs, us, K[:, 0], cost, iters, status inside the timed region
   roofline     the dominant kernel against the FP64 (non-tensor) peak measured in-run by a DFMA probe,
-               plus its HBM side; durations from CUDA-event pairs around every launch of the step
+               plus its HBM side; durations from CUDA-event pairs around every launch of the serial pass
   cpu_baseline the CPU restatement (oracle, OpenMP one problem per thread) on a bounded sample
 --impl reference times that CPU restatement as the reference arm (Crocoddyl itself cannot be installed:
 its sources are not in the reference tree and there is no network).
@@ -275,6 +277,44 @@ def run_ours(args):
     out = prob.alloc_outputs()
     stats = torch.empty(B, 3, dtype=torch.float64, device=dev)
     gathered = torch.empty(world * B, 3, dtype=torch.float64, device=dev) if world > 1 else None
+    # Several batches in flight: the sequential kernels of one batch (one warp per problem, or per four) leave SMs idle in
+    # their last wave and the forward pass fills less than one wave, so a second, independent batch on its own handle
+    # and stream runs in those gaps (measured: 392 k -> 427 k solves/s with two in flight, 434 k with three, 427 k with four; splitting ONE batch into
+    # two slabs gains nothing).  Every step is still one complete solve of B problems; step i runs on handle i % IN_FLIGHT.
+    IN_FLIGHT = max(1, int(os.environ.get("AGX_IN_FLIGHT", "3")))
+    probs, outs = [prob], [out]
+    for _ in range(IN_FLIGHT - 1):
+        pb = BatchedShootingProblem(panda_table(), np.full(T_NODES, DT), B, device=dev)
+        pb.set_refs(refs_d)
+        probs.append(pb)
+        outs.append(pb.alloc_outputs())
+    s_solve = [torch.cuda.Stream(device=dev) for _ in range(IN_FLIGHT)]
+    solved_ev = [torch.cuda.Event() for _ in range(IN_FLIGHT)]
+    gathered_ev = [None] * IN_FLIGHT
+    pipe_state = {"i": 0}
+
+    def step_pipelined():
+        i = pipe_state["i"]
+        pipe_state["i"] = i + 1
+        j = i % IN_FLIGHT
+        main_stream = torch.cuda.current_stream()
+        if gathered_ev[j] is not None:
+            s_solve[j].wait_event(gathered_ev[j])   # this handle's previous results have been gathered
+        with torch.cuda.stream(s_solve[j]):
+            probs[j].solve(x0_d, xs_d, us_d, N_ITERS, opts, out=outs[j])
+            solved_ev[j].record(s_solve[j])
+        if world > 1:
+            main_stream.wait_event(solved_ev[j])
+            stats[:, 0] = outs[j]["cost"]
+            stats[:, 1] = outs[j]["iters"]
+            stats[:, 2] = outs[j]["status"]
+            dist.all_gather_into_tensor(gathered, stats)
+            gathered_ev[j] = torch.cuda.Event()
+            gathered_ev[j].record(main_stream)
+
+    def drain_pipelined():
+        for st_ in s_solve:
+            torch.cuda.current_stream().wait_stream(st_)
 
     solve_events = []
 
@@ -295,9 +335,10 @@ def run_ours(args):
             dist.all_gather_into_tensor(gathered, stats)
 
     # ---- end-to-end arm: HOST buffers in, HOST results out, every step.  The public API is stream-ordered, so the
-    # copies of step i+1 (H2D) and of step i-1 (D2H) run on their own streams while step i solves: two slots of
-    # device inputs / outputs / pinned results.  Every step still moves all its bytes inside the timed region and the
-    # host waits for step i-1's results before it issues step i+1.
+    # copies of step i+1 (H2D) and of step i-1 (D2H) run on their own streams while step i solves, and IN_FLIGHT solves
+    # overlap on their own handles: IN_FLIGHT + 1 slots of device inputs / outputs / pinned results.  Every step still
+    # moves all its bytes inside the timed region and the host waits for step (i - IN_FLIGHT)'s results before it issues
+    # step i + 1.
     pin = lambda a: torch.as_tensor(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
     h_in = [pin(w[k]) for k in ("refs", "x0", "xs_ws", "us_ws")]
     h2d_bytes = sum(t.numel() * t.element_size() for t in h_in)
@@ -315,16 +356,18 @@ def run_ours(args):
                             iters=torch.empty(B, dtype=torch.int32).pin_memory(),
                             status=torch.empty(B, dtype=torch.int32).pin_memory())
             self.ev_in, self.ev_solved, self.ev_out = (torch.cuda.Event() for _ in range(3))
+            self.ev_gathered = None
             self.busy = False
 
-    slots = [Slot(), Slot()]
+    slots = [Slot() for _ in range(IN_FLIGHT + 1)]
     d2h_bytes = sum(t.numel() * t.element_size() for t in slots[0].res.values())
     e2e_state = {"i": 0}
 
     def step_e2e():
         i = e2e_state["i"]
         e2e_state["i"] = i + 1
-        sl, prev = slots[i % 2], slots[(i + 1) % 2]
+        ns = len(slots)
+        sl, prev = slots[i % ns], slots[(i - IN_FLIGHT) % ns]   # ns = IN_FLIGHT + 1 slots
         cur_stream = torch.cuda.current_stream()
         if sl.busy:
             sl.ev_out.synchronize()       # this slot's previous solve and result copy (two steps ago) are complete
@@ -332,15 +375,22 @@ def run_ours(args):
             for d, h_ in zip(sl.d_in, h_in):
                 d.copy_(h_, non_blocking=True)
             sl.ev_in.record(s_in)
-        cur_stream.wait_event(sl.ev_in)
-        prob.set_refs(sl.d_in[0])
-        prob.solve(sl.d_in[1], sl.d_in[2], sl.d_in[3], N_ITERS, opts, out=sl.out)
+        j = i % IN_FLIGHT
+        s_solve[j].wait_event(sl.ev_in)
+        if sl.ev_gathered is not None:
+            s_solve[j].wait_event(sl.ev_gathered)
+        with torch.cuda.stream(s_solve[j]):   # step i solves on handle i % IN_FLIGHT while step i-1 still runs on the other
+            probs[j].set_refs(sl.d_in[0])
+            probs[j].solve(sl.d_in[1], sl.d_in[2], sl.d_in[3], N_ITERS, opts, out=sl.out)
+            sl.ev_solved.record(s_solve[j])
         if world > 1:
+            cur_stream.wait_event(sl.ev_solved)
             stats[:, 0] = sl.out["cost"]
             stats[:, 1] = sl.out["iters"]
             stats[:, 2] = sl.out["status"]
             dist.all_gather_into_tensor(gathered, stats)
-        sl.ev_solved.record(cur_stream)
+            sl.ev_gathered = torch.cuda.Event()
+            sl.ev_gathered.record(cur_stream)
         with torch.cuda.stream(s_out):    # D2H of this step's results
             s_out.wait_event(sl.ev_solved)
             sl.res["xs"].copy_(sl.out["xs"], non_blocking=True)
@@ -354,14 +404,16 @@ def run_ours(args):
             sl.res["status"].copy_(sl.out["status"], non_blocking=True)
             sl.ev_out.record(s_out)
         sl.busy = True
-        if prev.busy:
-            prev.ev_out.synchronize()     # the caller reads step i-1's results on the host
+        if i >= IN_FLIGHT and prev.busy:
+            prev.ev_out.synchronize()     # the caller reads step (i - IN_FLIGHT)'s results on the host
 
     def drain_e2e():
         for sl in slots:
             if sl.busy:
                 sl.ev_out.synchronize()
         torch.cuda.current_stream().wait_stream(s_out)
+        for st_ in s_solve:
+            torch.cuda.current_stream().wait_stream(st_)
 
     def barrier():
         if world > 1:
@@ -400,17 +452,24 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+    # (a) the headline: K steps, IN_FLIGHT batches in flight
+    for _ in range(IN_FLIGHT):
+        step_pipelined()
+    drain_pipelined()
+    l0 = sum(p_.launch_count for p_ in probs)
+    ms_total = timed(step_pipelined, args.steps, finish=drain_pipelined, tag="resident")
+    launches = sum(p_.launch_count for p_ in probs) - l0
+    # (b) the same K steps one at a time on one stream, with event pairs around every kernel: per-kernel durations for
+    # the roofline (kernels of two batches overlapping would inflate each other's event intervals)
     prob.set_timing(True)
-    l0 = prob.launch_count
     solve_events.clear()
-    ms_total = timed(step_resident, args.steps, tag="resident")
+    ms_serial = timed(step_resident, args.steps, tag="resident_serial")
     if world > 1:
         mine = torch.tensor([float(np.mean([x.elapsed_time(y) for x, y in solve_events])) if solve_events else 0.0],
                             dtype=torch.float64, device=dev)
         allm = torch.empty(world, dtype=torch.float64, device=dev)
         dist.all_gather_into_tensor(allm, mine)
         per_rank["solve_only"] = [float(v) for v in allm.cpu()]
-    launches = prob.launch_count - l0
     phases = prob.get_timing()
     prob.set_timing(False)
     clocks = sampler.stop() if sampler else None
@@ -425,7 +484,7 @@ def run_ours(args):
     # ocp_base_croco.py:173-177): + 157 MB of D2H per step
     e2e_full = None
     if not args.no_full_k:
-        slots[:] = [Slot(full_K=True), Slot(full_K=True)]
+        slots[:] = [Slot(full_K=True) for _ in range(IN_FLIGHT + 1)]
         e2e_state["i"] = 0
         for _ in range(2):
             step_e2e()
@@ -576,7 +635,7 @@ def run_ours(args):
             # (dividing by the launch count would flatter the per-launch figure)
             full = min(v["launches"], N_ITERS * timing_steps) if k != "node_cost" else min(v["launches"], (N_ITERS + 1) * timing_steps)
             mean_ms = v["ms"] / full
-            per[k] = {"ms_per_launch": mean_ms, "launches": v["launches"], "share_of_step": v["ms"] / ms_total,
+            per[k] = {"ms_per_launch": mean_ms, "launches": v["launches"], "share_of_step": v["ms"] / ms_serial,
                       "tflops": flops[k] / (mean_ms * 1e-3) / 1e12, "gbs": bytes_alg[k] / (mean_ms * 1e-3) / 1e9}
     top = max((k for k in per if flops[k] > 0), key=lambda k: per[k]["ms_per_launch"] * per[k]["launches"]) if per else None
     peaks = {}
@@ -641,14 +700,19 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 1), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "serial": {"value": solves / (ms_serial * 1e-3), "ms_per_step": ms_serial / args.steps,
+                   "what": "the same K steps one batch at a time on one stream (the roofline's kernel durations come "
+                           "from this pass)"},
         "config": {"workload": WORKLOAD, "B_per_gpu": B, "T": T_NODES, "dt": DT, "fddp_iters": N_ITERS,
+                   "batches_in_flight": IN_FLIGHT,
                    "l2": "inputs_larger_than_L2 (node records 481 MB + gains 161 MB per step vs 126 MB L2)",
                    "parallelism": f"independent slabs x{world}, NCCL all_gather of cost/iters/status only"},
         "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps,
                 "returned": "xs, us, K[:,0] (the gain the controller applies), cost, iters, status",
-                "pipelining": "copies of step i+1 (H2D) and i-1 (D2H) overlap the solve of step i on separate streams; "
-                              "the host waits for step i-1's results before issuing step i+1"},
+                "pipelining": "copies of step i+1 (H2D) and i-1 (D2H) overlap the solve of step i on separate streams, "
+                              f"step i solves on handle i % {IN_FLIGHT} while the previous ones finish on theirs; the host "
+                              f"waits for step i-{IN_FLIGHT}'s results before issuing step i+1"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "latency_b1": lat, "sqp_mode": sqp, "e2e_full_K": e2e_full, "strong_scaling": strong, "cfg4_nv9": cfg4,
         "ms_per_step_per_rank": per_rank, "rank0_numa": numa,
