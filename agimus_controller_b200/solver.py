@@ -279,3 +279,75 @@ class BatchedShootingProblem:
             _ptr(out["us"]), _ptr(out["K"]), _ptr(out.get("k")), _ptr(out["cost"]), _ptr(out["iters"]),
             _ptr(out["status"]), _ptr(out.get("stop")), self._stream()))
         return out
+
+
+class SolvePipeline:
+    """Several independent batches in flight on one GPU: ``n_in_flight`` handles of the same problem layout, each with
+    its own stream, served round robin.
+
+    Why: at the benchmark's batch (4096 problems) the per-problem kernels of one solve (Riccati sweep: one warp per
+    problem; forward pass: four problems per warp) leave SMs idle in their last wave, and the forward pass fills less
+    than one wave.  Kernels of another, independent batch run in those gaps: 379 k -> 434 k solves/s with three batches
+    in flight on one B200 (``bench.py``).  Splitting ONE batch into slabs does not help (each slab's kernels are
+    latency-bound and take almost as long as the whole batch's).
+
+    Every submitted batch is an ordinary ``BatchedShootingProblem.solve``: same results, bit for bit, as the same
+    batch solved alone (``tests/test_gpu_tick_graph.py``).
+    """
+
+    class Ticket:
+        def __init__(self, out, event, index):
+            self.out, self.event, self.index = out, event, index
+
+        def wait(self) -> dict:
+            """Blocks the host until this batch's results are complete; returns them."""
+            self.event.synchronize()
+            return self.out
+
+    def __init__(self, tables, dts, B: int, n_in_flight: int = 3, device=None):
+        if n_in_flight < 1:
+            raise ValueError("n_in_flight must be at least 1")
+        self.problems = [BatchedShootingProblem(tables, dts, B, device=device) for _ in range(n_in_flight)]
+        self.device = self.problems[0].device
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(n_in_flight)]
+        self._outs = [p.alloc_outputs() for p in self.problems]
+        self._next = 0
+
+    @property
+    def launch_count(self) -> int:
+        return sum(p.launch_count for p in self.problems)
+
+    def set_refs(self, refs) -> None:
+        """The same reference rows for every handle (a per-batch set goes through ``submit(refs=...)``)."""
+        for p in self.problems:
+            p.set_refs(refs)
+
+    def submit(self, x0, xs_ws, us_ws, max_iter: int, opts=None, refs=None, out: T.Optional[dict] = None,
+               after_current_stream: bool = True) -> "SolvePipeline.Ticket":
+        """Queues one batch on the next handle's stream and never blocks the host.  By default the batch is ordered
+        after the work already queued on the caller's current stream (which produced the inputs); a caller whose inputs
+        are ready and whose current stream carries work that waits on EARLIER batches (a collective over their results,
+        say) passes ``after_current_stream=False`` so that the batches do not serialise through it.  Without ``out`` the
+        results land in the handle's own buffers, valid until that handle's next turn (``n_in_flight`` submits later)."""
+        j = self._next
+        self._next = (j + 1) % len(self.problems)
+        p, s = self.problems[j], self.streams[j]
+        if after_current_stream:
+            s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            if refs is not None:
+                p.set_refs(refs)
+            res = p.solve(x0, xs_ws, us_ws, max_iter, opts, out=out if out is not None else self._outs[j])
+            ev = torch.cuda.Event()
+            ev.record(s)
+        return SolvePipeline.Ticket(res, ev, j)
+
+    def join(self) -> None:
+        """Orders the caller's current stream after everything submitted so far."""
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            cur.wait_stream(s)
+
+    def close(self) -> None:
+        for p in self.problems:
+            p.close()

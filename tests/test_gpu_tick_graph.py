@@ -48,3 +48,38 @@ def test_ticks_queued_back_to_back_without_a_synchronisation(tmp_path):
     for k in range(ticks):
         for name in ("iters", "status", "xs", "us", "K", "cost"):
             np.testing.assert_array_equal(q[f"{name}_{k}"], s[f"{name}_{k}"], err_msg=f"{name} tick {k}")
+
+
+def test_solve_pipeline_gives_the_bits_of_solving_each_batch_alone():
+    """SolvePipeline (independent batches in flight on their own handles and streams): every batch gets the results it
+    gets when solved alone."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from agimus_controller_b200 import _abi, panda_table
+    from agimus_controller_b200.solver import BatchedShootingProblem, SolvePipeline
+    from agimus_controller_b200.workloads import goal_reaching_batch
+
+    B, T = 512, 50
+    table = panda_table()
+    helper = BatchedShootingProblem(table, np.full(2, 0.01), 1)
+    rn = lambda q, v, a: helper.rnea(q, v, a).cpu().numpy()  # noqa: E731
+    batches = [goal_reaching_batch(B, T=T, rnea=rn, seed=s) for s in range(5)]
+    opts = _abi.default_fddp_opts()
+    alone = BatchedShootingProblem(table, batches[0]["dts"], B)
+    want = []
+    for w in batches:
+        alone.set_refs(w["refs"])
+        want.append({k: v.cpu().numpy() for k, v in alone.solve(w["x0"], w["xs_ws"], w["us_ws"], 10, opts).items()})
+    pipe = SolvePipeline(table, batches[0]["dts"], B, n_in_flight=3)
+    dev_in = [{k: torch.as_tensor(w[k], device="cuda") for k in ("refs", "x0", "xs_ws", "us_ws")} for w in batches]
+    outs = [pipe.problems[0].alloc_outputs() for _ in batches]
+    torch.cuda.synchronize()
+    tickets = [pipe.submit(d["x0"], d["xs_ws"], d["us_ws"], 10, opts, refs=d["refs"], out=o)
+               for d, o in zip(dev_in, outs)]
+    for t, w_ in zip(tickets, want):
+        got = t.wait()
+        for k in ("iters", "status", "xs", "us", "K", "cost"):
+            np.testing.assert_array_equal(got[k].cpu().numpy(), w_[k], err_msg=k)
+    assert [t.index for t in tickets] == [0, 1, 2, 0, 1]
+    pipe.join()
+    pipe.close()
