@@ -302,12 +302,11 @@ struct agx_handle {
     cudaGraphExec_t exec = nullptr;
     cudaStream_t capture_stream = nullptr;
     agx::IoTable* d_io = nullptr;   // the caller's pointers of the current tick, read by the graph's first and last kernel
-    int32_t* d_round = nullptr;     // round counter of the loop
+    int32_t* d_round = nullptr;     // [0] round counter of the loop, [1] step-length counter of the SQP line search
     int nodes_fixed = 0, nodes_round = 0;  // kernels outside / inside the loop (agx_launch_count)
-    int max_iter = -1;
-    agx_fddp_opts opts{};
+    std::string key;                // iteration budget + options the graph was built for
     bool failed = false;            // the driver refused the graph once: the stream path serves this handle
-  } tick;
+  } tick, tick_sqp;
 #endif
 };
 
@@ -390,6 +389,97 @@ struct DeviceGuard {
 };
 #else
 struct DeviceGuard { explicit DeviceGuard(int) {} };
+#endif
+
+#if AGX_GPU
+// Pieces of a tick graph (agx_solve / agx_solve_sqp in latency mode): kernels are recorded by stream capture into the
+// graph or into the body of a conditional WHILE node; any failure makes every later step a no-op and `ok` false.
+struct TickGraphBuilder {
+  agx_handle::TickGraph& G;
+  bool ok = true;
+  long long launches_before = 0;
+  explicit TickGraphBuilder(agx_handle* h, agx_handle::TickGraph& g) : G(g), launches_before(h->launches) {
+    if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+    if (G.graph) { cudaGraphDestroy(G.graph); G.graph = nullptr; }
+    if (!G.capture_stream) ok = ok && cudaStreamCreateWithFlags(&G.capture_stream, cudaStreamNonBlocking) == cudaSuccess;
+    if (!G.d_io) ok = ok && dev_alloc((void**)&G.d_io, sizeof(agx::IoTable));
+    if (!G.d_round) ok = ok && dev_alloc((void**)&G.d_round, 2 * sizeof(int32_t));
+    ok = ok && cudaGraphCreate(&G.graph, 0) == cudaSuccess;
+  }
+  // start recording into `g`, behind `dep` (or at its root)
+  bool begin(cudaGraph_t g, cudaGraphNode_t dep = nullptr) {
+    ok = ok && cudaStreamBeginCaptureToGraph(G.capture_stream, g, dep ? &dep : nullptr, nullptr, dep ? 1 : 0,
+                                             cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    return ok;
+  }
+  bool end(cudaGraph_t g) {
+    if (!ok) return false;
+    ok = cudaStreamEndCapture(G.capture_stream, &g) == cudaSuccess;
+    return ok;
+  }
+  // the node of `g` nothing depends on yet (the recorded pieces are chains: there is one)
+  cudaGraphNode_t leaf(cudaGraph_t g) {
+    size_t n = 0;
+    if (!ok || cudaGraphGetNodes(g, nullptr, &n) != cudaSuccess || n == 0) { ok = false; return nullptr; }
+    std::vector<cudaGraphNode_t> nodes(n);
+    if (cudaGraphGetNodes(g, nodes.data(), &n) != cudaSuccess) { ok = false; return nullptr; }
+    cudaGraphNode_t out = nullptr;
+    for (size_t i = 0; i < n; ++i) {
+      size_t n_dep = 0;
+      if (cudaGraphNodeGetDependentNodes(nodes[i], nullptr, &n_dep) == cudaSuccess && n_dep == 0) out = nodes[i];
+    }
+    if (!out) ok = false;
+    return out;
+  }
+  // a WHILE node at the end of `parent`; enter_by_default: the loop runs at least once per graph launch, otherwise a
+  // kernel upstream of the node arms it (a loop nested in a loop has to be armed on every pass of the outer one)
+  bool add_while(cudaGraph_t parent, bool enter_by_default, cudaGraphConditionalHandle* handle, cudaGraphNode_t* node,
+                 cudaGraph_t* body) {
+    cudaGraphNode_t dep = leaf(parent);
+    ok = ok && cudaGraphConditionalHandleCreate(handle, parent, enter_by_default ? 1u : 0u,
+                                                enter_by_default ? cudaGraphCondAssignDefault : 0u) == cudaSuccess;
+    if (!ok) return false;
+    cudaGraphNodeParams np = {};
+    np.type = cudaGraphNodeTypeConditional;
+    np.conditional.handle = *handle;
+    np.conditional.type = cudaGraphCondTypeWhile;
+    np.conditional.size = 1;
+    ok = cudaGraphAddNode(node, parent, &dep, 1, &np) == cudaSuccess;
+    if (ok) *body = np.conditional.phGraph_out[0];
+    return ok;
+  }
+  bool finish(agx_handle* h, const std::string& key) {
+    ok = ok && cudaGraphInstantiate(&G.exec, G.graph, 0) == cudaSuccess;
+    h->launches = launches_before;  // capturing is not launching
+    if (!ok) {
+      // a driver without conditional nodes: remember, clear the error, serve this handle on the stream path
+      cudaGetLastError();
+      cudaStreamCaptureStatus cst;
+      if (G.capture_stream && cudaStreamIsCapturing(G.capture_stream, &cst) == cudaSuccess && cst != cudaStreamCaptureStatusNone) {
+        cudaGraph_t junk = nullptr;
+        cudaStreamEndCapture(G.capture_stream, &junk);
+      }
+      cudaGetLastError();
+      if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+      G.failed = true;
+    } else {
+      G.key = key;
+    }
+    return ok;
+  }
+};
+
+// refresh the pointer table and launch; the loop's further rounds are decided on the device
+int launch_tick_graph(agx_handle* h, agx_handle::TickGraph& G, const agx::IoTable& io, stream_t st, const char* what) {
+  // pageable source on purpose: the runtime stages such a small copy before it returns, so ticks may be queued back
+  // to back without the next call overwriting a table the previous copy has not read yet
+  if (cudaMemcpyAsync(G.d_io, &io, sizeof(agx::IoTable), cudaMemcpyHostToDevice, st) != cudaSuccess)
+    return fail(h, AGX_ECUDA, "pointer table copy failed");
+  if (cudaGraphLaunch(G.exec, st) != cudaSuccess) return fail(h, AGX_ECUDA, "graph launch failed");
+  // at least one round runs; how many more is decided on the device (agx_launch_count counts the first)
+  h->launches += G.nodes_fixed + G.nodes_round;
+  return check_launch(h, what);
+}
 #endif
 
 void launch_backward(agx_handle* h, const agx::Problem& P, const agx::Work& W, const agx::FddpOpts& O, stream_t st) {
@@ -651,10 +741,12 @@ int agx_destroy(agx_handle* h) {
     dev_free(h->state_block);
 #if AGX_GPU
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
-    if (h->tick.exec) cudaGraphExecDestroy(h->tick.exec);
-    if (h->tick.graph) cudaGraphDestroy(h->tick.graph);
-    if (h->tick.capture_stream) cudaStreamDestroy(h->tick.capture_stream);
-    dev_free(h->tick.d_io); dev_free(h->tick.d_round);
+    for (agx_handle::TickGraph* G : {&h->tick, &h->tick_sqp}) {
+      if (G->exec) cudaGraphExecDestroy(G->exec);
+      if (G->graph) cudaGraphDestroy(G->graph);
+      if (G->capture_stream) cudaStreamDestroy(G->capture_stream);
+      dev_free(G->d_io); dev_free(G->d_round);
+    }
 #endif
   }
   delete h;
@@ -1153,91 +1245,36 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
       W.K = h->d_K_internal;
     }
     W.x0 = h->d_x0;
-    const bool stale = !G.exec || G.max_iter != max_iter || std::memcmp(&G.opts, opts, sizeof(agx_fddp_opts)) != 0;
-    if (stale) {
-      if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
-      if (G.graph) { cudaGraphDestroy(G.graph); G.graph = nullptr; }
-      bool ok = true;
-      if (!G.capture_stream) ok = ok && cudaStreamCreateWithFlags(&G.capture_stream, cudaStreamNonBlocking) == cudaSuccess;
-      if (!G.d_io) ok = ok && dev_alloc((void**)&G.d_io, sizeof(IoTable));
-      if (!G.d_round) ok = ok && dev_alloc((void**)&G.d_round, sizeof(int32_t));
-      const long long before = h->launches;
+    std::string key((const char*)&max_iter, sizeof(max_iter));
+    key.append((const char*)opts, sizeof(agx_fddp_opts));
+    if (!G.exec || G.key != key) {
+      TickGraphBuilder gb(h, G);
       cudaStream_t cs = G.capture_stream;
+      cudaGraphConditionalHandle cond{};
       cudaGraphNode_t loop_node = nullptr;
       cudaGraph_t body = nullptr;
-      ok = ok && cudaGraphCreate(&G.graph, 0) == cudaSuccess;
-      // head of the graph
-      ok = ok && cudaStreamBeginCaptureToGraph(cs, G.graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
-      if (ok) {
+      if (gb.begin(G.graph)) {   // head
         AGX_LAUNCH(h, init_io_kernel, (n_init + 255) / 256, 256, 0, cs, P, W, h->S, O, (const IoTable*)G.d_io, h->d_x0, G.d_round);
         enqueue_first_costs(cs);
-        ok = cudaStreamEndCapture(cs, &G.graph) == cudaSuccess;
+        gb.end(G.graph);
       }
-      // the loop: a WHILE node behind the head's last kernel
-      if (ok) {
-        size_t n_nodes = 0;
-        ok = cudaGraphGetNodes(G.graph, nullptr, &n_nodes) == cudaSuccess && n_nodes > 0;
-        std::vector<cudaGraphNode_t> nodes(n_nodes);
-        ok = ok && cudaGraphGetNodes(G.graph, nodes.data(), &n_nodes) == cudaSuccess;
-        cudaGraphNode_t leaf = nullptr;
-        for (size_t i = 0; ok && i < n_nodes; ++i) {
-          size_t n_dep = 0;
-          if (cudaGraphNodeGetDependentNodes(nodes[i], nullptr, &n_dep) == cudaSuccess && n_dep == 0) leaf = nodes[i];
-        }
-        cudaGraphConditionalHandle cond{};
-        ok = ok && leaf && cudaGraphConditionalHandleCreate(&cond, G.graph, 1, cudaGraphCondAssignDefault) == cudaSuccess;
-        cudaGraphNodeParams np = {};
-        np.type = cudaGraphNodeTypeConditional;
-        np.conditional.handle = cond;
-        np.conditional.type = cudaGraphCondTypeWhile;
-        np.conditional.size = 1;
-        ok = ok && cudaGraphAddNode(&loop_node, G.graph, &leaf, 1, &np) == cudaSuccess;
-        if (ok) body = np.conditional.phGraph_out[0];
-        G.nodes_fixed = (int)(h->launches - before);
-        ok = ok && cudaStreamBeginCaptureToGraph(cs, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
-        if (ok) {
-          enqueue_round(cs, 0, (const int32_t*)h->S.recalc_cost, (const int32_t*)G.d_round);
-          AGX_LAUNCH(h, loop_condition_kernel, 1, 64, 0, cs, h->B, (const int32_t*)h->S.done, G.d_round, rounds, cond);
-          ok = cudaStreamEndCapture(cs, &body) == cudaSuccess;
-        }
-        G.nodes_round = (int)(h->launches - before) - G.nodes_fixed;
+      G.nodes_fixed = (int)(h->launches - gb.launches_before);
+      if (gb.add_while(G.graph, true, &cond, &loop_node, &body) && gb.begin(body)) {   // the loop
+        enqueue_round(cs, 0, (const int32_t*)h->S.recalc_cost, (const int32_t*)G.d_round);
+        AGX_LAUNCH(h, loop_condition_kernel, 1, 64, 0, cs, h->B, (const int32_t*)h->S.done, G.d_round, rounds, cond);
+        gb.end(body);
       }
-      // tail: the results go to the caller's buffers
-      ok = ok && cudaStreamBeginCaptureToGraph(cs, G.graph, &loop_node, nullptr, 1, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
-      if (ok) {
+      G.nodes_round = (int)(h->launches - gb.launches_before) - G.nodes_fixed;
+      if (gb.begin(G.graph, loop_node)) {   // tail: the results go to the caller's buffers
         AGX_LAUNCH(h, finalize_io_kernel, (n_fin + 255) / 256, 256, 0, cs, P, W, h->S, (const IoTable*)G.d_io);
-        ok = cudaStreamEndCapture(cs, &G.graph) == cudaSuccess;
+        gb.end(G.graph);
         ++G.nodes_fixed;
       }
-      ok = ok && cudaGraphInstantiate(&G.exec, G.graph, 0) == cudaSuccess;
-      h->launches = before;  // capturing is not launching
-      if (!ok) {
-        // a driver without conditional nodes: remember, clear the error, serve this handle on the stream path
-        cudaGetLastError();
-        cudaStreamCaptureStatus cst;
-        if (G.capture_stream && cudaStreamIsCapturing(G.capture_stream, &cst) == cudaSuccess && cst != cudaStreamCaptureStatusNone) {
-          cudaGraph_t junk = nullptr;
-          cudaStreamEndCapture(G.capture_stream, &junk);
-          if (junk && junk != G.graph) cudaGraphDestroy(junk);
-        }
-        cudaGetLastError();
-        if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
-        G.failed = true;
-      } else {
-        G.max_iter = max_iter;
-        G.opts = *opts;
-      }
+      gb.finish(h, key);
     }
     if (G.exec) {
-      IoTable io{x0, xs_ws, us_ws, out_xs, out_us, out_K, out_k, out_cost, out_iters, out_status, out_stop};
-      // pageable source on purpose: the runtime stages such a small copy before it returns, so ticks may be queued back
-      // to back without the next call overwriting a table the previous copy has not read yet
-      if (cudaMemcpyAsync(G.d_io, &io, sizeof(IoTable), cudaMemcpyHostToDevice, st) != cudaSuccess)
-        return fail(h, AGX_ECUDA, "agx_solve: pointer table copy failed");
-      if (cudaGraphLaunch(G.exec, st) != cudaSuccess) return fail(h, AGX_ECUDA, "agx_solve: graph launch failed");
-      // at least one round runs; how many more is decided on the device (agx_launch_count counts the first)
-      h->launches += G.nodes_fixed + G.nodes_round;
-      return check_launch(h, "agx_solve");
+      const IoTable io{x0, xs_ws, us_ws, out_xs, out_us, out_K, out_k, out_cost, out_iters, out_status, out_stop};
+      return launch_tick_graph(h, G, io, st, "agx_solve");
     }
   }
 #endif
@@ -1316,55 +1353,137 @@ int agx_solve_sqp(agx_handle* h, const double* x0, const double* xs_ws, const do
     return tree_solve_sqp(h, x0, xs_ws, us_ws, max_iter, opts, Q, O, Of, out_xs, out_us, out_K, out_k, out_cost, out_iters,
                           out_status, out_stop, st);
   const size_t nB = (size_t)h->B, T = (size_t)h->T, T1 = T + 1;
-  if (!out_K && !h->d_K_internal) {
+  if (!h->d_K_internal && (!out_K || (opts->eager_exit && h->B <= 64))) {
     if (!dev_alloc((void**)&h->d_K_internal, sizeof(double) * nB * T * NJ * NX))
       return fail(h, AGX_ENOMEM, "allocation of the internal gain buffer failed");
   }
   Work W = h->W;
-  W.K = out_K ? out_K : h->d_K_internal;
   W.x0 = h->d_x0;
-  if (!copy_d2d(h->d_x0, x0, sizeof(double) * nB * NX, st)) return fail(h, AGX_ECUDA, "agx_solve_sqp: x0 copy failed");
   const Problem P = problem_of(h);
   const long long n_init = (long long)(nB * T1 * NX);
-  AGX_LAUNCH(h, init_kernel, (n_init + 255) / 256, 256, 0, st, P, W, h->S, O, xs_ws, us_ws);
+  const long long n_fin = (long long)(nB * T * NJ * NX);
   const long long ents = (long long)(nB * T1);
   const int opc_n = NODE_CTA / 8, opc_s = SEQ_CTA / 8;
   const long long cost_ctas = (ents + COST_CTA - 1) / COST_CTA;
-  auto derivatives = [&]() {
+  int32_t* pend = h->d_live + 1;  // d_live[1 + n] = problems entering step length n (see sqp_direction_kernel)
+  // timing phases (agx_set_timing): 0 calc_diff, 1 Riccati sweep, 2 QP direction / KKT, 3 cost records, 4 line search
+  auto derivatives = [&](stream_t s) {
     // problem.calc + calcDiff at the candidate (finished problems are skipped)
-    phase_begin(h, 3, st);
-    AGX_LAUNCH_NODE_COST(h, cost_ctas, COST_CTA, COST_SMEM, st, P, (const double*)W.xs, (const double*)W.us,
+    phase_begin(h, 3, s);
+    AGX_LAUNCH_NODE_COST(h, cost_ctas, COST_CTA, COST_SMEM, s, P, (const double*)W.xs, (const double*)W.us,
                (const int32_t*)h->S.cur, 0, (const int32_t*)h->S.done, (const int32_t*)nullptr, W.crec, (double*)nullptr);
-    phase_end(h, st);
-    phase_begin(h, 0, st);
-    AGX_LAUNCH_COL(h, calc_diff_kernel, (ents + (CD_CTA / 8) - 1) / (CD_CTA / 8), CD_CTA, sizeof(double) * OCT_BOARD * (CD_CTA / 8), st, P,
+    phase_end(h, s);
+    phase_begin(h, 0, s);
+    AGX_LAUNCH_COL(h, calc_diff_kernel, (ents + (CD_CTA / 8) - 1) / (CD_CTA / 8), CD_CTA, sizeof(double) * OCT_BOARD * (CD_CTA / 8), s, P,
                (const double*)W.xs, (const double*)W.us, (const int32_t*)h->S.cur, (const int32_t*)nullptr,
                (const int32_t*)nullptr, 0, (const int32_t*)h->S.done, W.rec, W.crec);
-    phase_end(h, st);
+    phase_end(h, s);
   };
-  // timing phases (agx_set_timing): 0 calc_diff, 1 Riccati sweep, 2 QP direction / KKT, 3 cost records, 4 line search
-  for (int it = 0; it < max_iter; ++it) {
-    derivatives();
-    phase_begin(h, 1, st);
-    launch_backward(h, P, W, O, st);
-    phase_end(h, st);
-    phase_begin(h, 2, st);
-    // d_live[1 + n] = problems entering step length n (see sqp_direction_kernel)
-    int32_t* pend = h->d_live + 1;
+  // derivatives, Riccati sweep, QP direction + KKT test (which also counts the problems entering the line search)
+  auto direction = [&](stream_t s) {
+    derivatives(s);
+    phase_begin(h, 1, s);
+    launch_backward(h, P, W, O, s);
+    phase_end(h, s);
+    phase_begin(h, 2, s);
 #if AGX_GPU
-    cudaMemsetAsync(pend, 0, sizeof(int32_t) * 12, st);
+    cudaMemsetAsync(pend, 0, sizeof(int32_t) * 12, s);
 #else
     std::memset(pend, 0, sizeof(int32_t) * 12);
 #endif
-    AGX_LAUNCH(h, sqp_direction_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, 0, st, P, W, h->S, Q, pend);
-    phase_end(h, st);
+    AGX_LAUNCH(h, sqp_direction_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, 0, s, P, W, h->S, Q, pend);
+    phase_end(h, s);
+  };
+  // one step length of the line search: `n` on the stream path, the device-side counter `idx` in the tick graph
+  auto try_step = [&](stream_t s, int n, const int32_t* idx) {
+    // the first step lengths meet most problems: one octet per entry; the later ones meet few and stride
+    const long long try_ctas = (idx || n < 3) ? (ents + opc_n - 1) / opc_n : std::min<long long>((ents + opc_n - 1) / opc_n, 148 * 8);
+    int32_t* counter = idx ? pend : pend + n;
+    AGX_LAUNCH_COL(h, sqp_try_kernel, try_ctas, NODE_CTA, sizeof(double) * OCT_BOARD * opc_n, s, P, W,
+               h->S, (const int32_t*)counter, idx);
+    AGX_LAUNCH(h, sqp_accept_kernel, (h->B + 127) / 128, 128, 0, s, P, W, h->S, Q, counter, idx);
+  };
+  // the gains the solver holds are those of its last backward pass (sigma + reg on the diagonals), at the final iterate
+  auto final_sweep = [&](stream_t s) {
+    derivatives(s);
+    AGX_LAUNCH(h, sqp_final_prepare_kernel, (h->B + 255) / 256, 256, 0, s, h->B, h->S, Q);
+    launch_backward(h, P, W, Of, s);
+  };
+
+#if AGX_GPU
+  // ---- latency mode: the whole tick is ONE graph launch (as in agx_solve) ------------------------------------------
+  // init -> WHILE (somebody unfinished, iterations left) { direction; arm; WHILE (somebody searching) { try; accept } }
+  // -> final sweep -> finalize; both loop conditions are set on the device
+  static const bool tick_graph_on = [] { const char* e = std::getenv("AGX_TICK_GRAPH"); return !(e && e[0] == '0'); }();
+  if (tick_graph_on && opts->eager_exit && h->B <= 64 && !h->timing && !h->tick_sqp.failed && max_iter > 0) {
+    auto& G = h->tick_sqp;
+    W.K = h->d_K_internal;
+    std::string key((const char*)&max_iter, sizeof(max_iter));
+    key.append((const char*)opts, sizeof(agx_sqp_opts));
+    if (!G.exec || G.key != key) {
+      TickGraphBuilder gb(h, G);
+      cudaStream_t cs = G.capture_stream;
+      cudaGraphConditionalHandle outer{}, inner{};
+      cudaGraphNode_t outer_node = nullptr, inner_node = nullptr;
+      cudaGraph_t body = nullptr, ls_body = nullptr;
+      if (gb.begin(G.graph)) {   // head
+        AGX_LAUNCH(h, init_io_kernel, (n_init + 255) / 256, 256, 0, cs, P, W, h->S, O, (const IoTable*)G.d_io, h->d_x0, G.d_round);
+        gb.end(G.graph);
+      }
+      G.nodes_fixed = (int)(h->launches - gb.launches_before);
+      if (gb.add_while(G.graph, true, &outer, &outer_node, &body)) {
+        // the line-search loop is created first: the kernel that arms it needs its handle
+        if (gb.ok) gb.ok = cudaGraphConditionalHandleCreate(&inner, body, 0, 0) == cudaSuccess;
+        if (gb.begin(body)) {
+          direction(cs);
+          AGX_LAUNCH(h, sqp_arm_linesearch_kernel, 1, 1, 0, cs, G.d_round + 1, (const int32_t*)pend, inner);
+          gb.end(body);
+        }
+        if (gb.ok) {
+          cudaGraphNode_t dep = gb.leaf(body);
+          cudaGraphNodeParams np = {};
+          np.type = cudaGraphNodeTypeConditional;
+          np.conditional.handle = inner;
+          np.conditional.type = cudaGraphCondTypeWhile;
+          np.conditional.size = 1;
+          gb.ok = gb.ok && cudaGraphAddNode(&inner_node, body, &dep, 1, &np) == cudaSuccess;
+          if (gb.ok) ls_body = np.conditional.phGraph_out[0];
+        }
+        if (gb.begin(ls_body)) {
+          try_step(cs, 0, (const int32_t*)(G.d_round + 1));
+          AGX_LAUNCH(h, sqp_linesearch_condition_kernel, 1, 1, 0, cs, G.d_round + 1, (const int32_t*)pend, Q.n_alphas, inner);
+          gb.end(ls_body);
+        }
+        if (gb.begin(body, inner_node)) {
+          AGX_LAUNCH(h, loop_condition_kernel, 1, 64, 0, cs, h->B, (const int32_t*)h->S.done, G.d_round, max_iter, outer);
+          gb.end(body);
+        }
+      }
+      G.nodes_round = (int)(h->launches - gb.launches_before) - G.nodes_fixed;
+      if (gb.begin(G.graph, outer_node)) {   // tail
+        const long long before_tail = h->launches;
+        final_sweep(cs);
+        AGX_LAUNCH(h, finalize_io_kernel, (n_fin + 255) / 256, 256, 0, cs, P, W, h->S, (const IoTable*)G.d_io);
+        gb.end(G.graph);
+        G.nodes_fixed += (int)(h->launches - before_tail);
+      }
+      gb.finish(h, key);
+    }
+    if (G.exec) {
+      const IoTable io{x0, xs_ws, us_ws, out_xs, out_us, out_K, out_k, out_cost, out_iters, out_status, out_stop};
+      return launch_tick_graph(h, G, io, st, "agx_solve_sqp");
+    }
+  }
+#endif
+
+  W.K = out_K ? out_K : h->d_K_internal;
+  if (!copy_d2d(h->d_x0, x0, sizeof(double) * nB * NX, st)) return fail(h, AGX_ECUDA, "agx_solve_sqp: x0 copy failed");
+  AGX_LAUNCH(h, init_kernel, (n_init + 255) / 256, 256, 0, st, P, W, h->S, O, xs_ws, us_ws);
+  for (int it = 0; it < max_iter; ++it) {
+    direction(st);
     phase_begin(h, 4, st);
     for (int n = 0; n < Q.n_alphas; ++n) {
-      // the first step lengths meet most problems: one octet per entry; the later ones meet few and stride
-      const long long try_ctas = n < 3 ? (ents + opc_n - 1) / opc_n : std::min<long long>((ents + opc_n - 1) / opc_n, 148 * 8);
-      AGX_LAUNCH_COL(h, sqp_try_kernel, try_ctas, NODE_CTA, sizeof(double) * OCT_BOARD * opc_n, st, P, W,
-                 h->S, (const int32_t*)(pend + n));
-      AGX_LAUNCH(h, sqp_accept_kernel, (h->B + 127) / 128, 128, 0, st, P, W, h->S, Q, pend + n);
+      try_step(st, n, nullptr);
       // latency mode: stop queueing step lengths once nobody is searching any more
       if (opts->eager_exit && h->B <= 64 && !h->timing && n + 1 < Q.n_alphas && read_counter_sync(h, pend + n + 1, st) == 0)
         break;
@@ -1387,11 +1506,7 @@ int agx_solve_sqp(agx_handle* h, const double* x0, const double* xs_ws, const do
       if (live == 0) break;
     }
   }
-  // the gains the solver holds are those of its last backward pass (sigma + reg on the diagonals), at the final iterate
-  derivatives();
-  AGX_LAUNCH(h, sqp_final_prepare_kernel, (h->B + 255) / 256, 256, 0, st, h->B, h->S, Q);
-  launch_backward(h, P, W, Of, st);
-  const long long n_fin = (long long)(nB * T * NJ * NX);
+  final_sweep(st);
   AGX_LAUNCH(h, finalize_kernel, (n_fin + 255) / 256, 256, 0, st, P, W, h->S, out_xs, out_us, out_K, out_k, out_cost,
              out_iters, out_status, out_stop);
   return check_launch(h, "agx_solve_sqp");

@@ -177,8 +177,12 @@ __global__ void sqp_direction_kernel(Problem P, Work W, SolverState S, SqpOpts Q
 
 // SolverCSQP::tryStep for the step length 2^-n the problem is at: one octet per (problem, node) evaluates the node
 // cost and the gap to the next trial state of xs + a dx, us + a du, which it writes into the trial buffer.
+// `pend` = counter of the problems entering this step length; the tick graph passes the counter array and the
+// device-side index of the step length (`idx`), the stream path the counter itself (`idx` null)
 template <bool COL>
-__global__ void sqp_try_kernel(Problem P, Work W, SolverState S, const int32_t* __restrict__ pend) {
+__global__ void sqp_try_kernel(Problem P, Work W, SolverState S, const int32_t* __restrict__ pend,
+                               const int32_t* __restrict__ idx) {
+  if (idx) pend += *idx;
   if (*pend == 0) return;
   AGX_SMEM(smem);
   AGX_OCTET_SETUP();
@@ -232,7 +236,9 @@ __global__ void sqp_try_kernel(Problem P, Work W, SolverState S, const int32_t* 
 }
 
 // merit_try < merit: take the step; otherwise the next step length (SolverCSQP::solve, merit line search)
-__global__ void sqp_accept_kernel(Problem P, Work W, SolverState S, SqpOpts Q, int32_t* __restrict__ pend) {
+__global__ void sqp_accept_kernel(Problem P, Work W, SolverState S, SqpOpts Q, int32_t* __restrict__ pend,
+                                  const int32_t* __restrict__ idx) {
+  if (idx) pend += *idx;
   if (*pend == 0) return;
   const int b = (int)(blockIdx.x * blockDim.x + threadIdx.x);
   if (b >= P.B) return;
@@ -276,6 +282,23 @@ __global__ void sqp_final_prepare_kernel(int B, SolverState S, SqpOpts Q) {
   S.is_feasible[b] = 0;
   if (S.status[b] != 3) S.done[b] = 0;
 }
+
+#if AGX_GPU
+// ---- tick graph of agx_solve_sqp (agx_api.cu): loop control on the device ------------------------------------------
+// before the line-search loop of an iteration: first step length, and enter the loop only if somebody searches
+__global__ void sqp_arm_linesearch_kernel(int32_t* __restrict__ n_ctr, const int32_t* __restrict__ pend,
+                                          cudaGraphConditionalHandle inner) {
+  *n_ctr = 0;
+  cudaGraphSetConditional(inner, pend[0] != 0 ? 1u : 0u);
+}
+// last kernel of the line-search loop: next step length while some problem entered it
+__global__ void sqp_linesearch_condition_kernel(int32_t* __restrict__ n_ctr, const int32_t* __restrict__ pend,
+                                                int n_alphas, cudaGraphConditionalHandle inner) {
+  const int n = *n_ctr + 1;
+  *n_ctr = n;
+  cudaGraphSetConditional(inner, (n < n_alphas && pend[n] != 0) ? 1u : 0u);
+}
+#endif
 
 }  // namespace agx
 #endif  // AGX_SQP_CUH_

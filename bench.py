@@ -214,7 +214,7 @@ def mpc_latency(prob, dev, ticks, solver="fddp", with_cpu=False):
     return {"p50_ms": float(np.percentile(ts, 50)), "p99_ms": float(np.percentile(ts, 99)), "ticks": int(len(ts)),
             "mean_iters": float(np.mean(iters[20:])), "final_tracking_error_rad": track, "cpu_baseline": cpu,
             "workload": "cfg1: B=1, T=20, dt=0.01, sine in configuration space (0.2 rad, 4 s), closed loop with shift "
-                        "warm start, <=10 FDDP iterations per tick (eager_exit: the FDDP tick is one graph launch whose WHILE node stops at convergence; the CSQP tick reads the completion flags back per iteration); host wall clock of set_refs_window + solve + D2H of us[0], K[0]"}
+                        "warm start, <=10 FDDP iterations per tick (eager_exit: a tick is one graph launch whose WHILE node stops at convergence, in FDDP and in CSQP mode); host wall clock of set_refs_window + solve + D2H of us[0], K[0]"}
 
 
 def pin_to_gpu_numa_node(local):

@@ -11,22 +11,23 @@ from agimus_controller_b200.solver import BatchedShootingProblem
 from agimus_controller_b200.workloads import goal_reaching_batch
 
 
-def run(B, ticks, queue_without_sync):
+def run(B, ticks, queue_without_sync, mode="fddp"):
     table = panda_table()
     helper = BatchedShootingProblem(table, np.full(2, 0.01), 1)
     rn = lambda q, v, a: helper.rnea(q, v, a).cpu().numpy()  # noqa: E731
     w = goal_reaching_batch(B, T=20, rnea=rn, seed=5)
     p = BatchedShootingProblem(table, w["dts"], B)
     p.set_refs(w["refs"])
-    opts = _abi.default_fddp_opts()
+    opts = _abi.default_fddp_opts() if mode == "fddp" else _abi.default_sqp_opts()
     opts.eager_exit = 1
+    solve = p.solve if mode == "fddp" else p.solve_sqp
     x = torch.as_tensor(w["x0"], device="cuda")
     xs = torch.as_tensor(w["xs_ws"], device="cuda")
     us = torch.as_tensor(w["us_ws"], device="cuda")
     res = {}
     outs = [p.alloc_outputs() for _ in range(ticks)] if queue_without_sync else None
     for k in range(ticks):
-        out = p.solve(x, xs, us, 10, opts, out=outs[k] if outs else None)
+        out = solve(x, xs, us, 10, opts, out=outs[k] if outs else None)
         if not queue_without_sync:
             for name in ("xs", "us", "K", "cost", "iters", "status"):
                 res[f"{name}_{k}"] = out[name].cpu().numpy()
@@ -43,4 +44,5 @@ def run(B, ticks, queue_without_sync):
 
 if __name__ == "__main__":
     out_path, B, ticks, queue = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
-    np.savez(out_path, **run(B, ticks, bool(queue)))
+    mode = sys.argv[5] if len(sys.argv) > 5 else "fddp"
+    np.savez(out_path, **run(B, ticks, bool(queue), mode))

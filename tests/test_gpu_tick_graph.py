@@ -15,12 +15,12 @@ ROOT = pathlib.Path(__file__).resolve().parent.parent
 CASE = ROOT / "tests" / "gpu_tick_case.py"
 
 
-def _run(tmp_path, tag, B, ticks, queue, graph):
+def _run(tmp_path, tag, B, ticks, queue, graph, mode="fddp"):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     out = tmp_path / f"{tag}.npz"
     env = dict(os.environ, PYTHONPATH=str(ROOT), AGX_TICK_GRAPH="1" if graph else "0")
-    subprocess.run([sys.executable, str(CASE), str(out), str(B), str(ticks), str(int(queue))], check=True, env=env,
+    subprocess.run([sys.executable, str(CASE), str(out), str(B), str(ticks), str(int(queue)), mode], check=True, env=env,
                    cwd=str(ROOT), timeout=600)
     return dict(np.load(out))
 
@@ -37,6 +37,20 @@ def test_tick_graph_gives_the_bits_of_the_stream_path(tmp_path, B):
     iters = np.stack([g[f"iters_{k}"] for k in range(ticks)])
     assert iters.max() > 1 and iters.min() >= 1
     assert np.isfinite(g[f"xs_{ticks - 1}"]).all()
+
+
+@pytest.mark.parametrize("B", [1, 16])
+def test_sqp_tick_graph_gives_the_bits_of_the_stream_path(tmp_path, B):
+    """agx_solve_sqp in latency mode: nested WHILE nodes (iterations around the line search) against the stream path
+    that reads a counter back per step length and the completion flags per iteration."""
+    ticks = 10
+    g = _run(tmp_path, "graph", B, ticks, False, True, "sqp")
+    s = _run(tmp_path, "stream", B, ticks, False, False, "sqp")
+    for k in range(ticks):
+        for name in ("iters", "status", "xs", "us", "K", "cost"):
+            np.testing.assert_array_equal(g[f"{name}_{k}"], s[f"{name}_{k}"], err_msg=f"{name} tick {k}")
+    iters = np.stack([g[f"iters_{k}"] for k in range(ticks)])
+    assert iters.max() > 1 and np.isfinite(g[f"xs_{ticks - 1}"]).all()
 
 
 def test_ticks_queued_back_to_back_without_a_synchronisation(tmp_path):
