@@ -1261,7 +1261,7 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
       G.nodes_fixed = (int)(h->launches - gb.launches_before);
       if (gb.add_while(G.graph, true, &cond, &loop_node, &body) && gb.begin(body)) {   // the loop
         enqueue_round(cs, 0, (const int32_t*)h->S.recalc_cost, (const int32_t*)G.d_round);
-        AGX_LAUNCH(h, loop_condition_kernel, 1, 64, 0, cs, h->B, (const int32_t*)h->S.done, G.d_round, rounds, cond);
+        AGX_LAUNCH(h, loop_condition_kernel, 1, 256, 0, cs, h->B, (const int32_t*)h->S.done, G.d_round, rounds, cond);
         gb.end(body);
       }
       G.nodes_round = (int)(h->launches - gb.launches_before) - G.nodes_fixed;
@@ -1353,7 +1353,7 @@ int agx_solve_sqp(agx_handle* h, const double* x0, const double* xs_ws, const do
     return tree_solve_sqp(h, x0, xs_ws, us_ws, max_iter, opts, Q, O, Of, out_xs, out_us, out_K, out_k, out_cost, out_iters,
                           out_status, out_stop, st);
   const size_t nB = (size_t)h->B, T = (size_t)h->T, T1 = T + 1;
-  if (!h->d_K_internal && (!out_K || (opts->eager_exit && h->B <= 64))) {
+  if (!h->d_K_internal) {
     if (!dev_alloc((void**)&h->d_K_internal, sizeof(double) * nB * T * NJ * NX))
       return fail(h, AGX_ENOMEM, "allocation of the internal gain buffer failed");
   }
@@ -1415,7 +1415,11 @@ int agx_solve_sqp(agx_handle* h, const double* x0, const double* xs_ws, const do
   // init -> WHILE (somebody unfinished, iterations left) { direction; arm; WHILE (somebody searching) { try; accept } }
   // -> final sweep -> finalize; both loop conditions are set on the device
   static const bool tick_graph_on = [] { const char* e = std::getenv("AGX_TICK_GRAPH"); return !(e && e[0] == '0'); }();
-  if (tick_graph_on && opts->eager_exit && h->B <= 64 && !h->timing && !h->tick_sqp.failed && max_iter > 0) {
+  // The graph also serves large batches (AGX_SQP_GRAPH=latency keeps it to the latency mode): the stream path has to
+  // queue a try / accept pair for every one of the n_alphas step lengths of every iteration, whether or not anybody is
+  // still searching; the graph's line-search loop runs exactly as many as the slowest problem needs
+  static const bool graph_any_batch = [] { const char* e = std::getenv("AGX_SQP_GRAPH"); return !(e && std::strcmp(e, "latency") == 0); }();
+  if (tick_graph_on && ((opts->eager_exit && h->B <= 64) || graph_any_batch) && !h->timing && !h->tick_sqp.failed && max_iter > 0) {
     auto& G = h->tick_sqp;
     W.K = h->d_K_internal;
     std::string key((const char*)&max_iter, sizeof(max_iter));
@@ -1455,7 +1459,7 @@ int agx_solve_sqp(agx_handle* h, const double* x0, const double* xs_ws, const do
           gb.end(ls_body);
         }
         if (gb.begin(body, inner_node)) {
-          AGX_LAUNCH(h, loop_condition_kernel, 1, 64, 0, cs, h->B, (const int32_t*)h->S.done, G.d_round, max_iter, outer);
+          AGX_LAUNCH(h, loop_condition_kernel, 1, 256, 0, cs, h->B, (const int32_t*)h->S.done, G.d_round, max_iter, outer);
           gb.end(body);
         }
       }

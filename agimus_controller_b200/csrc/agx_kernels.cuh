@@ -1431,7 +1431,9 @@ __global__ void finalize_io_kernel(Problem P, Work W, SolverState S, const IoTab
 // last kernel of the loop body: one more round while some problem is unfinished and the budget allows it
 __global__ void loop_condition_kernel(int B, const int32_t* __restrict__ done, int32_t* __restrict__ round_ctr,
                                       int rounds, cudaGraphConditionalHandle handle) {
-  const int live = __syncthreads_or((int)threadIdx.x < B && !done[threadIdx.x]);
+  int mine = 0;
+  for (int b = (int)threadIdx.x; b < B; b += (int)blockDim.x) mine |= !done[b];
+  const int live = __syncthreads_or(mine);
   if (threadIdx.x == 0) {
     const int r = *round_ctr + 1;
     *round_ctr = r;

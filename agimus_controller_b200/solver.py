@@ -323,12 +323,13 @@ class SolvePipeline:
             p.set_refs(refs)
 
     def submit(self, x0, xs_ws, us_ws, max_iter: int, opts=None, refs=None, out: T.Optional[dict] = None,
-               after_current_stream: bool = True) -> "SolvePipeline.Ticket":
+               after_current_stream: bool = True, sqp: bool = False) -> "SolvePipeline.Ticket":
         """Queues one batch on the next handle's stream and never blocks the host.  By default the batch is ordered
         after the work already queued on the caller's current stream (which produced the inputs); a caller whose inputs
         are ready and whose current stream carries work that waits on EARLIER batches (a collective over their results,
         say) passes ``after_current_stream=False`` so that the batches do not serialise through it.  Without ``out`` the
-        results land in the handle's own buffers, valid until that handle's next turn (``n_in_flight`` submits later)."""
+        results land in the handle's own buffers, valid until that handle's next turn (``n_in_flight`` submits later).
+        ``sqp=True`` runs ``solve_sqp`` (``opts``: ``AgxSqpOpts``) instead of FDDP."""
         j = self._next
         self._next = (j + 1) % len(self.problems)
         p, s = self.problems[j], self.streams[j]
@@ -337,7 +338,8 @@ class SolvePipeline:
         with torch.cuda.stream(s):
             if refs is not None:
                 p.set_refs(refs)
-            res = p.solve(x0, xs_ws, us_ws, max_iter, opts, out=out if out is not None else self._outs[j])
+            res = (p.solve_sqp if sqp else p.solve)(x0, xs_ws, us_ws, max_iter, opts,
+                                                    out=out if out is not None else self._outs[j])
             ev = torch.cuda.Event()
             ev.record(s)
         return SolvePipeline.Ticket(res, ev, j)
