@@ -469,6 +469,14 @@ struct TickGraphBuilder {
   }
 };
 
+// a caller recording its own graph on `st` gets the stream path: its kernels can be captured, a pageable copy and a
+// nested graph launch cannot
+bool stream_is_capturing(stream_t st) {
+  cudaStreamCaptureStatus cst = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cst) != cudaSuccess) { cudaGetLastError(); return false; }
+  return cst != cudaStreamCaptureStatusNone;
+}
+
 // refresh the pointer table and launch; the loop's further rounds are decided on the device
 int launch_tick_graph(agx_handle* h, agx_handle::TickGraph& G, const agx::IoTable& io, stream_t st, const char* what) {
   // pageable source on purpose: the runtime stages such a small copy before it returns, so ticks may be queued back
@@ -1236,7 +1244,7 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
   // and the call stays stream-ordered (the stream path below reads the completion flags back after every round).
   // AGX_TICK_GRAPH=0 keeps the stream path.
   static const bool tick_graph_on = [] { const char* e = std::getenv("AGX_TICK_GRAPH"); return !(e && e[0] == '0'); }();
-  if (tick_graph_on && latency_mode && !h->timing && !h->tick.failed && max_iter > 0) {
+  if (tick_graph_on && latency_mode && !h->timing && !h->tick.failed && max_iter > 0 && !stream_is_capturing(st)) {
     auto& G = h->tick;
     W.K = h->d_K_internal;
     if (!W.K) {
@@ -1419,7 +1427,8 @@ int agx_solve_sqp(agx_handle* h, const double* x0, const double* xs_ws, const do
   // queue a try / accept pair for every one of the n_alphas step lengths of every iteration, whether or not anybody is
   // still searching; the graph's line-search loop runs exactly as many as the slowest problem needs
   static const bool graph_any_batch = [] { const char* e = std::getenv("AGX_SQP_GRAPH"); return !(e && std::strcmp(e, "latency") == 0); }();
-  if (tick_graph_on && ((opts->eager_exit && h->B <= 64) || graph_any_batch) && !h->timing && !h->tick_sqp.failed && max_iter > 0) {
+  if (tick_graph_on && ((opts->eager_exit && h->B <= 64) || graph_any_batch) && !h->timing && !h->tick_sqp.failed && max_iter > 0 &&
+      !stream_is_capturing(st)) {
     auto& G = h->tick_sqp;
     W.K = h->d_K_internal;
     std::string key((const char*)&max_iter, sizeof(max_iter));

@@ -97,3 +97,36 @@ def test_solve_pipeline_gives_the_bits_of_solving_each_batch_alone():
     assert [t.index for t in tickets] == [0, 1, 2, 0, 1]
     pipe.join()
     pipe.close()
+
+
+def test_solves_can_be_recorded_into_the_callers_own_graph():
+    """A caller that records its stream into a CUDA graph gets the plain stream path of both solvers (kernels only: no
+    pointer-table copy, no nested graph launch), and the replay gives the direct call's results."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from agimus_controller_b200 import _abi, panda_table
+    from agimus_controller_b200.solver import BatchedShootingProblem
+    from agimus_controller_b200.workloads import goal_reaching_batch
+
+    B, T = 128, 30
+    table = panda_table()
+    helper = BatchedShootingProblem(table, np.full(2, 0.01), 1)
+    w = goal_reaching_batch(B, T=T, rnea=lambda q, v, a: helper.rnea(q, v, a).cpu().numpy(), seed=3)
+    p = BatchedShootingProblem(table, w["dts"], B)
+    p.set_refs(w["refs"])
+    x0, xs, us = (torch.as_tensor(w[k], device="cuda") for k in ("x0", "xs_ws", "us_ws"))
+    fo = _abi.default_fddp_opts(fixed_iters=True)
+    for name, call in (("fddp", lambda out: p.solve(x0, xs, us, 5, fo, out=out)),
+                       ("sqp", lambda out: p.solve_sqp(x0, xs, us, 5, None, out=out))):
+        want = {k: v.clone() for k, v in call(p.alloc_outputs()).items()}   # also allocates what the call allocates once
+        out = p.alloc_outputs()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            call(out)
+        for v in out.values():
+            v.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        for k in ("iters", "status", "xs", "us", "K", "cost"):
+            assert torch.equal(out[k], want[k]), (name, k)
