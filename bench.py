@@ -223,6 +223,52 @@ def mpc_latency(prob, dev, ticks, solver="fddp", with_cpu=False):
                         "warm start, <=10 FDDP iterations per tick (eager_exit: a tick is one graph launch whose WHILE node stops at convergence, in FDDP and in CSQP mode); host wall clock of set_refs_window + solve + D2H of us[0], K[0] into pinned host buffers"}
 
 
+def ocp_class_latency(dev, ticks):
+    """The same closed loop through the drop-in OCP class, the way the reference's MPC.run drives an OCP (mpc.py:38-66):
+    per tick set_reference_weighted_trajectory(list of T+1 WeightedTrajectoryPoint), solve(x0, list of states, list of
+    controls), ocp_results (lists of numpy arrays).  Timed span = those three calls: the host-side packing of the
+    reference list, H2D, solve, D2H of the whole result."""
+    from agimus_controller_b200 import PANDA_Q_NOMINAL, panda_table
+    from agimus_controller_b200.ocp_batched import OCPBatchedFDDP
+    from agimus_controller_b200.ocp_interface import (DTFactorsNSeq, OCPParamsBaseCroco, SE3, TrajectoryPoint,
+                                                      TrajectoryPointWeights, WeightedTrajectoryPoint)
+
+    T, nv = 20, 7
+    yaml_path = os.path.join(ROOT, "tests", "golden", "ocp_goal_reaching.yaml")
+    params = OCPParamsBaseCroco(dt=DT, solver_iters=N_ITERS, dt_factor_n_seq=DTFactorsNSeq([1], [T]), horizon_size=T)
+    ocp = OCPBatchedFDDP(panda_table(), params, yaml_path, batch_size=1, solver="fddp")
+    pose = SE3(np.diag([1.0, -1.0, -1.0]), np.array([0.5, 0.2, 0.5]))
+
+    def wpoint(i):
+        q = PANDA_Q_NOMINAL + 0.2 * np.sin(2 * np.pi * i * DT / 4.0) * np.ones(nv)
+        return WeightedTrajectoryPoint(
+            point=TrajectoryPoint(id=i, time_ns=i * 10_000_000, robot_configuration=q, robot_velocity=np.zeros(nv),
+                                  robot_acceleration=np.zeros(nv), robot_effort=np.zeros(nv),
+                                  end_effector_poses={"panda_hand_tcp": pose}),
+            weights=TrajectoryPointWeights(w_robot_configuration=np.full(nv, 1.0), w_robot_velocity=np.full(nv, 0.1),
+                                           w_robot_acceleration=np.zeros(nv), w_robot_effort=np.full(nv, 1e-3),
+                                           w_end_effector_poses={"panda_hand_tcp": np.full(6, 0.1)}))
+
+    buffer = [wpoint(i) for i in range(ticks + T + 2)]
+    x = np.concatenate([PANDA_Q_NOMINAL, np.zeros(nv)])
+    u_grav = ocp.problem.rnea(PANDA_Q_NOMINAL, np.zeros(nv), np.zeros(nv))[0].cpu().numpy()
+    xs, us = [x] * (T + 1), [u_grav] * T
+    ts = []
+    for k in range(ticks):
+        t0 = time.perf_counter()
+        ocp.set_reference_weighted_trajectory(buffer[k: k + T + 1])
+        ocp.solve(x, xs, us)
+        res = ocp.ocp_results
+        ts.append(time.perf_counter() - t0)
+        x = ocp.integrate(x, res.feed_forward_terms[0])
+        xs = [x] + list(res.states[2:]) + [res.states[-1]]
+        us = list(res.feed_forward_terms[1:]) + [res.feed_forward_terms[-1]]
+    ts = np.array(ts[20:]) * 1e3
+    return {"p50_ms": float(np.percentile(ts, 50)), "p99_ms": float(np.percentile(ts, 99)), "ticks": int(len(ts)),
+            "what": "OCPBatchedFDDP (the OCPBase drop-in) driven as MPC.run drives an OCP: reference list of T+1 "
+                    "points packed on the host, solve from Python lists, results back as lists of numpy arrays"}
+
+
 def pin_to_gpu_numa_node(local):
     """CPU affinity of this process := the cores of the NUMA node GPU `local` hangs off (sysfs); None when unknown."""
     try:
@@ -537,6 +583,7 @@ def run_ours(args):
         lat = mpc_latency(prob, dev, args.latency_ticks, with_cpu=not args.no_cpu)
         lat_sqp = mpc_latency(prob, dev, args.latency_ticks, solver="csqp")
         lat["csqp_mode"] = {k: lat_sqp[k] for k in ("p50_ms", "p99_ms", "mean_iters", "final_tracking_error_rad")}
+        lat["ocp_class"] = ocp_class_latency(dev, min(args.latency_ticks, 300))
 
     # the reference's own solver mode on the same workload (secondary figure, rank 0, N = 1): SQP = SolverCSQP without
     # active constraints, same budget of 10 iterations, per-problem KKT stop at the reference's tolerance 1e-3
