@@ -15,7 +15,15 @@ def run(B, ticks, queue_without_sync, mode="fddp"):
     table = panda_table()
     helper = BatchedShootingProblem(table, np.full(2, 0.01), 1)
     rn = lambda q, v, a: helper.rnea(q, v, a).cpu().numpy()  # noqa: E731
-    w = goal_reaching_batch(B, T=20, rnea=rn, seed=5)
+    if mode.endswith("_col"):
+        # capsule-pair collision costs: the COL instantiations of the kernels inside the graph
+        from agimus_controller_b200.workloads import pick_and_place_collision_batch
+
+        w = pick_and_place_collision_batch(B, T=20, rnea=rn)
+        table = w["table"]
+        mode = mode[:-4]
+    else:
+        w = goal_reaching_batch(B, T=20, rnea=rn, seed=5)
     p = BatchedShootingProblem(table, w["dts"], B)
     p.set_refs(w["refs"])
     opts = _abi.default_fddp_opts() if mode == "fddp" else _abi.default_sqp_opts()

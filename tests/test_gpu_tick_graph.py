@@ -53,6 +53,18 @@ def test_sqp_tick_graph_gives_the_bits_of_the_stream_path(tmp_path, B):
     assert iters.max() > 1 and np.isfinite(g[f"xs_{ticks - 1}"]).all()
 
 
+@pytest.mark.parametrize("mode", ["fddp_col", "sqp_col"])
+def test_tick_graph_with_collision_costs(tmp_path, mode):
+    """The graphs record the collision-pair instantiations of the kernels when the model carries pairs."""
+    ticks = 6
+    g = _run(tmp_path, "graph", 4, ticks, False, True, mode)
+    s = _run(tmp_path, "stream", 4, ticks, False, False, mode)
+    for k in range(ticks):
+        for name in ("iters", "status", "xs", "us", "K", "cost"):
+            np.testing.assert_array_equal(g[f"{name}_{k}"], s[f"{name}_{k}"], err_msg=f"{name} tick {k}")
+    assert np.isfinite(g[f"xs_{ticks - 1}"]).all()
+
+
 def test_ticks_queued_back_to_back_without_a_synchronisation(tmp_path):
     """The graph path never blocks the host: ticks queued on the stream one after the other (each into its own output
     buffers, each reading the previous one's shifted solution) give the results of the tick-by-tick loop."""
