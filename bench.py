@@ -764,6 +764,16 @@ def run_ours(args):
                     "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
             "phases": per,
         }
+        # the whole step against the same peak: algorithmic flops of the 10 iterations (+ the first cost pass) over the
+        # step time, with the batches in flight (the headline) and one batch at a time
+        step_flop = N_ITERS * (flops["calc_diff"] + flops["backward"] + flops["rollout_try"]) + (N_ITERS + 1) * flops["node_cost"]
+        if fp64_peak:
+            roofline["whole_step"] = {
+                "flop_per_step": step_flop,
+                "tflops": step_flop / (ms_total / args.steps * 1e-3) / 1e12,
+                "frac": step_flop / (ms_total / args.steps * 1e-3) / 1e12 / fp64_peak,
+                "serial_tflops": step_flop / (ms_serial / args.steps * 1e-3) / 1e12,
+                "serial_frac": step_flop / (ms_serial / args.steps * 1e-3) / 1e12 / fp64_peak}
 
     # CPU baseline beside it (bounded sample, rank 0, N = 1 only)
     cpu = None
