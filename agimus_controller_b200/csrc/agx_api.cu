@@ -598,29 +598,73 @@ int tree_solve(agx_handle* h, const double* x0, const double* xs_ws, const doubl
                double* out_cost, int32_t* out_iters, int32_t* out_status, double* out_stop, stream_t st) {
   const size_t nB = (size_t)h->B, T = (size_t)h->T, T1 = T + 1;
   const int nx = h->nx, nv = h->nv;
-  if (!out_K && !h->d_K_internal) {
+  if (!h->d_K_internal && (!out_K || (opts->eager_exit && h->B <= 64))) {
     if (!dev_alloc((void**)&h->d_K_internal, sizeof(double) * nB * T * nv * nx))
       return fail(h, AGX_ENOMEM, "allocation of the internal gain buffer failed");
   }
   Work W = h->W;
-  W.K = out_K ? out_K : h->d_K_internal;
   W.x0 = h->d_x0;
-  if (!copy_d2d(h->d_x0, x0, sizeof(double) * nB * nx, st)) return fail(h, AGX_ECUDA, "agx_solve: x0 copy failed");
   const Problem P = problem_of(h);
   const long long n_init = (long long)(nB * T1 * nx);
-  AGX_LAUNCH(h, init_kernel_n, (n_init + 255) / 256, 256, 0, st, P, nx, nv, W, h->S, O, xs_ws, us_ws);
+  const long long n_fin = (long long)(nB * T * nv * nx);
   const int gpc = TREE_SEQ_CTA / tree::GW;
-  for (int it = 0; it < max_iter; ++it) {
-    phase_begin(h, 0, st);
-    tree_launch_calc_diff(h, P, W.xs, W.us, h->S.cur, h->S.recalc, h->S.done, st);
-    phase_end(h, st);
-    phase_begin(h, 1, st);
-    tree_launch_backward(h, P, W, O, st);
-    phase_end(h, st);
-    phase_begin(h, 4, st);
-    AGX_TREE_LAUNCH(h, tree_forward_kernel, (h->B + gpc - 1) / gpc, TREE_SEQ_CTA, sizeof(double) * h->tree_board * gpc, st,
+  // one iteration: records, sweep, forward pass with its line search and the acceptance
+  auto enqueue_round = [&](stream_t s) {
+    phase_begin(h, 0, s);
+    tree_launch_calc_diff(h, P, W.xs, W.us, h->S.cur, h->S.recalc, h->S.done, s);
+    phase_end(h, s);
+    phase_begin(h, 1, s);
+    tree_launch_backward(h, P, W, O, s);
+    phase_end(h, s);
+    phase_begin(h, 4, s);
+    AGX_TREE_LAUNCH(h, tree_forward_kernel, (h->B + gpc - 1) / gpc, TREE_SEQ_CTA, sizeof(double) * h->tree_board * gpc, s,
                     P, W, h->S, O);
-    phase_end(h, st);
+    phase_end(h, s);
+  };
+#if AGX_GPU
+  // latency mode: the tick as one graph launch, as on the chain kernels (agx_solve below)
+  static const bool tick_graph_on = [] { const char* e = std::getenv("AGX_TICK_GRAPH"); return !(e && e[0] == '0'); }();
+  if (tick_graph_on && opts->eager_exit && h->B <= 64 && !h->timing && !h->tick.failed && max_iter > 0 &&
+      !stream_is_capturing(st)) {
+    auto& G = h->tick;
+    W.K = h->d_K_internal;
+    std::string key((const char*)&max_iter, sizeof(max_iter));
+    key.append((const char*)opts, sizeof(agx_fddp_opts));
+    if (!G.exec || G.key != key) {
+      TickGraphBuilder gb(h, G);
+      cudaStream_t cs = G.capture_stream;
+      cudaGraphConditionalHandle cond{};
+      cudaGraphNode_t loop_node = nullptr;
+      cudaGraph_t body = nullptr;
+      if (gb.begin(G.graph)) {
+        AGX_LAUNCH(h, init_io_kernel, (n_init + 255) / 256, 256, 0, cs, P, nx, nv, W, h->S, O, (const IoTable*)G.d_io, h->d_x0, G.d_round);
+        gb.end(G.graph);
+      }
+      G.nodes_fixed = (int)(h->launches - gb.launches_before);
+      if (gb.add_while(G.graph, true, &cond, &loop_node, &body) && gb.begin(body)) {
+        enqueue_round(cs);
+        AGX_LAUNCH(h, loop_condition_kernel, 1, 256, 0, cs, h->B, (const int32_t*)h->S.done, G.d_round, max_iter, cond);
+        gb.end(body);
+      }
+      G.nodes_round = (int)(h->launches - gb.launches_before) - G.nodes_fixed;
+      if (gb.begin(G.graph, loop_node)) {
+        AGX_LAUNCH(h, finalize_io_kernel, (n_fin + 255) / 256, 256, 0, cs, P, nx, nv, W, h->S, (const IoTable*)G.d_io);
+        gb.end(G.graph);
+        ++G.nodes_fixed;
+      }
+      gb.finish(h, key);
+    }
+    if (G.exec) {
+      const IoTable io{x0, xs_ws, us_ws, out_xs, out_us, out_K, out_k, out_cost, out_iters, out_status, out_stop};
+      return launch_tick_graph(h, G, io, st, "agx_solve");
+    }
+  }
+#endif
+  W.K = out_K ? out_K : h->d_K_internal;
+  if (!copy_d2d(h->d_x0, x0, sizeof(double) * nB * nx, st)) return fail(h, AGX_ECUDA, "agx_solve: x0 copy failed");
+  AGX_LAUNCH(h, init_kernel_n, (n_init + 255) / 256, 256, 0, st, P, nx, nv, W, h->S, O, xs_ws, us_ws);
+  for (int it = 0; it < max_iter; ++it) {
+    enqueue_round(st);
     if (it + 1 >= max_iter) break;
     if (opts->eager_exit && h->B <= 64 && !h->timing) {
       if (all_done_sync(h, st)) break;
@@ -639,7 +683,6 @@ int tree_solve(agx_handle* h, const double* x0, const double* xs_ws, const doubl
       if (live == 0) break;
     }
   }
-  const long long n_fin = (long long)(nB * T * nv * nx);
   AGX_LAUNCH(h, finalize_kernel_n, (n_fin + 255) / 256, 256, 0, st, P, nx, nv, W, h->S, out_xs, out_us, out_K, out_k,
              out_cost, out_iters, out_status, out_stop);
   return check_launch(h, "agx_solve");
@@ -1262,7 +1305,7 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
       cudaGraphNode_t loop_node = nullptr;
       cudaGraph_t body = nullptr;
       if (gb.begin(G.graph)) {   // head
-        AGX_LAUNCH(h, init_io_kernel, (n_init + 255) / 256, 256, 0, cs, P, W, h->S, O, (const IoTable*)G.d_io, h->d_x0, G.d_round);
+        AGX_LAUNCH(h, init_io_kernel, (n_init + 255) / 256, 256, 0, cs, P, NX, NJ, W, h->S, O, (const IoTable*)G.d_io, h->d_x0, G.d_round);
         enqueue_first_costs(cs);
         gb.end(G.graph);
       }
@@ -1274,7 +1317,7 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
       }
       G.nodes_round = (int)(h->launches - gb.launches_before) - G.nodes_fixed;
       if (gb.begin(G.graph, loop_node)) {   // tail: the results go to the caller's buffers
-        AGX_LAUNCH(h, finalize_io_kernel, (n_fin + 255) / 256, 256, 0, cs, P, W, h->S, (const IoTable*)G.d_io);
+        AGX_LAUNCH(h, finalize_io_kernel, (n_fin + 255) / 256, 256, 0, cs, P, NX, NJ, W, h->S, (const IoTable*)G.d_io);
         gb.end(G.graph);
         ++G.nodes_fixed;
       }
@@ -1440,7 +1483,7 @@ int agx_solve_sqp(agx_handle* h, const double* x0, const double* xs_ws, const do
       cudaGraphNode_t outer_node = nullptr, inner_node = nullptr;
       cudaGraph_t body = nullptr, ls_body = nullptr;
       if (gb.begin(G.graph)) {   // head
-        AGX_LAUNCH(h, init_io_kernel, (n_init + 255) / 256, 256, 0, cs, P, W, h->S, O, (const IoTable*)G.d_io, h->d_x0, G.d_round);
+        AGX_LAUNCH(h, init_io_kernel, (n_init + 255) / 256, 256, 0, cs, P, NX, NJ, W, h->S, O, (const IoTable*)G.d_io, h->d_x0, G.d_round);
         gb.end(G.graph);
       }
       G.nodes_fixed = (int)(h->launches - gb.launches_before);
@@ -1476,7 +1519,7 @@ int agx_solve_sqp(agx_handle* h, const double* x0, const double* xs_ws, const do
       if (gb.begin(G.graph, outer_node)) {   // tail
         const long long before_tail = h->launches;
         final_sweep(cs);
-        AGX_LAUNCH(h, finalize_io_kernel, (n_fin + 255) / 256, 256, 0, cs, P, W, h->S, (const IoTable*)G.d_io);
+        AGX_LAUNCH(h, finalize_io_kernel, (n_fin + 255) / 256, 256, 0, cs, P, NX, NJ, W, h->S, (const IoTable*)G.d_io);
         gb.end(G.graph);
         G.nodes_fixed += (int)(h->launches - before_tail);
       }

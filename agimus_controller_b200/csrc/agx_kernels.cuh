@@ -1386,14 +1386,15 @@ struct IoTable {
 
 // init_kernel + the x0 copy; the cost records are written by the node_cost launch that follows in the graph, so the
 // first calc_diff of the loop finds recalc_cost = 0
-__global__ void init_io_kernel(Problem P, Work W, SolverState S, FddpOpts O, const IoTable* __restrict__ io,
-                               double* __restrict__ x0_dst, int32_t* __restrict__ round_ctr) {
+__global__ void init_io_kernel(Problem P, int nx, int nv, Work W, SolverState S, FddpOpts O,
+                               const IoTable* __restrict__ io, double* __restrict__ x0_dst,
+                               int32_t* __restrict__ round_ctr) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int T1 = P.T + 1;
-  const long long nxs = (long long)P.B * T1 * NX, nus = (long long)P.B * P.T * NJ;
+  const long long nxs = (long long)P.B * T1 * nx, nus = (long long)P.B * P.T * nv;
   if (gid < nxs) W.xs[gid] = io->xs_ws[gid];
   if (gid < nus) W.us[gid] = io->us_ws[gid];
-  if (gid < (long long)P.B * NX) x0_dst[gid] = io->x0[gid];
+  if (gid < (long long)P.B * nx) x0_dst[gid] = io->x0[gid];
   if (gid == 0) { *S.t0 = agx_now_ns(); *round_ctr = 0; }
   if (gid < P.B) {
     const int b = (int)gid;
@@ -1405,10 +1406,10 @@ __global__ void init_io_kernel(Problem P, Work W, SolverState S, FddpOpts O, con
   }
 }
 
-__global__ void finalize_io_kernel(Problem P, Work W, SolverState S, const IoTable* __restrict__ io) {
+__global__ void finalize_io_kernel(Problem P, int nx, int nv, Work W, SolverState S, const IoTable* __restrict__ io) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int T1 = P.T + 1;
-  const long long per_xs = (long long)T1 * NX, per_us = (long long)P.T * NJ, per_K = (long long)P.T * NJ * NX;
+  const long long per_xs = (long long)T1 * nx, per_us = (long long)P.T * nv, per_K = (long long)P.T * nv * nx;
   if (gid < P.B * per_xs) {
     const int b = (int)(gid / per_xs);
     io->out_xs[gid] = W.xs[(size_t)(S.cur[b] & 1) * P.B * per_xs + gid];

@@ -110,7 +110,7 @@ typedef struct agx_model {
  * fixed_iters != 0: run exactly max_iter iterations, no early exit (benchmark mode).
  * eager_exit != 0 (and not fixed_iters): latency mode of the single MPC tick (B <= 64; ignored for larger batches): no
  * kernel runs past the iteration in which the last problem finishes.
- *   agx_solve and agx_solve_sqp on the 7-joint chain: the whole solve is ONE graph launch -- init, (FDDP: first costs,)
+ *   agx_solve (chain and general-tree kernels) and agx_solve_sqp on the 7-joint chain: the whole solve is ONE graph launch -- init, (FDDP: first costs,)
  *   a conditional WHILE node around the iteration whose condition the iteration's last kernel sets on the device (in
  *   agx_solve_sqp the line search is a second WHILE node nested in it, armed per iteration), (SQP: final sweep,)
  *   finalize -- so there is no host round trip between iterations and the call stays stream-ordered (no
@@ -118,7 +118,7 @@ typedef struct agx_model {
  *   table refreshed by one copy per call.  AGX_TICK_GRAPH=0 in the environment, a timing run (agx_set_timing) or a
  *   driver that refuses conditional nodes select the stream path below; both give the same bits
  *   (tests/test_gpu_tick_graph.py).
- *   Other trees (general-tree kernels) and the stream path: after every iteration (and, in agx_solve_sqp, after every
+ *   agx_solve_sqp on other trees, and the stream path: after every iteration (and, in agx_solve_sqp, after every
  *   step length of the line search) a completion flag / counter is read back (one small device-to-host copy and a
  *   stream synchronisation each) and the call returns as soon as every problem has finished.
  * In this mode the FDDP forward pass of the chain runs on a kernel that puts two warps on each problem group; its

@@ -22,6 +22,16 @@ def run(B, ticks, queue_without_sync, mode="fddp"):
         w = pick_and_place_collision_batch(B, T=20, rnea=rn)
         table = w["table"]
         mode = mode[:-4]
+    elif mode.endswith("_nv9"):
+        # the nine-joint Panda (fingers unlocked): general-tree kernels inside the graph
+        from agimus_controller_b200.workloads import pick_and_place_collision_batch
+
+        t9 = panda_table(lock_fingers=False)
+        h9 = BatchedShootingProblem(t9, np.full(2, 0.01), 1)
+        w = pick_and_place_collision_batch(B, T=20, rnea=lambda q, v, a: h9.rnea(q, v, a).cpu().numpy(),
+                                           lock_fingers=False)
+        table = w["table"]
+        mode = mode[:-4]
     else:
         w = goal_reaching_batch(B, T=20, rnea=rn, seed=5)
     p = BatchedShootingProblem(table, w["dts"], B)

@@ -53,9 +53,10 @@ def test_sqp_tick_graph_gives_the_bits_of_the_stream_path(tmp_path, B):
     assert iters.max() > 1 and np.isfinite(g[f"xs_{ticks - 1}"]).all()
 
 
-@pytest.mark.parametrize("mode", ["fddp_col", "sqp_col"])
+@pytest.mark.parametrize("mode", ["fddp_col", "sqp_col", "fddp_nv9"])
 def test_tick_graph_with_collision_costs(tmp_path, mode):
-    """The graphs record the collision-pair instantiations of the kernels when the model carries pairs."""
+    """The graphs record the collision-pair instantiations of the kernels when the model carries pairs, and the
+    general-tree kernels for the nine-joint Panda."""
     ticks = 6
     g = _run(tmp_path, "graph", 4, ticks, False, True, mode)
     s = _run(tmp_path, "stream", 4, ticks, False, False, mode)
