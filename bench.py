@@ -278,18 +278,18 @@ def pin_to_gpu_numa_node(local):
         bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
         node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
         if node < 0:
-            return None
+            return {"node": None, "why": f"sysfs reports numa_node {node} for {bdf} (no NUMA topology exposed)"}
         cpus = set()
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
             lo, _, hi = part.partition("-")
             cpus.update(range(int(lo), int(hi or lo) + 1))
         cpus &= os.sched_getaffinity(0)
         if not cpus:
-            return None
+            return {"node": node, "why": "none of the node's cores is in this process's affinity mask"}
         os.sched_setaffinity(0, cpus)
         return {"node": node, "cores": len(cpus)}
-    except Exception:
-        return None
+    except Exception as e:  # no sysfs entry, no permission: report, do not pin
+        return {"node": None, "why": f"{type(e).__name__}: {e}"}
 
 
 def run_ours(args):
