@@ -1287,7 +1287,12 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
   // and the call stays stream-ordered (the stream path below reads the completion flags back after every round).
   // AGX_TICK_GRAPH=0 keeps the stream path.
   static const bool tick_graph_on = [] { const char* e = std::getenv("AGX_TICK_GRAPH"); return !(e && e[0] == '0'); }();
-  if (tick_graph_on && latency_mode && !h->timing && !h->tick.failed && max_iter > 0 && !stream_is_capturing(st)) {
+  // Long budgets solved to convergence (no fixed iteration count, more than 32 iterations: the controller's first solve,
+  // a batch run until every problem stops) take the graph too, at any batch size: the stream path has to interrupt the
+  // queue every 16 rounds to ask the device whether anything is still running
+  const bool long_budget = !opts->fixed_iters && max_iter > 32;
+  if (tick_graph_on && (latency_mode || long_budget) && !h->timing && !h->tick.failed && max_iter > 0 &&
+      !stream_is_capturing(st)) {
     auto& G = h->tick;
     W.K = h->d_K_internal;
     if (!W.K) {

@@ -121,7 +121,9 @@ typedef struct agx_model {
  *   agx_solve_sqp on other trees, and the stream path: after every iteration (and, in agx_solve_sqp, after every
  *   step length of the line search) a completion flag / counter is read back (one small device-to-host copy and a
  *   stream synchronisation each) and the call returns as soon as every problem has finished.
- * In this mode the FDDP forward pass of the chain runs on a kernel that puts two warps on each problem group; its
+ * agx_solve uses the same graph, at any batch size, for budgets above 32 iterations without fixed_iters (a batch solved
+ * to convergence, the controller's first solve with max_iter = 1000): the loop ends with the last problem.
+ * In latency mode the FDDP forward pass of the chain runs on a kernel that puts two warps on each problem group; its
  * results agree with the throughput kernels' to rounding (1e-15), not bitwise.
  */
 typedef struct agx_fddp_opts {

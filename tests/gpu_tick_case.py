@@ -36,8 +36,14 @@ def run(B, ticks, queue_without_sync, mode="fddp"):
         w = goal_reaching_batch(B, T=20, rnea=rn, seed=5)
     p = BatchedShootingProblem(table, w["dts"], B)
     p.set_refs(w["refs"])
-    opts = _abi.default_fddp_opts() if mode == "fddp" else _abi.default_sqp_opts()
-    opts.eager_exit = 1
+    max_iter = 10
+    if mode == "fddp_long":
+        # a budget above 32 iterations solved to convergence: the graph serves it at any batch size
+        mode, max_iter = "fddp", 60
+        opts = _abi.default_fddp_opts()
+    else:
+        opts = _abi.default_fddp_opts() if mode == "fddp" else _abi.default_sqp_opts()
+        opts.eager_exit = 1
     solve = p.solve if mode == "fddp" else p.solve_sqp
     x = torch.as_tensor(w["x0"], device="cuda")
     xs = torch.as_tensor(w["xs_ws"], device="cuda")
@@ -45,7 +51,7 @@ def run(B, ticks, queue_without_sync, mode="fddp"):
     res = {}
     outs = [p.alloc_outputs() for _ in range(ticks)] if queue_without_sync else None
     for k in range(ticks):
-        out = solve(x, xs, us, 10, opts, out=outs[k] if outs else None)
+        out = solve(x, xs, us, max_iter, opts, out=outs[k] if outs else None)
         if not queue_without_sync:
             for name in ("xs", "us", "K", "cost", "iters", "status"):
                 res[f"{name}_{k}"] = out[name].cpu().numpy()

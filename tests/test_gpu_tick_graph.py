@@ -66,6 +66,19 @@ def test_tick_graph_with_collision_costs(tmp_path, mode):
     assert np.isfinite(g[f"xs_{ticks - 1}"]).all()
 
 
+def test_long_budget_to_convergence_runs_as_a_graph_at_any_batch_size(tmp_path):
+    """max_iter > 32 without fixed_iters: the stream path polls the device every 16 rounds, the graph loops on the
+    device until the last problem stops; 256 problems from a cold start (tens of iterations), then warm ticks."""
+    ticks = 3
+    g = _run(tmp_path, "graph", 256, ticks, False, True, "fddp_long")
+    s = _run(tmp_path, "stream", 256, ticks, False, False, "fddp_long")
+    for k in range(ticks):
+        for name in ("iters", "status", "xs", "us", "K", "cost"):
+            np.testing.assert_array_equal(g[f"{name}_{k}"], s[f"{name}_{k}"], err_msg=f"{name} tick {k}")
+    assert g["iters_0"].max() > 10
+    assert g["launches"][0] < s["launches"][0]   # the graph counts one round per solve, the stream path every launch
+
+
 def test_ticks_queued_back_to_back_without_a_synchronisation(tmp_path):
     """The graph path never blocks the host: ticks queued on the stream one after the other (each into its own output
     buffers, each reading the previous one's shifted solution) give the results of the tick-by-tick loop."""
