@@ -429,7 +429,8 @@ class OCPBatchedFDDP(OCPBase):
         # single-problem form (numpy / list inputs): pinned host staging for the three inputs and for the results, so that
         # a tick costs three asynchronous H2D copies, the solve, seven asynchronous D2H copies and ONE synchronisation
         self._pin = None
-        if self._B == 1:
+        dev_ = getattr(self._problem, "device", None)
+        if self._B == 1 and isinstance(dev_, torch.device) and dev_.type == "cuda":
             nx_, T_ = 2 * nv, self._problem.T
             dev = self._problem.device
             host = lambda *shape, dtype=torch.float64: torch.empty(shape, dtype=dtype).pin_memory()  # noqa: E731
@@ -573,6 +574,13 @@ class OCPBatchedFDDP(OCPBase):
         assert self._B == 1, "numpy / list inputs are the single-problem form; pass torch tensors for a batch"
         nx, nv, T_ = self._problem.nx, self._problem.nv, self.n_controls
         pin = self._pin
+        if pin is None:
+            # a problem object without a CUDA device (the CPU SIMT emulator of the tests): plain copies
+            out = run(np.asarray(x0, dtype=np.float64).reshape(1, nx),
+                      np.asarray(x_warmstart, dtype=np.float64).reshape(1, T_ + 1, nx),
+                      np.asarray(u_warmstart, dtype=np.float64).reshape(1, T_, nv), max_iters)
+            pin = dict(h_out={k: out[k].cpu() for k in ("xs", "us", "K", "cost", "iters", "status", "stop")})
+            return self._pack_single_result(out, pin["h_out"])
         pin["np_in"]["x0"][...] = np.asarray(x0, dtype=np.float64).reshape(1, nx)
         pin["np_in"]["xs"][...] = np.asarray(x_warmstart, dtype=np.float64).reshape(1, T_ + 1, nx)
         pin["np_in"]["us"][...] = np.asarray(u_warmstart, dtype=np.float64).reshape(1, T_, nv)
@@ -583,7 +591,12 @@ class OCPBatchedFDDP(OCPBase):
         for k, h_ in pin["h_out"].items():
             h_.copy_(out[k], non_blocking=True)
         torch.cuda.current_stream(self._problem.device).synchronize()   # the one synchronisation of the tick
-        ho = pin["h_out"]
+        self._pack_single_result(out, pin["h_out"])
+
+    def _pack_single_result(self, out: dict, ho: dict) -> None:
+        """Host copies of one problem's results -> ``OCPResults`` / ``OCPDebugData`` (``ocp_base_croco.py:134-140,
+        :173-177``)."""
+        self._results_batched = out
         xs_h, us_h, K_h = ho["xs"][0].numpy().copy(), ho["us"][0].numpy().copy(), ho["K"][0].numpy().copy()
         ocp_results = OCPResults(states=list(xs_h), ricatti_gains=list(K_h), feed_forward_terms=list(us_h))
         if self._ocp_params.use_debug_data:
