@@ -963,7 +963,6 @@ int agx_calc_diff(agx_handle* h, const double* xs, const double* us, double* out
   DeviceGuard g(h->device);
   if (h->tree) return tree_calc_diff(h, xs, us, out_cost, out_xnext, Fx, Fu, Lx, Lu, Lxx, Lxu, Luu, (stream_t)stream);
   const long long ents = (long long)h->B * (h->T + 1);
-  const int opc = NODE_CTA / 8;
   AGX_LAUNCH_COL(h, calc_diff_kernel, (ents + (CD_CTA / 8) - 1) / (CD_CTA / 8), CD_CTA, sizeof(double) * OCT_BOARD * (CD_CTA / 8), (stream_t)stream,
              problem_of(h), xs, us, (const int32_t*)nullptr, (const int32_t*)nullptr, (const int32_t*)nullptr, 1,
              (const int32_t*)nullptr, h->W.rec, h->W.crec);
@@ -1003,7 +1002,6 @@ int agx_cost_derivatives(agx_handle* h, const double* xs, const double* us, doub
     if (h->tree) {
       tree_launch_calc_diff(h, P, xs, us, nullptr, nullptr, nullptr, st);
     } else {
-      const int opc = NODE_CTA / 8;
       AGX_LAUNCH_COL(h, calc_diff_kernel, (ents + (CD_CTA / 8) - 1) / (CD_CTA / 8), CD_CTA, sizeof(double) * OCT_BOARD * (CD_CTA / 8), st, P, xs, us,
                      (const int32_t*)nullptr, (const int32_t*)nullptr, (const int32_t*)nullptr, 1,
                      (const int32_t*)nullptr, h->W.rec, h->W.crec);
@@ -1097,7 +1095,6 @@ int agx_riccati(agx_handle* h, const double* x0, const double* xs, const double*
   }
   AGX_LAUNCH(h, init_kernel, (n_init + 255) / 256, 256, 0, st, P, W, h->S, O, xs, us);
   const long long ents = (long long)(nB * T1);
-  const int opc_n = NODE_CTA / 8, opc_s = SEQ_CTA / 8;
   AGX_LAUNCH_COL(h, calc_diff_kernel, (ents + (CD_CTA / 8) - 1) / (CD_CTA / 8), CD_CTA, sizeof(double) * OCT_BOARD * (CD_CTA / 8), st, P,
              (const double*)W.xs, (const double*)W.us, (const int32_t*)h->S.cur, (const int32_t*)h->S.recalc,
              (const int32_t*)h->S.recalc_cost, 0, (const int32_t*)h->S.done, W.rec, W.crec);
