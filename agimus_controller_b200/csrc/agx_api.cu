@@ -1242,12 +1242,23 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
   const bool two_warp = forced ? forced == 2 : latency_mode;
   // first iteration: every cost record is stale; the thread-per-node kernel is the cheap way to fill them
   // (later iterations only meet stale cost records after a line search, handled in line by calc_diff_kernel)
-  auto enqueue_first_costs = [&](stream_t s) {
+  // latency mode: the cost records come from the octet path of calc_diff_kernel (six short warps for 21 nodes) instead
+  // of the thread-per-node kernel (one long warp): the same record to rounding.  AGX_LAT_COST=thread keeps the latter
+  // (measured on the B = 1 tick: 0.299 -> 0.287 ms)
+  static const bool lat_cost_octet = [] { const char* e = std::getenv("AGX_LAT_COST"); return !(e && std::strcmp(e, "thread") == 0); }();
+  const bool octet_costs = latency_mode && lat_cost_octet;
+  auto enqueue_costs = [&](stream_t s, int other) {
     phase_begin(h, 3, s);
-    AGX_LAUNCH_NODE_COST(h, cost_ctas, COST_CTA, COST_SMEM, s, P, (const double*)W.xs, (const double*)W.us,
-               (const int32_t*)h->S.cur, 0, (const int32_t*)h->S.done, (const int32_t*)nullptr, W.crec, (double*)nullptr);
+    if (octet_costs)
+      AGX_LAUNCH_COL(h, calc_diff_kernel, (ents + (CD_CTA / 8) - 1) / (CD_CTA / 8), CD_CTA, sizeof(double) * OCT_BOARD * (CD_CTA / 8), s, P,
+                 (const double*)W.xs, (const double*)W.us, (const int32_t*)h->S.cur, (const int32_t*)nullptr,
+                 (const int32_t*)nullptr, other ? 3 : 2, (const int32_t*)h->S.done, W.rec, W.crec);
+    else
+      AGX_LAUNCH_NODE_COST(h, cost_ctas, COST_CTA, COST_SMEM, s, P, (const double*)W.xs, (const double*)W.us,
+                 (const int32_t*)h->S.cur, other, (const int32_t*)h->S.done, (const int32_t*)nullptr, W.crec, (double*)nullptr);
     phase_end(h, s);
   };
+  auto enqueue_first_costs = [&](stream_t s) { enqueue_costs(s, 0); };
   // one round: problem.calc + calcDiff at the candidate (dynamics records, plus the cost records where they are stale:
   // after an alpha = 1 acceptance they were already written for the trial by node_cost_kernel), Riccati sweep, trial
   // rollout, trial costs, acceptance.  `round_dev` = the device-side round counter of the tick graph, else null
@@ -1267,10 +1278,7 @@ int agx_solve(agx_handle* h, const double* x0, const double* xs_ws, const double
       AGX_LAUNCH(h, rollout_try_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * FW_BOARD * opc_s, s, P, W,
                  h->S);
     phase_end(h, s);
-    phase_begin(h, 3, s);
-    AGX_LAUNCH_NODE_COST(h, cost_ctas, COST_CTA, COST_SMEM, s, P, (const double*)W.xs, (const double*)W.us,
-               (const int32_t*)h->S.cur, 1, (const int32_t*)h->S.done, (const int32_t*)nullptr, W.crec, (double*)nullptr);
-    phase_end(h, s);
+    enqueue_costs(s, 1);
     phase_begin(h, 4, s);
     AGX_LAUNCH_COL(h, accept_linesearch_kernel, (h->B + opc_s - 1) / opc_s, SEQ_CTA, sizeof(double) * FW_BOARD * opc_s, s, P, W,
                h->S, O, it, round_dev);

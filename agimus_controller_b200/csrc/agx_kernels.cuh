@@ -184,9 +184,11 @@ calc_diff_kernel(Problem P, const double* __restrict__ xs, const double* __restr
   const int f_done = done ? done[b] : 0;
   const int f_dyn = recalc ? recalc[b] : 1;
   const int f_cost = recalc_cost ? recalc_cost[b] : 0;
-  const int f_cur = cur ? (cur[b] & 1) : 0;
+  // cost_everywhere: 0 = cost records where they are stale, 1 = everywhere, 2 = everywhere and no dynamics records,
+  // 3 = as 2 on the OTHER trajectory buffer (the trial of the line search): the latency mode's cost evaluation
+  const int f_cur = cur ? ((cur[b] ^ (cost_everywhere == 3 ? 1 : 0)) & 1) : 0;
   if (f_done) return;
-  const bool do_dyn = f_dyn != 0;
+  const bool do_dyn = f_dyn != 0 && cost_everywhere < 2;
   const bool do_cost = cost_everywhere || f_cost != 0;
   if (!do_dyn && !do_cost) return;
   double* sb = smem + oct_in_cta * OCT_BOARD;

@@ -123,8 +123,9 @@ typedef struct agx_model {
  *   stream synchronisation each) and the call returns as soon as every problem has finished.
  * agx_solve uses the same graph, at any batch size, for budgets above 32 iterations without fixed_iters (a batch solved
  * to convergence, the controller's first solve with max_iter = 1000): the loop ends with the last problem.
- * In latency mode the FDDP forward pass of the chain runs on a kernel that puts two warps on each problem group; its
- * results agree with the throughput kernels' to rounding (1e-15), not bitwise.
+ * In latency mode the FDDP forward pass of the chain runs on a kernel that puts two warps on each problem group and the
+ * cost records come from the octet path of the derivative kernel instead of the thread-per-node kernel; the results
+ * agree with the throughput kernels' to rounding (1e-15 per operation), not bitwise.
  */
 typedef struct agx_fddp_opts {
   double reg_min, reg_max, reg_incfactor, reg_decfactor;

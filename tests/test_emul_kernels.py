@@ -498,8 +498,12 @@ def test_eager_exit_gives_the_same_results_with_fewer_launches(orc, m7):
     opts = _abi.default_fddp_opts()
     opts.eager_exit = 1
     e = emu.solve(m7, w["refs"], w["dts"], w["x0"], w["xs_ws"], w["us_ws"], 24, opts)
-    for k in ("xs", "us", "K", "cost", "iters", "status"):
+    # the latency mode evaluates the cost records on the octet path of calc_diff_kernel (the throughput mode on the
+    # thread-per-node kernel): the same numbers to rounding, the same decisions
+    for k in ("iters", "status"):
         np.testing.assert_array_equal(e[k], ref[k])
+    for k in ("xs", "us", "K", "cost"):
+        assert rel(e[k], ref[k]) < 1e-9, k
     assert int(ref["iters"].max()) < 24 and e["launches"] < ref["launches"]
     assert e["launches"] <= 5 * (int(ref["iters"].max()) + 1) + 3
     so = _abi.default_sqp_opts()
