@@ -434,12 +434,31 @@ class OCPBatchedFDDP(OCPBase):
             nx_, T_ = 2 * nv, self._problem.T
             dev = self._problem.device
             host = lambda *shape, dtype=torch.float64: torch.empty(shape, dtype=dtype).pin_memory()  # noqa: E731
-            h_in = dict(x0=host(1, nx_), xs=host(1, T_ + 1, nx_), us=host(1, T_, nv))
+
+            def carve(buf, shapes):
+                """Views of consecutive pieces of one flat buffer (every piece starts on an even index: 16 bytes)."""
+                out_, o = {}, 0
+                for k, shp in shapes.items():
+                    n = int(np.prod(shp))
+                    out_[k] = buf[o:o + n].view(*shp)
+                    o += n + (n & 1)
+                return out_
+
+            size = lambda shapes: sum(int(np.prod(v)) + (int(np.prod(v)) & 1) for v in shapes.values())  # noqa: E731
+            # inputs, results and integer results each live in ONE device buffer with ONE pinned mirror: a tick is one
+            # H2D copy, the solve, two D2H copies and one synchronisation
+            in_shapes = dict(x0=(1, nx_), xs=(1, T_ + 1, nx_), us=(1, T_, nv))
+            f_shapes = dict(xs=(1, T_ + 1, nx_), us=(1, T_, nv), K=(1, T_, nv, nx_), k=(1, T_, nv), cost=(1,), stop=(1,))
+            i_shapes = dict(iters=(1,), status=(1,))
+            h_in, d_in = host(size(in_shapes)), torch.empty(size(in_shapes), dtype=torch.float64, device=dev)
+            h_f, d_f = host(size(f_shapes)), torch.empty(size(f_shapes), dtype=torch.float64, device=dev)
+            h_i = host(size(i_shapes), dtype=torch.int32)
+            d_i = torch.empty(size(i_shapes), dtype=torch.int32, device=dev)
+            self._out = {**carve(d_f, f_shapes), **carve(d_i, i_shapes)}
             self._pin = dict(
-                h_in=h_in, np_in={k: v.numpy() for k, v in h_in.items()},
-                d_in={k: torch.empty_like(v, device=dev) for k, v in h_in.items()},
-                h_out={k: host(*self._out[k].shape, dtype=self._out[k].dtype)
-                       for k in ("xs", "us", "K", "cost", "iters", "status", "stop")},
+                h_in=h_in, d_in=d_in, np_in={k: v.numpy() for k, v in carve(h_in, in_shapes).items()},
+                d_in_views=carve(d_in, in_shapes), h_f=h_f, d_f=d_f, h_i=h_i, d_i=d_i,
+                h_out={**carve(h_f, f_shapes), **carve(h_i, i_shapes)},
                 h_refs=host(1, T_ + 1, self._problem.ref_size))
             self._pin["d_refs"] = torch.empty_like(self._pin["h_refs"], device=dev)
         # transforms requested by the OCP and provided externally (BuildData.transforms, ocp_croco_generic.py:84-88)
@@ -584,12 +603,12 @@ class OCPBatchedFDDP(OCPBase):
         pin["np_in"]["x0"][...] = np.asarray(x0, dtype=np.float64).reshape(1, nx)
         pin["np_in"]["xs"][...] = np.asarray(x_warmstart, dtype=np.float64).reshape(1, T_ + 1, nx)
         pin["np_in"]["us"][...] = np.asarray(u_warmstart, dtype=np.float64).reshape(1, T_, nv)
-        for k in ("x0", "xs", "us"):
-            pin["d_in"][k].copy_(pin["h_in"][k], non_blocking=True)
-        out = run(pin["d_in"]["x0"], pin["d_in"]["xs"], pin["d_in"]["us"], max_iters)
+        pin["d_in"].copy_(pin["h_in"], non_blocking=True)
+        dv = pin["d_in_views"]
+        out = run(dv["x0"], dv["xs"], dv["us"], max_iters)   # writes into self._out: views of d_f / d_i
         self._results_batched = out
-        for k, h_ in pin["h_out"].items():
-            h_.copy_(out[k], non_blocking=True)
+        pin["h_f"].copy_(pin["d_f"], non_blocking=True)
+        pin["h_i"].copy_(pin["d_i"], non_blocking=True)
         torch.cuda.current_stream(self._problem.device).synchronize()   # the one synchronisation of the tick
         self._pack_single_result(out, pin["h_out"])
 
