@@ -156,3 +156,42 @@ def test_solves_can_be_recorded_into_the_callers_own_graph():
         torch.cuda.synchronize()
         for k in ("iters", "status", "xs", "us", "K", "cost"):
             assert torch.equal(out[k], want[k]), (name, k)
+
+
+def test_graph_is_rebuilt_when_the_options_change():
+    """One handle, options changing from call to call (the graph is keyed on the iteration budget and the options):
+    every call gives what a fresh throughput-mode solve with the same options gives (same decisions, iterates to
+    rounding), and returning to the first options reproduces the first result bit for bit."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from agimus_controller_b200 import _abi, panda_table
+    from agimus_controller_b200.solver import BatchedShootingProblem
+    from agimus_controller_b200.workloads import goal_reaching_batch
+
+    B, T = 4, 20
+    table = panda_table()
+    helper = BatchedShootingProblem(table, np.full(2, 0.01), 1)
+    w = goal_reaching_batch(B, T=T, rnea=lambda q, v, a: helper.rnea(q, v, a).cpu().numpy(), seed=9)
+    p = BatchedShootingProblem(table, w["dts"], B)
+    p.set_refs(w["refs"])
+    ref = BatchedShootingProblem(table, w["dts"], B)
+    ref.set_refs(w["refs"])
+
+    def run(th_stop, max_iter, eager):
+        o = _abi.default_fddp_opts()
+        o.th_stop, o.eager_exit = th_stop, int(eager)
+        h = p if eager else ref
+        return {k: v.cpu().numpy().copy() for k, v in h.solve(w["x0"], w["xs_ws"], w["us_ws"], max_iter, o).items()}
+
+    cases = [(1e-9, 30), (1e-2, 30), (1e-9, 12), (1e-9, 30)]
+    got = [run(th, mi, True) for th, mi in cases]
+    for (th, mi), g in zip(cases, got):
+        want = run(th, mi, False)
+        np.testing.assert_array_equal(g["iters"], want["iters"])
+        np.testing.assert_array_equal(g["status"], want["status"])
+        for k in ("xs", "us", "cost"):
+            assert np.abs(g[k] - want[k]).max() <= 1e-9 * max(np.abs(want[k]).max(), 1.0), k
+    assert got[1]["iters"].max() < got[0]["iters"].max()      # the looser stop criterion ends earlier
+    assert got[2]["iters"].max() <= 12
+    for k in ("iters", "status", "xs", "us", "K", "cost"):
+        np.testing.assert_array_equal(got[3][k], got[0][k])
